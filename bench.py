@@ -1,0 +1,253 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: ray-samples/s/GPU on BASELINE.json configs[1]
+(fg-bob deformable field, 2048 rays x 128 samples per GPU, synthetic rays, synthetic "trained-like"
+weights, rays sharded data-parallel = weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pass forward]
+
+One "step" = one pass of the hot path over one batch: weight packing (weights change every
+optimiser step in training), the fused query_field kernel and the compositing kernel.
+`value` times the step with inputs resident in HBM; `e2e` goes through the public API with pinned
+HOST buffers (H2D of rays + per-frame tables and D2H of the rendered pixels inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+
+# algorithmic FLOPs per ray-sample of what the fused forward computes (hook-measured on
+# the reference): F_query,fwd(fg-bob) = 1 914 380 incl. the 1/16-ray eikonal forward (71 616), which
+# stays on PyTorch -> 1 842 764.
+FLOP_PER_SAMPLE_FWD = 1_914_380 - 71_616
+WORKLOAD = dict(M=128, N=16, D=128)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["bf16_tflops"]), float(d["hbm_gbs"]), "measured"
+    return 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def make_problem(device, rank, M, N, D):
+    import synth
+    from lab4d_b200 import spec
+    from test_gpu_parity import synth_tables
+
+    cfg = spec.FG_BOB
+    st = synth.synth_state(spec.field_param_shapes(cfg), 0, "fg")
+    P = {k: torch.from_numpy(v).to(device) for k, v in st.items()}
+    rays_np = synth.synth_rays(M, N, seed=10 + rank)
+    rays = {k: torch.from_numpy(v).to(device) for k, v in rays_np.items()}
+    tab = synth_tables(cfg, M, device, seed=10 + rank, rays=rays, P=P)
+    return cfg, P, rays, tab
+
+
+def cpu_port_rate(M, N, D, threads, reps=1):
+    """The oracle restatement (a port of the reference's PyTorch path) on the host cores."""
+    import lab4d_oracle as O
+
+    torch.set_num_threads(threads)
+    cfg, P, rays, tab = make_problem("cpu", 0, M, N, D)
+    with torch.no_grad():
+        O.render_pixel(*O.query_field(P, cfg.as_oracle_cfg(), rays, tab, D))  # warm-up
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            O.render_pixel(*O.query_field(P, cfg.as_oracle_cfg(), rays, tab, D))
+        dt = (time.perf_counter() - t0) / reps
+    return M * N * D / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU PyTorch path (oracle port) on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    Ms = 8  # bounded sample: 8 frames x 16 rays x 128 samples = 16 384 ray-samples per step
+    times = []
+    for i in range(args.warmup + args.steps):
+        rate, dt = cpu_port_rate(Ms, WORKLOAD["N"], WORKLOAD["D"], threads)
+        if i >= args.warmup:
+            times.append(dt)
+    S = Ms * WORKLOAD["N"] * WORKLOAD["D"]
+    val = S / float(np.mean(times))
+    sample = f"{Ms} of {WORKLOAD['M']} frames x {WORKLOAD['N']} rays x {WORKLOAD['D']} samples per step, forward, fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": "ray-samples/s/GPU", "value": val, "unit": "ray-samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "fg-bob 2048 rays x 128 samples (configs[1]), forward", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "ray-samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch.distributed as dist
+
+    from lab4d_b200.render import FieldRenderer, render_pixel
+
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    M, N, D = WORKLOAD["M"], WORKLOAD["N"], WORKLOAD["D"]
+    S = M * N * D
+    cfg, P, rays, tab = make_problem(device, rank, M, N, D)
+    r = FieldRenderer(cfg, device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+    launches = {"n": 0}
+
+    def step():
+        r.pack(P)
+        feat, deltas = r.query_field(P, rays, tab, D)
+        rend = render_pixel(feat, deltas)
+        launches["n"] += 1 + 1 + 2  # pack, field_fwd, composite (14 channels -> 2 launches)
+        return rend
+
+    # pinned host copies for the end-to-end arm
+    host_in = {k: v.cpu().pin_memory() for k, v in {**rays, **tab}.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+    out_host = torch.empty(M, N, 3).pin_memory()
+
+    def step_e2e():
+        dev_in = {k: v.to(device, non_blocking=True) for k, v in host_in.items()}
+        rr = {k: dev_in[k] for k in rays}
+        tt = {k: dev_in[k] for k in tab}
+        r.pack(P)
+        feat, deltas = r.query_field(P, rr, tt, D)
+        rend = render_pixel(feat, deltas)
+        out_host.copy_(rend["rgb"], non_blocking=True)
+        return rend
+
+    def timed(fn, steps, kernel_events=None):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            flush.fill_(i & 0xFF)  # evict L2 between timed iterations
+            ev[i][0].record()
+            fn()
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in ev]
+
+    for _ in range(args.warmup):
+        step()
+        step_e2e()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches["n"] = 0
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    ms = timed(step, args.steps)
+    n_launch = launches["n"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms_e2e = timed(step_e2e, args.steps)
+    # the dominant kernel alone (same stream, CUDA events around the C-ABI call only)
+    kern = []
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        r.time_next_launch = True
+        r.query_field(P, rays, tab, D)
+        torch.cuda.synchronize()
+        kern.append(r.last_kernel_ms)
+    clocks = sampler.stop()
+    tot = torch.tensor([sum(ms), sum(ms_e2e)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms_step = float(tot[0]) / args.steps
+    ms_step_e2e = float(tot[1]) / args.steps
+    if rank == 0:
+        peak_tf, peak_bw, how = peaks()
+        kms = float(np.mean(kern))
+        achieved = FLOP_PER_SAMPLE_FWD * S / (kms * 1e-3) / 1e12
+        line = {
+            "metric": "ray-samples/s/GPU", "value": world * S / (ms_step * 1e-3), "unit": "ray-samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+            "config": {"workload": "fg-bob 2048 rays x 128 samples per GPU (configs[1]), forward query_field + render_pixel",
+                       "rays_per_gpu": M * N, "samples_per_ray": D, "bones": cfg.B, "l2": "flushed between iterations (256 MB write)",
+                       "pass": "forward", "parallelism": f"dp{world} (rays sharded, no data-path collective in forward)"},
+            "e2e": {"value": world * S / (ms_step_e2e * 1e-3), "unit": "ray-samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": out_host.numel() * 4},
+            "gpu_launches": n_launch,
+            "roofline": {"bound": "tensor", "kernel": "field_fwd_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf, "traffic": None, "kernel_ms": kms, "peak_source": how + " bf16 dense burst"},
+            "clocks": clocks, "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            Ms = 8
+            rate, dt = cpu_port_rate(Ms, N, D, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "ray-samples/s", "cores": threads, "kind": "port",
+                                    "sample": f"{Ms} of {M} frames x {N} rays x {D} samples, forward, fp32 oracle port, {dt:.2f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,124 @@
+"""ctypes binding of libb200render.so (C ABI: include/b200r.h).  No torch types cross this boundary:
+only integers, floats and raw device pointers.  Import fails loudly if the library is missing or the
+device is not sm_100 - there is no CPU or PyTorch fallback for the hot path."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200render.so")
+
+MAX_LAYERS = 24
+MAX_CHANNELS = 12
+CH_NORM, CH_NORM_FROZEN, CH_MEAN, CH_FLOW, CH_WEIGHTSUM, CH_VIS = range(6)
+
+f32p = C.c_void_p  # device pointers are passed as integers
+
+
+class FieldDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("category", "D", "W", "L_xyz", "L_dir", "appr_channels", "skip", "n_bones",
+                                         "has_feature", "operand_dtype")]
+
+
+_FIELD_PTRS_IN = ["hxy", "Kinv", "near_far", "field2cam", "logibeta", "logscale"]
+_FIELD_PTRS_MID = ["delta1_bias_fwd", "sdf_w", "sdf_b", "rgb2_w", "rgb2_b", "rgb0_dir_w", "vis_final_w", "vis_final_b",
+                   "bone_inv_t", "bone_inv_rest", "se3_bwd", "se3_fwd", "inv_gauss", "bone_center", "warp_logibeta"]
+FIELD_OUTPUTS = [("rgb", 3), ("density", 1), ("vis", 1), ("xyz", 3), ("xyz_cam", 3), ("xyz_t", 3), ("dir", 3), ("depth", 1),
+                 ("deltas", 1), ("feature", 16), ("flow", 3), ("cyc_dist", 1), ("delta_skin", 1), ("skin_entropy", 1),
+                 ("gauss_density", 1), ("sdf", 1)]
+
+
+class FieldArgs(C.Structure):
+    _fields_ = ([("M", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("flow_thresh", C.c_float)]
+                + [(n, f32p) for n in _FIELD_PTRS_IN]
+                + [("bias", f32p * MAX_LAYERS), ("bias_stride", C.c_int32 * MAX_LAYERS)]
+                + [(n, f32p) for n in _FIELD_PTRS_MID]
+                + [(n, f32p) for n, _ in FIELD_OUTPUTS])
+
+
+class CompositeArgs(C.Structure):
+    _fields_ = [("R", C.c_int32), ("D", C.c_int32), ("density", f32p), ("deltas", f32p), ("mask", f32p),
+                ("weights", f32p), ("transmit", f32p), ("n_channels", C.c_int32), ("src", f32p * MAX_CHANNELS),
+                ("dst", f32p * MAX_CHANNELS), ("nch", C.c_int32 * MAX_CHANNELS), ("mode", C.c_int32 * MAX_CHANNELS)]
+
+
+class CompositeBwdArgs(C.Structure):
+    _fields_ = [("fwd", CompositeArgs), ("g_mask", f32p), ("g_dst", f32p * MAX_CHANNELS), ("g_density", f32p),
+                ("g_src", f32p * MAX_CHANNELS)]
+
+
+EXPORTS = ["b200r_layer_count", "b200r_packed_bytes", "b200r_create", "b200r_destroy", "b200r_last_error",
+           "b200r_pack_weights", "b200r_field_fwd", "b200r_composite_fwd", "b200r_composite_bwd"]
+
+_lib = None
+
+
+def load():
+    """dlopen the library (works without a GPU: used by the CPU test that checks the exported symbols)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m lab4d_b200.build` (or __graft_entry__.build()); "
+                           "the renderer has no non-CUDA fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.b200r_layer_count.argtypes = [C.POINTER(FieldDesc)]
+    lib.b200r_layer_count.restype = C.c_int
+    lib.b200r_packed_bytes.argtypes = [C.POINTER(FieldDesc)]
+    lib.b200r_packed_bytes.restype = C.c_size_t
+    lib.b200r_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.b200r_create.restype = C.c_int
+    lib.b200r_destroy.argtypes = [C.c_void_p]
+    lib.b200r_destroy.restype = None
+    lib.b200r_last_error.argtypes = [C.c_void_p]
+    lib.b200r_last_error.restype = C.c_char_p
+    lib.b200r_pack_weights.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.POINTER(C.c_void_p), C.c_int, C.c_float,
+                                       C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.b200r_pack_weights.restype = C.c_int
+    lib.b200r_field_fwd.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldArgs), C.c_void_p]
+    lib.b200r_field_fwd.restype = C.c_int
+    lib.b200r_composite_fwd.argtypes = [C.c_void_p, C.POINTER(CompositeArgs), C.c_void_p]
+    lib.b200r_composite_fwd.restype = C.c_int
+    lib.b200r_composite_bwd.argtypes = [C.c_void_p, C.POINTER(CompositeBwdArgs), C.c_void_p]
+    lib.b200r_composite_bwd.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+class Handle:
+    """Per-device library handle; raises RuntimeError(b200r_last_error) on any failure."""
+
+    def __init__(self, device_index):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.b200r_create(int(device_index), C.byref(h))
+        if rc != 0:
+            raise RuntimeError({-3: "b200r: device is not sm_100 (B200); no fallback path exists",
+                                -2: "b200r: CUDA error while opening the device"}.get(rc, f"b200r_create failed ({rc})"))
+        self.h = h
+        self.device_index = int(device_index)
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: {self.lib.b200r_last_error(self.h).decode()} (code {rc})")
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.b200r_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+_handles = {}
+
+
+def handle_for(device):
+    import torch
+
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _handles:
+        _handles[idx] = Handle(idx)
+    return _handles[idx]
