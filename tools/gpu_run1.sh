@@ -2,7 +2,7 @@
 # first GPU contact: parity tests, smoke, short bench.  Output under gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -q -s -x --timeout=300 > gpurun_out/pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -s --timeout=300 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -40 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
