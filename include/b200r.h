@@ -73,65 +73,86 @@ int b200r_create(int device, b200r_handle** out);
 void b200r_destroy(b200r_handle* h);
 const char* b200r_last_error(const b200r_handle* h);
 
-/* weights[i]: (out_i, in_i) row-major fp32 nn.Linear weight of canonical layer i.
- * alpha: PosEmbedding annealing window (nnutils/embedding.py:112-125) folded into the packed
- * weights of basefield / colorfield; pass a negative value for "None". */
-int b200r_pack_weights(b200r_handle* h, const b200r_field_desc* desc, const float* const* weights, int n_weights,
-                       float alpha, void* packed, size_t packed_bytes, b200r_stream stream);
-
-/* Inputs and outputs of one training-mode query_field call on M frames x N rays x D samples. */
+/* Parameters of one field: device pointers into the reference modules' own storage (state_dict
+ * layout).  Nothing is copied or owned by the library. */
 typedef struct {
-  int32_t M, N, D;
-  float flow_thresh;          /* < 0: None */
-  const float* hxy;           /* (M,N,3) homogeneous pixel coordinates */
-  const float* Kinv;          /* (M,3,3) */
-  const float* near_far;      /* (M,2) */
-  const float* field2cam;     /* (M,8): quaternion w,x,y,z ; translation x,y,z ; 0 */
+  const float* weight[B200R_MAX_LAYERS]; /* (out_i, in_i) row-major nn.Linear weight of canonical layer i */
+  const float* bias[B200R_MAX_LAYERS];   /* (out_i) */
+  const float* sdf_w;         /* sdf.weight (W) */
+  const float* sdf_b;         /* (1) */
+  const float* rgb2_w;        /* rgb.2.weight (3, W/2) */
+  const float* rgb2_b;        /* (3) */
+  const float* vis_final_w;   /* vis_mlp.basefield.linear_final.weight (64) */
+  const float* vis_final_b;   /* (1) */
   const float* logibeta;      /* (1) */
   const float* logscale;      /* (1) */
-  /* per-layer bias rows: bias[i] + frame * bias_stride[i]; stride 0 = shared by all frames.
-   * Per-frame rows carry b + W[:, code columns] @ code (instance / time / appearance codes are
-   * constant per frame: nnutils/base.py:140-146, nerf.py:200-204, skinning.py:113-116). */
-  const float* bias[B200R_MAX_LAYERS];
-  int32_t bias_stride[B200R_MAX_LAYERS];
-  const float* delta1_bias_fwd; /* (M,64) delta_field.linear_1 rows for FORWARD warps (mean time code) */
-  /* heads evaluated on CUDA cores in the epilogues */
-  const float* sdf_w;         /* (W) */
-  const float* sdf_b;         /* (1) */
-  const float* rgb2_w;        /* (3, W/2) */
-  const float* rgb2_b;        /* (3) */
-  const float* rgb0_dir_w;    /* (W/2, 3) columns of rgb.0 that multiply the raw direction, L_dir == 0 */
-  const float* vis_final_w;   /* (64) */
-  const float* vis_final_b;   /* (1) */
-  /* skinning tables, n_bones > 0 (per frame, computed from the articulation dual quaternions) */
-  const float* bone_inv_t;    /* (M,B,8): inverse of t_articulation as rotation q(4), translation(3), 0 */
-  const float* bone_inv_rest; /* (M,B,8): inverse of rest_articulation */
-  const float* se3_bwd;       /* (M,B,8): rest (x) t^-1 as dual quaternion real(4), dual(4) */
-  const float* se3_fwd;       /* (M,B,8): t (x) rest^-1 */
-  const float* inv_gauss;     /* (B,4): 1/exp(log_gauss) xyz, 0 */
-  const float* bone_center;   /* (B,4): rest bone centres of frame 0, 0 */
-  const float* warp_logibeta; /* (1) */
-  /* outputs, (M*N*D, c) row-major; any may be NULL */
-  float* rgb;                 /* 3 */
-  float* density;             /* 1 */
-  float* vis;                 /* 1 */
-  float* xyz;                 /* 3 canonical */
-  float* xyz_cam;             /* 3 */
-  float* xyz_t;               /* 3 time-t object space */
-  float* dir;                 /* 3 field-space ray direction */
-  float* depth;               /* 1 (already divided by exp(logscale)) */
-  float* deltas;              /* 1 */
-  float* feature;             /* 16 */
-  float* flow;                /* 3 */
-  float* cyc_dist;            /* 1 */
-  float* delta_skin;          /* 1 */
-  float* skin_entropy;        /* 1 */
-  float* gauss_density;       /* 1 */
-  float* sdf;                 /* 1 */
-} b200r_field_args;
+  const float* warp_logibeta; /* warp.logibeta (1), n_bones > 0 */
+  const float* log_gauss;     /* warp.skinning_model.log_gauss (B,3), n_bones > 0 */
+  const int32_t* symm_idx;    /* (B) left/right bone pairing or NULL (nnutils/skinning.py:150-153) */
+} b200r_field_params;
 
-int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_args* args,
-                    b200r_stream stream);
+/* Per-frame inputs (M rows each): what get_samples() hands to query_field
+ * (nnutils/nerf.py:530-578, deformable.py:254-289) plus the per-frame codes the MLPs are conditioned on. */
+typedef struct {
+  int32_t M;
+  int32_t pad_;
+  const float* Kinv;             /* (M,3,3) */
+  const float* near_far;         /* (M,2) */
+  const float* field2cam_q;      /* (M,4) real-first quaternion */
+  const float* field2cam_t;      /* (M,3) already scaled by exp(logscale) */
+  const float* inst_base;        /* (M,32) basefield.inst_embedding rows */
+  const float* inst_color;       /* (M,32) */
+  const float* inst_vis;         /* (M,32) */
+  const float* appr_code;        /* (M,appr_channels) or NULL */
+  const float* inst_skin;        /* (M,32)  n_bones > 0 */
+  const float* skin_t_embed;     /* (M,128) skinning time embedding of each frame */
+  const float* skin_t_embed_mean;/* (128)   mean time embedding (forward warps, warping.py:313-314) */
+  const float* t_art_qr;         /* (M,B,4) t_articulation real part */
+  const float* t_art_qd;         /* (M,B,4) dual part */
+  const float* rest_art_qr;      /* (M,B,4) */
+  const float* rest_art_qd;      /* (M,B,4) */
+} b200r_frame_tables;
+
+typedef struct {
+  int32_t N, D;        /* rays per frame, samples per ray (D >= 2) */
+  float flow_thresh;   /* < 0: None */
+  int32_t pad_;
+  const float* hxy;    /* (M,N,3) homogeneous pixel coordinates */
+} b200r_ray_batch;
+
+/* Per-sample outputs, (M*N*D, c) row-major fp32; any pointer may be NULL. */
+typedef struct {
+  float* rgb;           /* 3 */
+  float* density;       /* 1 */
+  float* vis;           /* 1 */
+  float* xyz;           /* 3 canonical */
+  float* xyz_cam;       /* 3 */
+  float* xyz_t;         /* 3 time-t object space */
+  float* dir;           /* 3 field-space ray direction */
+  float* depth;         /* 1 (already divided by exp(logscale)) */
+  float* deltas;        /* 1 */
+  float* feature;       /* 16 */
+  float* flow;          /* 3 */
+  float* cyc_dist;      /* 1 */
+  float* delta_skin;    /* 1 */
+  float* skin_entropy;  /* 1 */
+  float* gauss_density; /* 1 */
+  float* sdf;           /* 1 */
+} b200r_field_outputs;
+
+/* alpha: PosEmbedding annealing window (nnutils/embedding.py:112-125) folded into the packed weights
+ * of basefield / colorfield; negative = None.  Call after every optimiser step / set_alpha. */
+int b200r_pack_weights(b200r_handle* h, const b200r_field_desc* desc, const b200r_field_params* params, float alpha,
+                       void* packed, size_t packed_bytes, b200r_stream stream);
+
+/* Bytes of scratch the forward needs for M frames (per-frame blocks built by the prologue kernel). */
+size_t b200r_workspace_bytes(const b200r_field_desc* desc, int32_t M);
+
+/* One training-mode query_field call on M frames x N rays x D samples: a per-frame prologue kernel
+ * (bias rows with the per-frame codes folded in, bone transforms) then the fused per-sample kernel. */
+int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* params,
+                    const b200r_frame_tables* frames, const b200r_ray_batch* rays, const b200r_field_outputs* out,
+                    void* workspace, size_t workspace_bytes, b200r_stream stream);
 
 /* ------------------------------------------------------------------ compositing (render_pixel) */
 #define B200R_MAX_CHANNELS 12

@@ -19,20 +19,31 @@ class FieldDesc(C.Structure):
                                          "has_feature", "operand_dtype")]
 
 
-_FIELD_PTRS_IN = ["hxy", "Kinv", "near_far", "field2cam", "logibeta", "logscale"]
-_FIELD_PTRS_MID = ["delta1_bias_fwd", "sdf_w", "sdf_b", "rgb2_w", "rgb2_b", "rgb0_dir_w", "vis_final_w", "vis_final_b",
-                   "bone_inv_t", "bone_inv_rest", "se3_bwd", "se3_fwd", "inv_gauss", "bone_center", "warp_logibeta"]
 FIELD_OUTPUTS = [("rgb", 3), ("density", 1), ("vis", 1), ("xyz", 3), ("xyz_cam", 3), ("xyz_t", 3), ("dir", 3), ("depth", 1),
                  ("deltas", 1), ("feature", 16), ("flow", 3), ("cyc_dist", 1), ("delta_skin", 1), ("skin_entropy", 1),
                  ("gauss_density", 1), ("sdf", 1)]
 
 
-class FieldArgs(C.Structure):
-    _fields_ = ([("M", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("flow_thresh", C.c_float)]
-                + [(n, f32p) for n in _FIELD_PTRS_IN]
-                + [("bias", f32p * MAX_LAYERS), ("bias_stride", C.c_int32 * MAX_LAYERS)]
-                + [(n, f32p) for n in _FIELD_PTRS_MID]
-                + [(n, f32p) for n, _ in FIELD_OUTPUTS])
+class FieldParams(C.Structure):
+    _fields_ = ([("weight", f32p * MAX_LAYERS), ("bias", f32p * MAX_LAYERS)]
+                + [(n, f32p) for n in ("sdf_w", "sdf_b", "rgb2_w", "rgb2_b", "vis_final_w", "vis_final_b", "logibeta",
+                                       "logscale", "warp_logibeta", "log_gauss", "symm_idx")])
+
+
+FRAME_PTRS = ["Kinv", "near_far", "field2cam_q", "field2cam_t", "inst_base", "inst_color", "inst_vis", "appr_code",
+              "inst_skin", "skin_t_embed", "skin_t_embed_mean", "t_art_qr", "t_art_qd", "rest_art_qr", "rest_art_qd"]
+
+
+class FrameTables(C.Structure):
+    _fields_ = [("M", C.c_int32), ("pad_", C.c_int32)] + [(n, f32p) for n in FRAME_PTRS]
+
+
+class RayBatch(C.Structure):
+    _fields_ = [("N", C.c_int32), ("D", C.c_int32), ("flow_thresh", C.c_float), ("pad_", C.c_int32), ("hxy", f32p)]
+
+
+class FieldOutputs(C.Structure):
+    _fields_ = [(n, f32p) for n, _ in FIELD_OUTPUTS]
 
 
 class CompositeArgs(C.Structure):
@@ -47,7 +58,7 @@ class CompositeBwdArgs(C.Structure):
 
 
 EXPORTS = ["b200r_layer_count", "b200r_packed_bytes", "b200r_create", "b200r_destroy", "b200r_last_error",
-           "b200r_pack_weights", "b200r_field_fwd", "b200r_composite_fwd", "b200r_composite_bwd"]
+           "b200r_pack_weights", "b200r_workspace_bytes", "b200r_field_fwd", "b200r_composite_fwd", "b200r_composite_bwd"]
 
 _lib = None
 
@@ -71,10 +82,14 @@ def load():
     lib.b200r_destroy.restype = None
     lib.b200r_last_error.argtypes = [C.c_void_p]
     lib.b200r_last_error.restype = C.c_char_p
-    lib.b200r_pack_weights.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.POINTER(C.c_void_p), C.c_int, C.c_float,
-                                       C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.b200r_pack_weights.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.POINTER(FieldParams), C.c_float, C.c_void_p,
+                                       C.c_size_t, C.c_void_p]
     lib.b200r_pack_weights.restype = C.c_int
-    lib.b200r_field_fwd.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldArgs), C.c_void_p]
+    lib.b200r_workspace_bytes.argtypes = [C.POINTER(FieldDesc), C.c_int32]
+    lib.b200r_workspace_bytes.restype = C.c_size_t
+    lib.b200r_field_fwd.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldParams),
+                                    C.POINTER(FrameTables), C.POINTER(RayBatch), C.POINTER(FieldOutputs), C.c_void_p,
+                                    C.c_size_t, C.c_void_p]
     lib.b200r_field_fwd.restype = C.c_int
     lib.b200r_composite_fwd.argtypes = [C.c_void_p, C.POINTER(CompositeArgs), C.c_void_p]
     lib.b200r_composite_fwd.restype = C.c_int

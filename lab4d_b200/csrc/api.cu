@@ -56,25 +56,25 @@ void b200r_destroy(b200r_handle* h) {
 
 const char* b200r_last_error(const b200r_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
-int b200r_pack_weights(b200r_handle* h, const b200r_field_desc* desc, const float* const* weights, int n_weights,
-                       float alpha, void* packed, size_t packed_bytes, b200r_stream stream_) {
+int b200r_pack_weights(b200r_handle* h, const b200r_field_desc* desc, const b200r_field_params* params, float alpha,
+                       void* packed, size_t packed_bytes, b200r_stream stream_) {
   if (!h) return B200R_E_INVALID;
-  if (!desc || !weights || !packed) return fail(h, B200R_E_INVALID, "pack_weights: null argument");
+  if (!desc || !params || !packed) return fail(h, B200R_E_INVALID, "pack_weights: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
   b200r::BuiltProgram bp = b200r::build_program(*desc);
   if (!bp.ok) return fail(h, B200R_E_INVALID, std::string("pack_weights: ") + bp.err);
-  if (n_weights != (int)bp.layer_out.size()) return fail(h, B200R_E_INVALID, "pack_weights: wrong number of layers");
+  const int n_weights = (int)bp.layer_out.size();
   if (packed_bytes < bp.packed_bytes) return fail(h, B200R_E_INVALID, "pack_weights: packed buffer too small");
   if ((reinterpret_cast<uintptr_t>(packed) & 15) != 0) return fail(h, B200R_E_INVALID, "pack_weights: packed must be 16-B aligned");
   for (int i = 0; i < n_weights; ++i)
-    if (!weights[i]) return fail(h, B200R_E_INVALID, "pack_weights: null weight pointer");
+    if (!params->weight[i]) return fail(h, B200R_E_INVALID, "pack_weights: null weight pointer");
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
   if ((int)bp.slices.size() > b200r::kMaxPackSlices) return fail(h, B200R_E_INVALID, "pack_weights: too many slices");
   b200r::PackParams pp;
   memset(&pp, 0, sizeof(pp));
   for (size_t i = 0; i < bp.slices.size(); ++i) pp.slices[i] = bp.slices[i];
-  for (int i = 0; i < n_weights; ++i) pp.weights[i] = weights[i];
+  for (int i = 0; i < n_weights; ++i) pp.weights[i] = params->weight[i];
   pp.n_slices = (int)bp.slices.size();
   pp.total_groups = (uint32_t)(bp.packed_bytes / 16);
   pp.packed = (uint8_t*)packed;
@@ -85,36 +85,73 @@ int b200r_pack_weights(b200r_handle* h, const b200r_field_desc* desc, const floa
   return B200R_OK;
 }
 
-int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_args* a,
-                    b200r_stream stream_) {
+size_t b200r_workspace_bytes(const b200r_field_desc* desc, int32_t M) {
+  if (!desc || M < 1) return 0;
+  b200r::BuiltProgram bp = b200r::build_program(*desc);
+  return bp.ok ? b200r::workspace_floats(bp.prog, M) * sizeof(float) : 0;
+}
+
+int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
+                    const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_field_outputs* out,
+                    void* workspace, size_t workspace_bytes, b200r_stream stream_) {
   if (!h) return B200R_E_INVALID;
-  if (!desc || !packed || !a) return fail(h, B200R_E_INVALID, "field_fwd: null argument");
+  if (!desc || !packed || !par || !fr || !rays || !out || !workspace) return fail(h, B200R_E_INVALID, "field_fwd: null argument");
   b200r::BuiltProgram bp = b200r::build_program(*desc);
   if (!bp.ok) return fail(h, B200R_E_INVALID, std::string("field_fwd: ") + bp.err);
-  if (a->M < 1 || a->N < 1 || a->D < 2) return fail(h, B200R_E_INVALID, "field_fwd: need M,N >= 1 and D >= 2");
-  if ((long long)a->M * a->N * a->D > 0x7fffffffLL) return fail(h, B200R_E_INVALID, "field_fwd: too many samples");
-  if (a->M >= 2 && (a->M & 1)) return fail(h, B200R_E_INVALID, "field_fwd: frames must come in adjacent pairs (M even)");
-  if (!a->hxy || !a->Kinv || !a->near_far || !a->field2cam || !a->logibeta || !a->logscale)
+  const int M = fr->M;
+  if (M < 1 || rays->N < 1 || rays->D < 2) return fail(h, B200R_E_INVALID, "field_fwd: need M,N >= 1 and D >= 2");
+  if ((long long)M * rays->N * rays->D > 0x7fffffffLL) return fail(h, B200R_E_INVALID, "field_fwd: too many samples");
+  if (M >= 2 && (M & 1)) return fail(h, B200R_E_INVALID, "field_fwd: frames must come in adjacent pairs (M even)");
+  if (!rays->hxy || !fr->Kinv || !fr->near_far || !fr->field2cam_q || !fr->field2cam_t)
     return fail(h, B200R_E_INVALID, "field_fwd: missing ray/camera input");
-  if (!a->sdf_w || !a->sdf_b || !a->rgb2_w || !a->rgb2_b || !a->vis_final_w || !a->vis_final_b)
+  if (!fr->inst_base || !fr->inst_color || !fr->inst_vis) return fail(h, B200R_E_INVALID, "field_fwd: missing instance codes");
+  if (desc->appr_channels > 0 && !fr->appr_code) return fail(h, B200R_E_INVALID, "field_fwd: missing appearance codes");
+  if (!par->sdf_w || !par->sdf_b || !par->rgb2_w || !par->rgb2_b || !par->vis_final_w || !par->vis_final_b || !par->logibeta ||
+      !par->logscale)
     return fail(h, B200R_E_INVALID, "field_fwd: missing head weights");
-  if (desc->L_dir == 0 && !a->rgb0_dir_w) return fail(h, B200R_E_INVALID, "field_fwd: rgb0_dir_w required when L_dir == 0");
   const int nl = (int)bp.layer_out.size();
-  for (int i = 0; i < nl; ++i) {
-    if (!a->bias[i]) return fail(h, B200R_E_INVALID, "field_fwd: missing bias row");
-    if ((reinterpret_cast<uintptr_t>(a->bias[i]) & 15) || (a->bias_stride[i] & 3))
-      return fail(h, B200R_E_INVALID, "field_fwd: bias rows must be 16-B aligned");
-  }
+  for (int i = 0; i < nl; ++i)
+    if (!par->weight[i] || !par->bias[i]) return fail(h, B200R_E_INVALID, "field_fwd: missing layer weight/bias");
   if (desc->n_bones > 0) {
-    if (!a->bone_inv_t || !a->bone_inv_rest || !a->se3_bwd || !a->se3_fwd || !a->inv_gauss || !a->bone_center ||
-        !a->warp_logibeta || !a->delta1_bias_fwd)
-      return fail(h, B200R_E_INVALID, "field_fwd: missing skinning table");
+    if (!fr->inst_skin || !fr->skin_t_embed || !fr->skin_t_embed_mean || !fr->t_art_qr || !fr->t_art_qd || !fr->rest_art_qr ||
+        !fr->rest_art_qd || !par->warp_logibeta || !par->log_gauss)
+      return fail(h, B200R_E_INVALID, "field_fwd: missing skinning input");
   }
   if (reinterpret_cast<uintptr_t>(packed) & 15) return fail(h, B200R_E_INVALID, "field_fwd: packed must be 16-B aligned");
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(h, B200R_E_INVALID, "field_fwd: workspace must be 16-B aligned");
+  if (workspace_bytes < b200r::workspace_floats(bp.prog, M) * sizeof(float))
+    return fail(h, B200R_E_INVALID, "field_fwd: workspace too small (see b200r_workspace_bytes)");
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
-  e = b200r::launch_field_fwd_desc(*desc, bp.prog, *a, packed, h->n_sm, (cudaStream_t)stream_);
-  if (e != cudaSuccess) return fail_cuda(h, e, "field_fwd kernel");
+  cudaStream_t stream = (cudaStream_t)stream_;
+
+  static_assert(sizeof(b200r::PrologueParams) <= 4096 && sizeof(b200r::FieldKernelParams) <= 4096, "kernel parameter space");
+  b200r::PrologueParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.prog = bp.prog;
+  pp.desc = *desc;
+  pp.par = *par;
+  pp.fr = *fr;
+  pp.workspace = (float*)workspace;
+  pp.n_layers = nl;
+  pp.rgb0_layer = b200r::layer_ids(*desc).rgb0;
+  for (int i = 0; i < nl; ++i) { pp.layer_out[i] = (int16_t)bp.layer_out[i]; pp.layer_in[i] = (int16_t)bp.layer_in[i]; }
+  if ((e = b200r::launch_prologue(pp, stream)) != cudaSuccess) return fail_cuda(h, e, "prologue kernel");
+
+  b200r::FieldKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.prog = bp.prog;
+  kp.desc = *desc;
+  kp.rays = *rays;
+  kp.out = *out;
+  kp.packed = (const uint8_t*)packed;
+  kp.workspace = (const float*)workspace;
+  kp.M = M;
+  kp.ND = rays->N * rays->D;
+  kp.tiles_per_frame = (kp.ND + b200r::kTileRows - 1) / b200r::kTileRows;
+  kp.n_tiles = M * kp.tiles_per_frame;
+  kp.Lmax = desc->L_xyz + 2 > 10 ? 12 : 10;
+  if ((e = b200r::launch_field_fwd(kp, h->n_sm, stream)) != cudaSuccess) return fail_cuda(h, e, "field_fwd kernel");
   return B200R_OK;
 }
 

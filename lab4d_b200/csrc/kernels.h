@@ -18,10 +18,36 @@ struct PackParams {
   int L_base, L_color;
 };
 
+struct PrologueParams {
+  Program prog;
+  b200r_field_desc desc;
+  b200r_field_params par;
+  b200r_frame_tables fr;
+  float* workspace;  // [const block][M frame blocks]
+  int32_t n_layers;
+  int32_t rgb0_layer;
+  int16_t layer_out[B200R_MAX_LAYERS];
+  int16_t layer_in[B200R_MAX_LAYERS];
+};
+
+struct FieldKernelParams {
+  Program prog;
+  b200r_field_desc desc;
+  b200r_ray_batch rays;
+  b200r_field_outputs out;
+  const uint8_t* packed;
+  const float* workspace;
+  int32_t M;
+  int32_t ND;              // N * D samples per frame
+  int32_t tiles_per_frame;
+  int32_t n_tiles;
+  int32_t Lmax;            // frequencies of the shared embedding chunk(s): 10 or 12
+};
+
 cudaError_t launch_pack(const PackParams& p, int operand_dtype, cudaStream_t stream);
+cudaError_t launch_prologue(const PrologueParams& p, cudaStream_t stream);
 cudaError_t launch_composite_fwd(const b200r_composite_args& a, cudaStream_t stream);
 cudaError_t launch_composite_bwd(const b200r_composite_bwd_args& b, cudaStream_t stream);
-cudaError_t launch_field_fwd_desc(const b200r_field_desc& desc, const Program& prog, const b200r_field_args& args,
-                                  const void* packed, int n_sm, cudaStream_t stream);
+cudaError_t launch_field_fwd(const FieldKernelParams& p, int n_sm, cudaStream_t stream);
 
 }  // namespace b200r

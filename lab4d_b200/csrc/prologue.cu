@@ -1,0 +1,153 @@
+// Per-frame prologue: one launch builds the scratch the fused field kernel stages into shared memory.
+//
+//   block 0..M-1 : the frame block of frame f (program.h FrameLayout) -
+//       cameras of the frame and of its flip_pair partner (nnutils/nerf.py:929-946),
+//       bias rows b + W[:, code columns] @ code[f] of the layers that see a per-frame code
+//       (instance / time / appearance codes are constant per frame: nnutils/base.py:140-146,
+//       nerf.py:200-204, skinning.py:109-116),
+//       bone tables: inverse bone transforms (utils/transforms.py:9-25) and the per-bone blend
+//       transforms rest (x) t^-1 / t (x) rest^-1 as dual quaternions (nnutils/warping.py:304-314).
+//   block M      : the constant block - plain bias rows, head weights, Gaussian bone scales
+//       (nnutils/skinning.py:141-153), rest bone centres (utils/transforms.py:28-40), scalars.
+// M x B rows of quaternion algebra and a few (N x 32) mat-vecs: ~0.1 % of the step's FLOPs.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "kernels.h"
+
+namespace b200r {
+
+struct Q4 { float w, x, y, z; };
+__device__ __forceinline__ Q4 qmul(const Q4& a, const Q4& b) {
+  return {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+          a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w};
+}
+__device__ __forceinline__ Q4 qconj(const Q4& a) { return {a.w, -a.x, -a.y, -a.z}; }
+__device__ __forceinline__ Q4 qadd(const Q4& a, const Q4& b) { return {a.w + b.w, a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ Q4 ld4(const float* p) { return {p[0], p[1], p[2], p[3]}; }
+__device__ __forceinline__ void st4(float* p, const Q4& q) { p[0] = q.w; p[1] = q.x; p[2] = q.y; p[3] = q.z; }
+
+__device__ void write_cam(float* dst, const PrologueParams& p, int f) {
+  for (int i = threadIdx.x; i < 24; i += blockDim.x) {
+    float v = 0.f;
+    if (i < 9) v = p.fr.Kinv[(size_t)f * 9 + i];
+    else if (i < 11) v = p.fr.near_far[(size_t)f * 2 + (i - 9)];
+    else if (i < 15) v = p.fr.field2cam_q[(size_t)f * 4 + (i - 11)];
+    else if (i < 18) v = p.fr.field2cam_t[(size_t)f * 3 + (i - 15)];
+    dst[i] = v;
+  }
+}
+
+// inverse of a bone transform as rotation quaternion + translation: (q*, 2 (qd* q)_xyz)
+__device__ void write_binv(float* dst, const float* qr_, const float* qd_, int B) {
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const Q4 qr = qconj(ld4(qr_ + b * 4)), qd = qconj(ld4(qd_ + b * 4));
+    const Q4 t = qmul(qd, qconj(qr));
+    float* o = dst + b * 8;
+    st4(o, qr);
+    o[4] = 2.f * t.x; o[5] = 2.f * t.y; o[6] = 2.f * t.z; o[7] = 0.f;
+  }
+}
+// a (x) b^-1 as (real, dual)
+__device__ void write_se3(float* dst, const float* ar_, const float* ad_, const float* br_, const float* bd_, int B) {
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const Q4 ar = ld4(ar_ + b * 4), ad = ld4(ad_ + b * 4);
+    const Q4 bir = qconj(ld4(br_ + b * 4)), bid = qconj(ld4(bd_ + b * 4));
+    st4(dst + b * 8, qmul(ar, bir));
+    st4(dst + b * 8 + 4, qadd(qmul(ar, bid), qmul(ad, bir)));
+  }
+}
+
+__global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ PrologueParams p) {
+  const Program& P = p.prog;
+  const int M = p.fr.M, B = p.desc.n_bones;
+  float* cblock = p.workspace;
+  if ((int)blockIdx.x == M) {
+    // ---------------------------------------------------------------- constant block
+    const ConstLayout& C = P.cl;
+    for (int i = threadIdx.x; i < C.n_floats; i += blockDim.x) cblock[i] = 0.f;
+    __syncthreads();
+    for (int l = 0; l < p.n_layers; ++l) {
+      if (C.plain_off[l] < 0) continue;
+      for (int i = threadIdx.x; i < p.layer_out[l]; i += blockDim.x) cblock[C.plain_off[l] + i] = p.par.bias[l][i];
+    }
+    const int W = p.desc.W, H = W / 2;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) cblock[C.sdf_w + i] = p.par.sdf_w[i];
+    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) cblock[C.rgb2_w + i] = p.par.rgb2_w[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) cblock[C.vis_w + i] = p.par.vis_final_w[i];
+    if (p.desc.L_dir == 0) {
+      const float* w0 = p.par.weight[p.rgb0_layer];
+      const int in_dim = p.layer_in[p.rgb0_layer];
+      for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) cblock[C.dir_w + i] = w0[(size_t)(i / 3) * in_dim + W + (i % 3)];
+    }
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+      for (int c = 0; c < 3; ++c) {
+        float lg = p.par.log_gauss[b * 3 + c];
+        if (p.par.symm_idx) lg = 0.5f * (p.par.log_gauss[p.par.symm_idx[b] * 3 + c] + lg);
+        cblock[C.inv_gauss + b * 4 + c] = expf(-lg);
+      }
+      const Q4 qr = ld4(p.fr.rest_art_qr + b * 4), qd = ld4(p.fr.rest_art_qd + b * 4);  // frame 0
+      const Q4 t = qmul(qd, qconj(qr));
+      cblock[C.center + b * 4 + 0] = 2.f * t.x;
+      cblock[C.center + b * 4 + 1] = 2.f * t.y;
+      cblock[C.center + b * 4 + 2] = 2.f * t.z;
+    }
+    if (threadIdx.x == 0) {
+      float* s = cblock + C.scalars;
+      s[SC_IBETA] = expf(p.par.logibeta[0]);
+      s[SC_INV_SCALE] = 1.0f / expf(p.par.logscale[0]);
+      s[SC_WARP_IBETA] = B > 0 ? expf(p.par.warp_logibeta[0]) : 0.f;
+      s[SC_SDF_B] = p.par.sdf_b[0];
+      s[SC_RGB2_B0] = p.par.rgb2_b[0]; s[SC_RGB2_B1] = p.par.rgb2_b[1]; s[SC_RGB2_B2] = p.par.rgb2_b[2];
+      s[SC_VIS_B] = p.par.vis_final_b[0];
+    }
+    return;
+  }
+  // ------------------------------------------------------------------ frame block
+  const FrameLayout& F = P.fl;
+  const int f = blockIdx.x;
+  const int fn = (M >= 2) ? (f ^ 1) : f;
+  float* fb = p.workspace + P.cl.n_floats + (size_t)f * F.n_floats;
+  write_cam(fb + F.cam, p, f);
+  write_cam(fb + F.cam_partner, p, fn);
+  const float* codes[kNumCodes];
+  codes[CODE_INST_BASE] = p.fr.inst_base ? p.fr.inst_base + (size_t)f * 32 : nullptr;
+  codes[CODE_INST_COLOR] = p.fr.inst_color ? p.fr.inst_color + (size_t)f * 32 : nullptr;
+  codes[CODE_INST_VIS] = p.fr.inst_vis ? p.fr.inst_vis + (size_t)f * 32 : nullptr;
+  codes[CODE_APPR] = p.fr.appr_code ? p.fr.appr_code + (size_t)f * p.desc.appr_channels : nullptr;
+  codes[CODE_INST_SKIN] = p.fr.inst_skin ? p.fr.inst_skin + (size_t)f * 32 : nullptr;
+  codes[CODE_T_EMBED] = p.fr.skin_t_embed ? p.fr.skin_t_embed + (size_t)f * 128 : nullptr;
+  codes[CODE_T_EMBED_MEAN] = p.fr.skin_t_embed_mean;
+  for (int ci = 0; ci < F.n_cond; ++ci) {
+    const CondRow& c = F.cond[ci];
+    const float* Wm = p.par.weight[c.layer];
+    const float* bv = p.par.bias[c.layer];
+    for (int n = threadIdx.x; n < c.n; n += blockDim.x) {
+      float acc = bv[n];
+      for (int sgi = 0; sgi < c.n_seg; ++sgi) {
+        const float* code = codes[c.code[sgi]];
+        const float* wr = Wm + (size_t)n * c.in_dim + c.col0[sgi];
+        float a2 = 0.f;
+        for (int k = 0; k < c.width[sgi]; ++k) a2 += wr[k] * code[k];
+        acc += a2;
+      }
+      fb[c.frame_off + n] = acc;
+    }
+  }
+  if (B > 0) {
+    const size_t o = (size_t)f * B * 4, on = (size_t)fn * B * 4;
+    write_binv(fb + F.binv_t, p.fr.t_art_qr + o, p.fr.t_art_qd + o, B);
+    write_binv(fb + F.binv_rest, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, B);
+    write_binv(fb + F.binv_rest_partner, p.fr.rest_art_qr + on, p.fr.rest_art_qd + on, B);
+    write_se3(fb + F.se3_bwd, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, p.fr.t_art_qr + o, p.fr.t_art_qd + o, B);
+    write_se3(fb + F.se3_fwd, p.fr.t_art_qr + o, p.fr.t_art_qd + o, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, B);
+    write_se3(fb + F.se3_fwd_partner, p.fr.t_art_qr + on, p.fr.t_art_qd + on, p.fr.rest_art_qr + on, p.fr.rest_art_qd + on, B);
+  }
+}
+
+cudaError_t launch_prologue(const PrologueParams& p, cudaStream_t stream) {
+  prologue_kernel<<<p.fr.M + 1, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace b200r

@@ -1,5 +1,5 @@
-"""Host side of the B200 renderer: per-frame prologue (tiny, M rows), pointer marshalling into the
-C ABI, output assembly.  The per-sample work is entirely inside libb200render.so.
+"""Host side of the B200 renderer: pointer marshalling into the C ABI and output assembly.  All
+arithmetic (per-frame prologue and per-sample work) is inside libb200render.so.
 
 Functional mirror of the reference entry points:
   FieldRenderer.query_field  <-> {NeRF,FeatureNeRF,Deformable}.query_field (training mode)
@@ -11,8 +11,8 @@ import ctypes as C
 
 import torch
 
-from . import _lib, quat
-from .spec import INST_CH, T_EMBED_CH, FieldConfig, pe_dim
+from . import _lib
+from .spec import FieldConfig, pe_dim
 
 
 def _ptr(t):
@@ -79,61 +79,48 @@ class FieldRenderer:
             L.append(("feature_field.linear_final", None))
         return L
 
+    def _params(self, P):
+        """Pointer table into the caller's parameter storage (no copies unless a tensor is non-contiguous)."""
+        par = _lib.FieldParams()
+        keep = []
+
+        def ptr(t):
+            t = _f32c(t)
+            keep.append(t)
+            return t.data_ptr()
+
+        for i, (name, _) in enumerate(self._layers):
+            par.weight[i] = ptr(P[name + ".weight"])
+            par.bias[i] = ptr(P[name + ".bias"])
+        par.sdf_w, par.sdf_b = ptr(P["sdf.weight"]), ptr(P["sdf.bias"])
+        par.rgb2_w, par.rgb2_b = ptr(P["rgb.2.weight"]), ptr(P["rgb.2.bias"])
+        par.vis_final_w = ptr(P["vis_mlp.basefield.linear_final.weight"])
+        par.vis_final_b = ptr(P["vis_mlp.basefield.linear_final.bias"])
+        par.logibeta, par.logscale = ptr(P["logibeta"]), ptr(P["logscale"])
+        if self.cfg.motion != "rigid":
+            par.warp_logibeta = ptr(P["warp.logibeta"])
+            par.log_gauss = ptr(P["warp.skinning_model.log_gauss"])
+            if self.cfg.symm_idx is not None:
+                if getattr(self, "_symm", None) is None:
+                    self._symm = torch.tensor(list(self.cfg.symm_idx), dtype=torch.int32, device=self.device)
+                par.symm_idx = self._symm.data_ptr()
+        return par, keep
+
     def pack(self, P, alpha=None):
         """Convert the nn.Linear weights to 16-bit swizzled UMMA operand tiles (call after every
         optimiser step / set_alpha)."""
-        ws = [_f32c(P[name + ".weight"]) for name, _ in self._layers]
-        arr = (C.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
-        rc = self.handle.lib.b200r_pack_weights(self.handle.h, C.byref(self.desc), arr, len(ws),
+        par, keep = self._params(P)
+        rc = self.handle.lib.b200r_pack_weights(self.handle.h, C.byref(self.desc), C.byref(par),
                                                 C.c_float(-1.0 if alpha is None else float(alpha)),
                                                 _ptr(self.packed), self.packed.numel(), _stream(self.device))
         self.handle.check(rc, "b200r_pack_weights")
-        self._keep = ws
+        self._keep = keep
 
-    # ------------------------------------------------------------------ per-frame prologue (M rows)
-    def _bias_rows(self, P, tab, M):
-        """b + W[:, code columns] @ code for layers that see a per-frame code
-        (nnutils/base.py:140-146, nerf.py:200-204, skinning.py:109-116)."""
-        rows, extra = [], {}
-        for name, cond in self._layers:
-            W, b = P[name + ".weight"], P[name + ".bias"]
-            if cond is None:
-                rows.append((_f32c(b), 0))
-            elif cond == "delta1":
-                xb = 3 * self.cfg.B
-                Wt, Wi = W[:, xb:xb + T_EMBED_CH], W[:, xb + T_EMBED_CH:xb + T_EMBED_CH + INST_CH]
-                inst = tab["inst_skin"] @ Wi.t()
-                rows.append((_f32c(b + tab["skin_t_embed"] @ Wt.t() + inst), W.shape[0]))
-                extra["delta1_bias_fwd"] = _f32c(b + tab["skin_t_embed_mean"].expand(M, -1) @ Wt.t() + inst)
-            else:
-                key, col = cond
-                code = tab[key]
-                rows.append((_f32c(b + code @ W[:, col:col + code.shape[1]].t()), W.shape[0]))
-        return rows, extra
-
-    def _bone_tables(self, P, tab):
-        """Inverse bone transforms, per-bone blend transforms and Gaussian scales
-        (nnutils/warping.py:304-314, utils/transforms.py:9-25, nnutils/skinning.py:141-153)."""
-        t_art = (tab["t_articulation_qr"], tab["t_articulation_qd"])
-        r_art = (tab["rest_articulation_qr"], tab["rest_articulation_qd"])
-        z = torch.zeros_like(t_art[0][..., :1])
-
-        def inv_table(art):
-            inv = quat.dq_inv(art)
-            return _f32c(torch.cat([inv[0], quat.dq_translation(inv), z], -1))
-
-        def se3_table(dq):
-            return _f32c(torch.cat([dq[0], dq[1]], -1))
-
-        lg = P["warp.skinning_model.log_gauss"]
-        if self.cfg.symm_idx is not None:
-            lg = (lg[list(self.cfg.symm_idx)] + lg) / 2
-        inv_gauss = torch.cat([(-lg).exp(), torch.zeros_like(lg[:, :1])], -1)
-        center = quat.dq_translation((r_art[0][:1], r_art[1][:1]))[0]
-        return dict(bone_inv_t=inv_table(t_art), bone_inv_rest=inv_table(r_art),
-                    se3_bwd=se3_table(quat.dq_mul(r_art, quat.dq_inv(t_art))),
-                    se3_fwd=se3_table(quat.dq_mul(t_art, quat.dq_inv(r_art))),
-                    inv_gauss=_f32c(inv_gauss), bone_center=_f32c(torch.cat([center, torch.zeros_like(center[:, :1])], -1)))
+    # names of the per-frame tables (keys of `tab`) in the order of b200r_frame_tables
+    _TAB_KEYS = {"inst_base": "inst_base", "inst_color": "inst_color", "inst_vis": "inst_vis", "appr_code": "appr_code",
+                 "inst_skin": "inst_skin", "skin_t_embed": "skin_t_embed", "skin_t_embed_mean": "skin_t_embed_mean",
+                 "t_art_qr": "t_articulation_qr", "t_art_qd": "t_articulation_qd", "rest_art_qr": "rest_articulation_qr",
+                 "rest_art_qd": "rest_articulation_qd", "field2cam_q": "field2cam_q", "field2cam_t": "field2cam_t"}
 
     # ------------------------------------------------------------------ query_field
     @torch.no_grad()
@@ -141,47 +128,32 @@ class FieldRenderer:
         """Training-mode query_field.  rays: hxy (M,N,3), Kinv (M,3,3), near_far (M,2);
         tab: per-frame tables (field2cam_q/t, codes, articulations).  Returns (feat_dict, deltas)
         with the reference's keys and (M,N,D,c) shapes.  `eikonal` is returned as zeros: its
-        second-order term stays on PyTorch autograd (SURVEY.md §8f row 4)."""
+        second-order term stays on PyTorch autograd (SURVEY.md 8f row 4)."""
         c = self.cfg
         hxy = _f32c(rays["hxy"])
         M, N = hxy.shape[:2]
         S = M * N * D
-        a = _lib.FieldArgs()
-        a.M, a.N, a.D = M, N, int(D)
-        a.flow_thresh = -1.0 if flow_thresh is None else float(flow_thresh)
         keep = [hxy]
+        par, kp = self._params(P)
+        keep += kp
+        fr = _lib.FrameTables()
+        fr.M = M
 
-        def put(name, t):
+        def put(obj, name, t):
             t = _f32c(t)
             keep.append(t)
-            setattr(a, name, t.data_ptr())
+            setattr(obj, name, t.data_ptr())
 
-        put("hxy", hxy)
-        put("Kinv", rays["Kinv"])
-        put("near_far", rays["near_far"])
-        q, t = tab["field2cam_q"], tab["field2cam_t"]
-        put("field2cam", torch.cat([q, t, torch.zeros_like(t[:, :1])], -1))
-        put("logibeta", P["logibeta"])
-        put("logscale", P["logscale"])
-        rows, extra = self._bias_rows(P, tab, M)
-        for i, (row, stride) in enumerate(rows):
-            keep.append(row)
-            a.bias[i] = row.data_ptr()
-            a.bias_stride[i] = stride
-        put("sdf_w", P["sdf.weight"].reshape(-1))
-        put("sdf_b", P["sdf.bias"])
-        put("rgb2_w", P["rgb.2.weight"])
-        put("rgb2_b", P["rgb.2.bias"])
-        if c.L_dir == 0:
-            put("rgb0_dir_w", P["rgb.0.weight"][:, c.W:c.W + 3])
-        put("vis_final_w", P["vis_mlp.basefield.linear_final.weight"].reshape(-1))
-        put("vis_final_b", P["vis_mlp.basefield.linear_final.bias"])
-        if c.motion != "rigid":
-            put("delta1_bias_fwd", extra["delta1_bias_fwd"])
-            for k, v in self._bone_tables(P, tab).items():
-                put(k, v)
-            put("warp_logibeta", P["warp.logibeta"])
-        out = {}
+        put(fr, "Kinv", rays["Kinv"])
+        put(fr, "near_far", rays["near_far"])
+        for field, key in self._TAB_KEYS.items():
+            if key in tab and tab[key] is not None:
+                put(fr, field, tab[key])
+        rb = _lib.RayBatch()
+        rb.N, rb.D = N, int(D)
+        rb.flow_thresh = -1.0 if flow_thresh is None else float(flow_thresh)
+        rb.hxy = hxy.data_ptr()
+        out, oa = {}, _lib.FieldOutputs()
         for name, nch in _lib.FIELD_OUTPUTS:
             if want is not None and name not in want:
                 continue
@@ -190,13 +162,16 @@ class FieldRenderer:
             if name == "gauss_density" and c.motion == "rigid":
                 continue
             out[name] = torch.empty(S, nch, dtype=torch.float32, device=self.device)
-            setattr(a, name, out[name].data_ptr())
+            setattr(oa, name, out[name].data_ptr())
+        wbytes = self.handle.lib.b200r_workspace_bytes(C.byref(self.desc), M)
+        if getattr(self, "_ws", None) is None or self._ws.numel() < wbytes:
+            self._ws = torch.empty(wbytes, dtype=torch.uint8, device=self.device)
         timing = getattr(self, "time_next_launch", False)
         if timing:  # CUDA events on the launching stream, around the C-ABI call only (bench.py roofline)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(torch.cuda.current_stream(self.device))
-        rc = self.handle.lib.b200r_field_fwd(self.handle.h, C.byref(self.desc), _ptr(self.packed), C.byref(a),
-                                             _stream(self.device))
+        rc = self.handle.lib.b200r_field_fwd(self.handle.h, C.byref(self.desc), _ptr(self.packed), C.byref(par), C.byref(fr),
+                                             C.byref(rb), C.byref(oa), _ptr(self._ws), self._ws.numel(), _stream(self.device))
         self.handle.check(rc, "b200r_field_fwd")
         if timing:
             e1.record(torch.cuda.current_stream(self.device))
