@@ -63,6 +63,30 @@ __device__ __forceinline__ void store_group(uint8_t* chunk, uint32_t row, uint32
       make_uint4(Op::pack2(v[0], v[1]), Op::pack2(v[2], v[3]), Op::pack2(v[4], v[5]), Op::pack2(v[6], v[7]));
 }
 
+// explicit shared-window accessors (32-bit addresses from smem_u32)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
+template <class Op>
+__device__ __forceinline__ void sts_group(uint32_t a, const float* v) {
+  sts128(a, make_uint4(Op::pack2(v[0], v[1]), Op::pack2(v[2], v[3]), Op::pack2(v[4], v[5]), Op::pack2(v[6], v[7])));
+}
+
 template <int V>
 using IC = std::integral_constant<int, V>;
 
@@ -157,12 +181,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     const int q = warp & 3, hsel = warp >> 2;
     const uint32_t row = (uint32_t)(q * 32 + lane);  // tile row == TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint8_t* const extra = arena + CH_EXTRA * kAChunkBytes;
     uint32_t acc_phase = 0;
     const int W = p.desc.W;
     const ConstLayout& CL = P.cl;
     const FrameLayout& FL = P.fl;
-    const float* const sc = cblk + CL.scalars;
+    // 32-bit shared-window addresses (explicit ld/st.shared keeps the hot loops off the generic path)
+    const uint32_t arena_s = smem_u32(arena), cblk_s = smem_u32(cblk), fblk_s = smem_u32(fblk);
+    const uint32_t rowx = row * 128u + ((row & 7u) << 4);  // row base with the swizzle phase folded in:
+                                                           // group g of this row lives at chunk + (rowx ^ (g << 4))
+    const uint32_t sc_s = cblk_s + 4u * CL.scalars;
 
     // stage the constant block once (made visible by the first named barrier of the tile loop)
     {
@@ -174,12 +201,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     // Exchange between the two threads of a row: 12 floats per thread inside the unused part of the
     // CH_EXTRA rows (the MMA only reads their first 32 B).  Every exchange round uses its own floats
     // and rounds that reuse an address are separated by a run_gemm() (a barrier of all compute threads).
-    float* const my_x0 = reinterpret_cast<float*>(extra + sw128_off(row, 2 + 3 * hsel));
-    float* const my_x1 = reinterpret_cast<float*>(extra + sw128_off(row, 3 + 3 * hsel));
-    float* const my_x2 = reinterpret_cast<float*>(extra + sw128_off(row, 4 + 3 * hsel));
-    const float* const pr_x0 = reinterpret_cast<const float*>(extra + sw128_off(row, 2 + 3 * (hsel ^ 1)));
-    const float* const pr_x1 = reinterpret_cast<const float*>(extra + sw128_off(row, 3 + 3 * (hsel ^ 1)));
-    const float* const pr_x2 = reinterpret_cast<const float*>(extra + sw128_off(row, 4 + 3 * (hsel ^ 1)));
+    const uint32_t extra_s = arena_s + CH_EXTRA * kAChunkBytes;
+    const uint32_t my_x0 = extra_s + (rowx ^ ((2u + 3u * hsel) << 4)), my_x1 = extra_s + (rowx ^ ((3u + 3u * hsel) << 4)),
+                   my_x2 = extra_s + (rowx ^ ((4u + 3u * hsel) << 4));
+    const uint32_t pr_x0 = extra_s + (rowx ^ ((2u + 3u * (hsel ^ 1)) << 4)), pr_x1 = extra_s + (rowx ^ ((3u + 3u * (hsel ^ 1)) << 4)),
+                   pr_x2 = extra_s + (rowx ^ ((4u + 3u * (hsel ^ 1)) << 4));
     auto pair_sync = [&]() { named_bar_sync(1 + q, 64); };
 
     // hand the operands to the MMA warp, then wait for the layer's accumulator
@@ -191,30 +217,37 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       acc_phase ^= 1;
       tc_fence_after_sync();
     };
-    auto bias_of = [&](int s_idx) -> const float* {
+    auto bias_s = [&](int s_idx) -> uint32_t {
       const GemmDesc& G = P.seq[s_idx];
-      return (G.bias_frame ? fblk : cblk) + G.bias_off;
+      return (G.bias_frame ? fblk_s : cblk_s) + 4u * G.bias_off;
     };
-    // relu(acc + bias) -> 16-bit operand rows; this thread covers its half of the columns
+    // relu(acc + bias) -> 16-bit operand rows; this thread covers its half of the columns.
     auto epi_relu_store = [&](int s_idx, int dst_chunk) {
       const GemmDesc& G = P.seq[s_idx];
-      const float* bias = bias_of(s_idx);
-      const int ncols = G.n_pad >> 1, cb = hsel * ncols;
-      for (int c0 = cb; c0 < cb + ncols; c0 += 32) {
-        float v[32];
-        tmem_ld32(t_lane + G.tmem_col + c0, v);
-        uint8_t* chunk = arena + (dst_chunk + (c0 >> 6)) * kAChunkBytes;
+      const uint32_t bias = bias_s(s_idx);
+      const int ncols = G.n_pad >> 1, cb = hsel * ncols, nblk = ncols >> 5;
+      const uint32_t t0 = t_lane + G.tmem_col + cb;
+      auto process = [&](uint32_t (&r)[32], int c0) {
+        const uint32_t chunk = arena_s + (uint32_t)(dst_chunk + (c0 >> 6)) * kAChunkBytes;
+        const uint32_t gbase = (uint32_t)(c0 & 63) >> 3;
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
-          const float4 b0 = *reinterpret_cast<const float4*>(bias + c0 + g8 * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + g8 * 8 + 4);
+          const float4 b0 = lds128(bias + 4u * (c0 + g8 * 8));
+          const float4 b1 = lds128(bias + 4u * (c0 + g8 * 8 + 4));
           uint4 o;
-          o.x = Op::pack2_relu(v[g8 * 8 + 0] + b0.x, v[g8 * 8 + 1] + b0.y);
-          o.y = Op::pack2_relu(v[g8 * 8 + 2] + b0.z, v[g8 * 8 + 3] + b0.w);
-          o.z = Op::pack2_relu(v[g8 * 8 + 4] + b1.x, v[g8 * 8 + 5] + b1.y);
-          o.w = Op::pack2_relu(v[g8 * 8 + 6] + b1.z, v[g8 * 8 + 7] + b1.w);
-          *reinterpret_cast<uint4*>(chunk + sw128_off(row, ((c0 & 63) >> 3) + g8)) = o;
+          o.x = Op::pack2_relu(__uint_as_float(r[g8 * 8 + 0]) + b0.x, __uint_as_float(r[g8 * 8 + 1]) + b0.y);
+          o.y = Op::pack2_relu(__uint_as_float(r[g8 * 8 + 2]) + b0.z, __uint_as_float(r[g8 * 8 + 3]) + b0.w);
+          o.z = Op::pack2_relu(__uint_as_float(r[g8 * 8 + 4]) + b1.x, __uint_as_float(r[g8 * 8 + 5]) + b1.y);
+          o.w = Op::pack2_relu(__uint_as_float(r[g8 * 8 + 6]) + b1.z, __uint_as_float(r[g8 * 8 + 7]) + b1.w);
+          sts128(chunk + (rowx ^ ((gbase + g8) << 4)), o);
         }
+      };
+#pragma unroll 1
+      for (int blk = 0; blk < nblk; ++blk) {
+        uint32_t ra[32];
+        tmem_ld32_issue(t0 + 32 * blk, ra);
+        tmem_ld_wait32(ra);
+        process(ra, cb + 32 * blk);
       }
     };
 
@@ -264,15 +297,17 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       xyz_t.x += ti.x; xyz_t.y += ti.y; xyz_t.z += ti.z;
       const float3 dir_f = qrot(qi, dir_cam);
 
-      // ------------------------------------------------ skinning warp (SkinningWarp.forward)
+      // ------------------------------------------------ skinning warps (SkinningWarp.forward), three per sample:
+      //   w = 0 backward warp (time-t -> canonical), w = 1 forward warp with the pair partner's
+      //   articulation (flow), w = 2 forward warp with the frame's own articulation (cycle).
       // bone coordinates -> delta MLP on the tensor pipe -> softmax -> dual-quaternion blend.
       // Half 0 owns bones [0,BS), half 1 bones [BS,B); operand groups are split at a 16-B boundary.
       constexpr int BS = B == 25 ? 13 : (B == 18 ? 8 : 0);
       constexpr int XTRA = (8 - (3 * BS) % 8) % 8;  // values of bone BS that complete half 0's last group
       constexpr int I0 = 3 * BS + XTRA;             // first operand column written by half 1
       constexpr int BH = BS > B - BS ? BS : B - BS;
-      auto skin_warp = [&](auto half_tag, const float3& x, const float* binv, const float* se3, int s_first,
-                           float& entropy, float& delta_skin) -> float3 {
+      auto skin_warp = [&](auto half_tag, const float3& x, uint32_t binv, uint32_t se3, int s_first, float& entropy,
+                           float& delta_skin) -> float3 {
         constexpr int HALF = decltype(half_tag)::value;
         constexpr int b_lo = HALF == 0 ? 0 : BS;
         constexpr int b_hi = HALF == 0 ? BS : B;
@@ -281,31 +316,29 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         float dist2[BH > 0 ? BH : 1];
         {
           float v[NV > 0 ? NV : 1];
-          const float* ig = cblk + CL.inv_gauss;
 #pragma unroll
           for (int j = 0; j < (NV + 2) / 3; ++j) {
-            const int b = b_lo + j;
-            const Q4 qb = ldq(binv + b * 8);
-            const float4 t4 = *reinterpret_cast<const float4*>(binv + b * 8 + 4);
-            const float4 g4 = *reinterpret_cast<const float4*>(ig + b * 4);
-            float3 xb = qrot(qb, x);
-            xb.x = (xb.x + t4.x) * g4.x; xb.y = (xb.y + t4.y) * g4.y; xb.z = (xb.z + t4.z) * g4.z;
-            if (j < NB) dist2[j] = xb.x * xb.x + xb.y * xb.y + xb.z * xb.z;
-            if (3 * j < NV) v[3 * j] = xb.x;
-            if (3 * j + 1 < NV) v[3 * j + 1] = xb.y;
-            if (3 * j + 2 < NV) v[3 * j + 2] = xb.z;
+            const uint32_t ba = binv + 48u * (b_lo + j);
+            const float4 r0 = lds128(ba), r1 = lds128(ba + 16), r2 = lds128(ba + 32);
+            const float xb0 = r0.x * x.x + r0.y * x.y + r0.z * x.z + r0.w;
+            const float xb1 = r1.x * x.x + r1.y * x.y + r1.z * x.z + r1.w;
+            const float xb2 = r2.x * x.x + r2.y * x.y + r2.z * x.z + r2.w;
+            if (j < NB) dist2[j] = xb0 * xb0 + xb1 * xb1 + xb2 * xb2;
+            if (3 * j < NV) v[3 * j] = xb0;
+            if (3 * j + 1 < NV) v[3 * j + 1] = xb1;
+            if (3 * j + 2 < NV) v[3 * j + 2] = xb2;
           }
           if (HALF == 0) {
 #pragma unroll
-            for (int g = 0; g < NV / 8; ++g) store_group<Op>(arena + CH_H0 * kAChunkBytes, row, g, v + 8 * g);
+            for (int g = 0; g < NV / 8; ++g) sts_group<Op>(arena_s + CH_H0 * kAChunkBytes + (rowx ^ (g << 4)), v + 8 * g);
           } else {
             constexpr int END = (3 * B + 15) / 16 * 16;  // zero-padded to whole UMMA_K steps
 #pragma unroll
             for (int idx = I0; idx < END; idx += 8) {
               float w8[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) w8[j] = (idx + j < 3 * B) ? v[idx + j - 3 * BS] : 0.f;
-              store_group<Op>(arena + (idx < 64 ? CH_H0 : CH_H1) * kAChunkBytes, row, (idx & 63) >> 3, w8);
+              for (int j = 0; j < 8; ++j) w8[j] = (idx + j < 3 * B) ? v[(idx + j < 3 * B) ? idx + j - 3 * BS : 0] : 0.f;
+              sts_group<Op>(arena_s + (idx < 64 ? CH_H0 : CH_H1) * kAChunkBytes + (rowx ^ (((idx & 63) >> 3) << 4)), w8);
             }
           }
         }
@@ -317,123 +350,127 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         run_gemm();
         float dl[32];
         tmem_ld32(t_lane + P.seq[s_first + 2].tmem_col, dl);
-        const float* b3 = bias_of(s_first + 2);
+        const uint32_t b3 = bias_s(s_first + 2);
         float mx = -INFINITY, dsum = 0.f;
         int amax = 0;
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-          const float dv = 0.1f * fmaxf(dl[b_lo + j] + b3[b_lo + j], 0.f);
+          const float dv = 0.1f * fmaxf(dl[b_lo + j] + lds32(b3 + 4u * (b_lo + j)), 0.f);
           dsum += dv * dv;
           const float lg = -(dist2[j] + dv);
           dist2[j] = lg;
           if (lg > mx) { mx = lg; amax = b_lo + j; }
         }
         // round 1: global max / anchor bone (first maximum wins, like argmax)
-        my_x0[2] = mx;
-        my_x0[3] = __int_as_float(amax);
+        sts32(my_x0 + 8, mx);
+        sts32(my_x0 + 12, __int_as_float(amax));
         pair_sync();
         {
-          const float omx = pr_x0[2];
-          const int oam = __float_as_int(pr_x0[3]);
+          const float omx = lds32(pr_x0 + 8);
+          const int oam = __float_as_int(lds32(pr_x0 + 12));
           const bool take = HALF == 0 ? (omx > mx) : (omx >= mx);
           if (take) { mx = omx; amax = oam; }
         }
-        const Q4 qa = ldq(se3 + amax * 8);
+        const float4 qa = lds128(se3 + 32u * amax);
         float se = 0.f;
-        Q4 qr = {0, 0, 0, 0}, qd = {0, 0, 0, 0};
+        float4 qr = make_float4(0.f, 0.f, 0.f, 0.f), qd = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-          const int b = b_lo + j;
-          const float e = expf(dist2[j] - mx);
+          const uint32_t sa = se3 + 32u * (b_lo + j);
+          const float e = __expf(dist2[j] - mx);
           se += e;
-          const Q4 r = ldq(se3 + b * 8), dq = ldq(se3 + b * 8 + 4);
-          const float dot = qa.w * r.w + qa.x * r.x + qa.y * r.y + qa.z * r.z;
+          const float4 r = lds128(sa), dq = lds128(sa + 16);
+          const float dot = qa.x * r.x + qa.y * r.y + qa.z * r.z + qa.w * r.w;
           const float wgt = dot > 0.f ? e : -e;  // the softmax denominator cancels in the normalisation below
-          qr.w += wgt * r.w; qr.x += wgt * r.x; qr.y += wgt * r.y; qr.z += wgt * r.z;
-          qd.w += wgt * dq.w; qd.x += wgt * dq.x; qd.y += wgt * dq.y; qd.z += wgt * dq.z;
+          qr.x += wgt * r.x; qr.y += wgt * r.y; qr.z += wgt * r.z; qr.w += wgt * r.w;
+          qd.x += wgt * dq.x; qd.y += wgt * dq.y; qd.z += wgt * dq.z; qd.w += wgt * dq.w;
         }
         // round 2: partial sums
-        my_x0[0] = se;
-        my_x0[1] = dsum;
-        *reinterpret_cast<float4*>(my_x1) = make_float4(qr.w, qr.x, qr.y, qr.z);
-        *reinterpret_cast<float4*>(my_x2) = make_float4(qd.w, qd.x, qd.y, qd.z);
+        sts32(my_x0, se);
+        sts32(my_x0 + 4, dsum);
+        sts128f(my_x1, qr);
+        sts128f(my_x2, qd);
         pair_sync();
         {
-          const float ose = pr_x0[0], ods = pr_x0[1];
-          const float4 o1 = *reinterpret_cast<const float4*>(pr_x1), o2 = *reinterpret_cast<const float4*>(pr_x2);
+          const float ose = lds32(pr_x0), ods = lds32(pr_x0 + 4);
+          const float4 o1 = lds128(pr_x1), o2 = lds128(pr_x2);
           // add in bone order (half 0 first) so both threads of the row get bit-identical results
           if (HALF == 0) {
             se = se + ose; dsum = dsum + ods;
-            qr = {qr.w + o1.x, qr.x + o1.y, qr.y + o1.z, qr.z + o1.w};
-            qd = {qd.w + o2.x, qd.x + o2.y, qd.y + o2.z, qd.z + o2.w};
+            qr = make_float4(qr.x + o1.x, qr.y + o1.y, qr.z + o1.z, qr.w + o1.w);
+            qd = make_float4(qd.x + o2.x, qd.y + o2.y, qd.z + o2.z, qd.w + o2.w);
           } else {
             se = ose + se; dsum = ods + dsum;
-            qr = {o1.x + qr.w, o1.y + qr.x, o1.z + qr.y, o1.w + qr.z};
-            qd = {o2.x + qd.w, o2.y + qd.x, o2.z + qd.y, o2.w + qd.z};
+            qr = make_float4(o1.x + qr.x, o1.y + qr.y, o1.z + qr.z, o1.w + qr.w);
+            qd = make_float4(o2.x + qd.x, o2.y + qd.y, o2.z + qd.z, o2.w + qd.w);
           }
         }
-        entropy = logf(se);  // logsumexp - max  (cross_entropy_skin_loss)
+        entropy = __logf(se);  // logsumexp - max  (cross_entropy_skin_loss)
         delta_skin = dsum / (float)(B > 0 ? B : 1);
-        const float inv = 1.0f / sqrtf(qr.w * qr.w + qr.x * qr.x + qr.y * qr.y + qr.z * qr.z);
-        qr = {qr.w * inv, qr.x * inv, qr.y * inv, qr.z * inv};
-        qd = {qd.w * inv, qd.x * inv, qd.y * inv, qd.z * inv};
-        const Q4 tq = qmul(qd, qconj(qr));
-        float3 o = qrot(qr, x);
+        // stored order is (w,x,y,z) in (.x,.y,.z,.w)
+        const float inv = rsqrtf(qr.x * qr.x + qr.y * qr.y + qr.z * qr.z + qr.w * qr.w);
+        const Q4 Qr = {qr.x * inv, qr.y * inv, qr.z * inv, qr.w * inv};
+        const Q4 Qd = {qd.x * inv, qd.y * inv, qd.z * inv, qd.w * inv};
+        const Q4 tq = qmul(Qd, qconj(Qr));
+        float3 o = qrot(Qr, x);
         o.x += 2.f * tq.x; o.y += 2.f * tq.y; o.z += 2.f * tq.z;
         return o;
       };
 
-      float3 xyz = xyz_t;
-      float ent_b = 0.f, dsk_b = 0.f, ent_out = 0.f, dsk_out = 0.f;
+      float3 xyz = xyz_t, x_next = xyz_t;
+      float ent_b = 0.f, dsk_b = 0.f, ent_out = 0.f, dsk_out = 0.f, cyc = 0.f;
       if constexpr (B > 0) {
-        xyz = hsel == 0 ? skin_warp(IC<0>{}, xyz_t, fblk + FL.binv_t, fblk + FL.se3_bwd, P.seq_delta_bwd, ent_b, dsk_b)
-                        : skin_warp(IC<1>{}, xyz_t, fblk + FL.binv_t, fblk + FL.se3_bwd, P.seq_delta_bwd, ent_b, dsk_b);
+#pragma unroll 1
+        for (int w = 0; w < 3; ++w) {
+          const float3 src = w == 0 ? xyz_t : xyz;
+          const uint32_t binv = fblk_s + 4u * (w == 0 ? FL.binv_t : (w == 1 ? FL.binv_rest_partner : FL.binv_rest));
+          const uint32_t se3 = fblk_s + 4u * (w == 0 ? FL.se3_bwd : (w == 1 ? FL.se3_fwd_partner : FL.se3_fwd));
+          const int s_first = P.seq_delta_bwd + 3 * w;
+          float e, dk;
+          const float3 o = hsel == 0 ? skin_warp(IC<0>{}, src, binv, se3, s_first, e, dk) : skin_warp(IC<1>{}, src, binv, se3, s_first, e, dk);
+          if (w == 0) { xyz = o; ent_b = e; dsk_b = dk; }
+          else if (w == 1) { x_next = o; }
+          else {
+            const float dx = o.x - xyz_t.x, dy = o.y - xyz_t.y, dz = o.z - xyz_t.z;
+            cyc = sqrtf(dx * dx + dy * dy + dz * dz);
+            ent_out = 0.5f * (e + ent_b);
+            dsk_out = 0.5f * (dk + dsk_b);
+          }
+        }
+      } else {
+        x_next = xyz;
       }
 
       // ------------------------------------------------ positional embedding (PosEmbedding.forward)
-      // half 0: x and frequencies 0..5 (+ the first value of frequency 6) = 40 columns;
-      // half 1: frequencies 6..LMAX-1 -> columns 40..62, zero column 63, CH_EXTRA columns 0..15
-      if (hsel == 0) {
-        float v[40];
-        v[0] = xyz.x; v[1] = xyz.y; v[2] = xyz.z;
-        float fr = 1.0f;
-#pragma unroll
-        for (int kf = 0; kf < 6; ++kf) {
-          sincosf(fr * xyz.x, &v[3 + 6 * kf + 0], &v[3 + 6 * kf + 3]);
-          sincosf(fr * xyz.y, &v[3 + 6 * kf + 1], &v[3 + 6 * kf + 4]);
-          sincosf(fr * xyz.z, &v[3 + 6 * kf + 2], &v[3 + 6 * kf + 5]);
-          fr *= 2.0f;
-        }
-        v[39] = sinf(64.0f * xyz.x);
-#pragma unroll
-        for (int g = 0; g < 5; ++g) store_group<Op>(arena + CH_PE * kAChunkBytes, row, g, v + 8 * g);
-      } else {
-        constexpr int NF = LMAX - 6;
-        float v[6 * NF];  // embedding columns 39 .. 39+6*NF-1
-        float fr = 64.0f;
-#pragma unroll
-        for (int kf = 0; kf < NF; ++kf) {
-          sincosf(fr * xyz.x, &v[6 * kf + 0], &v[6 * kf + 3]);
-          sincosf(fr * xyz.y, &v[6 * kf + 1], &v[6 * kf + 4]);
-          sincosf(fr * xyz.z, &v[6 * kf + 2], &v[6 * kf + 5]);
-          fr *= 2.0f;
-        }
-        // columns 40..63 of CH_PE (column 63 is the zero pad)
-#pragma unroll
-        for (int g = 5; g < 8; ++g) {
-          float w8[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) w8[j] = (8 * g + j < 63 && 8 * g + j - 39 < 6 * NF) ? v[(8 * g + j - 39) < 6 * NF ? (8 * g + j - 39) : 0] : 0.f;
-          store_group<Op>(arena + CH_PE * kAChunkBytes, row, g, w8);
-        }
-        if (LMAX > 10) {
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            float w8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w8[j] = (24 + 8 * g + j < 6 * NF) ? v[(24 + 8 * g + j) < 6 * NF ? (24 + 8 * g + j) : 0] : 0.f;
-            store_group<Op>(extra, row, g, w8);
+      // Column e of the embedding: e < 3 -> x_e, else frequency (e-3)/6, sin for (e-3)%6 < 3.  Columns 0..62 live in
+      // CH_PE (column 63 = 0), columns 63.. in CH_EXTRA.  Half 0 writes frequencies 0..LMAX/2-1, half 1 the rest.
+      {
+        const uint32_t pe_s = arena_s + CH_PE * kAChunkBytes;
+        auto put = [&](int e, float val) {  // embedding column e -> 16-bit operand element
+          const uint32_t base = e < 63 ? pe_s : extra_s;
+          const int c = e < 63 ? e : e - 63;
+          sts16(base + (rowx ^ ((uint32_t)(c >> 3) << 4)) + 2u * (c & 7), Op::cvt(val));
+        };
+        if (hsel == 0) { put(0, xyz.x); put(1, xyz.y); put(2, xyz.z); }
+        else {
+          sts16(pe_s + (rowx ^ (7u << 4)) + 14u, (uint16_t)0);  // zero pad column 63 of CH_PE
+          if (LMAX > 10) {  // CH_EXTRA holds 12 values; its k-step reads 16 columns
+            sts32(extra_s + (rowx ^ (1u << 4)) + 8u, 0.f);
+            sts32(extra_s + (rowx ^ (1u << 4)) + 12u, 0.f);
           }
+        }
+        const int k0 = hsel == 0 ? 0 : LMAX / 2, k1 = hsel == 0 ? LMAX / 2 : LMAX;
+        float fr = hsel == 0 ? 1.0f : (float)(1 << (LMAX / 2));
+#pragma unroll 1
+        for (int kf = k0; kf < k1; ++kf) {
+          float sv[3], cv[3];
+          sincosf(fr * xyz.x, &sv[0], &cv[0]);
+          sincosf(fr * xyz.y, &sv[1], &cv[1]);
+          sincosf(fr * xyz.z, &sv[2], &cv[2]);
+          const int e0 = 3 + 6 * kf;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { put(e0 + c, sv[c]); put(e0 + 3 + c, cv[c]); }
+          fr *= 2.0f;
         }
       }
 
@@ -444,21 +481,28 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       run_gemm();
       float vis_out;
       {
-        const float* b2 = bias_of(seq + 1);
-        const float* vw = cblk + CL.vis_w;
+        const uint32_t b2 = bias_s(seq + 1) + 128u * hsel, vw = cblk_s + 4u * CL.vis_w + 128u * hsel;
         float v[32];
         tmem_ld32(t_lane + P.seq[seq + 1].tmem_col + 32 * hsel, v);
-        float accv = 0.f;
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) accv += fmaxf(v[j] + b2[32 * hsel + j], 0.f) * vw[32 * hsel + j];
-        my_x0[0] = accv;
+        for (int j = 0; j < 32; j += 8) {
+          const float4 ba = lds128(b2 + 4u * j), bb = lds128(b2 + 4u * j + 16), wa = lds128(vw + 4u * j), wb = lds128(vw + 4u * j + 16);
+          a0 += fmaxf(v[j] + ba.x, 0.f) * wa.x; a1 += fmaxf(v[j + 1] + ba.y, 0.f) * wa.y;
+          a0 += fmaxf(v[j + 2] + ba.z, 0.f) * wa.z; a1 += fmaxf(v[j + 3] + ba.w, 0.f) * wa.w;
+          a0 += fmaxf(v[j + 4] + bb.x, 0.f) * wb.x; a1 += fmaxf(v[j + 5] + bb.y, 0.f) * wb.y;
+          a0 += fmaxf(v[j + 6] + bb.z, 0.f) * wb.z; a1 += fmaxf(v[j + 7] + bb.w, 0.f) * wb.w;
+        }
+        const float accv = a0 + a1;
+        sts32(my_x0, accv);
         pair_sync();
-        const float other = pr_x0[0];
-        vis_out = (hsel == 0 ? accv + other : other + accv) + sc[SC_VIS_B];
+        const float other = lds32(pr_x0);
+        vis_out = (hsel == 0 ? accv + other : other + accv) + lds32(sc_s + 4u * SC_VIS_B);
       }
 
       // ------------------------------------------------ density branch (NeRF.forward, basefield + sdf)
       seq = P.seq_base;
+#pragma unroll 1
       for (int i = 0; i < p.desc.D; ++i) {
         run_gemm();
         epi_relu_store(seq + i, CH_H0);
@@ -468,78 +512,89 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       {
         const int sf = seq + p.desc.D;
         const GemmDesc& G = P.seq[sf];
-        const float* bb = bias_of(sf);
-        const float* sw = cblk + CL.sdf_w;
+        const uint32_t bb = bias_s(sf), sw = cblk_s + 4u * CL.sdf_w;
         const int ncols = W >> 1, cb = hsel * ncols;
-        float accs = 0.f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 1
         for (int c0 = cb; c0 < cb + ncols; c0 += 32) {
           float v[32];
           tmem_ld32(t_lane + G.tmem_col + c0, v);
-          uint8_t* chunk = arena + (CH_H0 + (c0 >> 6)) * kAChunkBytes;
+          const uint32_t chunk = arena_s + (uint32_t)(CH_H0 + (c0 >> 6)) * kAChunkBytes;
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
+            const float4 b0 = lds128(bb + 4u * (c0 + g8 * 8)), b1 = lds128(bb + 4u * (c0 + g8 * 8 + 4));
+            const float4 w0 = lds128(sw + 4u * (c0 + g8 * 8)), w1 = lds128(sw + 4u * (c0 + g8 * 8 + 4));
             float y[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              y[j] = fmaxf(v[g8 * 8 + j] + bb[c0 + g8 * 8 + j], 0.f);
-              accs += y[j] * sw[c0 + g8 * 8 + j];
-            }
-            store_group<Op>(chunk, row, ((c0 & 63) >> 3) + g8, y);
+            y[0] = fmaxf(v[g8 * 8 + 0] + b0.x, 0.f); y[1] = fmaxf(v[g8 * 8 + 1] + b0.y, 0.f);
+            y[2] = fmaxf(v[g8 * 8 + 2] + b0.z, 0.f); y[3] = fmaxf(v[g8 * 8 + 3] + b0.w, 0.f);
+            y[4] = fmaxf(v[g8 * 8 + 4] + b1.x, 0.f); y[5] = fmaxf(v[g8 * 8 + 5] + b1.y, 0.f);
+            y[6] = fmaxf(v[g8 * 8 + 6] + b1.z, 0.f); y[7] = fmaxf(v[g8 * 8 + 7] + b1.w, 0.f);
+            a0 += y[0] * w0.x; a1 += y[1] * w0.y; a2 += y[2] * w0.z; a3 += y[3] * w0.w;
+            a0 += y[4] * w1.x; a1 += y[5] * w1.y; a2 += y[6] * w1.z; a3 += y[7] * w1.w;
+            sts_group<Op>(chunk + (rowx ^ ((((uint32_t)(c0 & 63) >> 3) + g8) << 4)), y);
           }
         }
-        my_x1[0] = accs;
+        const float accs = (a0 + a1) + (a2 + a3);
+        sts32(my_x1, accs);
         pair_sync();
-        const float other = pr_x1[0];
-        sdf = (hsel == 0 ? accs + other : other + accs) + sc[SC_SDF_B];
+        const float other = lds32(pr_x1);
+        sdf = (hsel == 0 ? accs + other : other + accs) + lds32(sc_s + 4u * SC_SDF_B);
       }
-      const float ibeta = sc[SC_IBETA];
+      const float ibeta = lds32(sc_s + 4u * SC_IBETA);
       const float sgn = sdf > 0.f ? 1.f : (sdf < 0.f ? -1.f : 0.f);
       const float density = (0.5f + 0.5f * sgn * expm1f(-fabsf(sdf) * ibeta)) * ibeta;
 
       // ------------------------------------------------ colour branch: rgb.0 is linear in (base + colour)
       run_gemm();  // base features x rgb.0 -> TMEM[kTmemRgb..)
       seq = P.seq_color;
-      run_gemm();
-      epi_relu_store(seq, CH_H0);
-      run_gemm();
-      epi_relu_store(seq + 1, CH_H0);
-      run_gemm();
-      epi_relu_store(seq + 2, CH_H0);
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i) {
+        run_gemm();
+        epi_relu_store(seq + i, CH_H0);
+      }
       seq = P.seq_rgb2;
       run_gemm();  // + colour features x rgb.0
       float rgb[3];
       {
-        const float* b0 = bias_of(seq);
         const int H = W / 2, ncols = H >> 1, cb = hsel * ncols;
-        const float* w2 = cblk + CL.rgb2_w;
-        const float* wd = cblk + CL.dir_w;
+        const uint32_t b0 = bias_s(seq), w2 = cblk_s + 4u * CL.rgb2_w, wd = cblk_s + 4u * CL.dir_w;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 1
         for (int c0 = cb; c0 < cb + ncols; c0 += 32) {
           float v[32];
           tmem_ld32(t_lane + kTmemRgb + c0, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float pre = v[j] + b0[c0 + j];
-            if (p.desc.L_dir == 0) pre += wd[(c0 + j) * 3] * dir_f.x + wd[(c0 + j) * 3 + 1] * dir_f.y + wd[(c0 + j) * 3 + 2] * dir_f.z;
-            const float hh = fmaxf(pre, 0.f);
-            a0 += hh * w2[c0 + j];
-            a1 += hh * w2[H + c0 + j];
-            a2 += hh * w2[2 * H + c0 + j];
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = lds128(b0 + 4u * (c0 + j));
+            const float4 wr = lds128(w2 + 4u * (c0 + j)), wg = lds128(w2 + 4u * (H + c0 + j)), wb = lds128(w2 + 4u * (2 * H + c0 + j));
+            float pre[4] = {v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w};
+            if (p.desc.L_dir == 0) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t da = wd + 12u * (c0 + j + u);
+                pre[u] += lds32(da) * dir_f.x + lds32(da + 4) * dir_f.y + lds32(da + 8) * dir_f.z;
+              }
+            }
+            const float h0_ = fmaxf(pre[0], 0.f), h1_ = fmaxf(pre[1], 0.f), h2_ = fmaxf(pre[2], 0.f), h3_ = fmaxf(pre[3], 0.f);
+            a0 += h0_ * wr.x + h1_ * wr.y + h2_ * wr.z + h3_ * wr.w;
+            a1 += h0_ * wg.x + h1_ * wg.y + h2_ * wg.z + h3_ * wg.w;
+            a2 += h0_ * wb.x + h1_ * wb.y + h2_ * wb.z + h3_ * wb.w;
           }
         }
-        *reinterpret_cast<float4*>(my_x2) = make_float4(a0, a1, a2, 0.f);
+        sts128f(my_x2, make_float4(a0, a1, a2, 0.f));
         pair_sync();
-        const float4 o = *reinterpret_cast<const float4*>(pr_x2);
+        const float4 o = lds128(pr_x2);
         if (hsel == 0) { a0 = a0 + o.x; a1 = a1 + o.y; a2 = a2 + o.z; }
         else { a0 = o.x + a0; a1 = o.y + a1; a2 = o.z + a2; }
-        a0 += sc[SC_RGB2_B0]; a1 += sc[SC_RGB2_B1]; a2 += sc[SC_RGB2_B2];
-        rgb[0] = 1.f / (1.f + expf(-a0)); rgb[1] = 1.f / (1.f + expf(-a1)); rgb[2] = 1.f / (1.f + expf(-a2));
+        a0 += lds32(sc_s + 4u * SC_RGB2_B0); a1 += lds32(sc_s + 4u * SC_RGB2_B1); a2 += lds32(sc_s + 4u * SC_RGB2_B2);
+        rgb[0] = 1.f / (1.f + __expf(-a0)); rgb[1] = 1.f / (1.f + __expf(-a1)); rgb[2] = 1.f / (1.f + __expf(-a2));
       }
 
       // ------------------------------------------------ feature field (FeatureNeRF.compute_feat)
       float feat[16];
       if (p.desc.has_feature) {
         seq = P.seq_feat;
+#pragma unroll 1
         for (int i = 0; i < 5; ++i) {
           run_gemm();
           epi_relu_store(seq + i, CH_H0);
@@ -548,33 +603,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         if (hsel == 0) {  // warp-uniform: 16 outputs, one thread per row
           float v16[16];
           tmem_ld16(t_lane + P.seq[seq + 5].tmem_col, v16);
-          const float* bf = bias_of(seq + 5);
+          const uint32_t bf = bias_s(seq + 5);
           float nn = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { feat[j] = v16[j] + bf[j]; nn += feat[j] * feat[j]; }
-          const float inv = 1.0f / sqrtf(nn);
+          for (int j = 0; j < 16; ++j) { feat[j] = v16[j] + lds32(bf + 4u * j); nn += feat[j] * feat[j]; }
+          const float inv = rsqrtf(nn);
 #pragma unroll
           for (int j = 0; j < 16; ++j) feat[j] *= inv;
         }
       }
-
-      // ------------------------------------------------ flow + cycle warps (compute_flow, cycle_loss)
-      float flow[3] = {0.f, 0.f, 0.f};
-      float cyc = 0.f;
-      float3 x_next = xyz;
-      if constexpr (B > 0) {
-        float e1, d1, e2, d2;
-        x_next = hsel == 0 ? skin_warp(IC<0>{}, xyz, fblk + FL.binv_rest_partner, fblk + FL.se3_fwd_partner, P.seq_delta_flow, e1, d1)
-                           : skin_warp(IC<1>{}, xyz, fblk + FL.binv_rest_partner, fblk + FL.se3_fwd_partner, P.seq_delta_flow, e1, d1);
-        const float3 xc = hsel == 0 ? skin_warp(IC<0>{}, xyz, fblk + FL.binv_rest, fblk + FL.se3_fwd, P.seq_delta_cyc, e2, d2)
-                                    : skin_warp(IC<1>{}, xyz, fblk + FL.binv_rest, fblk + FL.se3_fwd, P.seq_delta_cyc, e2, d2);
-        const float dx = xc.x - xyz_t.x, dy = xc.y - xyz_t.y, dz = xc.z - xyz_t.z;
-        cyc = sqrtf(dx * dx + dy * dy + dz * dz);
-        ent_out = 0.5f * (e2 + ent_b);
-        dsk_out = 0.5f * (d2 + dsk_b);
-      }
       if (hsel == 1 || !live) continue;  // half 0 writes the sample's outputs
 
+      float flow[3];
       {
         // field_to_cam with the partner frame's camera, pinhole projection, flow (nerf.py:948-997)
         const float* cn = fblk + FL.cam_partner;
@@ -593,18 +633,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       }
 
       // ------------------------------------------------ Gaussian bone density (compute_gauss_density)
+      // max_b exp(-d2_b / 2) = exp(-min_b d2_b / 2)
       float gdens = 0.f;
       if constexpr (B > 0) {
-        float best = -INFINITY;
-        const float* ctr = cblk + CL.center;
-#pragma unroll
+        float best = INFINITY;
+        const uint32_t ctr = cblk_s + 4u * CL.center;
+#pragma unroll 5
         for (int b = 0; b < B; ++b) {
-          const float4 c = *reinterpret_cast<const float4*>(ctr + b * 4);
+          const float4 c = lds128(ctr + 16u * b);
           const float dx = xyz.x - c.x, dy = xyz.y - c.y, dz = xyz.z - c.z;
-          const float d2 = (dx * dx + dy * dy + dz * dz) / (0.01f * 0.01f);
-          best = fmaxf(best, expf(-0.5f * d2));
+          best = fminf(best, dx * dx + dy * dy + dz * dz);
         }
-        gdens = best * sc[SC_WARP_IBETA];
+        gdens = expf(-0.5f * (best / (0.01f * 0.01f))) * lds32(sc_s + 4u * SC_WARP_IBETA);
       }
 
       // ------------------------------------------------ per-sample outputs
@@ -619,7 +659,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         st3(p.out.xyz_cam, xyz_cam.x, xyz_cam.y, xyz_cam.z);
         st3(p.out.xyz_t, xyz_t.x, xyz_t.y, xyz_t.z);
         st3(p.out.dir, dir_f.x, dir_f.y, dir_f.z);
-        st1(p.out.depth, depth * sc[SC_INV_SCALE]);
+        st1(p.out.depth, depth * lds32(sc_s + 4u * SC_INV_SCALE));
         st1(p.out.deltas, delta);
         st3(p.out.flow, flow[0], flow[1], flow[2]);
         st1(p.out.cyc_dist, cyc);

@@ -78,7 +78,9 @@ enum : int { SC_IBETA = 0, SC_INV_SCALE, SC_WARP_IBETA, SC_SDF_B, SC_RGB2_B0, SC
 // float offsets inside one frame block
 struct FrameLayout {
   int16_t cam, cam_partner;  // 24 floats each: Kinv[9], near, far, q[4], t[3], pad
-  int16_t binv_t, se3_bwd, binv_rest, se3_fwd, binv_rest_partner, se3_fwd_partner;  // B*8 floats each
+  // bone tables: binv_* = scaled inverse bone transform as 3 rows (R'_i0 R'_i1 R'_i2 t'_i), B*12 floats;
+  // se3_* = blend transform as dual quaternion (real, dual), B*8 floats
+  int16_t binv_t, se3_bwd, binv_rest, se3_fwd, binv_rest_partner, se3_fwd_partner;
   int16_t delta1_fwd;        // bias row of delta_field.linear_1 with the MEAN time code
   int16_t n_cond;
   int16_t n_floats;          // multiple of 4
@@ -262,9 +264,9 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   if (d.appr_channels > 0) add_cond(L.rgb0, d.W + pe_dim(d.L_dir), d.appr_channels, CODE_APPR);
   add_cond(L.color[0], pe_c, INST, CODE_INST_COLOR);
   F.n_cond = (int16_t)nc;
-  auto bones = [&]() { int o = fo; fo += B * 8; return (int16_t)o; };
-  F.binv_t = bones(); F.se3_bwd = bones(); F.binv_rest = bones(); F.se3_fwd = bones();
-  F.binv_rest_partner = bones(); F.se3_fwd_partner = bones();
+  auto bones = [&](int per) { int o = fo; fo += B * per; return (int16_t)o; };
+  F.binv_t = bones(12); F.se3_bwd = bones(8); F.binv_rest = bones(12); F.se3_fwd = bones(8);
+  F.binv_rest_partner = bones(12); F.se3_fwd_partner = bones(8);
   F.n_floats = (int16_t)pad4(fo);
 
   // ---- constant block: plain bias rows, head weights, Gaussian scales, scalars
@@ -313,6 +315,10 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   };
   P.seq_delta_bwd = ns;
   if (B > 0) emit_delta(false);
+  P.seq_delta_flow = ns;
+  if (B > 0) emit_delta(true);
+  P.seq_delta_cyc = ns;
+  if (B > 0) emit_delta(true);
   P.seq_vis = ns;
   emit(L.vis[0], pe_ch(pe_v), kTmemMain, 0);
   emit(L.vis[1], {CH_H0}, kTmemMain, 0);
@@ -339,10 +345,6 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
     }
     emit(L.feat[5], hch(CH_H0, 2), kTmemMain, 0);
   }
-  P.seq_delta_flow = ns;
-  if (B > 0) emit_delta(true);
-  P.seq_delta_cyc = ns;
-  if (B > 0) emit_delta(true);
   P.n_seq = ns;
   bp.ok = true;
   return bp;

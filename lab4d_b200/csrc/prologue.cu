@@ -38,14 +38,22 @@ __device__ void write_cam(float* dst, const PrologueParams& p, int f) {
   }
 }
 
-// inverse of a bone transform as rotation quaternion + translation: (q*, 2 (qd* q)_xyz)
-__device__ void write_binv(float* dst, const float* qr_, const float* qd_, int B) {
+// Inverse of a bone transform, pre-scaled by the Gaussian bone scale, as three rows
+// (R'_i0, R'_i1, R'_i2, t'_i) with R' = diag(1/gauss) R(q*), t' = (1/gauss) * 2 (qd* q)_xyz, so that the
+// Gaussian bone coordinate of x is R' x + t' (utils/transforms.py:9-25, nnutils/skinning.py:122-139).
+__device__ void write_binv(float* dst, const float* qr_, const float* qd_, const float* cblock_inv_gauss, int B) {
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const Q4 qr = qconj(ld4(qr_ + b * 4)), qd = qconj(ld4(qd_ + b * 4));
-    const Q4 t = qmul(qd, qconj(qr));
-    float* o = dst + b * 8;
-    st4(o, qr);
-    o[4] = 2.f * t.x; o[5] = 2.f * t.y; o[6] = 2.f * t.z; o[7] = 0.f;
+    const Q4 q = qconj(ld4(qr_ + b * 4)), qd = qconj(ld4(qd_ + b * 4));
+    const Q4 t = qmul(qd, qconj(q));
+    const float tx = 2.f * t.x, ty = 2.f * t.y, tz = 2.f * t.z;
+    const float gx = cblock_inv_gauss[b * 4], gy = cblock_inv_gauss[b * 4 + 1], gz = cblock_inv_gauss[b * 4 + 2];
+    // rotation matrix of q (the quaternion sandwich q (0,p) q* expanded; |q| = 1 up to rounding)
+    const float ww = q.w * q.w, xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z;
+    const float xy = q.x * q.y, xz = q.x * q.z, yz = q.y * q.z, wx = q.w * q.x, wy = q.w * q.y, wz = q.w * q.z;
+    float* o = dst + b * 12;
+    o[0] = gx * (ww + xx - yy - zz); o[1] = gx * 2.f * (xy - wz); o[2] = gx * 2.f * (xz + wy); o[3] = gx * tx;
+    o[4] = gy * 2.f * (xy + wz); o[5] = gy * (ww - xx + yy - zz); o[6] = gy * 2.f * (yz - wx); o[7] = gy * ty;
+    o[8] = gz * 2.f * (xz - wy); o[9] = gz * 2.f * (yz + wx); o[10] = gz * (ww - xx - yy + zz); o[11] = gz * tz;
   }
 }
 // a (x) b^-1 as (real, dual)
@@ -135,10 +143,18 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
     }
   }
   if (B > 0) {
+    __shared__ float ig[32 * 4];
+    for (int b = threadIdx.x; b < B; b += blockDim.x)
+      for (int c = 0; c < 3; ++c) {
+        float lg = p.par.log_gauss[b * 3 + c];
+        if (p.par.symm_idx) lg = 0.5f * (p.par.log_gauss[p.par.symm_idx[b] * 3 + c] + lg);
+        ig[b * 4 + c] = expf(-lg);
+      }
+    __syncthreads();
     const size_t o = (size_t)f * B * 4, on = (size_t)fn * B * 4;
-    write_binv(fb + F.binv_t, p.fr.t_art_qr + o, p.fr.t_art_qd + o, B);
-    write_binv(fb + F.binv_rest, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, B);
-    write_binv(fb + F.binv_rest_partner, p.fr.rest_art_qr + on, p.fr.rest_art_qd + on, B);
+    write_binv(fb + F.binv_t, p.fr.t_art_qr + o, p.fr.t_art_qd + o, ig, B);
+    write_binv(fb + F.binv_rest, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, ig, B);
+    write_binv(fb + F.binv_rest_partner, p.fr.rest_art_qr + on, p.fr.rest_art_qd + on, ig, B);
     write_se3(fb + F.se3_bwd, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, p.fr.t_art_qr + o, p.fr.t_art_qd + o, B);
     write_se3(fb + F.se3_fwd, p.fr.t_art_qr + o, p.fr.t_art_qd + o, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, B);
     write_se3(fb + F.se3_fwd_partner, p.fr.t_art_qr + on, p.fr.t_art_qd + on, p.fr.rest_art_qr + on, p.fr.rest_art_qd + on, B);
