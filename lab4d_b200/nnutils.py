@@ -1,0 +1,118 @@
+"""Drop-in adapter for the reference's module surface.
+
+`install()` rebinds, inside an imported `lab4d` package,
+    lab4d.nnutils.nerf.NeRF.query_field            (also reached by FeatureNeRF / Deformable via super())
+    lab4d.nnutils.deformable.Deformable.query_field
+    lab4d.utils.render_utils.render_pixel and the by-name import lab4d.engine.model.render_pixel
+so that lab4d.engine.model.dvr_model.render_samples (engine/model.py:328-361) and lab4d/render.py call the
+B200 renderer unchanged.  Parameters stay nn.Parameters of the reference modules (checkpoints, optimiser
+param groups and DDP are untouched); per-frame codes / cameras / articulations are still produced by the
+reference's small per-frame MLPs and handed over as tables.
+
+Scope of this round: the forward pass.  query_field raises if autograd is recording and the caller did
+not ask for `forward_only=True` semantics (the field kernel's backward is the next milestone; the
+compositing backward is already native).
+"""
+import functools
+
+import torch
+
+from . import render as _render
+from .spec import FieldConfig
+
+
+def config_from_module(field) -> FieldConfig:
+    """Read the architecture of a reference NeRF / Deformable module."""
+    base = field.basefield
+    W, D = base.W, base.D
+    motion, B, symm = "rigid", 0, None
+    warp = getattr(field, "warp", None)
+    if warp is not None and hasattr(warp, "skinning_model"):
+        if hasattr(warp, "post_warp"):
+            raise NotImplementedError("ComposedWarp (skeleton + DenseWarp) is not accelerated yet")
+        B = warp.skinning_model.num_coords
+        motion = "bob" if type(warp.articulation).__name__ == "ArticulationFlatMLP" else "skel"
+        if warp.skinning_model.symm_idx is not None:
+            symm = tuple(int(i) for i in warp.skinning_model.symm_idx)
+    elif warp is not None and type(warp).__name__ != "IdentityWarp":
+        raise NotImplementedError(f"warp type {type(warp).__name__} is not accelerated yet")
+    return FieldConfig(category=field.category, D=D, W=W, L_xyz=field.pos_embedding.N_freqs,
+                       L_dir=field.dir_embedding.N_freqs, appr_channels=field.appr_channels, skip=base.skips[0],
+                       motion=motion, B=B, has_feature=hasattr(field, "feature_field"), symm_idx=symm)
+
+
+def tables_from_module(field, samples_dict):
+    """Per-frame tables of the hot path, computed with the reference's own per-frame modules
+    (nnutils/{appearance,embedding,pose}.py - M rows, out of scope as kernels)."""
+    frame_id, inst_id = samples_dict["frame_id"], samples_dict["inst_id"]
+    tab = {"field2cam_q": samples_dict["field2cam"][0], "field2cam_t": samples_dict["field2cam"][1],
+           "inst_base": field.basefield.inst_embedding(inst_id), "inst_color": field.colorfield.inst_embedding(inst_id),
+           "inst_vis": field.vis_mlp.basefield.inst_embedding(inst_id)}
+    if field.appr_channels > 0:
+        tab["appr_code"] = field.appr_embedding.get_vals(frame_id)
+    warp = getattr(field, "warp", None)
+    if warp is not None and hasattr(warp, "skinning_model"):
+        sk = warp.skinning_model
+        tab["inst_skin"] = sk.delta_field.inst_embedding(inst_id)
+        tab["skin_t_embed"] = sk.time_embedding(frame_id)
+        tab["skin_t_embed_mean"] = sk.time_embedding.get_mean_embedding(frame_id.device)
+        if "t_articulation" in samples_dict:
+            t_art, r_art = samples_dict["t_articulation"], samples_dict["rest_articulation"]
+        else:
+            t_art, r_art = warp.articulation.get_vals_and_mean(frame_id)
+        tab["t_articulation_qr"], tab["t_articulation_qd"] = t_art
+        tab["rest_articulation_qr"], tab["rest_articulation_qd"] = r_art
+    return tab
+
+
+def query_field(field, samples_dict, flow_thresh=None, n_depth=64):
+    """Replacement body of {NeRF,FeatureNeRF,Deformable}.query_field (training-mode path,
+    nnutils/nerf.py:580-684).  Returns (feat_dict, deltas, aux_dict) like the reference."""
+    if not field.training:
+        raise NotImplementedError("eval-mode query_field (importance sampling, aabb compaction, normals) is not accelerated yet")
+    if torch.is_grad_enabled() and any(p.requires_grad for p in field.parameters()):
+        raise NotImplementedError("lab4d_b200: the field kernel's backward is not implemented in this round; "
+                                  "call under torch.no_grad() for forward rendering")
+    if field.pos_embedding.alpha is not None and field.pos_embedding_color.alpha != field.pos_embedding.alpha:
+        raise NotImplementedError("different annealing windows for density and colour embeddings")
+    cfg = config_from_module(field)
+    cache = field.__dict__.setdefault("_b200_renderer", {})
+    dev = samples_dict["hxy"].device
+    key = (cfg, str(dev))
+    if key not in cache:
+        cache[key] = _render.FieldRenderer(cfg, dev)
+    r = cache[key]
+    P = {k: v for k, v in field.named_parameters()}
+    r.pack(P, alpha=field.pos_embedding.alpha)
+    rays = {"hxy": samples_dict["hxy"], "Kinv": samples_dict["Kinv"], "near_far": samples_dict["near_far"]}
+    feat, deltas = r.query_field(P, rays, tables_from_module(field, samples_dict), n_depth, flow_thresh=flow_thresh)
+    return feat, deltas, {}
+
+
+def install(lab4d=None, n_depth=64):
+    """Patch an imported reference package in place; returns a function that undoes the patch."""
+    if lab4d is None:
+        import lab4d  # noqa: F401
+    import lab4d.engine.model as rmodel
+    import lab4d.nnutils.deformable as rdef
+    import lab4d.nnutils.feature as rfeat
+    import lab4d.nnutils.nerf as rnerf
+    import lab4d.utils.render_utils as rru
+
+    saved = [(rnerf.NeRF, "query_field", rnerf.NeRF.query_field), (rfeat.FeatureNeRF, "query_field", rfeat.FeatureNeRF.query_field),
+             (rdef.Deformable, "query_field", rdef.Deformable.query_field), (rru, "render_pixel", rru.render_pixel),
+             (rmodel, "render_pixel", rmodel.render_pixel)]
+
+    def _qf(self, samples_dict, flow_thresh=None):
+        return query_field(self, samples_dict, flow_thresh=flow_thresh, n_depth=n_depth)
+
+    for cls in (rnerf.NeRF, rfeat.FeatureNeRF, rdef.Deformable):
+        cls.query_field = _qf
+    rru.render_pixel = _render.render_pixel
+    rmodel.render_pixel = _render.render_pixel
+
+    def undo():
+        for obj, name, val in saved:
+            setattr(obj, name, val)
+
+    return undo

@@ -218,39 +218,101 @@ def _channel_plan(field_dict):
     return plan
 
 
-@torch.no_grad()
+def _composite_call(h, device, dens, dl, plan_part, srcs, M, N, D, bwd=None):
+    """One b200r_composite_fwd (or _bwd) launch over <= MAX_CHANNELS arrays."""
+    R = M * N
+    a = _lib.CompositeArgs()
+    a.R, a.D = R, D
+    a.density, a.deltas = dens.data_ptr(), dl.data_ptr()
+    a.n_channels = len(plan_part)
+    outs = []
+    mask = torch.empty(M, N, 1, device=device)
+    a.mask = mask.data_ptr()
+    for i, ((k, mode, nout), src) in enumerate(zip(plan_part, srcs)):
+        a.src[i] = src.data_ptr()
+        a.nch[i], a.mode[i] = src.shape[-1], mode
+        if bwd is None:
+            dst = torch.empty(M, N, nout, device=device)
+            outs.append(dst)
+            a.dst[i] = dst.data_ptr()
+    if bwd is None:
+        h.check(h.lib.b200r_composite_fwd(h.h, C.byref(a), _stream(device)), "b200r_composite_fwd")
+        return mask, outs
+    g_mask, g_outs, need = bwd
+    b = _lib.CompositeBwdArgs()
+    b.fwd = a
+    b.g_mask = g_mask.data_ptr() if g_mask is not None else None
+    g_dens = torch.empty_like(dens)
+    b.g_density = g_dens.data_ptr()
+    g_srcs = []
+    for i, src in enumerate(srcs):
+        if g_outs[i] is not None:
+            b.g_dst[i] = g_outs[i].data_ptr()
+        if need[i]:
+            g = torch.empty_like(src)
+            b.g_src[i] = g.data_ptr()
+            g_srcs.append(g)
+        else:
+            g_srcs.append(None)
+    h.check(h.lib.b200r_composite_bwd(h.h, C.byref(b), _stream(device)), "b200r_composite_bwd")
+    return g_dens, g_srcs
+
+
+class _Composite(torch.autograd.Function):
+    """render_pixel's per-ray reductions with the hand-derived backward kernel (csrc/composite.cu)."""
+
+    @staticmethod
+    def forward(ctx, plan, density, deltas, *values):
+        device = density.device
+        h = _lib.handle_for(device)
+        M, N, D = density.shape[:3]
+        dens, dl = _f32c(density.detach()), _f32c(deltas.detach())
+        srcs = [_f32c(v.detach()) for v in values]
+        outs, mask = [], None
+        for c0 in range(0, max(len(plan), 1), _lib.MAX_CHANNELS):
+            m, o = _composite_call(h, device, dens, dl, plan[c0:c0 + _lib.MAX_CHANNELS], srcs[c0:c0 + _lib.MAX_CHANNELS], M, N, D)
+            mask = m
+            outs += o
+        ctx.plan, ctx.shape = plan, (M, N, D)
+        ctx.save_for_backward(dens, dl, *srcs)
+        return (mask, *outs)
+
+    @staticmethod
+    def backward(ctx, g_mask, *g_outs):
+        dens, dl, *srcs = ctx.saved_tensors
+        plan = ctx.plan
+        M, N, D = ctx.shape
+        device = dens.device
+        h = _lib.handle_for(device)
+        g_dens_total, g_vals = None, []
+        for c0 in range(0, max(len(plan), 1), _lib.MAX_CHANNELS):
+            part = plan[c0:c0 + _lib.MAX_CHANNELS]
+            go = [None if g is None else _f32c(g) for g in g_outs[c0:c0 + _lib.MAX_CHANNELS]]
+            need = [ctx.needs_input_grad[3 + c0 + i] for i in range(len(part))]
+            gm = _f32c(g_mask) if (g_mask is not None and c0 == 0) else None
+            g_dens, g_srcs = _composite_call(h, device, dens, dl, part, srcs[c0:c0 + _lib.MAX_CHANNELS], M, N, D, bwd=(gm, go, need))
+            g_dens_total = g_dens if g_dens_total is None else g_dens_total + g_dens
+            g_vals += g_srcs
+        return (None, g_dens_total.view(M, N, D, 1), None, *g_vals)
+
+
 def render_pixel(field_dict, deltas):
     """Volume-render per-sample field outputs along rays (utils/render_utils.py:59-184).
-    field_dict: key -> (M,N,D,c); deltas (M,N,D,1).  Returns key -> (M,N,c)."""
-    dens = _f32c(field_dict["density"])
+    field_dict: key -> (M,N,D,c); deltas (M,N,D,1).  Returns key -> (M,N,c).  Differentiable w.r.t.
+    every per-sample array (hand-derived backward kernel); deltas are treated as constants."""
+    dens = field_dict["density"]
     device = dens.device
-    h = _lib.handle_for(device)
     M, N, D = dens.shape[:3]
     R = M * N
     plan = _channel_plan(field_dict)
-    out = {"mask": torch.empty(M, N, 1, device=device)}
-    keep = [dens, _f32c(deltas)]
-    # the ABI takes at most MAX_CHANNELS arrays per launch
-    for c0 in range(0, max(len(plan), 1), _lib.MAX_CHANNELS):
-        a = _lib.CompositeArgs()
-        a.R, a.D = R, D
-        a.density, a.deltas = keep[0].data_ptr(), keep[1].data_ptr()
-        a.mask = out["mask"].data_ptr()
-        part = plan[c0:c0 + _lib.MAX_CHANNELS]
-        a.n_channels = len(part)
-        for i, (k, mode, nout) in enumerate(part):
-            src = _f32c(field_dict[k])
-            keep.append(src)
-            dst = torch.empty(M, N, nout, device=device)
-            out[k] = dst
-            a.src[i], a.dst[i] = src.data_ptr(), dst.data_ptr()
-            a.nch[i], a.mode[i] = src.shape[-1], mode
-        rc = h.lib.b200r_composite_fwd(h.h, C.byref(a), _stream(device))
-        h.check(rc, "b200r_composite_fwd")
+    res = _Composite.apply(plan, dens, deltas, *[field_dict[k] for k, _, _ in plan])
+    out = {"mask": res[0]}
+    for (k, mode, nout), v in zip(plan, res[1:]):
+        out[k] = v
     # per-batch normalisers (tiny (M,N) tensors)
     if "vis" in out:
         v = out["vis"]
-        out["vis"] = (-(v[..., :1] / D) / (v[..., 1].sum() / (R * D)))
+        out["vis"] = (-(v[..., :1] / D) / (v[..., 1].detach().sum() / (R * D)))
     for k in ("eikonal", "delta_skin"):
         if k in out:
             out[k] = out[k][..., 0]
