@@ -12,6 +12,11 @@ struct b200r_handle {
   int device;
   int n_sm;
   std::string err;
+  // device copy of the pack-slice table of the last descriptor packed
+  b200r::PackSlice* d_slices;
+  size_t d_slices_cap;
+  b200r_field_desc slices_desc;
+  bool slices_valid;
 };
 
 static int fail(b200r_handle* h, int code, const std::string& msg) {
@@ -45,12 +50,16 @@ int b200r_create(int device, b200r_handle** out) {
   b200r_handle* h = new b200r_handle();
   h->device = device;
   h->n_sm = prop.multiProcessorCount;
+  h->d_slices = nullptr;
+  h->d_slices_cap = 0;
+  h->slices_valid = false;
   *out = h;
   return B200R_OK;
 }
 
 void b200r_destroy(b200r_handle* h) {
   if (!h) return;
+  if (h->d_slices) cudaFree(h->d_slices);
   delete h;
 }
 
@@ -70,10 +79,23 @@ int b200r_pack_weights(b200r_handle* h, const b200r_field_desc* desc, const b200
     if (!params->weight[i]) return fail(h, B200R_E_INVALID, "pack_weights: null weight pointer");
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
-  if ((int)bp.slices.size() > b200r::kMaxPackSlices) return fail(h, B200R_E_INVALID, "pack_weights: too many slices");
+  const size_t sbytes = bp.slices.size() * sizeof(b200r::PackSlice);
+  if (!h->slices_valid || memcmp(&h->slices_desc, desc, sizeof(*desc)) != 0) {
+    if (sbytes > h->d_slices_cap) {
+      if (h->d_slices) cudaFree(h->d_slices);
+      h->d_slices = nullptr;
+      if ((e = cudaMalloc((void**)&h->d_slices, sbytes)) != cudaSuccess) return fail_cuda(h, e, "cudaMalloc");
+      h->d_slices_cap = sbytes;
+    }
+    // blocking copy of a few KB, once per descriptor (the table only depends on the architecture)
+    if ((e = cudaMemcpy(h->d_slices, bp.slices.data(), sbytes, cudaMemcpyHostToDevice)) != cudaSuccess)
+      return fail_cuda(h, e, "cudaMemcpy");
+    h->slices_desc = *desc;
+    h->slices_valid = true;
+  }
   b200r::PackParams pp;
   memset(&pp, 0, sizeof(pp));
-  for (size_t i = 0; i < bp.slices.size(); ++i) pp.slices[i] = bp.slices[i];
+  pp.slices = h->d_slices;
   for (int i = 0; i < n_weights; ++i) pp.weights[i] = params->weight[i];
   pp.n_slices = (int)bp.slices.size();
   pp.total_groups = (uint32_t)(bp.packed_bytes / 16);

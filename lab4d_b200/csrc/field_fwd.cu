@@ -9,8 +9,12 @@
 //               dual-quaternion blend skinning, write 16-bit operand rows into swizzled shared memory
 //               and run every layer's epilogue straight out of TMEM.
 //   warp 8    : TMA producer - streams its half of each pre-packed weight chunk (cp.async.bulk,
-//               multicast to both CTAs of the cluster) through a 3-stage ring.
-//   warp 9    : tcgen05.mma issuer (one elected lane) + TMEM owner.
+//               multicast to both CTAs of the cluster) through a 6-stage ring of 16 KB.
+//   warp 9    : tcgen05.mma issuer (one elected lane) + TMEM owner; walks the MmaStep list of program.h.
+// The 256-wide chains (basefield, colorfield) are software-pipelined: every layer is issued as two
+// N-halves into two TMEM accumulators, warps 0-3 / 4-7 run the epilogue of half 0 / 1 and write the
+// 16-bit activations back to TMEM, where the next layer's MMAs read them as the A operand (TS form),
+// so the epilogue of one half overlaps the MMAs of the other and of the next layer.
 // Per-frame tables (cameras, bias rows with the per-frame codes folded in, bone transforms) and the
 // constant block (plain biases, head weights) are staged in shared memory; hidden activations never
 // leave the SM; HBM sees O(100 B) per sample of outputs.
@@ -33,7 +37,7 @@
 namespace b200r {
 
 constexpr int kCluster = B200R_CLUSTER;
-constexpr int kNumStages = 3;
+constexpr int kNumStages = 6;
 constexpr int kComputeWarps = 8;
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kThreads = kComputeThreads + 64;
@@ -100,17 +104,19 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
   float* cblk = reinterpret_cast<float*>(ring + kSmemRing);
   float* fblk = cblk + p.prog.cl.n_floats;
   uint64_t* bars = reinterpret_cast<uint64_t*>(fblk + p.prog.fl.n_floats);
-  uint64_t* full_bar = bars;                       // [kNumStages]
-  uint64_t* empty_bar = bars + kNumStages;         // [kNumStages]
-  uint64_t* a_ready = bars + 2 * kNumStages;       // compute warps -> MMA warp
-  uint64_t* acc_full = bars + 2 * kNumStages + 1;  // MMA warp -> compute warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumStages + 2);
+  uint64_t* full_bar = bars;                  // [kNumStages]
+  uint64_t* empty_bar = bars + kNumStages;    // [kNumStages]
+  uint64_t* c2m = bars + 2 * kNumStages;      // [4] compute warps -> MMA thread, indexed by BAR_*
+  uint64_t* m2c = bars + 2 * kNumStages + 4;  // [4] MMA thread (tcgen05.commit) -> compute warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumStages + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], kCluster); }
-    mbar_init(a_ready, kComputeThreads);
-    mbar_init(acc_full, 1);
+    mbar_init(&c2m[BAR_ALL], kComputeThreads);
+    mbar_init(&c2m[BAR_H0], kComputeThreads / 2);
+    mbar_init(&c2m[BAR_H1], kComputeThreads / 2);
+    for (int i = 1; i < 4; ++i) mbar_init(&m2c[i], 1);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, kTmemCols);
@@ -129,50 +135,58 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < iters; ++it) {
-        for (int g = 0; g < P.n_seq; ++g) {
-          const GemmDesc& G = P.seq[g];
-          const uint32_t bytes = (uint32_t)G.n_pad * 128u;
+        for (int st = 0; st < P.n_steps; ++st) {
+          const MmaStep& S = P.steps[st];
+          const uint32_t bytes = (uint32_t)S.n * 128u;
           const uint32_t part = bytes / kCluster;
-          for (int c = 0; c < G.n_chunks; ++c) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);  // both CTAs' MMAs are done with this slot
-            mbar_arrive_expect_tx(&full_bar[stage], bytes);
-            const uint8_t* src = p.packed + G.w_off + (uint32_t)c * bytes + cta_rank * part;
-            uint8_t* dst = ring + stage * kWStageBytes + cta_rank * part;
-            if (kCluster > 1) tma_bulk_g2s_mcast(dst, src, part, &full_bar[stage], cmask);
-            else tma_bulk_g2s(dst, src, part, &full_bar[stage]);
-            if (++stage == kNumStages) { stage = 0; phase ^= 1; }
-          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);  // both CTAs' MMAs are done with this slot
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          const uint8_t* src = p.packed + S.w_off + cta_rank * part;
+          uint8_t* dst = ring + stage * kWStageBytes + cta_rank * part;
+          if (kCluster > 1) tma_bulk_g2s_mcast(dst, src, part, &full_bar[stage], cmask);
+          else tma_bulk_g2s(dst, src, part, &full_bar[stage]);
+          if (++stage == kNumStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 9) {
     // =============================================================== MMA issuer
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_phase = 0;
+      uint32_t stage = 0, phase = 0;
+      uint32_t bar_phase = 0;  // bit i = parity of c2m[i]
       const uint32_t arena_addr = smem_u32(arena), ring_addr = smem_u32(ring);
       for (int it = 0; it < iters; ++it) {
-        for (int g = 0; g < P.n_seq; ++g) {
-          const GemmDesc& G = P.seq[g];
-          const uint32_t idesc = umma_idesc_f16(Op::kFmt, G.n_pad);
-          mbar_wait(a_ready, a_phase);
-          a_phase ^= 1;
-          tc_fence_after_sync();
-          uint32_t acc = G.accumulate;
-          for (int c = 0; c < G.n_chunks; ++c) {
-            mbar_wait(&full_bar[stage], phase);
+        for (int st = 0; st < P.n_steps; ++st) {
+          const MmaStep& S = P.steps[st];
+          const uint32_t idesc = umma_idesc_f16(Op::kFmt, S.n);
+          if (S.wait) {
+            mbar_wait(&c2m[S.wait], (bar_phase >> S.wait) & 1u);
+            bar_phase ^= 1u << S.wait;
             tc_fence_after_sync();
-            const uint64_t adesc = umma_desc_k_sw128(arena_addr + G.a_chunk[c] * kAChunkBytes);
-            const uint64_t bdesc = umma_desc_k_sw128(ring_addr + stage * kWStageBytes);
-            for (int k = 0; k < G.ksteps[c]; ++k) {
-              umma_f16_ss(tmem_base + G.tmem_col, umma_desc_advance_k(adesc, k), umma_desc_advance_k(bdesc, k), idesc, acc);
+          }
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint64_t bdesc = umma_desc_k_sw128(ring_addr + stage * kWStageBytes);
+          const uint32_t d = tmem_base + S.d_col;
+          uint32_t acc = S.accumulate;
+          if (S.a_kind == 0) {
+            const uint64_t adesc = umma_desc_k_sw128(arena_addr + S.a_chunk * kAChunkBytes);
+            for (int k = 0; k < S.ksteps; ++k) {
+              umma_f16_ss(d, umma_desc_advance_k(adesc, k), umma_desc_advance_k(bdesc, k), idesc, acc);
               acc = 1;
             }
-            // frees the ring slot (in both CTAs) once these MMAs have read it
-            if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);
-            else umma_commit(&empty_bar[stage]);
-            if (++stage == kNumStages) { stage = 0; phase ^= 1; }
+          } else {
+            const uint32_t a = tmem_base + S.a_tmem_col;  // 16 halves per k-step = 8 TMEM columns
+            for (int k = 0; k < S.ksteps; ++k) {
+              umma_f16_ts(d, a + 8 * k, umma_desc_advance_k(bdesc, k), idesc, acc);
+              acc = 1;
+            }
           }
-          umma_commit(acc_full);
+          // frees the ring slot (in both CTAs) once these MMAs have read it
+          if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);
+          else umma_commit(&empty_bar[stage]);
+          if (++stage == kNumStages) { stage = 0; phase ^= 1; }
+          if (S.commit) umma_commit(&m2c[S.commit]);
         }
       }
     }
@@ -181,8 +195,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     const int q = warp & 3, hsel = warp >> 2;
     const uint32_t row = (uint32_t)(q * 32 + lane);  // tile row == TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t acc_phase = 0;
-    const int W = p.desc.W;
+    uint32_t all_phase = 0, half_phase = 0;  // parities of m2c[BAR_ALL] and of this half's m2c[BAR_H0 + hsel]
+    const int W = p.desc.W, HN = W / 2;
+    // canonical layer ids (same enumeration as program.h layer_ids)
+    const int lid_delta = 0, lid_vis = B > 0 ? 3 : 0, lid_base = lid_vis + 2, lid_rgb0 = lid_base + p.desc.D + 1,
+              lid_color = lid_rgb0 + 1, lid_feat = lid_color + 3;
+    uint64_t* const my_c2m = &c2m[BAR_H0 + hsel];
+    uint64_t* const my_m2c = &m2c[BAR_H0 + hsel];
     const ConstLayout& CL = P.cl;
     const FrameLayout& FL = P.fl;
     // 32-bit shared-window addresses (explicit ld/st.shared keeps the hot loops off the generic path)
@@ -209,24 +228,22 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     auto pair_sync = [&]() { named_bar_sync(1 + q, 64); };
 
     // hand the operands to the MMA warp, then wait for the layer's accumulator
-    auto run_gemm = [&]() {
+    auto arrive_all = [&]() {
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(a_ready);
-      mbar_wait(acc_full, acc_phase);
-      acc_phase ^= 1;
+      mbar_arrive(&c2m[BAR_ALL]);
+    };
+    auto wait_all = [&]() {
+      mbar_wait(&m2c[BAR_ALL], all_phase);
+      all_phase ^= 1;
       tc_fence_after_sync();
     };
-    auto bias_s = [&](int s_idx) -> uint32_t {
-      const GemmDesc& G = P.seq[s_idx];
-      return (G.bias_frame ? fblk_s : cblk_s) + 4u * G.bias_off;
-    };
+    auto run_gemm = [&]() { arrive_all(); wait_all(); };
+    auto bias_s = [&](int layer) -> uint32_t { return (P.bias[layer].frame ? fblk_s : cblk_s) + 4u * P.bias[layer].off; };
     // relu(acc + bias) -> 16-bit operand rows; this thread covers its half of the columns.
-    auto epi_relu_store = [&](int s_idx, int dst_chunk) {
-      const GemmDesc& G = P.seq[s_idx];
-      const uint32_t bias = bias_s(s_idx);
-      const int ncols = G.n_pad >> 1, cb = hsel * ncols, nblk = ncols >> 5;
-      const uint32_t t0 = t_lane + G.tmem_col + cb;
+    auto epi_relu_store = [&](uint32_t bias, int n_pad, int dst_chunk) {
+      const int ncols = n_pad >> 1, cb = hsel * ncols, nblk = ncols >> 5;
+      const uint32_t t0 = t_lane + kTmemD0 + cb;
       auto process = [&](uint32_t (&r)[32], int c0) {
         const uint32_t chunk = arena_s + (uint32_t)(dst_chunk + (c0 >> 6)) * kAChunkBytes;
         const uint32_t gbase = (uint32_t)(c0 & 63) >> 3;
@@ -249,6 +266,32 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         tmem_ld_wait32(ra);
         process(ra, cb + 32 * blk);
       }
+    };
+    // Pipelined chain: epilogue of THIS thread's N-half (HN columns of accumulator D<hsel>):
+    // relu(acc + bias) -> 16-bit activations -> TMEM buffer `wbuf` columns [hsel*HN/2, ...), then signal the MMA thread.
+    auto epi_half_to_tmem = [&](int layer, int wbuf) {
+      mbar_wait(my_m2c, half_phase);
+      half_phase ^= 1;
+      tc_fence_after_sync();
+      const uint32_t bias = bias_s(layer) + 4u * (uint32_t)(hsel * HN);
+      const uint32_t tsrc = t_lane + (hsel ? kTmemD1 : kTmemD0);
+      const uint32_t tdst = t_lane + (wbuf ? kTmemA1 : kTmemA0) + (uint32_t)(hsel * (HN >> 1));
+#pragma unroll 1
+      for (int blk = 0; blk < (HN >> 5); ++blk) {
+        uint32_t ra[32], o[16];
+        tmem_ld32_issue(tsrc + 32 * blk, ra);
+        tmem_ld_wait32(ra);
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          const float4 b = lds128(bias + 4u * (32 * blk + 4 * g4));
+          o[2 * g4] = Op::pack2_relu(__uint_as_float(ra[4 * g4 + 0]) + b.x, __uint_as_float(ra[4 * g4 + 1]) + b.y);
+          o[2 * g4 + 1] = Op::pack2_relu(__uint_as_float(ra[4 * g4 + 2]) + b.z, __uint_as_float(ra[4 * g4 + 3]) + b.w);
+        }
+        tmem_st16(tdst + 16 * blk, o);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive(my_c2m);
     };
 
     for (int it = 0; it < iters; ++it) {
@@ -306,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       constexpr int XTRA = (8 - (3 * BS) % 8) % 8;  // values of bone BS that complete half 0's last group
       constexpr int I0 = 3 * BS + XTRA;             // first operand column written by half 1
       constexpr int BH = BS > B - BS ? BS : B - BS;
-      auto skin_warp = [&](auto half_tag, const float3& x, uint32_t binv, uint32_t se3, int s_first, float& entropy,
+      auto skin_warp = [&](auto half_tag, const float3& x, uint32_t binv, uint32_t se3, uint32_t bias1, float& entropy,
                            float& delta_skin) -> float3 {
         constexpr int HALF = decltype(half_tag)::value;
         constexpr int b_lo = HALF == 0 ? 0 : BS;
@@ -344,13 +387,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         }
         // delta_field.linear_1 / linear_2 (ReLU) and linear_final
         run_gemm();
-        epi_relu_store(s_first, CH_H2);
+        epi_relu_store(bias1, 64, CH_H2);
         run_gemm();
-        epi_relu_store(s_first + 1, CH_H2);
+        epi_relu_store(bias_s(lid_delta + 1), 64, CH_H2);
         run_gemm();
         float dl[32];
-        tmem_ld32(t_lane + P.seq[s_first + 2].tmem_col, dl);
-        const uint32_t b3 = bias_s(s_first + 2);
+        tmem_ld32(t_lane + kTmemD0, dl);
+        const uint32_t b3 = bias_s(lid_delta + 2);
         float mx = -INFINITY, dsum = 0.f;
         int amax = 0;
 #pragma unroll
@@ -425,9 +468,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           const float3 src = w == 0 ? xyz_t : xyz;
           const uint32_t binv = fblk_s + 4u * (w == 0 ? FL.binv_t : (w == 1 ? FL.binv_rest_partner : FL.binv_rest));
           const uint32_t se3 = fblk_s + 4u * (w == 0 ? FL.se3_bwd : (w == 1 ? FL.se3_fwd_partner : FL.se3_fwd));
-          const int s_first = P.seq_delta_bwd + 3 * w;
+          const uint32_t bias1 = w == 0 ? bias_s(lid_delta) : fblk_s + 4u * FL.delta1_fwd;  // forward warps: mean time code
           float e, dk;
-          const float3 o = hsel == 0 ? skin_warp(IC<0>{}, src, binv, se3, s_first, e, dk) : skin_warp(IC<1>{}, src, binv, se3, s_first, e, dk);
+          const float3 o = hsel == 0 ? skin_warp(IC<0>{}, src, binv, se3, bias1, e, dk) : skin_warp(IC<1>{}, src, binv, se3, bias1, e, dk);
           if (w == 0) { xyz = o; ent_b = e; dsk_b = dk; }
           else if (w == 1) { x_next = o; }
           else {
@@ -475,15 +518,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       }
 
       // ------------------------------------------------ visibility MLP (VisField.forward)
-      int seq = P.seq_vis;
       run_gemm();
-      epi_relu_store(seq, CH_H0);
+      epi_relu_store(bias_s(lid_vis), 64, CH_H0);
       run_gemm();
       float vis_out;
       {
-        const uint32_t b2 = bias_s(seq + 1) + 128u * hsel, vw = cblk_s + 4u * CL.vis_w + 128u * hsel;
+        const uint32_t b2 = bias_s(lid_vis + 1) + 128u * hsel, vw = cblk_s + 4u * CL.vis_w + 128u * hsel;
         float v[32];
-        tmem_ld32(t_lane + P.seq[seq + 1].tmem_col + 32 * hsel, v);
+        tmem_ld32(t_lane + kTmemD0 + 32 * hsel, v);
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
@@ -500,26 +542,53 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         vis_out = (hsel == 0 ? accv + other : other + accv) + lds32(sc_s + 4u * SC_VIS_B);
       }
 
-      // ------------------------------------------------ density branch (NeRF.forward, basefield + sdf)
-      seq = P.seq_base;
+      // ------------------------------------------------ feature field (FeatureNeRF.compute_feat)
+      float feat[16];
+      if (p.desc.has_feature) {
 #pragma unroll 1
-      for (int i = 0; i < p.desc.D; ++i) {
+        for (int i = 0; i < 5; ++i) {
+          run_gemm();
+          epi_relu_store(bias_s(lid_feat + i), 128, CH_H0);
+        }
         run_gemm();
-        epi_relu_store(seq + i, CH_H0);
+        if (hsel == 0) {  // warp-uniform: 16 outputs, one thread per row
+          float v16[16];
+          tmem_ld16(t_lane + kTmemD0, v16);
+          const uint32_t bf = bias_s(lid_feat + 5);
+          float nn = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { feat[j] = v16[j] + lds32(bf + 4u * j); nn += feat[j] * feat[j]; }
+          const float inv = rsqrtf(nn);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) feat[j] *= inv;
+        }
       }
-      run_gemm();
+
+      // ------------------------------------------------ density + colour chains (NeRF.forward), pipelined:
+      // the MMA thread issues every W-wide layer as two N-halves; this thread finishes its half's epilogue
+      // (writing 16-bit activations to TMEM) while the other half's / the next layer's MMAs run.
+      arrive_all();  // embedding operands written, accumulators free
+      int buf = 0;   // TMEM activation buffer the current layer READS; its epilogue writes buf ^ 1
+#pragma unroll 1
+      for (int j = 0; j < p.desc.D; ++j) {
+        epi_half_to_tmem(lid_base + j, buf ^ 1);
+        buf ^= 1;
+      }
       float sdf;
       {
-        const int sf = seq + p.desc.D;
-        const GemmDesc& G = P.seq[sf];
-        const uint32_t bb = bias_s(sf), sw = cblk_s + 4u * CL.sdf_w;
-        const int ncols = W >> 1, cb = hsel * ncols;
+        // basefield.linear_final: features go to shared memory (rgb.0 reads them at the very end), sdf head in fp32
+        mbar_wait(my_m2c, half_phase);
+        half_phase ^= 1;
+        tc_fence_after_sync();
+        const uint32_t bb = bias_s(lid_base + p.desc.D) + 4u * (uint32_t)(hsel * HN), sw = cblk_s + 4u * CL.sdf_w + 4u * (uint32_t)(hsel * HN);
+        const uint32_t tsrc = t_lane + (hsel ? kTmemD1 : kTmemD0);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 1
-        for (int c0 = cb; c0 < cb + ncols; c0 += 32) {
+        for (int c0 = 0; c0 < HN; c0 += 32) {
           float v[32];
-          tmem_ld32(t_lane + G.tmem_col + c0, v);
-          const uint32_t chunk = arena_s + (uint32_t)(CH_H0 + (c0 >> 6)) * kAChunkBytes;
+          tmem_ld32(tsrc + c0, v);
+          const int col = hsel * HN + c0;  // column of the full W-wide feature
+          const uint32_t chunk = arena_s + (uint32_t)(CH_H0 + (col >> 6)) * kAChunkBytes;
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
             const float4 b0 = lds128(bb + 4u * (c0 + g8 * 8)), b1 = lds128(bb + 4u * (c0 + g8 * 8 + 4));
@@ -531,9 +600,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
             y[6] = fmaxf(v[g8 * 8 + 6] + b1.z, 0.f); y[7] = fmaxf(v[g8 * 8 + 7] + b1.w, 0.f);
             a0 += y[0] * w0.x; a1 += y[1] * w0.y; a2 += y[2] * w0.z; a3 += y[3] * w0.w;
             a0 += y[4] * w1.x; a1 += y[5] * w1.y; a2 += y[6] * w1.z; a3 += y[7] * w1.w;
-            sts_group<Op>(chunk + (rowx ^ ((((uint32_t)(c0 & 63) >> 3) + g8) << 4)), y);
+            sts_group<Op>(chunk + (rowx ^ ((((uint32_t)(col & 63) >> 3) + g8) << 4)), y);
           }
         }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        mbar_arrive(my_c2m);  // D<hsel> is free, this half of the features is in shared memory
+        buf ^= 1;
         const float accs = (a0 + a1) + (a2 + a3);
         sts32(my_x1, accs);
         pair_sync();
@@ -544,29 +617,27 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       const float sgn = sdf > 0.f ? 1.f : (sdf < 0.f ? -1.f : 0.f);
       const float density = (0.5f + 0.5f * sgn * expm1f(-fabsf(sdf) * ibeta)) * ibeta;
 
-      // ------------------------------------------------ colour branch: rgb.0 is linear in (base + colour)
-      run_gemm();  // base features x rgb.0 -> TMEM[kTmemRgb..)
-      seq = P.seq_color;
+      // colorfield: three more pipelined layers (the first reads the embedding again)
 #pragma unroll 1
-      for (int i = 0; i < 3; ++i) {
-        run_gemm();
-        epi_relu_store(seq + i, CH_H0);
+      for (int j = 0; j < 3; ++j) {
+        epi_half_to_tmem(lid_color + j, buf ^ 1);
+        buf ^= 1;
       }
-      seq = P.seq_rgb2;
-      run_gemm();  // + colour features x rgb.0
+      // rgb.0 on (base features from shared memory) + (colour features from TMEM), then rgb.2 + sigmoid
+      wait_all();
       float rgb[3];
       {
-        const int H = W / 2, ncols = H >> 1, cb = hsel * ncols;
-        const uint32_t b0 = bias_s(seq), w2 = cblk_s + 4u * CL.rgb2_w, wd = cblk_s + 4u * CL.dir_w;
+        const int ncols = HN >> 1, cb = hsel * ncols;
+        const uint32_t b0 = bias_s(lid_rgb0), w2 = cblk_s + 4u * CL.rgb2_w, wd = cblk_s + 4u * CL.dir_w;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll 1
         for (int c0 = cb; c0 < cb + ncols; c0 += 32) {
           float v[32];
-          tmem_ld32(t_lane + kTmemRgb + c0, v);
+          tmem_ld32(t_lane + kTmemD0 + c0, v);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 bv = lds128(b0 + 4u * (c0 + j));
-            const float4 wr = lds128(w2 + 4u * (c0 + j)), wg = lds128(w2 + 4u * (H + c0 + j)), wb = lds128(w2 + 4u * (2 * H + c0 + j));
+            const float4 wr = lds128(w2 + 4u * (c0 + j)), wg = lds128(w2 + 4u * (HN + c0 + j)), wb = lds128(w2 + 4u * (2 * HN + c0 + j));
             float pre[4] = {v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w};
             if (p.desc.L_dir == 0) {
 #pragma unroll
@@ -588,29 +659,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         else { a0 = o.x + a0; a1 = o.y + a1; a2 = o.z + a2; }
         a0 += lds32(sc_s + 4u * SC_RGB2_B0); a1 += lds32(sc_s + 4u * SC_RGB2_B1); a2 += lds32(sc_s + 4u * SC_RGB2_B2);
         rgb[0] = 1.f / (1.f + __expf(-a0)); rgb[1] = 1.f / (1.f + __expf(-a1)); rgb[2] = 1.f / (1.f + __expf(-a2));
-      }
-
-      // ------------------------------------------------ feature field (FeatureNeRF.compute_feat)
-      float feat[16];
-      if (p.desc.has_feature) {
-        seq = P.seq_feat;
-#pragma unroll 1
-        for (int i = 0; i < 5; ++i) {
-          run_gemm();
-          epi_relu_store(seq + i, CH_H0);
-        }
-        run_gemm();
-        if (hsel == 0) {  // warp-uniform: 16 outputs, one thread per row
-          float v16[16];
-          tmem_ld16(t_lane + P.seq[seq + 5].tmem_col, v16);
-          const uint32_t bf = bias_s(seq + 5);
-          float nn = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { feat[j] = v16[j] + lds32(bf + 4u * j); nn += feat[j] * feat[j]; }
-          const float inv = rsqrtf(nn);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) feat[j] *= inv;
-        }
       }
       if (hsel == 1 || !live) continue;  // half 0 writes the sample's outputs
 

@@ -6,10 +6,8 @@
 
 namespace b200r {
 
-constexpr int kMaxPackSlices = 80;
-
 struct PackParams {
-  PackSlice slices[kMaxPackSlices];
+  const PackSlice* slices;                 // device copy of BuiltProgram::slices (cached in the handle)
   const float* weights[B200R_MAX_LAYERS];  // device pointers, per canonical layer
   int n_slices;
   uint32_t total_groups;  // packed_bytes / 16

@@ -17,7 +17,7 @@ __global__ void pack_kernel(const __grid_constant__ PackParams p) {
   int si = 0;
   for (int i = 1; i < p.n_slices; ++i)
     if (p.slices[i].dst_off <= byte) si = i;
-  const PackSlice& S = p.slices[si];
+  const PackSlice S = p.slices[si];
   const uint32_t local = byte - S.dst_off;
   const uint32_t row = local / 128u;
   const uint32_t slot = (local % 128u) >> 4;   // physical 16-B slot in the row
@@ -32,7 +32,7 @@ __global__ void pack_kernel(const __grid_constant__ PackParams p) {
       const int col = (int)g * 8 + j * 2 + h;
       float x = 0.f;
       if ((int)row < S.n && col < S.ncols) {
-        x = Wsrc[(size_t)row * S.in_dim + S.col0 + col];
+        x = Wsrc[(size_t)(S.row0 + (int)row) * S.in_dim + S.col0 + col];
         if (S.pe_window != 0 && p.alpha >= 0.f) {
           const int e = S.pe_col0 + col;  // index inside the positional embedding
           if (e >= 3) {

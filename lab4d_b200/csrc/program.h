@@ -18,31 +18,40 @@ namespace b200r {
 constexpr int kTileRows = 128;
 constexpr int kAChunkBytes = kTileRows * 128;  // 16 KB
 constexpr int kMaxN = 256;
-constexpr int kWStageBytes = kMaxN * 128;      // 32 KB weight ring stage
-constexpr int kMaxSeq = 48;
-constexpr int kMaxKChunks = 6;
+constexpr int kWStageBytes = 128 * 128;        // 16 KB weight ring stage ([<=128 rows x 64] chunks)
+constexpr int kMaxSteps = 136;
 constexpr int kMaxCond = 8;
 
 // arena chunk ids
 enum : int { CH_PE = 0, CH_EXTRA = 1, CH_H0 = 2, CH_H1 = 3, CH_H2 = 4, CH_H3 = 5, kArenaChunks = 6 };
 
-// TMEM columns
+// TMEM columns: two 128-column accumulators (N-halves of a 256-wide layer) and two 128-column
+// buffers of 16-bit activations (256 halves per row) that ping-pong between consecutive layers
 constexpr int kTmemCols = 512;
-constexpr int kTmemMain = 0;
-constexpr int kTmemRgb = 256;
+constexpr int kTmemD0 = 0;
+constexpr int kTmemD1 = 128;
+constexpr int kTmemA0 = 256;
+constexpr int kTmemA1 = 384;
 
-struct GemmDesc {
-  uint32_t w_off;      // byte offset of the first packed chunk
-  uint16_t n_pad;      // UMMA N (multiple of 16, <= 256)
-  uint16_t tmem_col;   // accumulator column offset
-  uint16_t bias_off;   // float offset of the bias row inside the constant block or the frame block
-  uint8_t bias_frame;  // 1: bias row lives in the per-frame block
-  uint8_t n_chunks;
-  uint8_t accumulate;  // 1: first MMA adds onto the existing accumulator
-  uint8_t layer;       // canonical layer id
-  uint8_t a_chunk[kMaxKChunks];
-  uint8_t ksteps[kMaxKChunks];
+// One MMA step = one packed weight chunk [n x 64] = up to 4 UMMA_K steps of D[128 x n] (+)= A * W^T.
+// The A operand is either an arena chunk in shared memory (SS) or 32 TMEM columns of 16-bit
+// activations written by the previous epilogue (TS).
+struct MmaStep {
+  uint32_t w_off;        // byte offset of the packed chunk
+  uint16_t n;            // UMMA N (multiple of 16, <= 256)
+  uint16_t d_col;        // accumulator TMEM column
+  uint16_t a_tmem_col;   // TS: TMEM column of the operand's first k-step
+  uint8_t a_kind;        // 0 = shared-memory chunk, 1 = TMEM
+  uint8_t a_chunk;       // SS: arena chunk id
+  uint8_t ksteps;        // 1..4
+  uint8_t accumulate;    // 1: first k-step adds onto the existing accumulator
+  uint8_t wait;          // BAR_* the MMA thread waits on before issuing this step (0 = none)
+  uint8_t commit;        // BAR_* committed (arrive when the MMAs so far are done) after this step (0 = none)
 };
+// barriers between the compute warps and the MMA thread (ids shared by both directions)
+enum : int { BAR_NONE = 0, BAR_ALL = 1, BAR_H0 = 2, BAR_H1 = 3 };
+
+struct LayerBias { uint16_t off; uint8_t frame; uint8_t pad_; };  // float offset in const / frame block
 
 struct LayerIds {
   int delta[3];  // -1 when absent
@@ -89,12 +98,14 @@ struct FrameLayout {
 };
 
 struct Program {
-  int32_t n_seq;
-  // positions in seq[] of the phases the compute warps walk through
-  int32_t seq_delta_bwd, seq_vis, seq_base, seq_rgb1, seq_color, seq_rgb2, seq_feat, seq_delta_flow, seq_delta_cyc;
+  int32_t n_steps;
+  // first step of each phase, in execution order: 3 skinning delta MLPs, vis, feature, base chain,
+  // colour chain, final rgb.0
+  int32_t st_delta[3], st_vis, st_feat, st_base, st_color, st_rgb;
   ConstLayout cl;
   FrameLayout fl;
-  GemmDesc seq[kMaxSeq];
+  LayerBias bias[B200R_MAX_LAYERS];
+  MmaStep steps[kMaxSteps];
 };
 
 // one source slice of a weight matrix that fills one packed K chunk
@@ -107,6 +118,7 @@ struct PackSlice {
   int ncols;      // valid columns (<= 64), rest zero
   int pe_window;  // 0: none, 1: basefield window (L_xyz freqs), 2: colorfield window (L_xyz+2)
   int pe_col0;    // index of this slice's first column inside the positional embedding
+  int row0;       // first output row of this chunk (N-halves of the pipelined layers)
   uint32_t dst_off;
 };
 
@@ -158,29 +170,15 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   bp.layer_in.assign(L.count, 0);
   const int INST = 32, TEMB = 128, B = d.n_bones;
   const int pe_b = pe_dim(d.L_xyz), pe_c = pe_dim(d.L_xyz + 2), pe_v = pe_dim(10), pe_f = pe_dim(6);
-  const int hw = d.W / 64;  // hidden chunks
+  const int W = d.W, HN = W / 2, KC = W / 64;  // half width of the pipelined layers, hidden K chunks
   uint32_t off = 0;
-  std::vector<uint32_t> layer_off(L.count, 0);
-  std::vector<std::vector<PackSlice>> layer_slices(L.count);
+  // chunk lists per layer; pipelined layers keep one list per N-half
+  struct Chunk { uint32_t w_off; int n; int ksteps; };
+  std::vector<std::vector<Chunk>> chunks(L.count), chunks_h1(L.count);
 
-  auto add_layer = [&](int id, int n, int in_dim, std::vector<PackSlice> sl) {
-    bp.layer_out[id] = n;
-    bp.layer_in[id] = in_dim;
-    layer_off[id] = off;
-    for (auto& s : sl) {
-      s.layer = id;
-      s.n = n;
-      s.n_pad = pad16(n);
-      s.in_dim = in_dim;
-      s.dst_off = off;
-      off += (uint32_t)s.n_pad * 128u;
-      bp.slices.push_back(s);
-    }
-    layer_slices[id] = sl;
-  };
-  auto sl = [](int col0, int ncols, int win = 0, int pe_col0 = 0) {
+  auto sl = [](int col0, int ncols, int win = 0) {
     PackSlice s{};
-    s.col0 = col0; s.ncols = ncols; s.pe_window = win; s.pe_col0 = pe_col0;
+    s.col0 = col0; s.ncols = ncols; s.pe_window = win; s.pe_col0 = col0;
     return s;
   };
   auto hidden = [&](int col0, int width) {
@@ -190,13 +188,34 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   };
   auto pe_slices = [&](int pe_n, int win) {  // embedding columns [0,pe_n) -> CH_PE (first 63) + CH_EXTRA
     std::vector<PackSlice> v;
-    v.push_back(sl(0, pe_n < 63 ? pe_n : 63, win, 0));
-    if (pe_n > 63) v.push_back(sl(63, pe_n - 63, win, 63));
+    v.push_back(sl(0, pe_n < 63 ? pe_n : 63, win));
+    if (pe_n > 63) v.push_back(sl(63, pe_n - 63, win));
     return v;
   };
   auto cat = [](std::vector<PackSlice> a, const std::vector<PackSlice>& b) {
     a.insert(a.end(), b.begin(), b.end());
     return a;
+  };
+  // pack rows [row0, row0+rows) of layer `id` as one chunk per slice
+  auto add_rows = [&](int id, int n_total, int in_dim, int row0, int rows, std::vector<PackSlice> sls, std::vector<Chunk>& out) {
+    bp.layer_out[id] = n_total;
+    bp.layer_in[id] = in_dim;
+    for (auto& s : sls) {
+      s.layer = id;
+      s.row0 = row0;
+      s.n = (n_total - row0) < rows ? (n_total - row0) : rows;  // valid rows in this chunk
+      s.n_pad = pad16(rows);
+      s.in_dim = in_dim;
+      s.dst_off = off;
+      out.push_back({off, s.n_pad, (s.ncols + 15) / 16});
+      off += (uint32_t)s.n_pad * 128u;
+      bp.slices.push_back(s);
+    }
+  };
+  auto add_layer = [&](int id, int n, int in_dim, const std::vector<PackSlice>& sls) { add_rows(id, n, in_dim, 0, n, sls, chunks[id]); };
+  auto add_split = [&](int id, int in_dim, const std::vector<PackSlice>& sls) {  // two N-halves of a W-wide layer
+    add_rows(id, W, in_dim, 0, HN, sls, chunks[id]);
+    add_rows(id, W, in_dim, HN, HN, sls, chunks_h1[id]);
   };
 
   if (B > 0) {
@@ -211,15 +230,15 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   add_layer(L.vis[0], 64, pe_v + INST, pe_slices(pe_v, 0));
   add_layer(L.vis[1], 64, 64, hidden(0, 64));
   for (int i = 0; i < d.D; ++i) {
-    if (i == 0) add_layer(L.base[i], d.W, pe_b + INST, pe_slices(pe_b, 1));
-    else if (i == d.skip) add_layer(L.base[i], d.W, pe_b + INST + d.W, cat(pe_slices(pe_b, 1), hidden(pe_b + INST, d.W)));
-    else add_layer(L.base[i], d.W, d.W, hidden(0, d.W));
+    if (i == 0) add_split(L.base[i], pe_b + INST, pe_slices(pe_b, 1));
+    else if (i == d.skip) add_split(L.base[i], pe_b + INST + W, cat(pe_slices(pe_b, 1), hidden(pe_b + INST, W)));
+    else add_split(L.base[i], W, hidden(0, W));
   }
-  add_layer(L.base[d.D], d.W, d.W, hidden(0, d.W));
-  add_layer(L.rgb0, d.W / 2, d.W + pe_dim(d.L_dir) + d.appr_channels, hidden(0, d.W));
-  add_layer(L.color[0], d.W, pe_c + INST, pe_slices(pe_c, 2));
-  add_layer(L.color[1], d.W, d.W, hidden(0, d.W));
-  add_layer(L.color[2], d.W, d.W, hidden(0, d.W));
+  add_split(L.base[d.D], W, hidden(0, W));
+  add_layer(L.rgb0, HN, W + pe_dim(d.L_dir) + d.appr_channels, hidden(0, W));
+  add_split(L.color[0], pe_c + INST, pe_slices(pe_c, 2));
+  add_split(L.color[1], W, hidden(0, W));
+  add_split(L.color[2], W, hidden(0, W));
   if (d.has_feature) {
     for (int i = 0; i < 5; ++i) {
       if (i == 0) add_layer(L.feat[i], 128, pe_f, pe_slices(pe_f, 0));
@@ -251,8 +270,7 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   if (B > 0) {
     add_cond(L.delta[0], 3 * B, TEMB, CODE_T_EMBED, 3 * B + TEMB, INST, CODE_INST_SKIN);
     F.delta1_fwd = (int16_t)fo;
-    // forward-warp variant of the same layer (mean time code); not referenced through cond_off
-    CondRow& c = F.cond[nc++];
+    CondRow& c = F.cond[nc++];  // forward-warp variant of the same layer (mean time code)
     c = F.cond[nc - 2];
     c.frame_off = (int16_t)fo;
     c.code[0] = CODE_T_EMBED_MEAN;
@@ -261,7 +279,7 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   add_cond(L.vis[0], pe_v, INST, CODE_INST_VIS);
   add_cond(L.base[0], pe_b, INST, CODE_INST_BASE);
   add_cond(L.base[d.skip], pe_b, INST, CODE_INST_BASE);
-  if (d.appr_channels > 0) add_cond(L.rgb0, d.W + pe_dim(d.L_dir), d.appr_channels, CODE_APPR);
+  if (d.appr_channels > 0) add_cond(L.rgb0, W + pe_dim(d.L_dir), d.appr_channels, CODE_APPR);
   add_cond(L.color[0], pe_c, INST, CODE_INST_COLOR);
   F.n_cond = (int16_t)nc;
   auto bones = [&](int per) { int o = fo; fo += B * per; return (int16_t)o; };
@@ -275,77 +293,111 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   for (int i = 0; i < B200R_MAX_LAYERS; ++i) C.plain_off[i] = -1;
   for (int i = 0; i < L.count; ++i)
     if (cond_off[i] < 0) { C.plain_off[i] = (int16_t)co; co += pad16(bp.layer_out[i]); }
-  C.sdf_w = (int16_t)co; co += d.W;
-  C.rgb2_w = (int16_t)co; co += 3 * (d.W / 2);
+  C.sdf_w = (int16_t)co; co += W;
+  C.rgb2_w = (int16_t)co; co += 3 * HN;
   C.vis_w = (int16_t)co; co += 64;
-  C.dir_w = (int16_t)co; co += (d.L_dir == 0) ? pad4(3 * (d.W / 2)) : 0;
+  C.dir_w = (int16_t)co; co += (d.L_dir == 0) ? pad4(3 * HN) : 0;
   C.inv_gauss = (int16_t)co; co += B * 4;
   C.center = (int16_t)co; co += B * 4;
   C.scalars = (int16_t)co; co += kNumScalars;
   C.n_floats = (int16_t)pad4(co);
-
-  // ---- per-tile sequence
-  int ns = 0;
-  auto emit = [&](int id, const std::vector<int>& a_chunks, int tmem_col, int accumulate, int bias_override = -1) {
-    GemmDesc& g = P.seq[ns++];
-    g = GemmDesc{};
-    g.w_off = layer_off[id];
-    g.n_pad = (uint16_t)pad16(bp.layer_out[id]);
-    g.tmem_col = (uint16_t)tmem_col;
-    g.accumulate = (uint8_t)accumulate;
-    g.layer = (uint8_t)id;
-    if (bias_override >= 0) { g.bias_frame = 1; g.bias_off = (uint16_t)bias_override; }
-    else if (cond_off[id] >= 0) { g.bias_frame = 1; g.bias_off = (uint16_t)cond_off[id]; }
-    else { g.bias_frame = 0; g.bias_off = (uint16_t)C.plain_off[id]; }
-    const auto& S = layer_slices[id];
-    g.n_chunks = (uint8_t)S.size();
-    for (size_t c = 0; c < S.size(); ++c) {
-      g.a_chunk[c] = (uint8_t)a_chunks[c];
-      g.ksteps[c] = (uint8_t)((S[c].ncols + 15) / 16);
-    }
-  };
-  auto hch = [&](int first, int n) { std::vector<int> v; for (int j = 0; j < n; ++j) v.push_back(first + j); return v; };
-  auto pe_ch = [&](int pe_n) { std::vector<int> v{CH_PE}; if (pe_n > 63) v.push_back(CH_EXTRA); return v; };
-  auto catv = [](std::vector<int> a, const std::vector<int>& b) { a.insert(a.end(), b.begin(), b.end()); return a; };
-  auto emit_delta = [&](bool fwd) {
-    const int xb = 3 * B;
-    emit(L.delta[0], xb > 64 ? std::vector<int>{CH_H0, CH_H1} : std::vector<int>{CH_H0}, kTmemMain, 0, fwd ? F.delta1_fwd : -1);
-    emit(L.delta[1], {CH_H2}, kTmemMain, 0);
-    emit(L.delta[2], {CH_H2}, kTmemMain, 0);
-  };
-  P.seq_delta_bwd = ns;
-  if (B > 0) emit_delta(false);
-  P.seq_delta_flow = ns;
-  if (B > 0) emit_delta(true);
-  P.seq_delta_cyc = ns;
-  if (B > 0) emit_delta(true);
-  P.seq_vis = ns;
-  emit(L.vis[0], pe_ch(pe_v), kTmemMain, 0);
-  emit(L.vis[1], {CH_H0}, kTmemMain, 0);
-  P.seq_base = ns;
-  for (int i = 0; i <= d.D; ++i) {
-    if (i == 0) emit(L.base[i], pe_ch(pe_b), kTmemMain, 0);
-    else if (i == d.skip) emit(L.base[i], catv(pe_ch(pe_b), hch(CH_H0, hw)), kTmemMain, 0);
-    else emit(L.base[i], hch(CH_H0, hw), kTmemMain, 0);
+  for (int i = 0; i < L.count; ++i) {
+    P.bias[i].frame = cond_off[i] >= 0;
+    P.bias[i].off = (uint16_t)(cond_off[i] >= 0 ? cond_off[i] : C.plain_off[i]);
   }
-  P.seq_rgb1 = ns;
-  emit(L.rgb0, hch(CH_H0, hw), kTmemRgb, 0);
-  P.seq_color = ns;
-  emit(L.color[0], pe_ch(pe_c), kTmemMain, 0);
-  emit(L.color[1], hch(CH_H0, hw), kTmemMain, 0);
-  emit(L.color[2], hch(CH_H0, hw), kTmemMain, 0);
-  P.seq_rgb2 = ns;
-  emit(L.rgb0, hch(CH_H0, hw), kTmemRgb, 1);
-  P.seq_feat = ns;
+
+  // ---- per-tile MMA step list
+  int ns = 0;
+  auto step = [&](const Chunk& c, int a_kind, int a_chunk, int a_tmem_col, int d_col, int acc, int wait, int commit) {
+    MmaStep& s = P.steps[ns++];
+    s = MmaStep{};
+    s.w_off = c.w_off; s.n = (uint16_t)c.n; s.d_col = (uint16_t)d_col; s.a_tmem_col = (uint16_t)a_tmem_col;
+    s.a_kind = (uint8_t)a_kind; s.a_chunk = (uint8_t)a_chunk; s.ksteps = (uint8_t)c.ksteps; s.accumulate = (uint8_t)acc;
+    s.wait = (uint8_t)wait; s.commit = (uint8_t)commit;
+  };
+  // sequential GEMM: all compute threads hand over operands (BAR_ALL) and wait for the result (BAR_ALL)
+  auto seq_gemm = [&](int id, const std::vector<int>& a_chunks) {
+    const auto& cs = chunks[id];
+    for (size_t c = 0; c < cs.size(); ++c)
+      step(cs[c], 0, a_chunks[c], 0, kTmemD0, c > 0, c == 0 ? BAR_ALL : BAR_NONE, c + 1 == cs.size() ? BAR_ALL : BAR_NONE);
+  };
+  auto pe_ch = [&](int pe_n) { std::vector<int> v{CH_PE}; if (pe_n > 63) v.push_back(CH_EXTRA); return v; };
+  auto hch = [&](int first, int n) { std::vector<int> v; for (int j = 0; j < n; ++j) v.push_back(first + j); return v; };
+  auto catv = [](std::vector<int> a, const std::vector<int>& b) { a.insert(a.end(), b.begin(), b.end()); return a; };
+  for (int w = 0; w < 3; ++w) {
+    P.st_delta[w] = ns;
+    if (B > 0) {
+      seq_gemm(L.delta[0], 3 * B > 64 ? std::vector<int>{CH_H0, CH_H1} : std::vector<int>{CH_H0});
+      seq_gemm(L.delta[1], {CH_H2});
+      seq_gemm(L.delta[2], {CH_H2});
+    }
+  }
+  P.st_vis = ns;
+  seq_gemm(L.vis[0], pe_ch(pe_v));
+  seq_gemm(L.vis[1], {CH_H0});
+  P.st_feat = ns;
   if (d.has_feature) {
     for (int i = 0; i < 5; ++i) {
-      if (i == 0) emit(L.feat[i], pe_ch(pe_f), kTmemMain, 0);
-      else if (i == 4) emit(L.feat[i], catv(pe_ch(pe_f), hch(CH_H0, 2)), kTmemMain, 0);
-      else emit(L.feat[i], hch(CH_H0, 2), kTmemMain, 0);
+      if (i == 0) seq_gemm(L.feat[i], pe_ch(pe_f));
+      else if (i == 4) seq_gemm(L.feat[i], catv(pe_ch(pe_f), hch(CH_H0, 2)));
+      else seq_gemm(L.feat[i], hch(CH_H0, 2));
     }
-    emit(L.feat[5], hch(CH_H0, 2), kTmemMain, 0);
+    seq_gemm(L.feat[5], hch(CH_H0, 2));
   }
-  P.n_seq = ns;
+  // pipelined chain layer: N-halves h = 0,1 into D0 / D1.  `n_ss` leading chunks read shared-memory operands
+  // (embedding), the remaining KC chunks read the previous layer's activations from TMEM buffer `a_buf`.
+  // Chunk kc of the hidden operand was written by half (kc*64)/HN of the previous layer's epilogue.
+  auto pipe_layer = [&](int id, const std::vector<int>& ss_chunks, bool has_hidden, int a_buf, bool first_of_chain_all) {
+    for (int h = 0; h < 2; ++h) {
+      const auto& cs = h == 0 ? chunks[id] : chunks_h1[id];
+      const int dcol = h == 0 ? kTmemD0 : kTmemD1;
+      const size_t n_ss = ss_chunks.size();
+      bool waited_h1 = (h == 1);
+      for (size_t c = 0; c < cs.size(); ++c) {
+        int wait = BAR_NONE;
+        const bool is_ss = c < n_ss;
+        const int kc = (int)(c - n_ss);
+        if (c == 0) wait = first_of_chain_all ? (h == 0 ? BAR_ALL : BAR_NONE) : (h == 0 ? BAR_H0 : BAR_NONE);
+        // first_of_chain_all: previous phase ended with everybody arriving on BAR_ALL (D0/D1 free, operands written)
+        if (!first_of_chain_all && h == 1 && c == 0 && !has_hidden) wait = BAR_H1;  // SS-only layer after a pipelined one
+        if (!is_ss && !waited_h1 && (kc * 64) / HN == 1) { wait = BAR_H1; waited_h1 = true; }
+        const int commit = c + 1 == cs.size() ? (h == 0 ? BAR_H0 : BAR_H1) : BAR_NONE;
+        if (is_ss) step(cs[c], 0, ss_chunks[c], 0, dcol, c > 0, wait, commit);
+        else step(cs[c], 1, 0, (a_buf == 0 ? kTmemA0 : kTmemA1) + kc * 32, dcol, c > 0, wait, commit);
+      }
+      (void)has_hidden;
+    }
+  };
+  P.st_base = ns;
+  int buf = 0;  // TMEM activation buffer holding the current layer's INPUT
+  for (int i = 0; i <= d.D; ++i) {
+    if (i == 0) pipe_layer(L.base[i], pe_ch(pe_b), false, buf, true);
+    else if (i == d.skip) pipe_layer(L.base[i], pe_ch(pe_b), true, buf, false);
+    else pipe_layer(L.base[i], {}, true, buf, false);
+    buf ^= 1;  // this layer's epilogue writes the other buffer, which the next layer reads
+  }
+  // base final's epilogue writes the features to shared memory (CH_H0..) instead: colour L1 reads the embedding
+  P.st_color = ns;
+  pipe_layer(L.color[0], pe_ch(pe_c), false, buf, false);
+  buf ^= 1;
+  pipe_layer(L.color[1], {}, true, buf, false);
+  buf ^= 1;
+  pipe_layer(L.color[2], {}, true, buf, false);
+  buf ^= 1;
+  // rgb.0 applied to base features (shared memory) + colour features (TMEM), one accumulator
+  P.st_rgb = ns;
+  {
+    const auto& cs = chunks[L.rgb0];
+    for (int c = 0; c < KC; ++c) step(cs[c], 0, CH_H0 + c, 0, kTmemD0, c > 0, c == 0 ? BAR_H0 : BAR_NONE, BAR_NONE);
+    bool waited_h1 = false;
+    for (int kc = 0; kc < KC; ++kc) {
+      int wait = BAR_NONE;
+      if (!waited_h1 && (kc * 64) / HN == 1) { wait = BAR_H1; waited_h1 = true; }
+      step(cs[kc], 1, 0, (buf == 0 ? kTmemA0 : kTmemA1) + kc * 32, kTmemD0, 1, wait, kc + 1 == KC ? BAR_ALL : BAR_NONE);
+    }
+  }
+  P.n_steps = ns;
+  if (ns > kMaxSteps) { bp.err = "too many MMA steps"; return bp; }
   bp.ok = true;
   return bp;
 }
