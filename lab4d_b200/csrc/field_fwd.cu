@@ -151,42 +151,43 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     }
   } else if (warp == 9) {
     // =============================================================== MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the step list converged; only lane 0's tcgen05 instructions are enabled (PTX predicate).
+    {
+      const uint32_t issue = lane == 0 ? 1u : 0u;
       uint32_t stage = 0, phase = 0;
       uint32_t bar_phase = 0;  // bit i = parity of c2m[i]
       const uint32_t arena_addr = smem_u32(arena), ring_addr = smem_u32(ring);
       for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
         for (int st = 0; st < P.n_steps; ++st) {
           const MmaStep& S = P.steps[st];
           const uint32_t idesc = umma_idesc_f16(Op::kFmt, S.n);
-          if (S.wait) {
-            mbar_wait(&c2m[S.wait], (bar_phase >> S.wait) & 1u);
-            bar_phase ^= 1u << S.wait;
-            tc_fence_after_sync();
+          const uint32_t wt = S.wait;
+          if (wt) {
+            mbar_wait(&c2m[wt], (bar_phase >> wt) & 1u);
+            bar_phase ^= 1u << wt;
           }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
           const uint64_t bdesc = umma_desc_k_sw128(ring_addr + stage * kWStageBytes);
           const uint32_t d = tmem_base + S.d_col;
-          uint32_t acc = S.accumulate;
+          const uint32_t acc0 = S.accumulate, ks = S.ksteps;
           if (S.a_kind == 0) {
             const uint64_t adesc = umma_desc_k_sw128(arena_addr + S.a_chunk * kAChunkBytes);
-            for (int k = 0; k < S.ksteps; ++k) {
-              umma_f16_ss(d, umma_desc_advance_k(adesc, k), umma_desc_advance_k(bdesc, k), idesc, acc);
-              acc = 1;
-            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < (int)ks) umma_f16_ss_pred(d, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : acc0, issue);
           } else {
             const uint32_t a = tmem_base + S.a_tmem_col;  // 16 halves per k-step = 8 TMEM columns
-            for (int k = 0; k < S.ksteps; ++k) {
-              umma_f16_ts(d, a + 8 * k, umma_desc_advance_k(bdesc, k), idesc, acc);
-              acc = 1;
-            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < (int)ks) umma_f16_ts_pred(d, a + 8 * k, bdesc + 2 * k, idesc, k ? 1u : acc0, issue);
           }
           // frees the ring slot (in both CTAs) once these MMAs have read it
-          if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);
-          else umma_commit(&empty_bar[stage]);
+          if (kCluster > 1) umma_commit_mcast_pred(&empty_bar[stage], cmask, issue);
+          else umma_commit_pred(&empty_bar[stage], issue);
           if (++stage == kNumStages) { stage = 0; phase ^= 1; }
-          if (S.commit) umma_commit(&m2c[S.commit]);
+          if (S.commit) umma_commit_pred(&m2c[S.commit], issue);
         }
       }
     }

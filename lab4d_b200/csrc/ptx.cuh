@@ -167,6 +167,46 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Predicated forms for a warp-converged issue loop: every lane executes the (cheap, uniform) address
+// arithmetic, only the lane with issue != 0 actually issues.  Keeps the MMA warp free of divergence
+// bookkeeping (ELECT / R2UR.BROADCAST per instruction), which otherwise caps the issue rate.
+__device__ __forceinline__ void umma_f16_ss_pred(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_pred(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast_pred(uint64_t* bar, uint16_t mask, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(mask), "r"(issue)
+      : "memory");
+}
 // mbarrier arrives when all tcgen05 ops previously issued by this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
