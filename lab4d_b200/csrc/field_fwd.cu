@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], kCluster); }
     mbar_init(&c2m[BAR_ALL], kComputeThreads);
-    mbar_init(&c2m[BAR_H0], kComputeThreads / 2);
-    mbar_init(&c2m[BAR_H1], kComputeThreads / 2);
+    mbar_init(&c2m[BAR_H0], kComputeThreads);
+    mbar_init(&c2m[BAR_H1], kComputeThreads);
     for (int i = 1; i < 4; ++i) mbar_init(&m2c[i], 1);
     fence_barrier_init();
   }
@@ -196,13 +196,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     const int q = warp & 3, hsel = warp >> 2;
     const uint32_t row = (uint32_t)(q * 32 + lane);  // tile row == TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t all_phase = 0, half_phase = 0;  // parities of m2c[BAR_ALL] and of this half's m2c[BAR_H0 + hsel]
+    uint32_t all_phase = 0, half_phase = 0;  // parity of m2c[BAR_ALL]; bit n of half_phase = parity of m2c[BAR_H0 + n]
     const int W = p.desc.W, HN = W / 2;
     // canonical layer ids (same enumeration as program.h layer_ids)
     const int lid_delta = 0, lid_vis = B > 0 ? 3 : 0, lid_base = lid_vis + 2, lid_rgb0 = lid_base + p.desc.D + 1,
               lid_color = lid_rgb0 + 1, lid_feat = lid_color + 3;
-    uint64_t* const my_c2m = &c2m[BAR_H0 + hsel];
-    uint64_t* const my_m2c = &m2c[BAR_H0 + hsel];
     const ConstLayout& CL = P.cl;
     const FrameLayout& FL = P.fl;
     // 32-bit shared-window addresses (explicit ld/st.shared keeps the hot loops off the generic path)
@@ -268,17 +266,23 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         process(ra, cb + 32 * blk);
       }
     };
-    // Pipelined chain: epilogue of THIS thread's N-half (HN columns of accumulator D<hsel>):
-    // relu(acc + bias) -> 16-bit activations -> TMEM buffer `wbuf` columns [hsel*HN/2, ...), then signal the MMA thread.
-    auto epi_half_to_tmem = [&](int layer, int wbuf) {
-      mbar_wait(my_m2c, half_phase);
-      half_phase ^= 1;
+    // Pipelined chain: epilogue of N-half `nh` (accumulator D<nh>, HN columns) of one layer.  All 8 warps take
+    // part: this thread covers HN/2 of the half's columns for its row.  relu(acc + bias) -> 16-bit activations ->
+    // TMEM buffer `wbuf`, then signal the MMA thread that D<nh> is free and this part of the operand is written.
+    auto wait_half = [&](int nh) {
+      mbar_wait(&m2c[BAR_H0 + nh], (half_phase >> nh) & 1u);
+      half_phase ^= 1u << nh;
       tc_fence_after_sync();
-      const uint32_t bias = bias_s(layer) + 4u * (uint32_t)(hsel * HN);
-      const uint32_t tsrc = t_lane + (hsel ? kTmemD1 : kTmemD0);
-      const uint32_t tdst = t_lane + (wbuf ? kTmemA1 : kTmemA0) + (uint32_t)(hsel * (HN >> 1));
+    };
+    auto epi_half_to_tmem = [&](int layer, int wbuf, int nh) {
+      wait_half(nh);
+      const int c_lo = hsel * (HN >> 1);                // first column (inside the half) of this thread
+      const int feat0 = nh * HN + c_lo;                 // same, as a feature index of the W-wide layer
+      const uint32_t bias = bias_s(layer) + 4u * (uint32_t)feat0;
+      const uint32_t tsrc = t_lane + (nh ? kTmemD1 : kTmemD0) + (uint32_t)c_lo;
+      const uint32_t tdst = t_lane + (wbuf ? kTmemA1 : kTmemA0) + (uint32_t)(feat0 >> 1);
 #pragma unroll 1
-      for (int blk = 0; blk < (HN >> 5); ++blk) {
+      for (int blk = 0; blk < (HN >> 6); ++blk) {
         uint32_t ra[32], o[16];
         tmem_ld32_issue(tsrc + 32 * blk, ra);
         tmem_ld_wait32(ra);
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       }
       tmem_st_wait();
       tc_fence_before_sync();
-      mbar_arrive(my_c2m);
+      mbar_arrive(&c2m[BAR_H0 + nh]);
     };
 
     for (int it = 0; it < iters; ++it) {
@@ -572,41 +576,44 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       int buf = 0;   // TMEM activation buffer the current layer READS; its epilogue writes buf ^ 1
 #pragma unroll 1
       for (int j = 0; j < p.desc.D; ++j) {
-        epi_half_to_tmem(lid_base + j, buf ^ 1);
+        epi_half_to_tmem(lid_base + j, buf ^ 1, 0);
+        epi_half_to_tmem(lid_base + j, buf ^ 1, 1);
         buf ^= 1;
       }
       float sdf;
       {
         // basefield.linear_final: features go to shared memory (rgb.0 reads them at the very end), sdf head in fp32
-        mbar_wait(my_m2c, half_phase);
-        half_phase ^= 1;
-        tc_fence_after_sync();
-        const uint32_t bb = bias_s(lid_base + p.desc.D) + 4u * (uint32_t)(hsel * HN), sw = cblk_s + 4u * CL.sdf_w + 4u * (uint32_t)(hsel * HN);
-        const uint32_t tsrc = t_lane + (hsel ? kTmemD1 : kTmemD0);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < HN; c0 += 32) {
-          float v[32];
-          tmem_ld32(tsrc + c0, v);
-          const int col = hsel * HN + c0;  // column of the full W-wide feature
-          const uint32_t chunk = arena_s + (uint32_t)(CH_H0 + (col >> 6)) * kAChunkBytes;
+        for (int nh = 0; nh < 2; ++nh) {
+          wait_half(nh);
+          const int c_lo = hsel * (HN >> 1), feat0 = nh * HN + c_lo;
+          const uint32_t bb = bias_s(lid_base + p.desc.D) + 4u * (uint32_t)feat0, sw = cblk_s + 4u * CL.sdf_w + 4u * (uint32_t)feat0;
+          const uint32_t tsrc = t_lane + (nh ? kTmemD1 : kTmemD0) + (uint32_t)c_lo;
+#pragma unroll 1
+          for (int c0 = 0; c0 < (HN >> 1); c0 += 32) {
+            float v[32];
+            tmem_ld32(tsrc + c0, v);
+            const int col = feat0 + c0;  // column of the full W-wide feature
+            const uint32_t chunk = arena_s + (uint32_t)(CH_H0 + (col >> 6)) * kAChunkBytes;
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            const float4 b0 = lds128(bb + 4u * (c0 + g8 * 8)), b1 = lds128(bb + 4u * (c0 + g8 * 8 + 4));
-            const float4 w0 = lds128(sw + 4u * (c0 + g8 * 8)), w1 = lds128(sw + 4u * (c0 + g8 * 8 + 4));
-            float y[8];
-            y[0] = fmaxf(v[g8 * 8 + 0] + b0.x, 0.f); y[1] = fmaxf(v[g8 * 8 + 1] + b0.y, 0.f);
-            y[2] = fmaxf(v[g8 * 8 + 2] + b0.z, 0.f); y[3] = fmaxf(v[g8 * 8 + 3] + b0.w, 0.f);
-            y[4] = fmaxf(v[g8 * 8 + 4] + b1.x, 0.f); y[5] = fmaxf(v[g8 * 8 + 5] + b1.y, 0.f);
-            y[6] = fmaxf(v[g8 * 8 + 6] + b1.z, 0.f); y[7] = fmaxf(v[g8 * 8 + 7] + b1.w, 0.f);
-            a0 += y[0] * w0.x; a1 += y[1] * w0.y; a2 += y[2] * w0.z; a3 += y[3] * w0.w;
-            a0 += y[4] * w1.x; a1 += y[5] * w1.y; a2 += y[6] * w1.z; a3 += y[7] * w1.w;
-            sts_group<Op>(chunk + (rowx ^ ((((uint32_t)(col & 63) >> 3) + g8) << 4)), y);
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const float4 b0 = lds128(bb + 4u * (c0 + g8 * 8)), b1 = lds128(bb + 4u * (c0 + g8 * 8 + 4));
+              const float4 w0 = lds128(sw + 4u * (c0 + g8 * 8)), w1 = lds128(sw + 4u * (c0 + g8 * 8 + 4));
+              float y[8];
+              y[0] = fmaxf(v[g8 * 8 + 0] + b0.x, 0.f); y[1] = fmaxf(v[g8 * 8 + 1] + b0.y, 0.f);
+              y[2] = fmaxf(v[g8 * 8 + 2] + b0.z, 0.f); y[3] = fmaxf(v[g8 * 8 + 3] + b0.w, 0.f);
+              y[4] = fmaxf(v[g8 * 8 + 4] + b1.x, 0.f); y[5] = fmaxf(v[g8 * 8 + 5] + b1.y, 0.f);
+              y[6] = fmaxf(v[g8 * 8 + 6] + b1.z, 0.f); y[7] = fmaxf(v[g8 * 8 + 7] + b1.w, 0.f);
+              a0 += y[0] * w0.x; a1 += y[1] * w0.y; a2 += y[2] * w0.z; a3 += y[3] * w0.w;
+              a0 += y[4] * w1.x; a1 += y[5] * w1.y; a2 += y[6] * w1.z; a3 += y[7] * w1.w;
+              sts_group<Op>(chunk + (rowx ^ ((((uint32_t)(col & 63) >> 3) + g8) << 4)), y);
+            }
           }
+          fence_proxy_async_smem();
+          tc_fence_before_sync();
+          mbar_arrive(&c2m[BAR_H0 + nh]);  // D<nh> is free, this part of the features is in shared memory
         }
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        mbar_arrive(my_c2m);  // D<hsel> is free, this half of the features is in shared memory
         buf ^= 1;
         const float accs = (a0 + a1) + (a2 + a3);
         sts32(my_x1, accs);
@@ -621,7 +628,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       // colorfield: three more pipelined layers (the first reads the embedding again)
 #pragma unroll 1
       for (int j = 0; j < 3; ++j) {
-        epi_half_to_tmem(lid_color + j, buf ^ 1);
+        epi_half_to_tmem(lid_color + j, buf ^ 1, 0);
+        epi_half_to_tmem(lid_color + j, buf ^ 1, 1);
         buf ^= 1;
       }
       // rgb.0 on (base features from shared memory) + (colour features from TMEM), then rgb.2 + sigmoid
