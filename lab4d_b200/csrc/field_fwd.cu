@@ -151,9 +151,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     }
   } else if (warp == 9) {
     // =============================================================== MMA issuer
-    // The whole warp walks the step list converged; only lane 0's tcgen05 instructions are enabled (PTX predicate).
+    // The whole warp walks the step list converged (all lanes poll the barriers); one elected lane issues.
     {
-      const uint32_t issue = lane == 0 ? 1u : 0u;
       uint32_t stage = 0, phase = 0;
       uint32_t bar_phase = 0;  // bit i = parity of c2m[i]
       const uint32_t arena_addr = smem_u32(arena), ring_addr = smem_u32(ring);
@@ -172,22 +171,25 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           const uint64_t bdesc = umma_desc_k_sw128(ring_addr + stage * kWStageBytes);
           const uint32_t d = tmem_base + S.d_col;
           const uint32_t acc0 = S.accumulate, ks = S.ksteps;
-          if (S.a_kind == 0) {
-            const uint64_t adesc = umma_desc_k_sw128(arena_addr + S.a_chunk * kAChunkBytes);
+          if (elect_one()) {
+            if (S.a_kind == 0) {
+              const uint64_t adesc = umma_desc_k_sw128(arena_addr + S.a_chunk * kAChunkBytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < (int)ks) umma_f16_ss_pred(d, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : acc0, issue);
-          } else {
-            const uint32_t a = tmem_base + S.a_tmem_col;  // 16 halves per k-step = 8 TMEM columns
+              for (int k = 0; k < 4; ++k)
+                if (k < (int)ks) umma_f16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : acc0);
+            } else {
+              const uint32_t a = tmem_base + S.a_tmem_col;  // 16 halves per k-step = 8 TMEM columns
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < (int)ks) umma_f16_ts_pred(d, a + 8 * k, bdesc + 2 * k, idesc, k ? 1u : acc0, issue);
+              for (int k = 0; k < 4; ++k)
+                if (k < (int)ks) umma_f16_ts(d, a + 8 * k, bdesc + 2 * k, idesc, k ? 1u : acc0);
+            }
+            // frees the ring slot (in both CTAs) once these MMAs have read it
+            if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);
+            else umma_commit(&empty_bar[stage]);
+            if (S.commit) umma_commit(&m2c[S.commit]);
           }
-          // frees the ring slot (in both CTAs) once these MMAs have read it
-          if (kCluster > 1) umma_commit_mcast_pred(&empty_bar[stage], cmask, issue);
-          else umma_commit_pred(&empty_bar[stage], issue);
+          __syncwarp();
           if (++stage == kNumStages) { stage = 0; phase ^= 1; }
-          if (S.commit) umma_commit_pred(&m2c[S.commit], issue);
         }
       }
     }
