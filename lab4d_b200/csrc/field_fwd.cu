@@ -9,7 +9,7 @@
 //               dual-quaternion blend skinning, write 16-bit operand rows into swizzled shared memory
 //               and run every layer's epilogue straight out of TMEM.
 //   warp 8    : TMA producer - streams its half of each pre-packed weight chunk (cp.async.bulk,
-//               multicast to both CTAs of the cluster) through a 6-stage ring of 16 KB.
+//               multicast to both CTAs of the cluster) through a 3-stage ring of 32 KB.
 //   warp 9    : tcgen05.mma issuer (one elected lane) + TMEM owner; walks the MmaStep list of program.h.
 // The 256-wide chains (basefield, colorfield) are software-pipelined: every layer is issued as two
 // N-halves into two TMEM accumulators, warps 0-3 / 4-7 run the epilogue of half 0 / 1 and write the
@@ -37,7 +37,7 @@
 namespace b200r {
 
 constexpr int kCluster = B200R_CLUSTER;
-constexpr int kNumStages = 6;
+constexpr int kNumStages = 3;
 constexpr int kComputeWarps = 8;
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kThreads = kComputeThreads + 64;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       for (int it = 0; it < iters; ++it) {
         for (int st = 0; st < P.n_steps; ++st) {
           const MmaStep& S = P.steps[st];
-          const uint32_t bytes = (uint32_t)S.n * 128u;
+          const uint32_t bytes = (uint32_t)S.n * 128u * S.n_sub;
           const uint32_t part = bytes / kCluster;
           mbar_wait(&empty_bar[stage], phase ^ 1);  // both CTAs' MMAs are done with this slot
           mbar_arrive_expect_tx(&full_bar[stage], bytes);
@@ -169,19 +169,27 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
           const uint64_t bdesc = umma_desc_k_sw128(ring_addr + stage * kWStageBytes);
+          const uint64_t bdesc2 = umma_desc_k_sw128(ring_addr + stage * kWStageBytes + (uint32_t)S.n * 128u);
           const uint32_t d = tmem_base + S.d_col;
-          const uint32_t acc0 = S.accumulate, ks = S.ksteps;
+          const uint32_t acc0 = S.accumulate, ks = S.ksteps, ks2 = S.ksteps2;
           if (elect_one()) {
             if (S.a_kind == 0) {
               const uint64_t adesc = umma_desc_k_sw128(arena_addr + S.a_chunk * kAChunkBytes);
+              const uint64_t adesc2 = umma_desc_k_sw128(arena_addr + S.a_chunk2 * kAChunkBytes);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 if (k < (int)ks) umma_f16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : acc0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < (int)ks2) umma_f16_ss(d, adesc2 + 2 * k, bdesc2 + 2 * k, idesc, 1u);
             } else {
               const uint32_t a = tmem_base + S.a_tmem_col;  // 16 halves per k-step = 8 TMEM columns
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 if (k < (int)ks) umma_f16_ts(d, a + 8 * k, bdesc + 2 * k, idesc, k ? 1u : acc0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < (int)ks2) umma_f16_ts(d, a + 32 + 8 * k, bdesc2 + 2 * k, idesc, 1u);
             }
             // frees the ring slot (in both CTAs) once these MMAs have read it
             if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);

@@ -18,8 +18,8 @@ namespace b200r {
 constexpr int kTileRows = 128;
 constexpr int kAChunkBytes = kTileRows * 128;  // 16 KB
 constexpr int kMaxN = 256;
-constexpr int kWStageBytes = 128 * 128;        // 16 KB weight ring stage ([<=128 rows x 64] chunks)
-constexpr int kMaxSteps = 136;
+constexpr int kWStageBytes = 2 * 128 * 128;    // 32 KB weight ring stage (two [<=128 rows x 64] tiles)
+constexpr int kMaxSteps = 88;
 constexpr int kMaxCond = 8;
 
 // arena chunk ids
@@ -33,17 +33,21 @@ constexpr int kTmemD1 = 128;
 constexpr int kTmemA0 = 256;
 constexpr int kTmemA1 = 384;
 
-// One MMA step = one packed weight chunk [n x 64] = up to 4 UMMA_K steps of D[128 x n] (+)= A * W^T.
-// The A operand is either an arena chunk in shared memory (SS) or 32 TMEM columns of 16-bit
-// activations written by the previous epilogue (TS).
+// One MMA step = one ring stage = one or two packed weight tiles [n x 64] (= up to 8 UMMA_K steps of
+// D[128 x n] (+)= A * W^T).  The A operand of each tile is either an arena chunk in shared memory (SS) or
+// 32 TMEM columns of 16-bit activations written by the previous epilogue (TS; the second tile's columns follow).
 struct MmaStep {
-  uint32_t w_off;        // byte offset of the packed chunk
+  uint32_t w_off;        // byte offset of the first packed tile (the second follows it)
   uint16_t n;            // UMMA N (multiple of 16, <= 256)
   uint16_t d_col;        // accumulator TMEM column
   uint16_t a_tmem_col;   // TS: TMEM column of the operand's first k-step
   uint8_t a_kind;        // 0 = shared-memory chunk, 1 = TMEM
-  uint8_t a_chunk;       // SS: arena chunk id
-  uint8_t ksteps;        // 1..4
+  uint8_t n_sub;         // 1 or 2 weight tiles in this step
+  uint8_t a_chunk;       // SS: arena chunk id of tile 0
+  uint8_t a_chunk2;      // SS: arena chunk id of tile 1
+  uint8_t ksteps;        // UMMA_K steps of tile 0 (1..4)
+  uint8_t ksteps2;       // UMMA_K steps of tile 1
+  uint8_t pad_[2];
   uint8_t accumulate;    // 1: first k-step adds onto the existing accumulator
   uint8_t wait;          // BAR_* the MMA thread waits on before issuing this step (0 = none)
   uint8_t commit;        // BAR_* committed (arrive when the MMAs so far are done) after this step (0 = none)
@@ -308,18 +312,24 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
 
   // ---- per-tile MMA step list
   int ns = 0;
-  auto step = [&](const Chunk& c, int a_kind, int a_chunk, int a_tmem_col, int d_col, int acc, int wait, int commit) {
+  // emit one step from 1 or 2 consecutive chunks (same operand kind)
+  auto step = [&](const Chunk* c, int n_sub, int a_kind, int a_chunk, int a_chunk2, int a_tmem_col, int d_col, int acc, int wait,
+                  int commit) {
     MmaStep& s = P.steps[ns++];
     s = MmaStep{};
-    s.w_off = c.w_off; s.n = (uint16_t)c.n; s.d_col = (uint16_t)d_col; s.a_tmem_col = (uint16_t)a_tmem_col;
-    s.a_kind = (uint8_t)a_kind; s.a_chunk = (uint8_t)a_chunk; s.ksteps = (uint8_t)c.ksteps; s.accumulate = (uint8_t)acc;
-    s.wait = (uint8_t)wait; s.commit = (uint8_t)commit;
+    s.w_off = c[0].w_off; s.n = (uint16_t)c[0].n; s.d_col = (uint16_t)d_col; s.a_tmem_col = (uint16_t)a_tmem_col;
+    s.a_kind = (uint8_t)a_kind; s.n_sub = (uint8_t)n_sub; s.a_chunk = (uint8_t)a_chunk; s.a_chunk2 = (uint8_t)a_chunk2;
+    s.ksteps = (uint8_t)c[0].ksteps; s.ksteps2 = (uint8_t)(n_sub > 1 ? c[1].ksteps : 0);
+    s.accumulate = (uint8_t)acc; s.wait = (uint8_t)wait; s.commit = (uint8_t)commit;
   };
   // sequential GEMM: all compute threads hand over operands (BAR_ALL) and wait for the result (BAR_ALL)
   auto seq_gemm = [&](int id, const std::vector<int>& a_chunks) {
     const auto& cs = chunks[id];
-    for (size_t c = 0; c < cs.size(); ++c)
-      step(cs[c], 0, a_chunks[c], 0, kTmemD0, c > 0, c == 0 ? BAR_ALL : BAR_NONE, c + 1 == cs.size() ? BAR_ALL : BAR_NONE);
+    for (size_t c = 0; c < cs.size(); c += 2) {
+      const int nsub = c + 1 < cs.size() ? 2 : 1;
+      step(&cs[c], nsub, 0, a_chunks[c], nsub > 1 ? a_chunks[c + 1] : 0, 0, kTmemD0, c > 0, c == 0 ? BAR_ALL : BAR_NONE,
+           c + (size_t)nsub == cs.size() ? BAR_ALL : BAR_NONE);
+    }
   };
   auto pe_ch = [&](int pe_n) { std::vector<int> v{CH_PE}; if (pe_n > 63) v.push_back(CH_EXTRA); return v; };
   auto hch = [&](int first, int n) { std::vector<int> v; for (int j = 0; j < n; ++j) v.push_back(first + j); return v; };
@@ -344,28 +354,38 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
     }
     seq_gemm(L.feat[5], hch(CH_H0, 2));
   }
-  // pipelined chain layer: N-halves h = 0,1 into D0 / D1.  `n_ss` leading chunks read shared-memory operands
+  // Pipelined chain layer: N-halves h = 0,1 into D0 / D1.  The leading chunks read shared-memory operands
   // (embedding), the remaining KC chunks read the previous layer's activations from TMEM buffer `a_buf`.
-  // Chunk kc of the hidden operand was written by half (kc*64)/HN of the previous layer's epilogue.
+  // Hidden chunk kc was written by half (kc*64)/HN of the previous layer's epilogue: the chunks of the first
+  // half are issued as soon as BAR_H0 fires, the others after BAR_H1.
   auto pipe_layer = [&](int id, const std::vector<int>& ss_chunks, bool has_hidden, int a_buf, bool first_of_chain_all) {
+    const int n_ss = (int)ss_chunks.size();
     for (int h = 0; h < 2; ++h) {
       const auto& cs = h == 0 ? chunks[id] : chunks_h1[id];
       const int dcol = h == 0 ? kTmemD0 : kTmemD1;
-      const size_t n_ss = ss_chunks.size();
+      const int total = (int)cs.size();
+      int first_wait = first_of_chain_all ? (h == 0 ? BAR_ALL : BAR_NONE) : (h == 0 ? BAR_H0 : (has_hidden ? BAR_NONE : BAR_H1));
       bool waited_h1 = (h == 1);
-      for (size_t c = 0; c < cs.size(); ++c) {
-        int wait = BAR_NONE;
-        const bool is_ss = c < n_ss;
-        const int kc = (int)(c - n_ss);
-        if (c == 0) wait = first_of_chain_all ? (h == 0 ? BAR_ALL : BAR_NONE) : (h == 0 ? BAR_H0 : BAR_NONE);
-        // first_of_chain_all: previous phase ended with everybody arriving on BAR_ALL (D0/D1 free, operands written)
-        if (!first_of_chain_all && h == 1 && c == 0 && !has_hidden) wait = BAR_H1;  // SS-only layer after a pipelined one
-        if (!is_ss && !waited_h1 && (kc * 64) / HN == 1) { wait = BAR_H1; waited_h1 = true; }
-        const int commit = c + 1 == cs.size() ? (h == 0 ? BAR_H0 : BAR_H1) : BAR_NONE;
-        if (is_ss) step(cs[c], 0, ss_chunks[c], 0, dcol, c > 0, wait, commit);
-        else step(cs[c], 1, 0, (a_buf == 0 ? kTmemA0 : kTmemA1) + kc * 32, dcol, c > 0, wait, commit);
+      int c = 0;
+      auto last = [&](int used) { return c + used == total ? (h == 0 ? BAR_H0 : BAR_H1) : BAR_NONE; };
+      // shared-memory operand chunks (1 or 2), one step
+      if (n_ss > 0) {
+        step(&cs[0], n_ss, 0, ss_chunks[0], n_ss > 1 ? ss_chunks[1] : 0, 0, dcol, 0, first_wait, last(n_ss));
+        c = n_ss;
+        first_wait = BAR_NONE;
       }
-      (void)has_hidden;
+      // hidden chunks from TMEM, paired when both belong to the same producing half
+      while (c < total) {
+        const int kc = c - n_ss;
+        const int owner = (kc * 64) / HN;
+        int nsub = 1;
+        if (c + 1 < total && ((kc + 1) * 64) / HN == owner) nsub = 2;
+        int wait = first_wait;
+        first_wait = BAR_NONE;
+        if (owner == 1 && !waited_h1) { wait = BAR_H1; waited_h1 = true; }
+        step(&cs[c], nsub, 1, 0, 0, (a_buf == 0 ? kTmemA0 : kTmemA1) + kc * 32, dcol, c > 0, wait, last(nsub));
+        c += nsub;
+      }
     }
   };
   P.st_base = ns;
@@ -388,12 +408,20 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   P.st_rgb = ns;
   {
     const auto& cs = chunks[L.rgb0];
-    for (int c = 0; c < KC; ++c) step(cs[c], 0, CH_H0 + c, 0, kTmemD0, c > 0, c == 0 ? BAR_H0 : BAR_NONE, BAR_NONE);
+    for (int c = 0; c < KC; c += 2) {
+      const int nsub = c + 1 < KC ? 2 : 1;
+      step(&cs[c], nsub, 0, CH_H0 + c, CH_H0 + c + 1, 0, kTmemD0, c > 0, c == 0 ? BAR_H0 : BAR_NONE, BAR_NONE);
+    }
     bool waited_h1 = false;
-    for (int kc = 0; kc < KC; ++kc) {
+    int kc = 0;
+    while (kc < KC) {
+      const int owner = (kc * 64) / HN;
+      int nsub = 1;
+      if (kc + 1 < KC && ((kc + 1) * 64) / HN == owner) nsub = 2;
       int wait = BAR_NONE;
-      if (!waited_h1 && (kc * 64) / HN == 1) { wait = BAR_H1; waited_h1 = true; }
-      step(cs[kc], 1, 0, (buf == 0 ? kTmemA0 : kTmemA1) + kc * 32, kTmemD0, 1, wait, kc + 1 == KC ? BAR_ALL : BAR_NONE);
+      if (owner == 1 && !waited_h1) { wait = BAR_H1; waited_h1 = true; }
+      step(&cs[kc], nsub, 1, 0, 0, (buf == 0 ? kTmemA0 : kTmemA1) + kc * 32, kTmemD0, 1, wait, kc + nsub == KC ? BAR_ALL : BAR_NONE);
+      kc += nsub;
     }
   }
   P.n_steps = ns;
