@@ -152,10 +152,12 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
   } else if (warp == 9) {
     // =============================================================== MMA issuer
     // The whole warp walks the step list converged (all lanes poll the barriers); one elected lane issues.
+    // Descriptors are base + small integer offsets (same swizzle/stride fields), so a step costs a handful of
+    // integer adds besides the barrier polls; the common shapes (4 or 4+4 k-steps) are fully unrolled.
     {
       uint32_t stage = 0, phase = 0;
       uint32_t bar_phase = 0;  // bit i = parity of c2m[i]
-      const uint32_t arena_addr = smem_u32(arena), ring_addr = smem_u32(ring);
+      const uint64_t adesc0 = umma_desc_k_sw128(smem_u32(arena)), bdesc0 = umma_desc_k_sw128(smem_u32(ring));
       for (int it = 0; it < iters; ++it) {
 #pragma unroll 1
         for (int st = 0; st < P.n_steps; ++st) {
@@ -168,28 +170,42 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          const uint64_t bdesc = umma_desc_k_sw128(ring_addr + stage * kWStageBytes);
-          const uint64_t bdesc2 = umma_desc_k_sw128(ring_addr + stage * kWStageBytes + (uint32_t)S.n * 128u);
+          const uint64_t bd = bdesc0 + (uint64_t)(stage * (kWStageBytes >> 4));
+          const uint64_t bd2 = bd + (uint64_t)((uint32_t)S.n << 3);  // second tile: n * 128 B further
           const uint32_t d = tmem_base + S.d_col;
           const uint32_t acc0 = S.accumulate, ks = S.ksteps, ks2 = S.ksteps2;
           if (elect_one()) {
             if (S.a_kind == 0) {
-              const uint64_t adesc = umma_desc_k_sw128(arena_addr + S.a_chunk * kAChunkBytes);
-              const uint64_t adesc2 = umma_desc_k_sw128(arena_addr + S.a_chunk2 * kAChunkBytes);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < (int)ks) umma_f16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : acc0);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < (int)ks2) umma_f16_ss(d, adesc2 + 2 * k, bdesc2 + 2 * k, idesc, 1u);
+              const uint64_t ad = adesc0 + (uint64_t)((uint32_t)S.a_chunk * (kAChunkBytes >> 4));
+              const uint64_t ad2 = adesc0 + (uint64_t)((uint32_t)S.a_chunk2 * (kAChunkBytes >> 4));
+              if (ks == 4) {
+                umma_f16_ss(d, ad, bd, idesc, acc0);
+                umma_f16_ss(d, ad + 2, bd + 2, idesc, 1u);
+                umma_f16_ss(d, ad + 4, bd + 4, idesc, 1u);
+                umma_f16_ss(d, ad + 6, bd + 6, idesc, 1u);
+              } else {
+                for (uint32_t k = 0; k < ks; ++k) umma_f16_ss(d, ad + 2 * k, bd + 2 * k, idesc, k ? 1u : acc0);
+              }
+              if (ks2 == 4) {
+                umma_f16_ss(d, ad2, bd2, idesc, 1u);
+                umma_f16_ss(d, ad2 + 2, bd2 + 2, idesc, 1u);
+                umma_f16_ss(d, ad2 + 4, bd2 + 4, idesc, 1u);
+                umma_f16_ss(d, ad2 + 6, bd2 + 6, idesc, 1u);
+              } else {
+                for (uint32_t k = 0; k < ks2; ++k) umma_f16_ss(d, ad2 + 2 * k, bd2 + 2 * k, idesc, 1u);
+              }
             } else {
               const uint32_t a = tmem_base + S.a_tmem_col;  // 16 halves per k-step = 8 TMEM columns
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < (int)ks) umma_f16_ts(d, a + 8 * k, bdesc + 2 * k, idesc, k ? 1u : acc0);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < (int)ks2) umma_f16_ts(d, a + 32 + 8 * k, bdesc2 + 2 * k, idesc, 1u);
+              umma_f16_ts(d, a, bd, idesc, acc0);
+              umma_f16_ts(d, a + 8, bd + 2, idesc, 1u);
+              umma_f16_ts(d, a + 16, bd + 4, idesc, 1u);
+              umma_f16_ts(d, a + 24, bd + 6, idesc, 1u);
+              if (ks2) {
+                umma_f16_ts(d, a + 32, bd2, idesc, 1u);
+                umma_f16_ts(d, a + 40, bd2 + 2, idesc, 1u);
+                umma_f16_ts(d, a + 48, bd2 + 4, idesc, 1u);
+                umma_f16_ts(d, a + 56, bd2 + 6, idesc, 1u);
+              }
             }
             // frees the ring slot (in both CTAs) once these MMAs have read it
             if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);
