@@ -203,3 +203,107 @@ def test_composite_backward_matches_oracle_autograd(path):
         rows.append(f"{k}={err:.1e}")
         assert err < 2e-4, (k, err)
     print("[parity] composite-bwd " + os.path.basename(path) + ": " + " ".join(rows))
+
+
+def _skel18_cfg():
+    from lab4d_b200 import spec
+
+    symm = tuple([0, 1, 2, 3] + [5, 4] + [7, 6] + [9, 8] + [11, 10] + [13, 12] + [15, 14] + [17, 16])
+    return spec.FieldConfig(motion="skel", B=18, symm_idx=symm)
+
+
+def test_query_field_skeleton18_with_symmetric_bones():
+    """configs[2] field type (skel-human: 18 bones, left/right Gaussian scales averaged, nnutils/skinning.py:150-153)."""
+    from lab4d_b200.render import render_pixel
+
+    cfg = _skel18_cfg()
+    P = synth_params(cfg, 4, device=DEV)
+    M, N, D = 4, 16, 48
+    rays = {k: torch.from_numpy(v).to(DEV) for k, v in synth.synth_rays(M, N, seed=6).items()}
+    tab = synth_tables(cfg, M, DEV, seed=6, rays=rays, P=P)
+    r = _renderer(cfg, P)
+    feat, deltas = r.query_field(P, rays, tab, D)
+    ofeat, odel = O.query_field(P, cfg.as_oracle_cfg(), rays, tab, D)
+    _report("oracle skel18", feat, ofeat)
+    for k in ("xyz", "rgb", "vis", "feature", "skin_entropy", "delta_skin", "gauss_density"):
+        assert rel_l2(feat[k].cpu(), ofeat[k].cpu()) < REL[k], k
+    assert float((feat["cyc_dist"] - ofeat["cyc_dist"]).abs().max()) <= ABS["cyc_dist"]
+    assert rel_l2(render_pixel(feat, deltas)["rgb"].cpu(), O.render_pixel(ofeat, odel)["rgb"].cpu()) < 1e-3
+
+
+@pytest.mark.parametrize("alpha", [0.3, 0.75])
+def test_annealing_window_folded_into_weights(alpha):
+    """PosEmbedding coarse-to-fine window (nnutils/embedding.py:112-125): the CUDA path folds it into the packed
+    weights of basefield / colorfield; vis and feature embeddings are not windowed (multifields.py:108-116)."""
+    from lab4d_b200 import spec
+    from lab4d_b200.render import FieldRenderer
+
+    cfg = spec.FG_RIGID
+    P = synth_params(cfg, 5, device=DEV)
+    M, N, D = 2, 8, 32
+    rays = {k: torch.from_numpy(v).to(DEV) for k, v in synth.synth_rays(M, N, seed=7).items()}
+    tab = synth_tables(cfg, M, DEV, seed=7, rays=rays, P=P)
+    r = FieldRenderer(cfg, DEV)
+    r.pack(P, alpha=alpha)
+    feat, _ = r.query_field(P, rays, tab, D)
+    ofeat, _ = O.query_field(P, cfg.as_oracle_cfg(), rays, tab, D, alpha=alpha)
+    ofeat0, _ = O.query_field(P, cfg.as_oracle_cfg(), rays, tab, D, alpha=None)
+    _report(f"window alpha={alpha}", feat, ofeat)
+    assert rel_l2(feat["rgb"].cpu(), ofeat["rgb"].cpu()) < REL["rgb"]
+    assert rel_l2(feat["density"].cpu(), ofeat["density"].cpu()) < REL["density"]
+    assert rel_l2(ofeat0["rgb"].cpu(), ofeat["rgb"].cpu()) > 10 * REL["rgb"]  # the window matters for this field
+    assert rel_l2(feat["vis"].cpu(), ofeat0["vis"].cpu()) < REL["vis"]          # vis embedding is never windowed
+
+
+def test_bf16_operands_selectable():
+    """configs[2] asks for bf16 MLP operands: same kernel, 8-bit mantissa -> ~8x the fp16 rounding."""
+    from lab4d_b200 import spec
+
+    cfg = spec.FG_BOB
+    P = synth_params(cfg, 3, device=DEV)
+    M, N, D = 4, 16, 64
+    rays = {k: torch.from_numpy(v).to(DEV) for k, v in synth.synth_rays(M, N, seed=8).items()}
+    tab = synth_tables(cfg, M, DEV, seed=8, rays=rays, P=P)
+    ofeat, _ = O.query_field(P, cfg.as_oracle_cfg(), rays, tab, D)
+    errs = {}
+    for dt in ("fp16", "bf16"):
+        feat, _ = _renderer(cfg, P, dtype=dt).query_field(P, rays, tab, D)
+        errs[dt] = rel_l2(feat["rgb"].cpu(), ofeat["rgb"].cpu())
+    print(f"[parity] operand dtype rgb rel-L2: {errs}")
+    assert errs["fp16"] < REL["rgb"] and errs["bf16"] < 8 * REL["rgb"] and errs["bf16"] > errs["fp16"]
+
+
+@pytest.mark.parametrize("M,N,D", [(2, 1, 2), (2, 3, 5), (6, 129, 2)])
+def test_minimal_and_ragged_shapes(M, N, D):
+    """Smallest legal batch (one pair, one ray, two samples) and tiles that straddle nothing but dead rows."""
+    from lab4d_b200 import spec
+
+    cfg = spec.BG
+    P = synth_params(cfg, 0, device=DEV)
+    rays = {k: torch.from_numpy(v).to(DEV) for k, v in synth.synth_rays(M, N, seed=9).items()}
+    tab = synth_tables(cfg, M, DEV, seed=9, rays=rays, P=P)
+    feat, deltas = _renderer(cfg, P).query_field(P, rays, tab, D)
+    ofeat, odel = O.query_field(P, cfg.as_oracle_cfg(), rays, tab, D)
+    assert rel_l2(deltas.cpu(), odel.cpu()) < 2e-5
+    for k in ("rgb", "density", "vis", "xyz", "depth"):
+        assert feat[k].shape == ofeat[k].shape
+        assert rel_l2(feat[k].cpu(), ofeat[k].cpu()) < REL[k], k
+
+
+def test_bad_arguments_are_rejected_not_crashed():
+    from lab4d_b200 import spec
+    from lab4d_b200.render import FieldRenderer
+
+    cfg = spec.BG
+    P = synth_params(cfg, 0, device=DEV)
+    r = _renderer(cfg, P)
+    rays = {k: torch.from_numpy(v).to(DEV) for k, v in synth.synth_rays(3, 4, seed=1).items()}  # odd M: pairs broken
+    tab = synth_tables(cfg, 3, DEV, seed=1, rays=rays, P=P)
+    with pytest.raises(RuntimeError, match="pairs"):
+        r.query_field(P, rays, tab, 8)
+    rays = {k: torch.from_numpy(v).to(DEV) for k, v in synth.synth_rays(2, 4, seed=1).items()}
+    tab = synth_tables(cfg, 2, DEV, seed=1, rays=rays, P=P)
+    with pytest.raises(RuntimeError, match="D >= 2"):
+        r.query_field(P, rays, tab, 1)
+    with pytest.raises(RuntimeError):
+        FieldRenderer(spec.FieldConfig(W=200), DEV)
