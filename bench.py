@@ -42,11 +42,32 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons DURING the timed region: NVML in-process (10 ms period), nvidia-smi as fallback."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self._halt.is_set():
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits.values()])
+                self._halt.wait(0.01)
+            return
+        except Exception:
+            pass
+        self._run_smi()
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._halt.is_set():
@@ -137,7 +158,7 @@ def run_reference(args, rank, world):
     val = S / float(np.mean(times))
     sample = f"{Ms} of {WORKLOAD['M']} frames x {WORKLOAD['N']} rays x {WORKLOAD['D']} samples per step, forward, fp32"
     print(json.dumps({
-        "impl": "reference", "metric": "ray-samples/s/GPU", "value": val, "unit": "ray-samples/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": "ray-samples/s", "value": val, "unit": "ray-samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "fg-bob 2048 rays x 128 samples (configs[1]), forward", "sample": sample},
@@ -149,8 +170,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -245,12 +266,12 @@ def main():
         kms = float(np.mean(kern))
         achieved = FLOP_PER_SAMPLE_FWD * S / (kms * 1e-3) / 1e12
         line = {
-            "metric": "ray-samples/s/GPU", "value": world * S / (ms_step * 1e-3), "unit": "ray-samples/s", "n_gpus": world,
+            "metric": "ray-samples/s", "value": world * S / (ms_step * 1e-3), "unit": "ray-samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
             "config": {"workload": "fg-bob 2048 rays x 128 samples per GPU (configs[1]), forward query_field + render_pixel",
                        "rays_per_gpu": M * N, "samples_per_ray": D, "bones": cfg.B, "l2": "flushed between iterations (256 MB write)",
-                       "pass": "forward", "parallelism": f"dp{world} (rays sharded, no data-path collective in forward)"},
+                       "pass": "forward", "per_gpu": "BASELINE metric ray-samples/s/GPU = value / n_gpus", "parallelism": f"dp{world} (rays sharded, no data-path collective in forward)"},
             "e2e": {"value": world * S / (ms_step_e2e * 1e-3), "unit": "ray-samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": out_host.numel() * 4},
             "gpu_launches": n_launch,

@@ -113,9 +113,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], kCluster); }
-    mbar_init(&c2m[BAR_ALL], kComputeThreads);
-    mbar_init(&c2m[BAR_H0], kComputeThreads);
-    mbar_init(&c2m[BAR_H1], kComputeThreads);
+    // one arrival per compute warp (lane 0 after __syncwarp), not per thread: 32x less mbarrier traffic
+    mbar_init(&c2m[BAR_ALL], kComputeWarps);
+    mbar_init(&c2m[BAR_H0], kComputeWarps);
+    mbar_init(&c2m[BAR_H1], kComputeWarps);
     for (int i = 1; i < 4; ++i) mbar_init(&m2c[i], 1);
     fence_barrier_init();
   }
@@ -253,10 +254,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     auto pair_sync = [&]() { named_bar_sync(1 + q, 64); };
 
     // hand the operands to the MMA warp, then wait for the layer's accumulator
+    // every lane orders its own writes (generic -> async proxy, tcgen05), the warp converges, lane 0 signals
+    auto warp_arrive = [&](uint64_t* bar) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
     auto arrive_all = [&]() {
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(&c2m[BAR_ALL]);
+      warp_arrive(&c2m[BAR_ALL]);
     };
     auto wait_all = [&]() {
       mbar_wait(&m2c[BAR_ALL], all_phase);
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       }
       tmem_st_wait();
       tc_fence_before_sync();
-      mbar_arrive(&c2m[BAR_H0 + nh]);
+      warp_arrive(&c2m[BAR_H0 + nh]);
     };
 
     for (int it = 0; it < iters; ++it) {
@@ -638,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           }
           fence_proxy_async_smem();
           tc_fence_before_sync();
-          mbar_arrive(&c2m[BAR_H0 + nh]);  // D<nh> is free, this part of the features is in shared memory
+          warp_arrive(&c2m[BAR_H0 + nh]);  // D<nh> is free, this part of the features is in shared memory
         }
         buf ^= 1;
         const float accs = (a0 + a1) + (a2 + a3);
