@@ -313,11 +313,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       const uint32_t bias = bias_s(layer) + 4u * (uint32_t)feat0;
       const uint32_t tsrc = t_lane + (nh ? kTmemD1 : kTmemD0) + (uint32_t)c_lo;
       const uint32_t tdst = t_lane + (wbuf ? kTmemA1 : kTmemA0) + (uint32_t)(feat0 >> 1);
-#pragma unroll 1
-      for (int blk = 0; blk < (HN >> 6); ++blk) {
-        uint32_t ra[32], o[16];
-        tmem_ld32_issue(tsrc + 32 * blk, ra);
-        tmem_ld_wait32(ra);
+      auto pack_store = [&](uint32_t (&ra)[32], int blk) {
+        uint32_t o[16];
 #pragma unroll
         for (int g4 = 0; g4 < 8; ++g4) {
           const float4 b = lds128(bias + 4u * (32 * blk + 4 * g4));
@@ -325,6 +322,20 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           o[2 * g4 + 1] = Op::pack2_relu(__uint_as_float(ra[4 * g4 + 2]) + b.z, __uint_as_float(ra[4 * g4 + 3]) + b.w);
         }
         tmem_st16(tdst + 16 * blk, o);
+      };
+      if (HN == 128) {  // 64 columns per thread: both TMEM loads in flight before the first wait
+        uint32_t ra[32], rb[32];
+        tmem_ld32_issue(tsrc, ra);
+        tmem_ld32_issue(tsrc + 32, rb);
+        tmem_ld_wait32(ra);
+        pack_store(ra, 0);
+        tmem_ld_wait32(rb);
+        pack_store(rb, 1);
+      } else {
+        uint32_t ra[32];
+        tmem_ld32_issue(tsrc, ra);
+        tmem_ld_wait32(ra);
+        pack_store(ra, 0);
       }
       tmem_st_wait();
       tc_fence_before_sync();

@@ -10,5 +10,5 @@ if [ $rc -ne 0 ]; then
   echo "pytest exit $? (cluster=1 build)" >> gpurun_out/pytest_gpu_c1.log
   grep -E "parity|passed|failed|Error|error|timed out" gpurun_out/pytest_gpu_c1.log | tail -30
 fi
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench exit $?" >> gpurun_out/bench.log
+timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench.log 2>&1; echo "bench exit $?" >> gpurun_out/bench.log
 tail -3 gpurun_out/bench.log
