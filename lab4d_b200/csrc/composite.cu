@@ -12,6 +12,7 @@
 namespace b200r {
 
 constexpr int kWarpsPerBlock = 8;
+constexpr int kWarpsPerRayFwd = 4;  // forward: the channels of one ray are spread over 4 warps (latency-bound otherwise)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -56,19 +57,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_fwd_kernel(cons
   float* w_s = sm + (size_t)warp * 3 * D;
   float* T_s = w_s + D;
   float* g_s = T_s + D;  // scratch weights (gauss)
-  const int r = blockIdx.x * kWarpsPerBlock + warp;
+  const int r = blockIdx.x * (kWarpsPerBlock / kWarpsPerRayFwd) + warp / kWarpsPerRayFwd;
+  const int cw = warp % kWarpsPerRayFwd;  // this warp's share of the channels; the weights are recomputed per warp
   if (r >= a.R) return;
   const size_t base = (size_t)r * D;
   const float mask = ray_weights(a.density + base, a.deltas + base, D, lane, w_s, T_s);
   __syncwarp();
-  if (lane == 0 && a.mask) a.mask[r] = mask;
-  if (a.weights)
-    for (int k = lane; k < D; k += 32) a.weights[base + k] = w_s[k];
-  if (a.transmit)
-    for (int k = lane; k < D; k += 32) a.transmit[base + k] = T_s[k];
+  if (cw == 0) {
+    if (lane == 0 && a.mask) a.mask[r] = mask;
+    if (a.weights)
+      for (int k = lane; k < D; k += 32) a.weights[base + k] = w_s[k];
+    if (a.transmit)
+      for (int k = lane; k < D; k += 32) a.transmit[base + k] = T_s[k];
+  }
   const float inv = 1.0f / (mask + 1e-6f);
 
-  for (int c = 0; c < a.n_channels; ++c) {
+  for (int c = cw; c < a.n_channels; c += kWarpsPerRayFwd) {
     const int nch = a.nch[c], mode = a.mode[c];
     const float* __restrict__ src = a.src[c] + base * nch;
     float* dst = a.dst[c];
@@ -263,7 +267,8 @@ cudaError_t launch_composite_fwd(const b200r_composite_args& a, cudaStream_t str
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int blocks = (a.R + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int rays_per_block = kWarpsPerBlock / kWarpsPerRayFwd;
+  const int blocks = (a.R + rays_per_block - 1) / rays_per_block;
   composite_fwd_kernel<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }

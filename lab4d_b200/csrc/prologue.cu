@@ -118,28 +118,41 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
   float* fb = p.workspace + P.cl.n_floats + (size_t)f * F.n_floats;
   write_cam(fb + F.cam, p, f);
   write_cam(fb + F.cam_partner, p, fn);
-  const float* codes[kNumCodes];
-  codes[CODE_INST_BASE] = p.fr.inst_base ? p.fr.inst_base + (size_t)f * 32 : nullptr;
-  codes[CODE_INST_COLOR] = p.fr.inst_color ? p.fr.inst_color + (size_t)f * 32 : nullptr;
-  codes[CODE_INST_VIS] = p.fr.inst_vis ? p.fr.inst_vis + (size_t)f * 32 : nullptr;
-  codes[CODE_APPR] = p.fr.appr_code ? p.fr.appr_code + (size_t)f * p.desc.appr_channels : nullptr;
-  codes[CODE_INST_SKIN] = p.fr.inst_skin ? p.fr.inst_skin + (size_t)f * 32 : nullptr;
-  codes[CODE_T_EMBED] = p.fr.skin_t_embed ? p.fr.skin_t_embed + (size_t)f * 128 : nullptr;
-  codes[CODE_T_EMBED_MEAN] = p.fr.skin_t_embed_mean;
-  for (int ci = 0; ci < F.n_cond; ++ci) {
-    const CondRow& c = F.cond[ci];
-    const float* Wm = p.par.weight[c.layer];
-    const float* bv = p.par.bias[c.layer];
-    for (int n = threadIdx.x; n < c.n; n += blockDim.x) {
-      float acc = bv[n];
-      for (int sgi = 0; sgi < c.n_seg; ++sgi) {
-        const float* code = codes[c.code[sgi]];
-        const float* wr = Wm + (size_t)n * c.in_dim + c.col0[sgi];
-        float a2 = 0.f;
-        for (int k = 0; k < c.width[sgi]; ++k) a2 += wr[k] * code[k];
-        acc += a2;
+  // code vectors of this frame -> shared memory (one slot of 160 floats per table)
+  __shared__ float code_s[kNumCodes][160];
+  {
+    const float* src[kNumCodes];
+    int width[kNumCodes];
+    src[CODE_INST_BASE] = p.fr.inst_base ? p.fr.inst_base + (size_t)f * 32 : nullptr; width[CODE_INST_BASE] = 32;
+    src[CODE_INST_COLOR] = p.fr.inst_color ? p.fr.inst_color + (size_t)f * 32 : nullptr; width[CODE_INST_COLOR] = 32;
+    src[CODE_INST_VIS] = p.fr.inst_vis ? p.fr.inst_vis + (size_t)f * 32 : nullptr; width[CODE_INST_VIS] = 32;
+    src[CODE_APPR] = p.fr.appr_code ? p.fr.appr_code + (size_t)f * p.desc.appr_channels : nullptr; width[CODE_APPR] = p.desc.appr_channels;
+    src[CODE_INST_SKIN] = p.fr.inst_skin ? p.fr.inst_skin + (size_t)f * 32 : nullptr; width[CODE_INST_SKIN] = 32;
+    src[CODE_T_EMBED] = p.fr.skin_t_embed ? p.fr.skin_t_embed + (size_t)f * 128 : nullptr; width[CODE_T_EMBED] = 128;
+    src[CODE_T_EMBED_MEAN] = p.fr.skin_t_embed_mean; width[CODE_T_EMBED_MEAN] = 128;
+    for (int t = 0; t < kNumCodes; ++t)
+      if (src[t])
+        for (int i = threadIdx.x; i < width[t]; i += blockDim.x) code_s[t][i] = src[t][i];
+  }
+  __syncthreads();
+  // one warp per output row: lanes stride the code columns (coalesced weight reads), shuffle-reduce
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int ci = 0; ci < F.n_cond; ++ci) {
+      const CondRow& c = F.cond[ci];
+      const float* Wm = p.par.weight[c.layer];
+      const float* bv = p.par.bias[c.layer];
+      for (int n = warp; n < c.n; n += nwarp) {
+        float acc = 0.f;
+        for (int sgi = 0; sgi < c.n_seg; ++sgi) {
+          const float* wr = Wm + (size_t)n * c.in_dim + c.col0[sgi];
+          const float* code = code_s[c.code[sgi]];
+          for (int k = lane; k < c.width[sgi]; k += 32) acc += wr[k] * code[k];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) fb[c.frame_off + n] = acc + bv[n];
       }
-      fb[c.frame_off + n] = acc;
     }
   }
   if (B > 0) {
