@@ -12,7 +12,7 @@
 namespace b200r {
 
 constexpr int kWarpsPerBlock = 8;
-constexpr int kWarpsPerRayFwd = 4;  // forward: the channels of one ray are spread over 4 warps (latency-bound otherwise)
+constexpr int kWarpsPerRayFwd = 1;  // (tried 4 warps per ray with the channels spread out: no gain on B200)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
