@@ -9,7 +9,6 @@
 //       transforms rest (x) t^-1 / t (x) rest^-1 as dual quaternions (nnutils/warping.py:304-314).
 //   block M      : the constant block - plain bias rows, head weights, Gaussian bone scales
 //       (nnutils/skinning.py:141-153), rest bone centres (utils/transforms.py:28-40), scalars.
-//   blocks > M   : the per-frame bias rows, 32 outputs of one conditioned layer x all frames per block.
 // M x B rows of quaternion algebra and a few (N x 32) mat-vecs: ~0.1 % of the step's FLOPs.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -112,59 +111,37 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
     }
     return;
   }
-  const FrameLayout& F = P.fl;
-  if ((int)blockIdx.x > M) {
-    // ---------------------------------------------------------------- conditioned bias rows
-    // One block = 32 outputs of one conditioned layer for ALL frames: the weight slice [32 x C] is staged in
-    // shared memory once (coalesced), then warp w walks frames w, w+8, ... with lane = output row.
-    int t = (int)blockIdx.x - (M + 1), ci = 0;
-    while (ci < F.n_cond && t >= (F.cond[ci].n + 31) / 32) { t -= (F.cond[ci].n + 31) / 32; ++ci; }
-    if (ci >= F.n_cond) return;
-    const CondRow& c = F.cond[ci];
-    const int n0 = t * 32, C = c.width[0] + (c.n_seg > 1 ? c.width[1] : 0);
-    __shared__ float wt[32 * 161];  // [output][code column], padded against bank conflicts
-    const float* Wm = p.par.weight[c.layer];
-    for (int i = threadIdx.x; i < 32 * C; i += blockDim.x) {
-      const int o = i / C, k = i - o * C;
-      const int col = k < c.width[0] ? c.col0[0] + k : c.col0[1] + (k - c.width[0]);
-      wt[o * 161 + k] = (n0 + o < c.n) ? Wm[(size_t)(n0 + o) * c.in_dim + col] : 0.f;
-    }
-    __syncthreads();
-    const float* code_tab[kNumCodes];
-    int code_w[kNumCodes];
-    code_tab[CODE_INST_BASE] = p.fr.inst_base; code_w[CODE_INST_BASE] = 32;
-    code_tab[CODE_INST_COLOR] = p.fr.inst_color; code_w[CODE_INST_COLOR] = 32;
-    code_tab[CODE_INST_VIS] = p.fr.inst_vis; code_w[CODE_INST_VIS] = 32;
-    code_tab[CODE_APPR] = p.fr.appr_code; code_w[CODE_APPR] = p.desc.appr_channels;
-    code_tab[CODE_INST_SKIN] = p.fr.inst_skin; code_w[CODE_INST_SKIN] = 32;
-    code_tab[CODE_T_EMBED] = p.fr.skin_t_embed; code_w[CODE_T_EMBED] = 128;
-    code_tab[CODE_T_EMBED_MEAN] = p.fr.skin_t_embed_mean; code_w[CODE_T_EMBED_MEAN] = 0;  // stride 0: shared by all frames
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    const int n = n0 + lane;
-    const float bias = n < c.n ? p.par.bias[c.layer][n] : 0.f;
-    const float* w_row = wt + lane * 161;
-    const float* cA = code_tab[c.code[0]];
-    const int sA = code_w[c.code[0]], wA = c.width[0];
-    const float* cB = c.n_seg > 1 ? code_tab[c.code[1]] : nullptr;
-    const int sB = c.n_seg > 1 ? code_w[c.code[1]] : 0, wB = c.n_seg > 1 ? c.width[1] : 0;
-    for (int f = warp; f < M; f += nwarp) {
-      float acc = 0.f;
-      const float* a = cA + (size_t)f * sA;
-      for (int k = 0; k < wA; ++k) acc += w_row[k] * a[k];
-      if (cB) {
-        const float* b2 = cB + (size_t)f * sB;
-        for (int k = 0; k < wB; ++k) acc += w_row[wA + k] * b2[k];
-      }
-      if (n < c.n) p.workspace[P.cl.n_floats + (size_t)f * F.n_floats + c.frame_off + n] = acc + bias;
-    }
-    return;
-  }
   // ------------------------------------------------------------------ frame block
+  const FrameLayout& F = P.fl;
   const int f = blockIdx.x;
   const int fn = (M >= 2) ? (f ^ 1) : f;
   float* fb = p.workspace + P.cl.n_floats + (size_t)f * F.n_floats;
   write_cam(fb + F.cam, p, f);
   write_cam(fb + F.cam_partner, p, fn);
+  const float* codes[kNumCodes];
+  codes[CODE_INST_BASE] = p.fr.inst_base ? p.fr.inst_base + (size_t)f * 32 : nullptr;
+  codes[CODE_INST_COLOR] = p.fr.inst_color ? p.fr.inst_color + (size_t)f * 32 : nullptr;
+  codes[CODE_INST_VIS] = p.fr.inst_vis ? p.fr.inst_vis + (size_t)f * 32 : nullptr;
+  codes[CODE_APPR] = p.fr.appr_code ? p.fr.appr_code + (size_t)f * p.desc.appr_channels : nullptr;
+  codes[CODE_INST_SKIN] = p.fr.inst_skin ? p.fr.inst_skin + (size_t)f * 32 : nullptr;
+  codes[CODE_T_EMBED] = p.fr.skin_t_embed ? p.fr.skin_t_embed + (size_t)f * 128 : nullptr;
+  codes[CODE_T_EMBED_MEAN] = p.fr.skin_t_embed_mean;
+  for (int ci = 0; ci < F.n_cond; ++ci) {
+    const CondRow& c = F.cond[ci];
+    const float* Wm = p.par.weight[c.layer];
+    const float* bv = p.par.bias[c.layer];
+    for (int n = threadIdx.x; n < c.n; n += blockDim.x) {
+      float acc = bv[n];
+      for (int sgi = 0; sgi < c.n_seg; ++sgi) {
+        const float* code = codes[c.code[sgi]];
+        const float* wr = Wm + (size_t)n * c.in_dim + c.col0[sgi];
+        float a2 = 0.f;
+        for (int k = 0; k < c.width[sgi]; ++k) a2 += wr[k] * code[k];
+        acc += a2;
+      }
+      fb[c.frame_off + n] = acc;
+    }
+  }
   if (B > 0) {
     __shared__ float ig[32 * 4];
     for (int b = threadIdx.x; b < B; b += blockDim.x)
@@ -185,9 +162,7 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
 }
 
 cudaError_t launch_prologue(const PrologueParams& p, cudaStream_t stream) {
-  int tiles = 0;
-  for (int i = 0; i < p.prog.fl.n_cond; ++i) tiles += (p.prog.fl.cond[i].n + 31) / 32;
-  prologue_kernel<<<p.fr.M + 1 + tiles, 256, 0, stream>>>(p);
+  prologue_kernel<<<p.fr.M + 1, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
