@@ -32,17 +32,21 @@ class FieldConfig:
     B: int = 25  # bones
     has_feature: bool = True
     symm_idx: Optional[Tuple[int, ...]] = None
+    dense: bool = False  # ComposedWarp: DenseWarp(D=2, W=256) soft deformation around the skinning warp
 
     def as_oracle_cfg(self):
         d = dict(category=self.category, D=self.D, W=self.W, L_xyz=self.L_xyz, L_dir=self.L_dir,
                  appr_channels=self.appr_channels, motion=self.motion, B=self.B, has_feature=self.has_feature)
         if self.symm_idx is not None:
             d["symm_idx"] = list(self.symm_idx)
+        d["dense"] = self.dense
         return d
 
 
 FG_BOB = FieldConfig()
 FG_RIGID = FieldConfig(motion="rigid", B=0)
+QUAD_SYMM = (0, 1, 2, 3, 8, 9, 10, 11, 4, 5, 6, 7, 12, 13, 14, 15, 16, 21, 22, 23, 24, 17, 18, 19, 20)
+FG_COMP_QUAD = FieldConfig(motion="skel", B=25, symm_idx=QUAD_SYMM, dense=True)  # comp_skel-quad_dense
 BG = FieldConfig(category="bg", D=5, W=128, L_xyz=6, L_dir=0, appr_channels=0, motion="rigid", B=0, has_feature=False)
 
 
@@ -75,4 +79,7 @@ def field_param_shapes(cfg: FieldConfig):
         s["warp.logibeta"] = (1,)
         s["warp.skinning_model.log_gauss"] = (cfg.B, 3)
         s.update(_mlp_shapes("warp.skinning_model.delta_field.", 3 * cfg.B + T_EMBED_CH + INST_CH, 64, 2, cfg.B, 4, False))
+        if cfg.dense:
+            for m in ("forward_map", "backward_map"):
+                s.update(_mlp_shapes(f"warp.post_warp.{m}.", pe_dim(6) + T_EMBED_CH + INST_CH, 256, 2, 3, 4, False))
     return s

@@ -223,6 +223,13 @@ def skinning_warp(P, xyz, t_art, rest_art, t_embed, t_embed_mean, inst_code, bac
     return out, {"skin_entropy": ent, "delta_skin": delta.pow(2).mean(-1, keepdim=True)}
 
 
+def dense_warp(P, x, t_embed, inst_code, backward):
+    """DenseWarp.forward inside ComposedWarp (nnutils/warping.py:143-170, 445-483): x + 0.1 * CondMLP([PE6(x), t, inst])."""
+    e = torch.cat([pos_embed(x, 6), _per_frame(t_embed, x), _per_frame(inst_code, x)], -1)
+    prefix = "warp.post_warp.backward_map." if backward else "warp.post_warp.forward_map."
+    return x + 0.1 * mlp(P, prefix, e, 2, final_act=False)
+
+
 def gauss_density(P, xyz, rest_art):
     """Deformable.compute_gauss_density / SkinningWarp.get_gauss_density
     (nnutils/deformable.py:329-356, warping.py:355-387, utils/transforms.py:28-40)."""
@@ -310,6 +317,8 @@ def query_field(P, cfg, rays, tab, D, flow_thresh=None, alpha=None, eikonal_rays
         r_art = (tab["rest_articulation_qr"], tab["rest_articulation_qd"])
         wargs = (tab["skin_t_embed"], tab["skin_t_embed_mean"], tab["inst_skin"])
         xyz, aux_b = skinning_warp(P, xyz_t, t_art, r_art, *wargs, backward=True, symm_idx=cfg.get("symm_idx"))
+        if cfg.get("dense", False):  # ComposedWarp: soft deformation after un-articulating (warping.py:472-476)
+            xyz = dense_warp(P, xyz, tab["dense_t_embed"], tab["inst_dense_bwd"], backward=True)
     else:
         xyz = xyz_t
     feat["vis"] = vis_forward(P, xyz, tab["inst_vis"])
@@ -323,7 +332,10 @@ def query_field(P, cfg, rays, tab, D, flow_thresh=None, alpha=None, eikonal_rays
     if skel:
         t_art_n = (flip_pair(t_art[0]), flip_pair(t_art[1]))
         r_art_n = (flip_pair(r_art[0]), flip_pair(r_art[1]))
-        x_next, _ = skinning_warp(P, xyz, t_art_n, r_art_n, *wargs, backward=False, symm_idx=cfg.get("symm_idx"))
+        x_in = xyz
+        if cfg.get("dense", False):  # soft deformation of the partner frame first (warping.py:459-463)
+            x_in = dense_warp(P, xyz, flip_pair(tab["dense_t_embed"]), tab["inst_dense_fwd"], backward=False)
+        x_next, _ = skinning_warp(P, x_in, t_art_n, r_art_n, *wargs, backward=False, symm_idx=cfg.get("symm_idx"))
     else:
         x_next = xyz
     xc_next = field_to_cam(x_next, qn, tn)
@@ -338,7 +350,8 @@ def query_field(P, cfg, rays, tab, D, flow_thresh=None, alpha=None, eikonal_rays
 
     # cycle consistency (nnutils/deformable.py:173-198, nerf.py:657-667)
     if skel:
-        x_cyc, aux_f = skinning_warp(P, xyz, t_art, r_art, *wargs, backward=False, symm_idx=cfg.get("symm_idx"))
+        x_in = dense_warp(P, xyz, tab["dense_t_embed"], tab["inst_dense_fwd"], backward=False) if cfg.get("dense", False) else xyz
+        x_cyc, aux_f = skinning_warp(P, x_in, t_art, r_art, *wargs, backward=False, symm_idx=cfg.get("symm_idx"))
         feat["cyc_dist"] = (x_cyc - xyz_t).norm(2, -1, keepdim=True)
         feat["delta_skin"] = (aux_f["delta_skin"] + aux_b["delta_skin"]) / 2
         feat["skin_entropy"] = (aux_f["skin_entropy"] + aux_b["skin_entropy"]) / 2

@@ -75,6 +75,11 @@ def frame_tables(field, rays):
             tabs["skin_t_embed"] = sk.time_embedding(fid)
             tabs["skin_t_embed_mean"] = sk.time_embedding.get_mean_embedding(fid.device)
             tabs["inst_skin"] = sk.delta_field.inst_embedding(iid)
+            if hasattr(field.warp, "post_warp"):
+                pw = field.warp.post_warp
+                tabs["dense_t_embed"] = pw.time_embedding(fid)
+                tabs["inst_dense_fwd"] = pw.forward_map.inst_embedding(iid)
+                tabs["inst_dense_bwd"] = pw.backward_map.inst_embedding(iid)
     return {k: v.detach().numpy() for k, v in tabs.items()}
 
 
