@@ -37,7 +37,7 @@ extern "C" {
 #define B200R_E_CUDA -2    /* CUDA runtime error (text in b200r_last_error) */
 #define B200R_E_ARCH -3    /* device is not sm_100 */
 
-#define B200R_MAX_LAYERS 24 /* distinct dense layers of one field */
+#define B200R_MAX_LAYERS 32 /* distinct dense layers of one field */
 
 typedef struct b200r_handle b200r_handle;
 typedef void* b200r_stream; /* cudaStream_t */
@@ -54,6 +54,9 @@ typedef struct {
   int32_t n_bones;       /* 0 = rigid field, else SkinningWarp with B bones (18 or 25) */
   int32_t has_feature;   /* FeatureNeRF feature field present */
   int32_t operand_dtype; /* tensor-core operand type: 0 = fp16, 1 = bf16 (fp32 accumulate) */
+  int32_t dense;         /* 1: ComposedWarp = SkinningWarp + DenseWarp(D=2, W=256, 6 xyz frequencies)
+                            (nnutils/warping.py:104-170, 417-483); needs n_bones > 0 */
+  int32_t pad_;
 } b200r_field_desc;
 
 /* Dense layers, in this canonical order (absent groups are skipped):
@@ -63,6 +66,8 @@ typedef struct {
  *   [rgb.0]
  *   [colorfield.linear_1, linear_2, linear_final]
  *   [feature_field.linear_1 .. linear_5, linear_final]     if has_feature
+ *   [post_warp.forward_map.linear_1, linear_2, linear_final,
+ *    post_warp.backward_map.linear_1, linear_2, linear_final] if dense
  * b200r_layer_count() returns how many that is for a descriptor. */
 int b200r_layer_count(const b200r_field_desc* desc);
 
@@ -107,6 +112,9 @@ typedef struct {
   const float* inst_skin;        /* (M,32)  n_bones > 0 */
   const float* skin_t_embed;     /* (M,128) skinning time embedding of each frame */
   const float* skin_t_embed_mean;/* (128)   mean time embedding (forward warps, warping.py:313-314) */
+  const float* dense_t_embed;    /* (M,128) post_warp.time_embedding rows            (dense) */
+  const float* inst_dense_fwd;   /* (M,32)  post_warp.forward_map.inst_embedding rows (dense) */
+  const float* inst_dense_bwd;   /* (M,32)  post_warp.backward_map.inst_embedding rows (dense) */
   const float* t_art_qr;         /* (M,B,4) t_articulation real part */
   const float* t_art_qd;         /* (M,B,4) dual part */
   const float* rest_art_qr;      /* (M,B,4) */

@@ -7,7 +7,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200render.so")
 
-MAX_LAYERS = 24
+MAX_LAYERS = 32
 MAX_CHANNELS = 12
 CH_NORM, CH_NORM_FROZEN, CH_MEAN, CH_FLOW, CH_WEIGHTSUM, CH_VIS = range(6)
 
@@ -16,7 +16,7 @@ f32p = C.c_void_p  # device pointers are passed as integers
 
 class FieldDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("category", "D", "W", "L_xyz", "L_dir", "appr_channels", "skip", "n_bones",
-                                         "has_feature", "operand_dtype")]
+                                         "has_feature", "operand_dtype", "dense", "pad_")]
 
 
 FIELD_OUTPUTS = [("rgb", 3), ("density", 1), ("vis", 1), ("xyz", 3), ("xyz_cam", 3), ("xyz_t", 3), ("dir", 3), ("depth", 1),
@@ -31,7 +31,7 @@ class FieldParams(C.Structure):
 
 
 FRAME_PTRS = ["Kinv", "near_far", "field2cam_q", "field2cam_t", "inst_base", "inst_color", "inst_vis", "appr_code",
-              "inst_skin", "skin_t_embed", "skin_t_embed_mean", "t_art_qr", "t_art_qd", "rest_art_qr", "rest_art_qd"]
+              "inst_skin", "skin_t_embed", "skin_t_embed_mean", "dense_t_embed", "inst_dense_fwd", "inst_dense_bwd", "t_art_qr", "t_art_qd", "rest_art_qr", "rest_art_qd"]
 
 
 class FrameTables(C.Structure):

@@ -139,6 +139,8 @@ int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
         !fr->rest_art_qd || !par->warp_logibeta || !par->log_gauss)
       return fail(h, B200R_E_INVALID, "field_fwd: missing skinning input");
   }
+  if (desc->dense && (!fr->dense_t_embed || !fr->inst_dense_fwd || !fr->inst_dense_bwd))
+    return fail(h, B200R_E_INVALID, "field_fwd: missing dense-warp codes");
   if (reinterpret_cast<uintptr_t>(packed) & 15) return fail(h, B200R_E_INVALID, "field_fwd: packed must be 16-B aligned");
   if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(h, B200R_E_INVALID, "field_fwd: workspace must be 16-B aligned");
   if (workspace_bytes < b200r::workspace_floats(bp.prog, M) * sizeof(float))

@@ -95,7 +95,7 @@ template <int V>
 using IC = std::integral_constant<int, V>;
 
 // ---------------------------------------------------------------------------------- the kernel
-template <class Op, int B, int LMAX>
+template <class Op, int B, int LMAX, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_constant__ FieldKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     const int W = p.desc.W, HN = W / 2;
     // canonical layer ids (same enumeration as program.h layer_ids)
     const int lid_delta = 0, lid_vis = B > 0 ? 3 : 0, lid_base = lid_vis + 2, lid_rgb0 = lid_base + p.desc.D + 1,
-              lid_color = lid_rgb0 + 1, lid_feat = lid_color + 3;
+              lid_color = lid_rgb0 + 1, lid_feat = lid_color + 3, lid_dense = lid_feat + (p.desc.has_feature ? 6 : 0);
     const ConstLayout& CL = P.cl;
     const FrameLayout& FL = P.fl;
     // 32-bit shared-window addresses (explicit ld/st.shared keeps the hot loops off the generic path)
@@ -340,6 +340,41 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       tmem_st_wait();
       tc_fence_before_sync();
       warp_arrive(&c2m[BAR_H0 + nh]);
+    };
+
+    // 16-bit element `c` (0..63) of this row in operand chunk `chunk_s`
+    auto put16 = [&](uint32_t chunk_s, int c, float val) { sts16(chunk_s + (rowx ^ ((uint32_t)(c >> 3) << 4)) + 2u * (c & 7), Op::cvt(val)); };
+    // DenseWarp.forward (nnutils/warping.py:143-170): x + 0.1 * CondMLP([PE6(x), t, inst]).  The time / instance codes
+    // are folded into the linear_1 bias row `bias1`; lid0 = canonical id of the map's linear_1.  Both threads of a
+    // row compute the same result.
+    auto dense_warp = [&](const float3& x, uint32_t bias1, int lid0) -> float3 {
+      const uint32_t pe_s = arena_s + CH_PE * kAChunkBytes;
+      if (hsel == 0) { put16(pe_s, 0, x.x); put16(pe_s, 1, x.y); put16(pe_s, 2, x.z); }
+      else {
+        put16(pe_s, 39, 0.f);  // 39 embedding columns; the third k-step reads up to column 47
+        sts128(pe_s + (rowx ^ (5u << 4)), make_uint4(0u, 0u, 0u, 0u));
+      }
+      float fr = hsel == 0 ? 1.0f : 8.0f;
+#pragma unroll 1
+      for (int kf = 3 * hsel; kf < 3 * hsel + 3; ++kf) {
+        float sv[3], cv[3];
+        sincosf(fr * x.x, &sv[0], &cv[0]);
+        sincosf(fr * x.y, &sv[1], &cv[1]);
+        sincosf(fr * x.z, &sv[2], &cv[2]);
+        const int e0 = 3 + 6 * kf;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { put16(pe_s, e0 + c, sv[c]); put16(pe_s, e0 + 3 + c, cv[c]); }
+        fr *= 2.0f;
+      }
+      run_gemm();
+      epi_relu_store(bias1, 256, CH_H0);
+      run_gemm();
+      epi_relu_store(bias_s(lid0 + 1), 256, CH_H0);
+      run_gemm();
+      float m[16];
+      tmem_ld16(t_lane + kTmemD0, m);
+      const uint32_t b3 = bias_s(lid0 + 2);
+      return make_float3(x.x + 0.1f * (m[0] + lds32(b3)), x.y + 0.1f * (m[1] + lds32(b3 + 4)), x.z + 0.1f * (m[2] + lds32(b3 + 8)));
     };
 
     for (int it = 0; it < iters; ++it) {
@@ -511,15 +546,26 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       float3 xyz = xyz_t, x_next = xyz_t;
       float ent_b = 0.f, dsk_b = 0.f, ent_out = 0.f, dsk_out = 0.f, cyc = 0.f;
       if constexpr (B > 0) {
+        // ComposedWarp (warping.py:445-483) interleaves the DenseWarp soft deformation: backward = skin then dense,
+        // forward = dense then skin.  One loop over stages keeps a single inlined copy of either body.
+        constexpr int NST = DENSE ? 6 : 3;
+        float3 cur = xyz_t;
 #pragma unroll 1
-        for (int w = 0; w < 3; ++w) {
-          const float3 src = w == 0 ? xyz_t : xyz;
+        for (int stg = 0; stg < NST; ++stg) {
+          const int w = DENSE ? (stg >> 1) : stg;
+          if (DENSE && (stg == 1 || stg == 2 || stg == 4)) {
+            const uint32_t bias1 = stg == 1 ? bias_s(lid_dense + 3) : (stg == 2 ? fblk_s + 4u * FL.dense1_partner : bias_s(lid_dense));
+            cur = dense_warp(stg == 1 ? cur : xyz, bias1, stg == 1 ? lid_dense + 3 : lid_dense);
+            if (stg == 1) xyz = cur;
+            continue;
+          }
+          const float3 src = w == 0 ? xyz_t : (DENSE ? cur : xyz);
           const uint32_t binv = fblk_s + 4u * (w == 0 ? FL.binv_t : (w == 1 ? FL.binv_rest_partner : FL.binv_rest));
           const uint32_t se3 = fblk_s + 4u * (w == 0 ? FL.se3_bwd : (w == 1 ? FL.se3_fwd_partner : FL.se3_fwd));
           const uint32_t bias1 = w == 0 ? bias_s(lid_delta) : fblk_s + 4u * FL.delta1_fwd;  // forward warps: mean time code
           float e, dk;
           const float3 o = hsel == 0 ? skin_warp(IC<0>{}, src, binv, se3, bias1, e, dk) : skin_warp(IC<1>{}, src, binv, se3, bias1, e, dk);
-          if (w == 0) { xyz = o; ent_b = e; dsk_b = dk; }
+          if (w == 0) { cur = o; xyz = o; ent_b = e; dsk_b = dk; }
           else if (w == 1) { x_next = o; }
           else {
             const float dx = o.x - xyz_t.x, dy = o.y - xyz_t.y, dz = o.z - xyz_t.z;
@@ -537,11 +583,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       // CH_PE (column 63 = 0), columns 63.. in CH_EXTRA.  Half 0 writes frequencies 0..LMAX/2-1, half 1 the rest.
       {
         const uint32_t pe_s = arena_s + CH_PE * kAChunkBytes;
-        auto put = [&](int e, float val) {  // embedding column e -> 16-bit operand element
-          const uint32_t base = e < 63 ? pe_s : extra_s;
-          const int c = e < 63 ? e : e - 63;
-          sts16(base + (rowx ^ ((uint32_t)(c >> 3) << 4)) + 2u * (c & 7), Op::cvt(val));
-        };
+        auto put = [&](int e, float val) { put16(e < 63 ? pe_s : extra_s, e < 63 ? e : e - 63, val); };  // embedding column e
         if (hsel == 0) { put(0, xyz.x); put(1, xyz.y); put(2, xyz.z); }
         else {
           sts16(pe_s + (rowx ^ (7u << 4)) + 14u, (uint16_t)0);  // zero pad column 63 of CH_PE
@@ -786,9 +828,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
   }
 }
 
-template <class Op, int B, int LMAX>
+template <class Op, int B, int LMAX, bool DENSE>
 static cudaError_t launch_one(const FieldKernelParams& p, int n_sm, cudaStream_t stream) {
-  auto kern = field_fwd_kernel<Op, B, LMAX>;
+  auto kern = field_fwd_kernel<Op, B, LMAX, DENSE>;
   const int smem = 1024 + kSmemArena + kSmemRing + (p.prog.cl.n_floats + p.prog.fl.n_floats) * 4 + 128;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -815,13 +857,15 @@ static cudaError_t launch_one(const FieldKernelParams& p, int n_sm, cudaStream_t
 
 cudaError_t launch_field_fwd(const FieldKernelParams& p, int n_sm, cudaStream_t stream) {
   const bool bf = p.desc.operand_dtype == 1;
-#define B200R_CASE(BN, LM)                                                        \
-  if (p.desc.n_bones == BN && p.Lmax == LM)                                       \
-    return bf ? launch_one<OpBF16, BN, LM>(p, n_sm, stream) : launch_one<OpF16, BN, LM>(p, n_sm, stream);
-  B200R_CASE(0, 10)
-  B200R_CASE(0, 12)
-  B200R_CASE(18, 12)
-  B200R_CASE(25, 12)
+#define B200R_CASE(BN, LM, DN)                                                    \
+  if (p.desc.n_bones == BN && p.Lmax == LM && (p.desc.dense != 0) == DN)          \
+    return bf ? launch_one<OpBF16, BN, LM, DN>(p, n_sm, stream) : launch_one<OpF16, BN, LM, DN>(p, n_sm, stream);
+  B200R_CASE(0, 10, false)
+  B200R_CASE(0, 12, false)
+  B200R_CASE(18, 12, false)
+  B200R_CASE(25, 12, false)
+  B200R_CASE(18, 12, true)
+  B200R_CASE(25, 12, true)
 #undef B200R_CASE
   return cudaErrorInvalidValue;
 }

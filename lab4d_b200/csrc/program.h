@@ -19,8 +19,8 @@ constexpr int kTileRows = 128;
 constexpr int kAChunkBytes = kTileRows * 128;  // 16 KB
 constexpr int kMaxN = 256;
 constexpr int kWStageBytes = 2 * 128 * 128;    // 32 KB weight ring stage (two [<=128 rows x 64] tiles)
-constexpr int kMaxSteps = 88;
-constexpr int kMaxCond = 8;
+constexpr int kMaxSteps = 96;
+constexpr int kMaxCond = 12;
 
 // arena chunk ids
 enum : int { CH_PE = 0, CH_EXTRA = 1, CH_H0 = 2, CH_H1 = 3, CH_H2 = 4, CH_H3 = 5, kArenaChunks = 6 };
@@ -64,11 +64,13 @@ struct LayerIds {
   int rgb0;
   int color[3];
   int feat[6];
+  int dense[6];  // forward_map L1, L2, final; backward_map L1, L2, final
   int count;
 };
 
 // code tables a conditioned layer can take its per-frame code from
-enum : int { CODE_INST_BASE = 0, CODE_INST_COLOR, CODE_INST_VIS, CODE_APPR, CODE_INST_SKIN, CODE_T_EMBED, CODE_T_EMBED_MEAN, kNumCodes };
+enum : int { CODE_INST_BASE = 0, CODE_INST_COLOR, CODE_INST_VIS, CODE_APPR, CODE_INST_SKIN, CODE_T_EMBED, CODE_T_EMBED_MEAN,
+              CODE_DENSE_T, CODE_DENSE_T_PARTNER, CODE_INST_DENSE_FWD, CODE_INST_DENSE_BWD, kNumCodes };
 
 // bias row that depends on the frame: b + sum_seg W[:, col0:col0+C] @ code_seg[frame]
 struct CondRow {
@@ -82,7 +84,7 @@ struct CondRow {
 
 // float offsets inside the constant block
 struct ConstLayout {
-  int16_t sdf_w, rgb2_w, vis_w, dir_w, inv_gauss, center, scalars;  // scalars: see SC_* below
+  int16_t sdf_w, rgb2_w, vis_w, dir_w, center, scalars, pad_;  // scalars: see SC_* below
   int16_t n_floats;
   int16_t plain_off[B200R_MAX_LAYERS];  // bias row of non-conditioned layers, -1 otherwise
 };
@@ -95,16 +97,16 @@ struct FrameLayout {
   // se3_* = blend transform as dual quaternion (real, dual), B*8 floats
   int16_t binv_t, se3_bwd, binv_rest, se3_fwd, binv_rest_partner, se3_fwd_partner;
   int16_t delta1_fwd;        // bias row of delta_field.linear_1 with the MEAN time code
+  int16_t dense1_partner;    // bias row of post_warp.forward_map.linear_1 with the PARTNER frame's time code
   int16_t n_cond;
   int16_t n_floats;          // multiple of 4
-  int16_t pad_;
   CondRow cond[kMaxCond];
 };
 
 struct Program {
   int32_t n_steps;
-  // first step of each phase, in execution order: 3 skinning delta MLPs, vis, feature, base chain,
-  // colour chain, final rgb.0
+  // first step of each phase, in execution order: 3 warps (dense MLP + skinning delta MLP, see the kernel),
+  // vis, feature, base chain, colour chain, final rgb.0
   int32_t st_delta[3], st_vis, st_feat, st_base, st_color, st_rgb;
   ConstLayout cl;
   FrameLayout fl;
@@ -139,6 +141,7 @@ inline LayerIds layer_ids(const b200r_field_desc& d) {
   L.rgb0 = c++;
   for (int i = 0; i < 3; ++i) L.color[i] = c++;
   for (int i = 0; i < 6; ++i) L.feat[i] = d.has_feature ? c++ : -1;
+  for (int i = 0; i < 6; ++i) L.dense[i] = d.dense ? c++ : -1;
   L.count = c;
   return L;
 }
@@ -169,6 +172,8 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   if (d.n_bones > 0 && d.L_xyz != 10) { bp.err = "skinned fields need L_xyz == 10"; return bp; }
   if (d.appr_channels < 0 || d.appr_channels > 64) { bp.err = "appr_channels out of range"; return bp; }
   if (d.operand_dtype != 0 && d.operand_dtype != 1) { bp.err = "operand_dtype must be 0 or 1"; return bp; }
+  if (d.dense != 0 && d.dense != 1) { bp.err = "dense must be 0 or 1"; return bp; }
+  if (d.dense && d.n_bones == 0) { bp.err = "dense (ComposedWarp) needs a skinned field"; return bp; }
   const LayerIds L = layer_ids(d);
   bp.layer_out.assign(L.count, 0);
   bp.layer_in.assign(L.count, 0);
@@ -251,6 +256,14 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
     }
     add_layer(L.feat[5], 16, 128, hidden(0, 128));
   }
+  const int pe_d = pe_dim(6), DW = 256;  // DenseWarp: 6 frequencies, two hidden layers of 256
+  if (d.dense) {
+    for (int m = 0; m < 2; ++m) {
+      add_layer(L.dense[3 * m + 0], DW, pe_d + TEMB + INST, pe_slices(pe_d, 0));
+      add_layer(L.dense[3 * m + 1], DW, DW, hidden(0, DW));
+      add_layer(L.dense[3 * m + 2], 3, DW, hidden(0, DW));
+    }
+  }
   bp.packed_bytes = off;
 
   // ---- frame block: cameras, conditioned bias rows, bone tables
@@ -285,13 +298,24 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   add_cond(L.base[d.skip], pe_b, INST, CODE_INST_BASE);
   if (d.appr_channels > 0) add_cond(L.rgb0, W + pe_dim(d.L_dir), d.appr_channels, CODE_APPR);
   add_cond(L.color[0], pe_c, INST, CODE_INST_COLOR);
+  F.dense1_partner = -1;
+  if (d.dense) {
+    add_cond(L.dense[3], pe_d, TEMB, CODE_DENSE_T, pe_d + TEMB, INST, CODE_INST_DENSE_BWD);
+    add_cond(L.dense[0], pe_d, TEMB, CODE_DENSE_T, pe_d + TEMB, INST, CODE_INST_DENSE_FWD);
+    F.dense1_partner = (int16_t)fo;
+    CondRow& c = F.cond[nc++];  // flow: the partner frame's time code (warping.py:459-463 with frame_id_next)
+    c = F.cond[nc - 2];
+    c.frame_off = (int16_t)fo;
+    c.code[0] = CODE_DENSE_T_PARTNER;
+    fo += DW;
+  }
   F.n_cond = (int16_t)nc;
   auto bones = [&](int per) { int o = fo; fo += B * per; return (int16_t)o; };
   F.binv_t = bones(12); F.se3_bwd = bones(8); F.binv_rest = bones(12); F.se3_fwd = bones(8);
   F.binv_rest_partner = bones(12); F.se3_fwd_partner = bones(8);
   F.n_floats = (int16_t)pad4(fo);
 
-  // ---- constant block: plain bias rows, head weights, Gaussian scales, scalars
+  // ---- constant block: plain bias rows, head weights, rest bone centres, scalars
   ConstLayout& C = P.cl;
   int co = 0;
   for (int i = 0; i < B200R_MAX_LAYERS; ++i) C.plain_off[i] = -1;
@@ -301,7 +325,6 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   C.rgb2_w = (int16_t)co; co += 3 * HN;
   C.vis_w = (int16_t)co; co += 64;
   C.dir_w = (int16_t)co; co += (d.L_dir == 0) ? pad4(3 * HN) : 0;
-  C.inv_gauss = (int16_t)co; co += B * 4;
   C.center = (int16_t)co; co += B * 4;
   C.scalars = (int16_t)co; co += kNumScalars;
   C.n_floats = (int16_t)pad4(co);
@@ -325,22 +348,30 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   // sequential GEMM: all compute threads hand over operands (BAR_ALL) and wait for the result (BAR_ALL)
   auto seq_gemm = [&](int id, const std::vector<int>& a_chunks) {
     const auto& cs = chunks[id];
-    for (size_t c = 0; c < cs.size(); c += 2) {
-      const int nsub = c + 1 < cs.size() ? 2 : 1;
+    for (size_t c = 0; c < cs.size();) {
+      const int nsub = (c + 1 < cs.size() && 2 * cs[c].n * 128 <= kWStageBytes) ? 2 : 1;  // two tiles must fit one ring stage
       step(&cs[c], nsub, 0, a_chunks[c], nsub > 1 ? a_chunks[c + 1] : 0, 0, kTmemD0, c > 0, c == 0 ? BAR_ALL : BAR_NONE,
            c + (size_t)nsub == cs.size() ? BAR_ALL : BAR_NONE);
+      c += (size_t)nsub;
     }
   };
   auto pe_ch = [&](int pe_n) { std::vector<int> v{CH_PE}; if (pe_n > 63) v.push_back(CH_EXTRA); return v; };
   auto hch = [&](int first, int n) { std::vector<int> v; for (int j = 0; j < n; ++j) v.push_back(first + j); return v; };
   auto catv = [](std::vector<int> a, const std::vector<int>& b) { a.insert(a.end(), b.begin(), b.end()); return a; };
+  auto dense_gemms = [&](int m) {  // DenseWarp MLP m (0 forward_map, 1 backward_map): PE6 -> 256 -> 256 -> 3
+    seq_gemm(L.dense[3 * m + 0], {CH_PE});
+    seq_gemm(L.dense[3 * m + 1], hch(CH_H0, 4));
+    seq_gemm(L.dense[3 * m + 2], hch(CH_H0, 4));
+  };
   for (int w = 0; w < 3; ++w) {
     P.st_delta[w] = ns;
+    if (d.dense && w > 0) dense_gemms(0);  // forward warps: soft deformation first (warping.py:459-463)
     if (B > 0) {
       seq_gemm(L.delta[0], 3 * B > 64 ? std::vector<int>{CH_H0, CH_H1} : std::vector<int>{CH_H0});
       seq_gemm(L.delta[1], {CH_H2});
       seq_gemm(L.delta[2], {CH_H2});
     }
+    if (d.dense && w == 0) dense_gemms(1);  // backward warp: un-articulate, then the soft deformation (warping.py:472-476)
   }
   P.st_vis = ns;
   seq_gemm(L.vis[0], pe_ch(pe_v));

@@ -7,8 +7,7 @@
 //       nerf.py:200-204, skinning.py:109-116),
 //       bone tables: inverse bone transforms (utils/transforms.py:9-25) and the per-bone blend
 //       transforms rest (x) t^-1 / t (x) rest^-1 as dual quaternions (nnutils/warping.py:304-314).
-//   block M      : the constant block - plain bias rows, head weights, Gaussian bone scales
-//       (nnutils/skinning.py:141-153), rest bone centres (utils/transforms.py:28-40), scalars.
+//   block M      : the constant block - plain bias rows, head weights, rest bone centres (utils/transforms.py:28-40), scalars.
 // M x B rows of quaternion algebra and a few (N x 32) mat-vecs: ~0.1 % of the step's FLOPs.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -89,11 +88,6 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
       for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) cblock[C.dir_w + i] = w0[(size_t)(i / 3) * in_dim + W + (i % 3)];
     }
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
-      for (int c = 0; c < 3; ++c) {
-        float lg = p.par.log_gauss[b * 3 + c];
-        if (p.par.symm_idx) lg = 0.5f * (p.par.log_gauss[p.par.symm_idx[b] * 3 + c] + lg);
-        cblock[C.inv_gauss + b * 4 + c] = expf(-lg);
-      }
       const Q4 qr = ld4(p.fr.rest_art_qr + b * 4), qd = ld4(p.fr.rest_art_qd + b * 4);  // frame 0
       const Q4 t = qmul(qd, qconj(qr));
       cblock[C.center + b * 4 + 0] = 2.f * t.x;
@@ -126,6 +120,10 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
   codes[CODE_INST_SKIN] = p.fr.inst_skin ? p.fr.inst_skin + (size_t)f * 32 : nullptr;
   codes[CODE_T_EMBED] = p.fr.skin_t_embed ? p.fr.skin_t_embed + (size_t)f * 128 : nullptr;
   codes[CODE_T_EMBED_MEAN] = p.fr.skin_t_embed_mean;
+  codes[CODE_DENSE_T] = p.fr.dense_t_embed ? p.fr.dense_t_embed + (size_t)f * 128 : nullptr;
+  codes[CODE_DENSE_T_PARTNER] = p.fr.dense_t_embed ? p.fr.dense_t_embed + (size_t)fn * 128 : nullptr;
+  codes[CODE_INST_DENSE_FWD] = p.fr.inst_dense_fwd ? p.fr.inst_dense_fwd + (size_t)f * 32 : nullptr;
+  codes[CODE_INST_DENSE_BWD] = p.fr.inst_dense_bwd ? p.fr.inst_dense_bwd + (size_t)f * 32 : nullptr;
   for (int ci = 0; ci < F.n_cond; ++ci) {
     const CondRow& c = F.cond[ci];
     const float* Wm = p.par.weight[c.layer];

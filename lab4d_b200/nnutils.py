@@ -25,11 +25,14 @@ def config_from_module(field) -> FieldConfig:
     """Read the architecture of a reference NeRF / Deformable module."""
     base = field.basefield
     W, D = base.W, base.D
-    motion, B, symm = "rigid", 0, None
+    motion, B, symm, dense = "rigid", 0, None, False
     warp = getattr(field, "warp", None)
     if warp is not None and hasattr(warp, "skinning_model"):
-        if hasattr(warp, "post_warp"):
-            raise NotImplementedError("ComposedWarp (skeleton + DenseWarp) is not accelerated yet")
+        if hasattr(warp, "post_warp"):  # ComposedWarp (nnutils/warping.py:417-443)
+            pw = warp.post_warp
+            if type(pw).__name__ != "DenseWarp" or pw.forward_map.D != 2 or pw.forward_map.W != 256 or pw.pos_embedding.N_freqs != 6:
+                raise NotImplementedError("ComposedWarp: only DenseWarp(D=2, W=256, 6 frequencies) post-warps are accelerated")
+            dense = True
         B = warp.skinning_model.num_coords
         motion = "bob" if type(warp.articulation).__name__ == "ArticulationFlatMLP" else "skel"
         if warp.skinning_model.symm_idx is not None:
@@ -38,7 +41,7 @@ def config_from_module(field) -> FieldConfig:
         raise NotImplementedError(f"warp type {type(warp).__name__} is not accelerated yet")
     return FieldConfig(category=field.category, D=D, W=W, L_xyz=field.pos_embedding.N_freqs,
                        L_dir=field.dir_embedding.N_freqs, appr_channels=field.appr_channels, skip=base.skips[0],
-                       motion=motion, B=B, has_feature=hasattr(field, "feature_field"), symm_idx=symm)
+                       motion=motion, B=B, has_feature=hasattr(field, "feature_field"), symm_idx=symm, dense=dense)
 
 
 def tables_from_module(field, samples_dict):
@@ -56,6 +59,11 @@ def tables_from_module(field, samples_dict):
         tab["inst_skin"] = sk.delta_field.inst_embedding(inst_id)
         tab["skin_t_embed"] = sk.time_embedding(frame_id)
         tab["skin_t_embed_mean"] = sk.time_embedding.get_mean_embedding(frame_id.device)
+        if hasattr(warp, "post_warp"):
+            pw = warp.post_warp
+            tab["dense_t_embed"] = pw.time_embedding(frame_id)
+            tab["inst_dense_fwd"] = pw.forward_map.inst_embedding(inst_id)
+            tab["inst_dense_bwd"] = pw.backward_map.inst_embedding(inst_id)
         if "t_articulation" in samples_dict:
             t_art, r_art = samples_dict["t_articulation"], samples_dict["rest_articulation"]
         else:

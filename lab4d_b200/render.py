@@ -44,7 +44,8 @@ class FieldRenderer:
         self.desc = _lib.FieldDesc(category=0 if cfg.category == "fg" else 1, D=cfg.D, W=cfg.W, L_xyz=cfg.L_xyz,
                                    L_dir=cfg.L_dir, appr_channels=cfg.appr_channels, skip=cfg.skip,
                                    n_bones=cfg.B if cfg.motion != "rigid" else 0, has_feature=int(cfg.has_feature),
-                                   operand_dtype={"fp16": 0, "bf16": 1}[operand_dtype])
+                                   operand_dtype={"fp16": 0, "bf16": 1}[operand_dtype],
+                                   dense=int(cfg.dense and cfg.motion != "rigid"))
         self.n_layers = self.handle.lib.b200r_layer_count(C.byref(self.desc))
         nbytes = self.handle.lib.b200r_packed_bytes(C.byref(self.desc))
         if self.n_layers <= 0 or nbytes == 0:
@@ -77,6 +78,11 @@ class FieldRenderer:
             for i in range(5):
                 L.append((f"feature_field.linear_{i+1}.0", None))
             L.append(("feature_field.linear_final", None))
+        if c.dense and c.motion != "rigid":
+            for m in ("forward_map", "backward_map"):
+                L.append((f"warp.post_warp.{m}.linear_1.0", None))
+                L.append((f"warp.post_warp.{m}.linear_2.0", None))
+                L.append((f"warp.post_warp.{m}.linear_final", None))
         return L
 
     def _params(self, P):
@@ -119,6 +125,7 @@ class FieldRenderer:
     # names of the per-frame tables (keys of `tab`) in the order of b200r_frame_tables
     _TAB_KEYS = {"inst_base": "inst_base", "inst_color": "inst_color", "inst_vis": "inst_vis", "appr_code": "appr_code",
                  "inst_skin": "inst_skin", "skin_t_embed": "skin_t_embed", "skin_t_embed_mean": "skin_t_embed_mean",
+                 "dense_t_embed": "dense_t_embed", "inst_dense_fwd": "inst_dense_fwd", "inst_dense_bwd": "inst_dense_bwd",
                  "t_art_qr": "t_articulation_qr", "t_art_qd": "t_articulation_qd", "rest_art_qr": "rest_articulation_qr",
                  "rest_art_qd": "rest_articulation_qd", "field2cam_q": "field2cam_q", "field2cam_t": "field2cam_t"}
 

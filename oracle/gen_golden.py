@@ -50,7 +50,14 @@ def one(name, field_type, motion, M, N, D, seed=0, flow_thresh=None, with_grad=T
         pack["rays/" + k] = v
     feats, dls, graphs = {}, {}, {}
     for cat in cats:
-        feat, deltas, rend, tabs, graph = H.run_field(mf, cat, rays, D, flow_thresh=flow_thresh)
+        if len(cats) > 1 and cat == "bg":
+            # every field has its own near/far in the reference (nnutils/nerf.py near_far parameter); identical planes
+            # would put fg and bg samples at exactly tied depths, whose order after argsort is arbitrary
+            rays_c = dict(rays, near_far=rays["near_far"] * np.array([[0.93, 1.11]], np.float32))
+            pack["bg/rays/near_far"] = rays_c["near_far"]
+        else:
+            rays_c = rays
+        feat, deltas, rend, tabs, graph = H.run_field(mf, cat, rays_c, D, flow_thresh=flow_thresh)
         feats[cat], dls[cat], graphs[cat] = feat, deltas, graph
         for k, v in tabs.items():
             pack[f"{cat}/tab/{k}"] = v

@@ -46,6 +46,8 @@ def synth_tensor(name, shape, seed=0, category="fg"):
             gain = 0.25
         if ".articulation.so3.2" in name or ".articulation.trans.2" in name:
             gain = 0.6
+        if ".post_warp." in name and ".linear_final" in name:
+            gain = 0.1  # soft deformation of a few % of the object size (x + 0.1 * mlp, warping.py:165), as after training
         a = gain * np.sqrt(6.0 / fan_in)  # He-uniform: keeps ReLU activations O(1) through 8 layers
         return rs.uniform(-a, a, shape).astype(np.float32)
     if leaf == "bias":

@@ -21,6 +21,13 @@ def test_adapter_reads_reference_modules():
     cfg = nnutils.config_from_module(field)
     assert cfg == spec.FG_BOB
     assert nnutils.config_from_module(H.build_field("bg", "rigid").field_params["bg"]) == spec.BG
+    comp = H.build_field("fg", "comp_skel-quad_dense")
+    assert nnutils.config_from_module(comp.field_params["fg"]) == spec.FG_COMP_QUAD
+    _, _, _, ctabs, cgraph = H.run_field(comp, "fg", synth.synth_rays(2, 4), 4)
+    with torch.no_grad():
+        ctab = nnutils.tables_from_module(comp.field_params["fg"], cgraph[3])
+    for k in ("dense_t_embed", "inst_dense_fwd", "inst_dense_bwd"):
+        assert torch.equal(ctab[k], torch.from_numpy(ctabs[k])), k
     rays = synth.synth_rays(4, 4)
     feat, deltas, rend, tabs, graph = H.run_field(mf, "fg", rays, 8)
     samples = graph[3]
