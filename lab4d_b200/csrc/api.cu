@@ -1,6 +1,7 @@
 // C ABI of libb200render.so (declarations and reference citations: include/b200r.h).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -19,6 +20,17 @@ struct b200r_handle {
   bool slices_valid;
 };
 
+// Field-kernel generation: 5 = two tiles in flight per CTA (field_fwd5.cu), 4 = one tile per CTA (field_fwd.cu).
+// Process-wide (packing and launch must agree); B200R_KERNEL=4 selects the older kernel for A/B measurements.
+static int kernel_version() {
+  static const int v = [] {
+    const char* e = getenv("B200R_KERNEL");
+    return (e && e[0] == '4') ? 4 : 5;
+  }();
+  return v;
+}
+static b200r::BuiltProgram build(const b200r_field_desc& d) { return b200r::build_program(d, kernel_version()); }
+
 static int fail(b200r_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   return code;
@@ -36,7 +48,7 @@ int b200r_layer_count(const b200r_field_desc* desc) {
 
 size_t b200r_packed_bytes(const b200r_field_desc* desc) {
   if (!desc) return 0;
-  b200r::BuiltProgram bp = b200r::build_program(*desc);
+  b200r::BuiltProgram bp = build(*desc);
   return bp.ok ? bp.packed_bytes : 0;
 }
 
@@ -70,7 +82,7 @@ int b200r_pack_weights(b200r_handle* h, const b200r_field_desc* desc, const b200
   if (!h) return B200R_E_INVALID;
   if (!desc || !params || !packed) return fail(h, B200R_E_INVALID, "pack_weights: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  b200r::BuiltProgram bp = b200r::build_program(*desc);
+  b200r::BuiltProgram bp = build(*desc);
   if (!bp.ok) return fail(h, B200R_E_INVALID, std::string("pack_weights: ") + bp.err);
   const int n_weights = (int)bp.layer_out.size();
   if (packed_bytes < bp.packed_bytes) return fail(h, B200R_E_INVALID, "pack_weights: packed buffer too small");
@@ -109,8 +121,9 @@ int b200r_pack_weights(b200r_handle* h, const b200r_field_desc* desc, const b200
 
 size_t b200r_workspace_bytes(const b200r_field_desc* desc, int32_t M) {
   if (!desc || M < 1) return 0;
-  b200r::BuiltProgram bp = b200r::build_program(*desc);
-  return bp.ok ? b200r::workspace_floats(bp.prog, M) * sizeof(float) : 0;
+  b200r::BuiltProgram bp = build(*desc);
+  if (!bp.ok) return 0;
+  return kernel_version() >= 5 ? b200r::workspace_bytes_v5(bp.prog, M) : b200r::workspace_floats(bp.prog, M) * sizeof(float);
 }
 
 int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
@@ -118,7 +131,7 @@ int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
                     void* workspace, size_t workspace_bytes, b200r_stream stream_) {
   if (!h) return B200R_E_INVALID;
   if (!desc || !packed || !par || !fr || !rays || !out || !workspace) return fail(h, B200R_E_INVALID, "field_fwd: null argument");
-  b200r::BuiltProgram bp = b200r::build_program(*desc);
+  b200r::BuiltProgram bp = build(*desc);
   if (!bp.ok) return fail(h, B200R_E_INVALID, std::string("field_fwd: ") + bp.err);
   const int M = fr->M;
   if (M < 1 || rays->N < 1 || rays->D < 2) return fail(h, B200R_E_INVALID, "field_fwd: need M,N >= 1 and D >= 2");
@@ -143,7 +156,7 @@ int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
     return fail(h, B200R_E_INVALID, "field_fwd: missing dense-warp codes");
   if (reinterpret_cast<uintptr_t>(packed) & 15) return fail(h, B200R_E_INVALID, "field_fwd: packed must be 16-B aligned");
   if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(h, B200R_E_INVALID, "field_fwd: workspace must be 16-B aligned");
-  if (workspace_bytes < b200r::workspace_floats(bp.prog, M) * sizeof(float))
+  if (workspace_bytes < b200r_workspace_bytes(desc, M))
     return fail(h, B200R_E_INVALID, "field_fwd: workspace too small (see b200r_workspace_bytes)");
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
@@ -175,7 +188,13 @@ int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
   kp.tiles_per_frame = (kp.ND + b200r::kTileRows - 1) / b200r::kTileRows;
   kp.n_tiles = M * kp.tiles_per_frame;
   kp.Lmax = desc->L_xyz + 2 > 10 ? 12 : 10;
-  if ((e = b200r::launch_field_fwd(kp, h->n_sm, stream)) != cudaSuccess) return fail_cuda(h, e, "field_fwd kernel");
+  if (kernel_version() >= 5) {
+    kp.scratch = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(workspace) + b200r::scratch_offset_bytes(bp.prog, M));
+    e = b200r::launch_field_fwd5(kp, h->n_sm, stream);
+  } else {
+    e = b200r::launch_field_fwd(kp, h->n_sm, stream);
+  }
+  if (e != cudaSuccess) return fail_cuda(h, e, "field_fwd kernel");
   return B200R_OK;
 }
 

@@ -1,0 +1,800 @@
+// Fused per-ray-sample forward of one Lab4D field (training-mode query_field) for sm_100a, version 5:
+// TWO 128-sample tiles in flight per CTA.
+//
+// Persistent kernel, one CTA per SM, CTAs paired in clusters of 2 that share every weight chunk through
+// TMA multicast.  Warp roles (320 threads):
+//   warps 0-3 : tile group 0, warps 4-7 : tile group 1.  One thread per sample (thread = tile row = TMEM lane):
+//               sample placement, camera -> field, dual-quaternion blend skinning (+ DenseWarp), Fourier embedding
+//               into swizzled shared memory, and every layer's epilogue straight out of TMEM.
+//   warp 8    : TMA producer - streams pre-packed weight chunks (cp.async.bulk, multicast to both CTAs of the
+//               cluster) through a 3-stage ring of 32 KB.
+//   warp 9    : tcgen05.mma issuer (one elected lane) + TMEM owner.  Walks the MmaStep list of program.h block by
+//               block (a block = one GEMM or one N-half of a 256-wide layer), issuing every block for group 0 and
+//               then for group 1: while one group runs an epilogue or its SIMT geometry, the tensor pipe works on
+//               the other group's tile, so the round-trip latencies of the 40-odd dependent GEMMs of a tile overlap.
+// TMEM (512 columns): per group 128 fp32 accumulator columns + 128 columns holding 256 16-bit activations.  All
+// hidden activations live in TMEM and feed the next layer as the A operand (TS form); the 256-wide layers run as
+// two N-halves on the same accumulator: the epilogue of half 0 drains it into registers while half 1 is being
+// multiplied, and both halves are written back in place once the layer's MMAs have read their input.
+// Shared memory holds only the embedding operand chunks (2 x 16 KB per group), the weight ring, the constant
+// block and one per-frame block per group.  HBM sees O(100 B) per sample of outputs.
+//
+// Restates (not ports) lab4d/nnutils/{nerf,deformable,feature,warping,skinning,embedding,visibility}.py
+// and lab4d/utils/{render_utils,geom_utils,quat_transform}.py - see include/b200r.h for file:line.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <type_traits>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+#ifndef B200R_CLUSTER
+#define B200R_CLUSTER 2
+#endif
+
+namespace b200r {
+namespace v5 {
+
+constexpr int kCluster = B200R_CLUSTER;
+constexpr int kNumStages = 3;
+constexpr int kGroups = 2;
+constexpr int kGroupThreads = 128;
+constexpr int kComputeThreads = kGroups * kGroupThreads;
+constexpr int kThreads = kComputeThreads + 128;  // warpgroup 2 = producer warp, MMA warp, two idle warps (register donors)
+constexpr int kRegsCompute = 208, kRegsAux = 88;        // setmaxnreg: 2 x 128 x 208 + 128 x 88 = 64512 <= 65536
+constexpr int kArenaGroup = 2 * kAChunkBytes;           // CH_PE, CH_EXTRA
+constexpr int kSmemArena = kGroups * kArenaGroup;        // 64 KB
+constexpr int kSmemRing = kNumStages * kWStageBytes;     // 96 KB
+constexpr int kTmemAcc = 0, kTmemAct = 256, kTmemGroup = 128;
+
+struct Q4 { float w, x, y, z; };
+__device__ __forceinline__ Q4 qmul(const Q4& a, const Q4& b) {
+  return {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+          a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w};
+}
+__device__ __forceinline__ Q4 qconj(const Q4& a) { return {a.w, -a.x, -a.y, -a.z}; }
+__device__ __forceinline__ float3 qrot(const Q4& q, const float3& p) {  // quaternion_apply
+  Q4 t = qmul(q, Q4{0.f, p.x, p.y, p.z});
+  Q4 r = qmul(t, qconj(q));
+  return make_float3(r.x, r.y, r.z);
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32u(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
+
+template <int V>
+using IC = std::integral_constant<int, V>;
+
+template <class Op, int B, int LMAX, bool DENSE, int WIDTH>
+__global__ void __launch_bounds__(kThreads, 1) field_fwd5_kernel(const __grid_constant__ FieldKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* arena = smem;
+  uint8_t* ring = smem + kSmemArena;
+  float* cblk = reinterpret_cast<float*>(ring + kSmemRing);
+  float* fblk = cblk + p.prog.cl.n_floats;  // one frame block per tile group
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fblk + kGroups * p.prog.fl.n_floats);
+  uint64_t* full_bar = bars;                  // [kNumStages]
+  uint64_t* empty_bar = bars + kNumStages;    // [kNumStages]
+  uint64_t* c2m = bars + 2 * kNumStages;      // [group][4] compute warps -> MMA thread, indexed by BAR_*
+  uint64_t* m2c = bars + 2 * kNumStages + 8;  // [group][4] MMA thread (tcgen05.commit) -> compute warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumStages + 16);
+  uint4* rec = reinterpret_cast<uint4*>(bars + 2 * kNumStages + 18);  // [group][kMaxSteps] decoded MMA steps
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNumStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], kCluster); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&c2m[i], 4); mbar_init(&m2c[i], 1); }  // one arrival per warp of the group
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // peer barriers are initialised before any multicast can land
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const Program& P = p.prog;
+  const int pair_stride = 2 * (int)gridDim.x;
+  const int iters = (p.n_tiles + pair_stride - 1) / pair_stride;  // identical in both CTAs of a cluster
+  const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << kCluster) - 1);
+  const int n_steps = P.n_steps;
+  // Decode the step list once: x = instruction descriptor, y / z = A operand of the two weight tiles (shared-memory
+  // descriptor low word, or TMEM address), w = ksteps | ksteps2 << 4 | TS << 8 | accumulate << 9 | wait << 10 |
+  // commit << 12 | steps-in-block << 14 (first step of a block) | byte offset >> 4 of the second weight tile << 16.
+  for (int i = threadIdx.x; i < kGroups * n_steps; i += kThreads) {
+    const int g = i / n_steps, st = i - g * n_steps;
+    const MmaStep& S = P.steps[st];
+    uint32_t cnt = 0;
+    if (st == 0 || P.steps[st - 1].commit != 0) {
+      int e = st;
+      while (P.steps[e].commit == 0) ++e;
+      cnt = (uint32_t)(e - st + 1);
+    }
+    uint4 r;
+    r.x = umma_idesc_f16(Op::kFmt, S.n);
+    if (S.a_kind == 0) {
+      const uint32_t a_lo = (uint32_t)umma_desc_k_sw128(smem_u32(arena));
+      r.y = a_lo + (uint32_t)(2 * g + S.a_chunk) * (kAChunkBytes >> 4);
+      r.z = a_lo + (uint32_t)(2 * g + S.a_chunk2) * (kAChunkBytes >> 4);
+    } else {
+      r.y = tmem_base + kTmemAct + kTmemGroup * g + S.a_tmem_col;
+      r.z = 0;
+    }
+    r.w = (uint32_t)S.ksteps | ((uint32_t)S.ksteps2 << 4) | ((uint32_t)(S.a_kind != 0) << 8) | ((uint32_t)S.accumulate << 9) |
+          ((uint32_t)S.wait << 10) | ((uint32_t)S.commit << 12) | (cnt << 14) | (((uint32_t)S.n << 3) << 16);
+    rec[g * kMaxSteps + st] = r;
+  }
+  __syncthreads();
+
+  if (warp >= 8) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));
+  if (warp == 8) {
+    // =============================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        int st = 0;
+        while (st < P.n_steps) {
+          int end = st;
+          while (P.steps[end].commit == 0) ++end;
+          ++end;
+          for (int g = 0; g < kGroups; ++g) {
+            for (int s = st; s < end; ++s) {
+              const MmaStep& S = P.steps[s];
+              const uint32_t bytes = (uint32_t)S.n * 128u * S.n_sub;
+              const uint32_t part = bytes / kCluster;
+              mbar_wait(&empty_bar[stage], phase ^ 1);  // both CTAs' MMAs are done with this slot
+              mbar_arrive_expect_tx(&full_bar[stage], bytes);
+              const uint8_t* src = p.packed + S.w_off + cta_rank * part;
+              uint8_t* dst = ring + stage * kWStageBytes + cta_rank * part;
+              if (kCluster > 1) tma_bulk_g2s_mcast(dst, src, part, &full_bar[stage], cmask);
+              else tma_bulk_g2s(dst, src, part, &full_bar[stage]);
+              if (++stage == kNumStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          st = end;
+        }
+      }
+    }
+  } else if (warp == 9 || warp == 10) {
+    // =============================================================== MMA issuers: warp 9 -> tile group 0, warp 10 -> group 1.
+    // Ring slots are filled in the global order [block b, group 0][block b, group 1][block b+1, group 0]...; each
+    // issuer consumes its own group's slots and steps over the other's.  Everything a step needs was decoded into
+    // one 16-byte record (rec[]) at kernel start, so a step costs one LDS, two barrier polls and the MMAs.
+    const int g = warp - 9;
+    uint32_t stage = 0, phase = 0;
+    uint32_t bar_phase = 0;  // bit i = parity of c2m[g][i]
+    const uint32_t desc_hi = (uint32_t)(umma_desc_k_sw128(0) >> 32);
+    const uint32_t bd_lo0 = (uint32_t)umma_desc_k_sw128(smem_u32(ring));
+    const uint32_t d = tmem_base + kTmemAcc + kTmemGroup * g;
+    const uint32_t rec_s = smem_u32(rec) + (uint32_t)g * kMaxSteps * 16u;
+    uint64_t* c2m_g = c2m + 4 * g;
+    uint64_t* m2c_g = m2c + 4 * g;
+    auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
+    // Step over the other group's slots.  Their fill is still observed: a parity wait cannot tell "fill n+1 done" from
+    // "fill n not yet done", so an issuer must never wait for a stage's next fill before it has seen the previous one.
+    auto skip = [&](uint32_t cnt) {
+      for (uint32_t j = 0; j < cnt; ++j) {
+        mbar_wait(&full_bar[stage], phase);
+        if (++stage == kNumStages) { stage = 0; phase ^= 1; }
+      }
+    };
+    for (int it = 0; it < iters; ++it) {
+      int st = 0;
+#pragma unroll 1
+      while (st < n_steps) {
+        const uint32_t cnt = (lds32u(rec_s + 16u * st + 12u) >> 14) & 3u;  // steps in this block (1..3)
+        if (g == 1) skip(cnt);
+#pragma unroll 1
+        for (uint32_t j = 0; j < cnt; ++j) {
+          const uint4 r = lds128u(rec_s + 16u * (st + j));
+          const uint32_t fl = r.w, wt = (fl >> 10) & 3u, cm = (fl >> 12) & 3u;
+          if (wt) {
+            mbar_wait(&c2m_g[wt], (bar_phase >> wt) & 1u);
+            bar_phase ^= 1u << wt;
+          }
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint32_t idesc = r.x, ks = fl & 15u, ks2 = (fl >> 4) & 15u, acc0 = (fl >> 9) & 1u;
+            const uint32_t bd = bd_lo0 + stage * (kWStageBytes >> 4), bd2 = bd + (fl >> 16);
+            if (fl & 256u) {  // TS: A operand from TMEM
+              const uint32_t a = r.y, a2 = r.y + 8u * ks;
+              if (ks == 4) {
+                umma_f16_ts(d, a, mk(bd), idesc, acc0);
+                umma_f16_ts(d, a + 8, mk(bd + 2), idesc, 1u);
+                umma_f16_ts(d, a + 16, mk(bd + 4), idesc, 1u);
+                umma_f16_ts(d, a + 24, mk(bd + 6), idesc, 1u);
+              } else {
+                for (uint32_t k = 0; k < ks; ++k) umma_f16_ts(d, a + 8 * k, mk(bd + 2 * k), idesc, k ? 1u : acc0);
+              }
+              if (ks2 == 4) {
+                umma_f16_ts(d, a2, mk(bd2), idesc, 1u);
+                umma_f16_ts(d, a2 + 8, mk(bd2 + 2), idesc, 1u);
+                umma_f16_ts(d, a2 + 16, mk(bd2 + 4), idesc, 1u);
+                umma_f16_ts(d, a2 + 24, mk(bd2 + 6), idesc, 1u);
+              } else {
+                for (uint32_t k = 0; k < ks2; ++k) umma_f16_ts(d, a2 + 8 * k, mk(bd2 + 2 * k), idesc, 1u);
+              }
+            } else {  // SS: A operand = embedding chunk(s) in shared memory
+              for (uint32_t k = 0; k < ks; ++k) umma_f16_ss(d, mk(r.y + 2 * k), mk(bd + 2 * k), idesc, k ? 1u : acc0);
+              for (uint32_t k = 0; k < ks2; ++k) umma_f16_ss(d, mk(r.z + 2 * k), mk(bd2 + 2 * k), idesc, 1u);
+            }
+            // frees the ring slot (in both CTAs) once these MMAs have read it
+            if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);
+            else umma_commit(&empty_bar[stage]);
+            if (cm) umma_commit(&m2c_g[cm]);
+          }
+          __syncwarp();
+          if (++stage == kNumStages) { stage = 0; phase ^= 1; }
+        }
+        if (g == 0) skip(cnt);
+        st += (int)cnt;
+      }
+    }
+  }
+  } else {
+    // =============================================================== compute / epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
+    const int g = warp >> 2, q = warp & 3;
+    const int gtid = threadIdx.x & (kGroupThreads - 1);
+    const uint32_t row = (uint32_t)(q * 32 + lane);  // tile row == TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t tD = t_lane + kTmemAcc + kTmemGroup * g;  // this group's accumulator
+    const uint32_t tA = t_lane + kTmemAct + kTmemGroup * g;  // this group's 16-bit activations (2 per column)
+    uint64_t* c2m_g = c2m + 4 * g;
+    uint64_t* m2c_g = m2c + 4 * g;
+    uint32_t all_phase = 0, half_phase = 0;
+    constexpr int HN = WIDTH / 2, NBLK = HN / 32;  // N-half of the wide layers; 32-column blocks per half
+    const int lid_delta = 0, lid_vis = B > 0 ? 3 : 0, lid_base = lid_vis + 2, lid_rgb0 = lid_base + p.desc.D + 1,
+              lid_color = lid_rgb0 + 1, lid_feat = lid_color + 3, lid_dense = lid_feat + (p.desc.has_feature ? 6 : 0);
+    const ConstLayout& CL = P.cl;
+    const FrameLayout& FL = P.fl;
+    float* fblk_g = fblk + g * FL.n_floats;
+    const uint32_t cblk_s = smem_u32(cblk), fblk_s = smem_u32(fblk_g);
+    const uint32_t pe_s = smem_u32(arena) + g * kArenaGroup, extra_s = pe_s + kAChunkBytes;
+    const uint32_t rowx = row * 128u + ((row & 7u) << 4);  // 16-B group gq of this row lives at chunk + (rowx ^ (gq << 4))
+    const uint32_t sc_s = cblk_s + 4u * CL.scalars;
+    uint4* scr = p.scratch + ((size_t)blockIdx.x * kGroups + g) * (kTileRows * 32) + row;  // [32 uint4][128 rows]
+
+    // stage the constant block once
+    {
+      const float4* src = reinterpret_cast<const float4*>(p.workspace);
+      float4* dst = reinterpret_cast<float4*>(cblk);
+      for (int i = threadIdx.x; i < CL.n_floats / 4; i += kComputeThreads) dst[i] = __ldg(src + i);
+    }
+    named_bar_sync(3, kComputeThreads);
+
+    auto warp_arrive = [&](uint64_t* bar) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    auto arrive_all = [&]() {
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      warp_arrive(&c2m_g[BAR_ALL]);
+    };
+    auto wait_all = [&]() {
+      mbar_wait(&m2c_g[BAR_ALL], all_phase);
+      all_phase ^= 1;
+      tc_fence_after_sync();
+    };
+    auto gemm = [&]() { arrive_all(); wait_all(); };
+    auto wait_half = [&](int nh) {
+      mbar_wait(&m2c_g[BAR_H0 + nh], (half_phase >> nh) & 1u);
+      half_phase ^= 1u << nh;
+      tc_fence_after_sync();
+    };
+    auto bias_s = [&](int layer) -> uint32_t { return (P.bias[layer].frame ? fblk_s : cblk_s) + 4u * P.bias[layer].off; };
+    // 32 accumulator columns + bias -> relu -> 16 packed columns
+    auto relu_pack32 = [&](const uint32_t (&ra)[32], uint32_t bias, uint32_t (&o)[16]) {
+#pragma unroll
+      for (int g4 = 0; g4 < 8; ++g4) {
+        const float4 b = lds128(bias + 16u * g4);
+        o[2 * g4] = Op::pack2_relu(__uint_as_float(ra[4 * g4 + 0]) + b.x, __uint_as_float(ra[4 * g4 + 1]) + b.y);
+        o[2 * g4 + 1] = Op::pack2_relu(__uint_as_float(ra[4 * g4 + 2]) + b.z, __uint_as_float(ra[4 * g4 + 3]) + b.w);
+      }
+    };
+    // finished GEMM of n (<= 128) columns: relu(acc + bias) -> activations [0, n)
+    auto epi_relu_act = [&](uint32_t bias, int n) {
+#pragma unroll 1
+      for (int blk = 0; blk < (n >> 5); ++blk) {
+        uint32_t ra[32], o[16];
+        tmem_ld32_issue(tD + 32 * blk, ra);
+        tmem_ld_wait32(ra);
+        relu_pack32(ra, bias + 128u * blk, o);
+        tmem_st16(tA + 16 * blk, o);
+      }
+      tmem_st_wait();
+    };
+    // One 2*hn-wide layer issued as two N-halves on this group's accumulator (program.h pipe5).
+    //   MODE 0: relu(acc + bias) -> activations (in place: half 0 is held in registers until the layer's MMAs are done)
+    //   MODE 1: basefield.linear_final: relu features -> packed into the per-row scratch, fp32 dot with sdf.weight
+    //   MODE 2: colorfield.linear_final: relu(acc + bias) + base features (scratch) -> activations (input of rgb.0)
+    float sdf_acc = 0.f;
+    auto chain_layer = [&](auto mode_tag, uint32_t bias) {
+      constexpr int MODE = decltype(mode_tag)::value;
+      uint32_t hold[NBLK][16];
+      auto math = [&](const uint32_t (&ra)[32], int col0, uint32_t (&o)[16]) {  // col0: first feature of these 32 columns
+        const uint32_t ba = bias + 4u * (uint32_t)col0;
+        if (MODE == 0) {
+          relu_pack32(ra, ba, o);
+        } else if (MODE == 1) {
+          const uint32_t wa = cblk_s + 4u * (CL.sdf_w + col0);
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int g4 = 0; g4 < 8; ++g4) {
+            const float4 b = lds128(ba + 16u * g4), w = lds128(wa + 16u * g4);
+            const float y0 = fmaxf(__uint_as_float(ra[4 * g4 + 0]) + b.x, 0.f), y1 = fmaxf(__uint_as_float(ra[4 * g4 + 1]) + b.y, 0.f);
+            const float y2 = fmaxf(__uint_as_float(ra[4 * g4 + 2]) + b.z, 0.f), y3 = fmaxf(__uint_as_float(ra[4 * g4 + 3]) + b.w, 0.f);
+            s0 += y0 * w.x + y2 * w.z;
+            s1 += y1 * w.y + y3 * w.w;
+            o[2 * g4] = Op::pack2(y0, y1);
+            o[2 * g4 + 1] = Op::pack2(y2, y3);
+          }
+          sdf_acc += s0 + s1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) scr[(size_t)((col0 >> 3) + j) * kTileRows] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 bf = scr[(size_t)((col0 >> 3) + j) * kTileRows];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int g4 = 2 * j + hh;
+              const float4 b = lds128(ba + 16u * g4);
+              const float2 f0 = Op::unpack2(hh ? bf.z : bf.x), f1 = Op::unpack2(hh ? bf.w : bf.y);
+              o[2 * g4] = Op::pack2(fmaxf(__uint_as_float(ra[4 * g4 + 0]) + b.x, 0.f) + f0.x, fmaxf(__uint_as_float(ra[4 * g4 + 1]) + b.y, 0.f) + f0.y);
+              o[2 * g4 + 1] = Op::pack2(fmaxf(__uint_as_float(ra[4 * g4 + 2]) + b.z, 0.f) + f1.x, fmaxf(__uint_as_float(ra[4 * g4 + 3]) + b.w, 0.f) + f1.y);
+            }
+          }
+        }
+      };
+      // ---- N-half 0: drain the accumulator so the MMAs of half 1 can start
+      wait_half(0);
+#pragma unroll
+      for (int blk = 0; blk < NBLK; ++blk) {
+        uint32_t ra[32];
+        tmem_ld32_issue(tD + 32 * blk, ra);
+        tmem_ld_wait32(ra);
+        math(ra, 32 * blk, hold[blk]);
+      }
+      tc_fence_before_sync();
+      warp_arrive(&c2m_g[BAR_H0]);
+      // ---- N-half 1: the layer's input has been read, activations can be overwritten
+      wait_half(1);
+      if (MODE != 1) {
+#pragma unroll
+        for (int blk = 0; blk < NBLK; ++blk) tmem_st16(tA + 16 * blk, hold[blk]);
+      }
+#pragma unroll
+      for (int blk = 0; blk < NBLK; ++blk) {
+        uint32_t ra[32], o[16];
+        tmem_ld32_issue(tD + 32 * blk, ra);
+        tmem_ld_wait32(ra);
+        math(ra, HN + 32 * blk, o);
+        if (MODE != 1) tmem_st16(tA + (HN >> 1) + 16 * blk, o);
+      }
+      if (MODE != 1) tmem_st_wait();
+      tc_fence_before_sync();
+      warp_arrive(&c2m_g[BAR_H1]);
+    };
+
+    // 16-bit element `c` (0..63) of this row in an operand chunk
+    auto put16 = [&](uint32_t chunk_s, int c, float val) { sts16(chunk_s + (rowx ^ ((uint32_t)(c >> 3) << 4)) + 2u * (c & 7), Op::cvt(val)); };
+    // Fourier features of x: column e < 3 -> x_e, else frequency (e-3)/6, sin for (e-3)%6 < 3 (PosEmbedding.forward,
+    // nnutils/embedding.py:69-125).  Columns 0..62 live in CH_PE, 63.. in CH_EXTRA.
+    auto embed = [&](const float3& x, int nfreq) {
+      auto put = [&](int e, float val) { put16(e < 63 ? pe_s : extra_s, e < 63 ? e : e - 63, val); };
+      put(0, x.x); put(1, x.y); put(2, x.z);
+      float fr = 1.0f;
+#pragma unroll 1
+      for (int kf = 0; kf < nfreq; ++kf) {
+        float s0, s1, s2, c0, c1, c2;
+        sincosf(fr * x.x, &s0, &c0);
+        sincosf(fr * x.y, &s1, &c1);
+        sincosf(fr * x.z, &s2, &c2);
+        const int e0 = 3 + 6 * kf;
+        put(e0, s0); put(e0 + 1, s1); put(e0 + 2, s2);
+        put(e0 + 3, c0); put(e0 + 4, c1); put(e0 + 5, c2);
+        fr *= 2.0f;
+      }
+    };
+    // DenseWarp.forward (nnutils/warping.py:143-170): x + 0.1 * CondMLP([PE6(x), t, inst]); the per-frame codes are
+    // folded into the linear_1 bias row `bias1`; lid0 = canonical id of the map's linear_1.
+    auto dense_warp = [&](const float3& x, uint32_t bias1, int lid0) -> float3 {
+      embed(x, 6);
+      put16(pe_s, 39, 0.f);  // 39 embedding columns; the third k-step reads up to column 47
+      sts128(pe_s + (rowx ^ (5u << 4)), make_uint4(0u, 0u, 0u, 0u));
+      arrive_all();
+#pragma unroll 1
+      for (int l = 0; l < 2; ++l) chain_layer(IC<0>{}, l == 0 ? bias1 : bias_s(lid0 + 1));
+      wait_all();
+      float m[16];
+      tmem_ld16(tD, m);
+      const uint32_t b3 = bias_s(lid0 + 2);
+      return make_float3(x.x + 0.1f * (m[0] + lds32(b3)), x.y + 0.1f * (m[1] + lds32(b3 + 4)), x.z + 0.1f * (m[2] + lds32(b3 + 8)));
+    };
+
+    for (int it = 0; it < iters; ++it) {
+      const int tile_raw = (2 * it + g) * (int)gridDim.x + (int)blockIdx.x;
+      const bool dead_tile = tile_raw >= p.n_tiles;
+      const int tile = dead_tile ? p.n_tiles - 1 : tile_raw;
+      const int f = tile / p.tiles_per_frame;
+      const int r_raw = (tile - f * p.tiles_per_frame) * kTileRows + (int)row;
+      const bool live = !dead_tile && r_raw < p.ND;
+      const int r_in = r_raw < p.ND ? r_raw : p.ND - 1;
+      const int n = r_in / p.rays.D;
+      const int k = r_in - n * p.rays.D;
+      const size_t s = (size_t)f * p.ND + r_in;
+
+      // ------------------------------------------------ stage this frame's block in shared memory
+      named_bar_sync(1 + g, kGroupThreads);  // the group is done with the previous block
+      {
+        const float4* src = reinterpret_cast<const float4*>(p.workspace + CL.n_floats + (size_t)f * FL.n_floats);
+        float4* dst = reinterpret_cast<float4*>(fblk_g);
+        for (int i = gtid; i < FL.n_floats / 4; i += kGroupThreads) dst[i] = __ldg(src + i);
+      }
+      named_bar_sync(1 + g, kGroupThreads);
+
+      // ------------------------------------------------ sample placement (sample_cam_rays)
+      const float* hx = p.rays.hxy + ((size_t)f * p.rays.N + n) * 3;
+      const float h0 = __ldg(hx), h1 = __ldg(hx + 1), h2 = __ldg(hx + 2);
+      const float* cam = fblk_g + FL.cam;
+      float3 d = make_float3(h0 * cam[0] + h1 * cam[1] + h2 * cam[2], h0 * cam[3] + h1 * cam[4] + h2 * cam[5],
+                             h0 * cam[6] + h1 * cam[7] + h2 * cam[8]);
+      const float dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+      const float nearv = cam[9], farv = cam[10];
+      const int Dn = p.rays.D;
+      const float step = 1.0f / (float)(Dn - 1);
+      auto lin = [&](int i) { return i < Dn / 2 ? step * (float)i : 1.0f - step * (float)(Dn - 1 - i); };
+      auto depth_at = [&](int i) { float z = lin(i); return nearv * (1.0f - z) + farv * z; };
+      const float depth = depth_at(k);
+      const float delta = (k + 1 < Dn ? depth_at(k + 1) - depth : depth - depth_at(k - 1)) * dn;
+      const float3 xyz_cam = make_float3(d.x * depth, d.y * depth, d.z * depth);
+      const float3 dir_cam = make_float3(d.x / dn, d.y / dn, d.z / dn);
+
+      // ------------------------------------------------ camera -> field (cam_to_field)
+      const Q4 qc = {cam[11], cam[12], cam[13], cam[14]};
+      const Q4 qi = qconj(qc);
+      const float3 ti = qrot(qi, make_float3(-cam[15], -cam[16], -cam[17]));
+      float3 xyz_t = qrot(qi, xyz_cam);
+      xyz_t.x += ti.x; xyz_t.y += ti.y; xyz_t.z += ti.z;
+      const float3 dir_f = qrot(qi, dir_cam);
+
+      // ------------------------------------------------ skinning warps (SkinningWarp.forward), three per sample:
+      //   w = 0 backward warp (time-t -> canonical), w = 1 forward warp with the pair partner's articulation (flow),
+      //   w = 2 forward warp with the frame's own articulation (cycle).
+      // bone coordinates -> delta MLP on the tensor pipe -> softmax -> dual-quaternion blend.
+      constexpr int NP = B > 0 ? (3 * B + 15) / 16 * 8 : 1;  // packed pairs of the zero-padded bone-coordinate row
+      auto skin_warp = [&](const float3& x, uint32_t binv, uint32_t se3, uint32_t bias1, float& entropy, float& delta_skin) -> float3 {
+        float dist2[B > 0 ? B : 1];
+        {
+          uint32_t u[NP];
+#pragma unroll
+          for (int i = 0; i < NP; ++i) u[i] = 0u;
+#pragma unroll
+          for (int b2 = 0; b2 < (B + 1) / 2; ++b2) {
+            float v[6];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int b = 2 * b2 + j;
+              if (b < B) {
+                const uint32_t ba = binv + 48u * b;
+                const float4 r0 = lds128(ba), r1 = lds128(ba + 16), r2 = lds128(ba + 32);
+                v[3 * j + 0] = r0.x * x.x + r0.y * x.y + r0.z * x.z + r0.w;
+                v[3 * j + 1] = r1.x * x.x + r1.y * x.y + r1.z * x.z + r1.w;
+                v[3 * j + 2] = r2.x * x.x + r2.y * x.y + r2.z * x.z + r2.w;
+                dist2[b] = v[3 * j] * v[3 * j] + v[3 * j + 1] * v[3 * j + 1] + v[3 * j + 2] * v[3 * j + 2];
+              } else {
+                v[3 * j] = v[3 * j + 1] = v[3 * j + 2] = 0.f;
+              }
+            }
+            u[3 * b2] = Op::pack2(v[0], v[1]);
+            u[3 * b2 + 1] = Op::pack2(v[2], v[3]);
+            u[3 * b2 + 2] = Op::pack2(v[4], v[5]);
+          }
+          tmem_st32(tA, u);
+          if (NP > 32) tmem_st8(tA + 32, u + (NP > 32 ? 32 : 0));
+          tmem_st_wait();
+        }
+        // delta_field.linear_1 / linear_2 (ReLU) and linear_final
+        gemm();
+        epi_relu_act(bias1, 64);
+        gemm();
+        epi_relu_act(bias_s(lid_delta + 1), 64);
+        gemm();
+        float dl[32];
+        tmem_ld32(tD, dl);
+        const uint32_t b3 = bias_s(lid_delta + 2);
+        float mx = -INFINITY, dsum = 0.f;
+        int amax = 0;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+          const float dv = 0.1f * fmaxf(dl[j] + lds32(b3 + 4u * j), 0.f);
+          dsum += dv * dv;
+          const float lg = -(dist2[j] + dv);
+          dist2[j] = lg;
+          if (lg > mx) { mx = lg; amax = j; }  // first maximum wins, like argmax
+        }
+        const float4 qa = lds128(se3 + 32u * amax);
+        float se = 0.f;
+        float4 qr = make_float4(0.f, 0.f, 0.f, 0.f), qd = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+          const uint32_t sa = se3 + 32u * j;
+          const float e = __expf(dist2[j] - mx);
+          se += e;
+          const float4 r = lds128(sa), dq = lds128(sa + 16);
+          const float dot = qa.x * r.x + qa.y * r.y + qa.z * r.z + qa.w * r.w;
+          const float wgt = dot > 0.f ? e : -e;  // the softmax denominator cancels in the normalisation below
+          qr.x += wgt * r.x; qr.y += wgt * r.y; qr.z += wgt * r.z; qr.w += wgt * r.w;
+          qd.x += wgt * dq.x; qd.y += wgt * dq.y; qd.z += wgt * dq.z; qd.w += wgt * dq.w;
+        }
+        entropy = __logf(se);  // logsumexp - max  (cross_entropy_skin_loss)
+        delta_skin = dsum / (float)(B > 0 ? B : 1);
+        // stored order is (w,x,y,z) in (.x,.y,.z,.w)
+        const float inv = rsqrtf(qr.x * qr.x + qr.y * qr.y + qr.z * qr.z + qr.w * qr.w);
+        const Q4 Qr = {qr.x * inv, qr.y * inv, qr.z * inv, qr.w * inv};
+        const Q4 Qd = {qd.x * inv, qd.y * inv, qd.z * inv, qd.w * inv};
+        const Q4 tq = qmul(Qd, qconj(Qr));
+        float3 o = qrot(Qr, x);
+        o.x += 2.f * tq.x; o.y += 2.f * tq.y; o.z += 2.f * tq.z;
+        return o;
+      };
+
+      float3 xyz = xyz_t, x_next = xyz_t;
+      float ent_b = 0.f, dsk_b = 0.f, ent_out = 0.f, dsk_out = 0.f, cyc = 0.f;
+      if constexpr (B > 0) {
+        // ComposedWarp (warping.py:445-483) interleaves the DenseWarp soft deformation: backward = skin then dense,
+        // forward = dense then skin.  One loop over stages keeps a single inlined copy of either body.
+        constexpr int NST = DENSE ? 6 : 3;
+        float3 cur = xyz_t;
+#pragma unroll 1
+        for (int stg = 0; stg < NST; ++stg) {
+          const int w = DENSE ? (stg >> 1) : stg;
+          if (DENSE && (stg == 1 || stg == 2 || stg == 4)) {
+            const uint32_t bias1 = stg == 1 ? bias_s(lid_dense + 3) : (stg == 2 ? fblk_s + 4u * FL.dense1_partner : bias_s(lid_dense));
+            cur = dense_warp(stg == 1 ? cur : xyz, bias1, stg == 1 ? lid_dense + 3 : lid_dense);
+            if (stg == 1) xyz = cur;
+            continue;
+          }
+          const float3 src = w == 0 ? xyz_t : (DENSE ? cur : xyz);
+          const uint32_t binv = fblk_s + 4u * (w == 0 ? FL.binv_t : (w == 1 ? FL.binv_rest_partner : FL.binv_rest));
+          const uint32_t se3 = fblk_s + 4u * (w == 0 ? FL.se3_bwd : (w == 1 ? FL.se3_fwd_partner : FL.se3_fwd));
+          const uint32_t bias1 = w == 0 ? bias_s(lid_delta) : fblk_s + 4u * FL.delta1_fwd;  // forward warps: mean time code
+          float e, dk;
+          const float3 o = skin_warp(src, binv, se3, bias1, e, dk);
+          if (w == 0) { cur = o; xyz = o; ent_b = e; dsk_b = dk; }
+          else if (w == 1) { x_next = o; }
+          else {
+            const float dx = o.x - xyz_t.x, dy = o.y - xyz_t.y, dz = o.z - xyz_t.z;
+            cyc = sqrtf(dx * dx + dy * dy + dz * dz);
+            ent_out = 0.5f * (e + ent_b);
+            dsk_out = 0.5f * (dk + dsk_b);
+          }
+        }
+      } else {
+        x_next = xyz;
+      }
+
+      // ------------------------------------------------ outputs that are final before the MLPs run
+      auto st3 = [&](float* dst, float a, float b, float c) { if (dst && live) { dst[s * 3] = a; dst[s * 3 + 1] = b; dst[s * 3 + 2] = c; } };
+      auto st1 = [&](float* dst, float a) { if (dst && live) dst[s] = a; };
+      {
+        // field_to_cam with the partner frame's camera, pinhole projection, flow (nerf.py:948-997)
+        const float* cn = fblk_g + FL.cam_partner;
+        const Q4 qn = {cn[11], cn[12], cn[13], cn[14]};
+        float3 xc = qrot(qn, x_next);
+        xc.x += cn[15]; xc.y += cn[16]; xc.z += cn[17];
+        const float k0 = cn[0], k1 = cn[4], k2 = cn[2], k3 = cn[5];
+        const float fx = 1.0f / k0, fy = 1.0f / k1, cx = -k2 / k0, cy = -k3 / k1;
+        const float hxn = (fx * xc.x + cx * xc.z) / (xc.z + 1e-6f);
+        const float hyn = (fy * xc.y + cy * xc.z) / (xc.z + 1e-6f);
+        const float fl0 = hxn - h0, fl1 = hyn - h1;
+        bool valid = xc.z > 1e-6f;
+        if (p.rays.flow_thresh >= 0.f) valid = valid && (sqrtf(fl0 * fl0 + fl1 * fl1) < p.rays.flow_thresh);
+        st3(p.out.flow, fl0, fl1, valid ? 1.f : 0.f);
+        // Gaussian bone density (compute_gauss_density): max_b exp(-d2_b / 2) = exp(-min_b d2_b / 2)
+        if constexpr (B > 0) {
+          float best = INFINITY;
+          const uint32_t ctr = cblk_s + 4u * CL.center;
+#pragma unroll 5
+          for (int b = 0; b < B; ++b) {
+            const float4 c = lds128(ctr + 16u * b);
+            const float dx = xyz.x - c.x, dy = xyz.y - c.y, dz = xyz.z - c.z;
+            best = fminf(best, dx * dx + dy * dy + dz * dz);
+          }
+          st1(p.out.gauss_density, expf(-0.5f * (best / (0.01f * 0.01f))) * lds32(sc_s + 4u * SC_WARP_IBETA));
+        }
+        st3(p.out.xyz, xyz.x, xyz.y, xyz.z);
+        st3(p.out.xyz_cam, xyz_cam.x, xyz_cam.y, xyz_cam.z);
+        st3(p.out.xyz_t, xyz_t.x, xyz_t.y, xyz_t.z);
+        st3(p.out.dir, dir_f.x, dir_f.y, dir_f.z);
+        st1(p.out.depth, depth * lds32(sc_s + 4u * SC_INV_SCALE));
+        st1(p.out.deltas, delta);
+        st1(p.out.cyc_dist, cyc);
+        st1(p.out.delta_skin, dsk_out);
+        st1(p.out.skin_entropy, ent_out);
+      }
+
+      // ------------------------------------------------ positional embedding of the canonical point
+      embed(xyz, LMAX);
+      sts16(pe_s + (rowx ^ (7u << 4)) + 14u, (uint16_t)0);  // zero pad column 63 of CH_PE
+      if (LMAX > 10) {  // CH_EXTRA holds 12 values (columns 63..74); its k-step reads 16 columns
+        sts32(extra_s + (rowx ^ (1u << 4)) + 8u, 0.f);
+        sts32(extra_s + (rowx ^ (1u << 4)) + 12u, 0.f);
+      }
+
+      // ------------------------------------------------ visibility MLP (VisField.forward)
+      gemm();
+      epi_relu_act(bias_s(lid_vis), 64);
+      gemm();
+      {
+        const uint32_t b2 = bias_s(lid_vis + 1), vw = cblk_s + 4u * CL.vis_w;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          float v[32];
+          tmem_ld32(tD + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 ba = lds128(b2 + 4u * (c0 + j)), wa = lds128(vw + 4u * (c0 + j));
+            a0 += fmaxf(v[j] + ba.x, 0.f) * wa.x + fmaxf(v[j + 2] + ba.z, 0.f) * wa.z;
+            a1 += fmaxf(v[j + 1] + ba.y, 0.f) * wa.y + fmaxf(v[j + 3] + ba.w, 0.f) * wa.w;
+          }
+        }
+        st1(p.out.vis, a0 + a1 + lds32(sc_s + 4u * SC_VIS_B));
+      }
+
+      // ------------------------------------------------ feature field (FeatureNeRF.compute_feat)
+      if (p.desc.has_feature) {
+#pragma unroll 1
+        for (int i = 0; i < 5; ++i) {
+          gemm();
+          epi_relu_act(bias_s(lid_feat + i), 128);
+        }
+        gemm();
+        float v16[16];
+        tmem_ld16(tD, v16);
+        const uint32_t bf = bias_s(lid_feat + 5);
+        float nn = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { v16[j] += lds32(bf + 4u * j); nn += v16[j] * v16[j]; }
+        const float inv = rsqrtf(nn);
+        if (p.out.feature && live) {
+          float4* fo = reinterpret_cast<float4*>(p.out.feature + s * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) fo[j] = make_float4(v16[4 * j] * inv, v16[4 * j + 1] * inv, v16[4 * j + 2] * inv, v16[4 * j + 3] * inv);
+        }
+      }
+
+      // ------------------------------------------------ density + colour chains (NeRF.forward, nnutils/nerf.py:167-215)
+      arrive_all();  // embedding operands written, accumulator and activations free
+      sdf_acc = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < p.desc.D; ++j) chain_layer(IC<0>{}, bias_s(lid_base + j));
+      chain_layer(IC<1>{}, bias_s(lid_base + p.desc.D));
+      const float sdf = sdf_acc + lds32(sc_s + 4u * SC_SDF_B);
+      const float ibeta = lds32(sc_s + 4u * SC_IBETA);
+      const float sgn = sdf > 0.f ? 1.f : (sdf < 0.f ? -1.f : 0.f);
+      st1(p.out.density, (0.5f + 0.5f * sgn * expm1f(-fabsf(sdf) * ibeta)) * ibeta);
+      st1(p.out.sdf, sdf);
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) chain_layer(IC<0>{}, bias_s(lid_color + j));
+      chain_layer(IC<2>{}, bias_s(lid_color + 2));
+      // rgb.0 on (base + colour features), then rgb.2 + sigmoid
+      wait_all();
+      {
+        const uint32_t b0 = bias_s(lid_rgb0), w2 = cblk_s + 4u * CL.rgb2_w, wd = cblk_s + 4u * CL.dir_w;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < HN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tD + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = lds128(b0 + 4u * (c0 + j));
+            const float4 wr = lds128(w2 + 4u * (c0 + j)), wg = lds128(w2 + 4u * (HN + c0 + j)), wb = lds128(w2 + 4u * (2 * HN + c0 + j));
+            float pre[4] = {v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w};
+            if (p.desc.L_dir == 0) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t da = wd + 12u * (c0 + j + u);
+                pre[u] += lds32(da) * dir_f.x + lds32(da + 4) * dir_f.y + lds32(da + 8) * dir_f.z;
+              }
+            }
+            const float h0_ = fmaxf(pre[0], 0.f), h1_ = fmaxf(pre[1], 0.f), h2_ = fmaxf(pre[2], 0.f), h3_ = fmaxf(pre[3], 0.f);
+            a0 += h0_ * wr.x + h1_ * wr.y + h2_ * wr.z + h3_ * wr.w;
+            a1 += h0_ * wg.x + h1_ * wg.y + h2_ * wg.z + h3_ * wg.w;
+            a2 += h0_ * wb.x + h1_ * wb.y + h2_ * wb.z + h3_ * wb.w;
+          }
+        }
+        a0 += lds32(sc_s + 4u * SC_RGB2_B0); a1 += lds32(sc_s + 4u * SC_RGB2_B1); a2 += lds32(sc_s + 4u * SC_RGB2_B2);
+        st3(p.out.rgb, 1.f / (1.f + __expf(-a0)), 1.f / (1.f + __expf(-a1)), 1.f / (1.f + __expf(-a2)));
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // no CTA exits while its peer may still signal its barriers
+  if (warp == 9) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <class Op, int B, int LMAX, bool DENSE, int WIDTH>
+static cudaError_t launch_one(const FieldKernelParams& p, int n_sm, cudaStream_t stream) {
+  auto kern = field_fwd5_kernel<Op, B, LMAX, DENSE, WIDTH>;
+  const int smem = 1024 + kSmemArena + kSmemRing + (p.prog.cl.n_floats + kGroups * p.prog.fl.n_floats) * 4 + 256 + kGroups * kMaxSteps * 16;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  int grid = (p.n_tiles + 1) / 2 < n_sm ? (p.n_tiles + 1) / 2 : n_sm;
+  grid = (grid + kCluster - 1) / kCluster * kCluster;
+  if (grid > n_sm) grid -= kCluster;
+  if (grid < kCluster) grid = kCluster;
+  if (grid > kMaxCtas) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+}  // namespace v5
+
+cudaError_t launch_field_fwd5(const FieldKernelParams& p, int n_sm, cudaStream_t stream) {
+  const bool bf = p.desc.operand_dtype == 1;
+#define B200R_CASE(BN, LM, DN, WD)                                                                    \
+  if (p.desc.n_bones == BN && p.Lmax == LM && (p.desc.dense != 0) == DN && p.desc.W == WD)            \
+    return bf ? v5::launch_one<OpBF16, BN, LM, DN, WD>(p, n_sm, stream) : v5::launch_one<OpF16, BN, LM, DN, WD>(p, n_sm, stream);
+  B200R_CASE(0, 10, false, 128)
+  B200R_CASE(0, 12, false, 128)
+  B200R_CASE(0, 10, false, 256)
+  B200R_CASE(0, 12, false, 256)
+  B200R_CASE(18, 12, false, 256)
+  B200R_CASE(25, 12, false, 256)
+  B200R_CASE(18, 12, true, 256)
+  B200R_CASE(25, 12, true, 256)
+#undef B200R_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace b200r

@@ -156,7 +156,7 @@ struct BuiltProgram {
   const char* err;
 };
 
-inline BuiltProgram build_program(const b200r_field_desc& d) {
+inline BuiltProgram build_program(const b200r_field_desc& d, int version = 4) {
   BuiltProgram bp;
   bp.ok = false;
   bp.err = "";
@@ -257,10 +257,19 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
     add_layer(L.feat[5], 16, 128, hidden(0, 128));
   }
   const int pe_d = pe_dim(6), DW = 256;  // DenseWarp: 6 frequencies, two hidden layers of 256
+  auto add_split_w = [&](int id, int width, int in_dim, const std::vector<PackSlice>& sls) {
+    add_rows(id, width, in_dim, 0, width / 2, sls, chunks[id]);
+    add_rows(id, width, in_dim, width / 2, width / 2, sls, chunks_h1[id]);
+  };
   if (d.dense) {
     for (int m = 0; m < 2; ++m) {
-      add_layer(L.dense[3 * m + 0], DW, pe_d + TEMB + INST, pe_slices(pe_d, 0));
-      add_layer(L.dense[3 * m + 1], DW, DW, hidden(0, DW));
+      if (version >= 5) {
+        add_split_w(L.dense[3 * m + 0], DW, pe_d + TEMB + INST, pe_slices(pe_d, 0));
+        add_split_w(L.dense[3 * m + 1], DW, DW, hidden(0, DW));
+      } else {
+        add_layer(L.dense[3 * m + 0], DW, pe_d + TEMB + INST, pe_slices(pe_d, 0));
+        add_layer(L.dense[3 * m + 1], DW, DW, hidden(0, DW));
+      }
       add_layer(L.dense[3 * m + 2], 3, DW, hidden(0, DW));
     }
   }
@@ -338,6 +347,7 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
   // emit one step from 1 or 2 consecutive chunks (same operand kind)
   auto step = [&](const Chunk* c, int n_sub, int a_kind, int a_chunk, int a_chunk2, int a_tmem_col, int d_col, int acc, int wait,
                   int commit) {
+    if (ns >= kMaxSteps) { ++ns; return; }  // reported by the caller
     MmaStep& s = P.steps[ns++];
     s = MmaStep{};
     s.w_off = c[0].w_off; s.n = (uint16_t)c[0].n; s.d_col = (uint16_t)d_col; s.a_tmem_col = (uint16_t)a_tmem_col;
@@ -345,6 +355,79 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
     s.ksteps = (uint8_t)c[0].ksteps; s.ksteps2 = (uint8_t)(n_sub > 1 ? c[1].ksteps : 0);
     s.accumulate = (uint8_t)acc; s.wait = (uint8_t)wait; s.commit = (uint8_t)commit;
   };
+  if (version >= 5) {
+    // ------------------------------------------------------------------ v5: two tiles in flight per CTA.
+    // Each tile group owns 128 accumulator columns and 128 columns of 16-bit activations in TMEM; the only
+    // shared-memory operands are the embedding chunks CH_PE / CH_EXTRA.  Steps are grouped in blocks (a block ends
+    // at the step that commits); the MMA warp issues block b for group 0, then for group 1, then block b+1, ...
+    struct Opnd { int kind; int where; };  // kind 0: arena chunk id, kind 1: activation column (16-bit pairs)
+    auto ss = [](int chunk) { return Opnd{0, chunk}; };
+    auto ts = [](int kc) { return Opnd{1, kc * 32}; };
+    auto tsn = [&](int n) { std::vector<Opnd> v; for (int j = 0; j < n; ++j) v.push_back(ts(j)); return v; };
+    auto pe5 = [&](int pe_n) { std::vector<Opnd> v{ss(CH_PE)}; if (pe_n > 63) v.push_back(ss(CH_EXTRA)); return v; };
+    auto cat5 = [](std::vector<Opnd> a, const std::vector<Opnd>& b) { a.insert(a.end(), b.begin(), b.end()); return a; };
+    // one block: D (+)= sum over the chunks of `cs`; consecutive chunks of the same kind share a step when they fit a stage
+    auto block = [&](const std::vector<Chunk>& cs, const std::vector<Opnd>& ops, int wait, int commit) {
+      const size_t n = cs.size();
+      for (size_t c = 0; c < n;) {
+        int nsub = 1;
+        if (c + 1 < n && ops[c].kind == ops[c + 1].kind && 2 * cs[c].n * 128 <= kWStageBytes &&
+            (ops[c].kind == 0 || ops[c + 1].where == ops[c].where + 8 * cs[c].ksteps))
+          nsub = 2;
+        step(&cs[c], nsub, ops[c].kind, ops[c].kind == 0 ? ops[c].where : 0, (nsub > 1 && ops[c].kind == 0) ? ops[c + 1].where : 0,
+             ops[c].kind == 1 ? ops[c].where : 0, 0, c > 0, c == 0 ? wait : BAR_NONE, c + (size_t)nsub == n ? commit : BAR_NONE);
+        c += (size_t)nsub;
+      }
+    };
+    auto seq5 = [&](int id, const std::vector<Opnd>& ops, int wait = BAR_ALL) { block(chunks[id], ops, wait, BAR_ALL); };
+    // split layer: N-half 0 then N-half 1 on the same accumulator (drained in between by the epilogue)
+    auto pipe5 = [&](int id, const std::vector<Opnd>& ops, int first_wait) {
+      block(chunks[id], ops, first_wait, BAR_H0);
+      block(chunks_h1[id], ops, BAR_H0, BAR_H1);
+    };
+    auto delta5 = [&]() {
+      seq5(L.delta[0], 3 * B > 64 ? tsn(2) : tsn(1));
+      seq5(L.delta[1], tsn(1));
+      seq5(L.delta[2], tsn(1));
+    };
+    auto dense5 = [&](int m) {
+      pipe5(L.dense[3 * m + 0], {ss(CH_PE)}, BAR_ALL);
+      pipe5(L.dense[3 * m + 1], tsn(4), BAR_H1);
+      seq5(L.dense[3 * m + 2], tsn(4), BAR_H1);
+    };
+    for (int w = 0; w < 3; ++w) {
+      P.st_delta[w] = ns;
+      if (d.dense && w > 0) dense5(0);
+      if (B > 0) delta5();
+      if (d.dense && w == 0) dense5(1);
+    }
+    P.st_vis = ns;
+    seq5(L.vis[0], pe5(pe_v));
+    seq5(L.vis[1], tsn(1));
+    P.st_feat = ns;
+    if (d.has_feature) {
+      seq5(L.feat[0], pe5(pe_f));
+      for (int i = 1; i < 4; ++i) seq5(L.feat[i], tsn(2));
+      seq5(L.feat[4], cat5(pe5(pe_f), tsn(2)));
+      seq5(L.feat[5], tsn(2));
+    }
+    P.st_base = ns;
+    for (int i = 0; i <= d.D; ++i) {
+      if (i == 0) pipe5(L.base[i], pe5(pe_b), BAR_ALL);
+      else if (i == d.skip) pipe5(L.base[i], cat5(pe5(pe_b), tsn(KC)), BAR_H1);
+      else pipe5(L.base[i], tsn(KC), BAR_H1);
+    }
+    P.st_color = ns;
+    pipe5(L.color[0], pe5(pe_c), BAR_H1);
+    pipe5(L.color[1], tsn(KC), BAR_H1);
+    pipe5(L.color[2], tsn(KC), BAR_H1);
+    P.st_rgb = ns;
+    seq5(L.rgb0, tsn(KC), BAR_H1);
+    P.n_steps = ns;
+    if (ns > kMaxSteps) { bp.err = "too many MMA steps"; return bp; }
+    bp.ok = true;
+    return bp;
+  }
   // sequential GEMM: all compute threads hand over operands (BAR_ALL) and wait for the result (BAR_ALL)
   auto seq_gemm = [&](int id, const std::vector<int>& a_chunks) {
     const auto& cs = chunks[id];
@@ -462,5 +545,10 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
 }
 
 inline size_t workspace_floats(const Program& P, int M) { return (size_t)P.cl.n_floats + (size_t)M * P.fl.n_floats; }
+// v5 keeps the 256 packed base features of every row of both tiles in flight in a per-CTA scratch (L2 resident)
+constexpr int kMaxCtas = 160;
+constexpr size_t kScratchPerCta = 2 * (size_t)kTileRows * 512;
+inline size_t scratch_offset_bytes(const Program& P, int M) { return (workspace_floats(P, M) * sizeof(float) + 255) / 256 * 256; }
+inline size_t workspace_bytes_v5(const Program& P, int M) { return scratch_offset_bytes(P, M) + kMaxCtas * kScratchPerCta; }
 
 }  // namespace b200r

@@ -41,8 +41,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef B200R_WATCHDOG
 #define B200R_WATCHDOG 1
 #endif
+#if B200R_WATCHDOG == 2
+static __device__ int g_b200r_abort;  // debugging: a timed-out wait reports itself and every wait of the kernel gives up
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#if B200R_WATCHDOG
+#if B200R_WATCHDOG == 2
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (((++spins) & 0xFFFFu) == 0) {
+      if (*(volatile int*)&g_b200r_abort) return;
+      if (spins > (1u << 23)) {
+        printf("b200r: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+               smem_u32(bar), parity);
+        *(volatile int*)&g_b200r_abort = 1;
+        __threadfence();
+        return;
+      }
+    }
+  }
+#elif B200R_WATCHDOG
   // A protocol bug would otherwise hang the GPU box: trap after ~seconds of spinning.
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -262,6 +279,25 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+#define B200R_I8(r, o) "r"(r[o + 0]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7])
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31,%32};" ::"r"(taddr),
+      B200R_I8(r, 0), B200R_I8(r, 8), B200R_I8(r, 16), B200R_I8(r, 24)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), B200R_I8(r, 0) : "memory");
+}
+__device__ __forceinline__ void tmem_st16p(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      B200R_I8(r, 0), B200R_I8(r, 8)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -293,6 +329,7 @@ struct OpF16 {
     __half h = __float2half_rn(a);
     return *reinterpret_cast<uint16_t*>(&h);
   }
+  __device__ static __forceinline__ float2 unpack2(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
 };
 struct OpBF16 {
   static constexpr uint32_t kFmt = 1;
@@ -309,6 +346,7 @@ struct OpBF16 {
     __nv_bfloat16 h = __float2bfloat16_rn(a);
     return *reinterpret_cast<uint16_t*>(&h);
   }
+  __device__ static __forceinline__ float2 unpack2(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v)); }
 };
 
 // Byte offset of the 16-byte group `g` (8 halves, g in [0,8)) of row `row` inside a
