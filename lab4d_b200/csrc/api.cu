@@ -165,7 +165,8 @@ int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
   static_assert(sizeof(b200r::PrologueParams) <= 4096 && sizeof(b200r::FieldKernelParams) <= 4096, "kernel parameter space");
   b200r::PrologueParams pp;
   memset(&pp, 0, sizeof(pp));
-  pp.prog = bp.prog;
+  pp.cl = bp.prog.cl;
+  pp.fl = bp.prog.fl;
   pp.desc = *desc;
   pp.par = *par;
   pp.fr = *fr;

@@ -103,9 +103,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd5_kernel(const __grid_co
   uint64_t* c2m = bars + 2 * kNumStages;      // [group][4] compute warps -> MMA thread, indexed by BAR_*
   uint64_t* m2c = bars + 2 * kNumStages + 8;  // [group][4] MMA thread (tcgen05.commit) -> compute warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumStages + 16);
-  uint4* rec = reinterpret_cast<uint4*>(bars + 2 * kNumStages + 18);  // [group][kMaxSteps] decoded MMA steps
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], kCluster); }
     for (int i = 0; i < 8; ++i) { mbar_init(&c2m[i], 4); mbar_init(&m2c[i], 1); }  // one arrival per warp of the group
@@ -116,40 +115,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd5_kernel(const __grid_co
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();  // peer barriers are initialised before any multicast can land
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  if (*tmem_slot != 0) __trap();        // the CTA allocates all 512 columns, so the allocation starts at column 0
+  constexpr uint32_t tmem_base = 0;
   const Program& P = p.prog;
   const int pair_stride = 2 * (int)gridDim.x;
   const int iters = (p.n_tiles + pair_stride - 1) / pair_stride;  // identical in both CTAs of a cluster
   const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0;
   const uint16_t cmask = (uint16_t)((1u << kCluster) - 1);
-  const int n_steps = P.n_steps;
-  // Decode the step list once: x = instruction descriptor, y / z = A operand of the two weight tiles (shared-memory
-  // descriptor low word, or TMEM address), w = ksteps | ksteps2 << 4 | TS << 8 | accumulate << 9 | wait << 10 |
-  // commit << 12 | steps-in-block << 14 (first step of a block) | byte offset >> 4 of the second weight tile << 16.
-  for (int i = threadIdx.x; i < kGroups * n_steps; i += kThreads) {
-    const int g = i / n_steps, st = i - g * n_steps;
-    const MmaStep& S = P.steps[st];
-    uint32_t cnt = 0;
-    if (st == 0 || P.steps[st - 1].commit != 0) {
-      int e = st;
-      while (P.steps[e].commit == 0) ++e;
-      cnt = (uint32_t)(e - st + 1);
-    }
-    uint4 r;
-    r.x = umma_idesc_f16(Op::kFmt, S.n);
-    if (S.a_kind == 0) {
-      const uint32_t a_lo = (uint32_t)umma_desc_k_sw128(smem_u32(arena));
-      r.y = a_lo + (uint32_t)(2 * g + S.a_chunk) * (kAChunkBytes >> 4);
-      r.z = a_lo + (uint32_t)(2 * g + S.a_chunk2) * (kAChunkBytes >> 4);
-    } else {
-      r.y = tmem_base + kTmemAct + kTmemGroup * g + S.a_tmem_col;
-      r.z = 0;
-    }
-    r.w = (uint32_t)S.ksteps | ((uint32_t)S.ksteps2 << 4) | ((uint32_t)(S.a_kind != 0) << 8) | ((uint32_t)S.accumulate << 9) |
-          ((uint32_t)S.wait << 10) | ((uint32_t)S.commit << 12) | (cnt << 14) | (((uint32_t)S.n << 3) << 16);
-    rec[g * kMaxSteps + st] = r;
-  }
-  __syncthreads();
 
   if (warp >= 8) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));
@@ -184,77 +156,93 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd5_kernel(const __grid_co
   } else if (warp == 9 || warp == 10) {
     // =============================================================== MMA issuers: warp 9 -> tile group 0, warp 10 -> group 1.
     // Ring slots are filled in the global order [block b, group 0][block b, group 1][block b+1, group 0]...; each
-    // issuer consumes its own group's slots and steps over the other's.  Everything a step needs was decoded into
-    // one 16-byte record (rec[]) at kernel start, so a step costs one LDS, two barrier polls and the MMAs.
+    // issuer consumes its own group's slots and steps over the other's.  Everything here is warp-uniform and comes
+    // from the kernel parameters (MmaBlock), so descriptors and addresses stay in uniform registers.
     const int g = warp - 9;
     uint32_t stage = 0, phase = 0;
     uint32_t bar_phase = 0;  // bit i = parity of c2m[g][i]
     const uint32_t desc_hi = (uint32_t)(umma_desc_k_sw128(0) >> 32);
     const uint32_t bd_lo0 = (uint32_t)umma_desc_k_sw128(smem_u32(ring));
-    const uint32_t d = tmem_base + kTmemAcc + kTmemGroup * g;
-    const uint32_t rec_s = smem_u32(rec) + (uint32_t)g * kMaxSteps * 16u;
+    const uint32_t ad_lo0 = (uint32_t)umma_desc_k_sw128(smem_u32(arena)) + (uint32_t)g * (kArenaGroup >> 4);
+    const uint32_t d = kTmemAcc + kTmemGroup * g;      // TMEM base is 0 (checked above): the CTA owns all 512 columns
+    const uint32_t act0 = kTmemAct + kTmemGroup * g;
     uint64_t* c2m_g = c2m + 4 * g;
     uint64_t* m2c_g = m2c + 4 * g;
     auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
+    auto advance = [&]() { if (++stage == kNumStages) { stage = 0; phase ^= 1; } };
     // Step over the other group's slots.  Their fill is still observed: a parity wait cannot tell "fill n+1 done" from
     // "fill n not yet done", so an issuer must never wait for a stage's next fill before it has seen the previous one.
     auto skip = [&](uint32_t cnt) {
       for (uint32_t j = 0; j < cnt; ++j) {
         mbar_wait(&full_bar[stage], phase);
-        if (++stage == kNumStages) { stage = 0; phase ^= 1; }
+        advance();
       }
     };
+    auto release = [&]() {  // frees the ring slot (in both CTAs) once the MMAs issued so far have read it
+      if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);
+      else umma_commit(&empty_bar[stage]);
+    };
+    const int n_blocks = P.n_blocks;
     for (int it = 0; it < iters; ++it) {
-      int st = 0;
 #pragma unroll 1
-      while (st < n_steps) {
-        const uint32_t cnt = (lds32u(rec_s + 16u * st + 12u) >> 14) & 3u;  // steps in this block (1..3)
+      for (int b = 0; b < n_blocks; ++b) {
+        const MmaBlock& Bk = P.blocks[b];
+        const uint32_t n = (uint32_t)Bk.n16 << 4, ss = Bk.ss, ts_slots = Bk.ts_slots, cnt = (ss ? 1u : 0u) + ts_slots;
+        const uint32_t idesc = umma_idesc_f16(Op::kFmt, 0) | ((n >> 3) << 17);
+        const uint32_t tile2 = n << 3;  // descriptor offset of a slot's second weight tile (n rows x 128 B)
         if (g == 1) skip(cnt);
-#pragma unroll 1
-        for (uint32_t j = 0; j < cnt; ++j) {
-          const uint4 r = lds128u(rec_s + 16u * (st + j));
-          const uint32_t fl = r.w, wt = (fl >> 10) & 3u, cm = (fl >> 12) & 3u;
-          if (wt) {
-            mbar_wait(&c2m_g[wt], (bar_phase >> wt) & 1u);
-            bar_phase ^= 1u << wt;
-          }
+        const uint32_t wt = Bk.wait, cm = Bk.commit;
+        if (wt) {
+          mbar_wait(&c2m_g[wt], (bar_phase >> wt) & 1u);
+          bar_phase ^= 1u << wt;
+        }
+        uint32_t acc = 0;
+        if (ss) {  // embedding chunk(s) from shared memory
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
+          const uint32_t bd = bd_lo0 + stage * (kWStageBytes >> 4);
           if (elect_one()) {
-            const uint32_t idesc = r.x, ks = fl & 15u, ks2 = (fl >> 4) & 15u, acc0 = (fl >> 9) & 1u;
-            const uint32_t bd = bd_lo0 + stage * (kWStageBytes >> 4), bd2 = bd + (fl >> 16);
-            if (fl & 256u) {  // TS: A operand from TMEM
-              const uint32_t a = r.y, a2 = r.y + 8u * ks;
-              if (ks == 4) {
-                umma_f16_ts(d, a, mk(bd), idesc, acc0);
-                umma_f16_ts(d, a + 8, mk(bd + 2), idesc, 1u);
-                umma_f16_ts(d, a + 16, mk(bd + 4), idesc, 1u);
-                umma_f16_ts(d, a + 24, mk(bd + 6), idesc, 1u);
-              } else {
-                for (uint32_t k = 0; k < ks; ++k) umma_f16_ts(d, a + 8 * k, mk(bd + 2 * k), idesc, k ? 1u : acc0);
-              }
-              if (ks2 == 4) {
-                umma_f16_ts(d, a2, mk(bd2), idesc, 1u);
-                umma_f16_ts(d, a2 + 8, mk(bd2 + 2), idesc, 1u);
-                umma_f16_ts(d, a2 + 16, mk(bd2 + 4), idesc, 1u);
-                umma_f16_ts(d, a2 + 24, mk(bd2 + 6), idesc, 1u);
-              } else {
-                for (uint32_t k = 0; k < ks2; ++k) umma_f16_ts(d, a2 + 8 * k, mk(bd2 + 2 * k), idesc, 1u);
-              }
-            } else {  // SS: A operand = embedding chunk(s) in shared memory
-              for (uint32_t k = 0; k < ks; ++k) umma_f16_ss(d, mk(r.y + 2 * k), mk(bd + 2 * k), idesc, k ? 1u : acc0);
-              for (uint32_t k = 0; k < ks2; ++k) umma_f16_ss(d, mk(r.z + 2 * k), mk(bd2 + 2 * k), idesc, 1u);
-            }
-            // frees the ring slot (in both CTAs) once these MMAs have read it
-            if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);
-            else umma_commit(&empty_bar[stage]);
-            if (cm) umma_commit(&m2c_g[cm]);
+            const uint32_t ks = ss & 7u, ks2 = (ss >> 3) & 7u;
+            const uint32_t a0 = ad_lo0 + (uint32_t)(Bk.ss_chunks & 15) * (kAChunkBytes >> 4);
+            const uint32_t a1 = ad_lo0 + (uint32_t)(Bk.ss_chunks >> 4) * (kAChunkBytes >> 4);
+            for (uint32_t k = 0; k < ks; ++k) umma_f16_ss(d, mk(a0 + 2 * k), mk(bd + 2 * k), idesc, k ? 1u : 0u);
+            for (uint32_t k = 0; k < ks2; ++k) umma_f16_ss(d, mk(a1 + 2 * k), mk(bd + tile2 + 2 * k), idesc, 1u);
+            release();
+            if (cm && ts_slots == 0) umma_commit(&m2c_g[cm]);
           }
           __syncwarp();
-          if (++stage == kNumStages) { stage = 0; phase ^= 1; }
+          advance();
+          acc = 1;
+        }
+        uint32_t a = act0;
+#pragma unroll 1
+        for (uint32_t j = 0; j < ts_slots; ++j) {  // activations from TMEM, 64 columns (128 values) per slot
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t bd = bd_lo0 + stage * (kWStageBytes >> 4), bd2 = bd + tile2;
+          const bool last = j + 1 == ts_slots;
+          if (elect_one()) {
+            umma_f16_ts(d, a, mk(bd), idesc, acc);
+            umma_f16_ts(d, a + 8, mk(bd + 2), idesc, 1u);
+            umma_f16_ts(d, a + 16, mk(bd + 4), idesc, 1u);
+            umma_f16_ts(d, a + 24, mk(bd + 6), idesc, 1u);
+            if (!last || Bk.ts_ks2_last == 4) {
+              umma_f16_ts(d, a + 32, mk(bd2), idesc, 1u);
+              umma_f16_ts(d, a + 40, mk(bd2 + 2), idesc, 1u);
+              umma_f16_ts(d, a + 48, mk(bd2 + 4), idesc, 1u);
+              umma_f16_ts(d, a + 56, mk(bd2 + 6), idesc, 1u);
+            } else {
+              for (uint32_t k = 0; k < Bk.ts_ks2_last; ++k) umma_f16_ts(d, a + 32 + 8 * k, mk(bd2 + 2 * k), idesc, 1u);
+            }
+            release();
+            if (last && cm) umma_commit(&m2c_g[cm]);
+          }
+          __syncwarp();
+          advance();
+          acc = 1;
+          a += 64;
         }
         if (g == 0) skip(cnt);
-        st += (int)cnt;
       }
     }
   }
@@ -753,7 +741,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd5_kernel(const __grid_co
 template <class Op, int B, int LMAX, bool DENSE, int WIDTH>
 static cudaError_t launch_one(const FieldKernelParams& p, int n_sm, cudaStream_t stream) {
   auto kern = field_fwd5_kernel<Op, B, LMAX, DENSE, WIDTH>;
-  const int smem = 1024 + kSmemArena + kSmemRing + (p.prog.cl.n_floats + kGroups * p.prog.fl.n_floats) * 4 + 256 + kGroups * kMaxSteps * 16;
+  const int smem = 1024 + kSmemArena + kSmemRing + (p.prog.cl.n_floats + kGroups * p.prog.fl.n_floats) * 4 + 256;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;

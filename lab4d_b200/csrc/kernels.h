@@ -17,7 +17,8 @@ struct PackParams {
 };
 
 struct PrologueParams {
-  Program prog;
+  ConstLayout cl;
+  FrameLayout fl;
   b200r_field_desc desc;
   b200r_field_params par;
   b200r_frame_tables fr;

@@ -103,8 +103,22 @@ struct FrameLayout {
   CondRow cond[kMaxCond];
 };
 
+// v5: one block = one GEMM (or one N-half of a wide layer) as the MMA issuers see it: an optional first ring slot
+// whose A operand is one or two embedding chunks in shared memory, then `ts_slots` slots whose A operand is the
+// group's activation buffer in TMEM, read front to back (4 + 4 k-steps per slot; the last slot has 4 + ts_ks2_last).
+struct MmaBlock {
+  uint8_t n16;          // UMMA N / 16
+  uint8_t ss;           // 0: no shared-memory slot; else 0x80 | ksteps | ksteps2 << 3
+  uint8_t ss_chunks;    // arena chunk of tile 0 | chunk of tile 1 << 4
+  uint8_t ts_slots;
+  uint8_t ts_ks2_last;
+  uint8_t wait, commit;
+  uint8_t pad_;
+};
+
 struct Program {
   int32_t n_steps;
+  int32_t n_blocks;
   // first step of each phase, in execution order: 3 warps (dense MLP + skinning delta MLP, see the kernel),
   // vis, feature, base chain, colour chain, final rgb.0
   int32_t st_delta[3], st_vis, st_feat, st_base, st_color, st_rgb;
@@ -112,6 +126,7 @@ struct Program {
   FrameLayout fl;
   LayerBias bias[B200R_MAX_LAYERS];
   MmaStep steps[kMaxSteps];
+  MmaBlock blocks[kMaxSteps];
 };
 
 // one source slice of a weight matrix that fills one packed K chunk
@@ -367,8 +382,13 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int version = 4) {
     auto pe5 = [&](int pe_n) { std::vector<Opnd> v{ss(CH_PE)}; if (pe_n > 63) v.push_back(ss(CH_EXTRA)); return v; };
     auto cat5 = [](std::vector<Opnd> a, const std::vector<Opnd>& b) { a.insert(a.end(), b.begin(), b.end()); return a; };
     // one block: D (+)= sum over the chunks of `cs`; consecutive chunks of the same kind share a step when they fit a stage
+    bool shape_ok = true;
     auto block = [&](const std::vector<Chunk>& cs, const std::vector<Opnd>& ops, int wait, int commit) {
       const size_t n = cs.size();
+      MmaBlock& Bk = P.blocks[P.n_blocks++];
+      Bk = MmaBlock{};
+      Bk.n16 = (uint8_t)(cs[0].n / 16); Bk.wait = (uint8_t)wait; Bk.commit = (uint8_t)commit;
+      int next_col = 0;
       for (size_t c = 0; c < n;) {
         int nsub = 1;
         if (c + 1 < n && ops[c].kind == ops[c + 1].kind && 2 * cs[c].n * 128 <= kWStageBytes &&
@@ -376,6 +396,17 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int version = 4) {
           nsub = 2;
         step(&cs[c], nsub, ops[c].kind, ops[c].kind == 0 ? ops[c].where : 0, (nsub > 1 && ops[c].kind == 0) ? ops[c + 1].where : 0,
              ops[c].kind == 1 ? ops[c].where : 0, 0, c > 0, c == 0 ? wait : BAR_NONE, c + (size_t)nsub == n ? commit : BAR_NONE);
+        const int ks = cs[c].ksteps, ks2 = nsub > 1 ? cs[c + 1].ksteps : 0;
+        if (ops[c].kind == 0) {  // shared-memory slot: only as the first slot of a block
+          shape_ok = shape_ok && c == 0 && ks <= 7 && ks2 <= 7;
+          Bk.ss = (uint8_t)(0x80 | ks | (ks2 << 3));
+          Bk.ss_chunks = (uint8_t)(ops[c].where | ((nsub > 1 ? ops[c + 1].where : 0) << 4));
+        } else {  // activation slot: columns are consumed front to back, 4 k-steps per tile except in the last slot
+          shape_ok = shape_ok && ops[c].where == next_col && ks == 4 && (c + (size_t)nsub == n || ks2 == 4);
+          next_col += 8 * (ks + ks2);
+          Bk.ts_slots++;
+          Bk.ts_ks2_last = (uint8_t)ks2;
+        }
         c += (size_t)nsub;
       }
     };
@@ -425,6 +456,7 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int version = 4) {
     seq5(L.rgb0, tsn(KC), BAR_H1);
     P.n_steps = ns;
     if (ns > kMaxSteps) { bp.err = "too many MMA steps"; return bp; }
+    if (!shape_ok) { bp.err = "internal: unsupported block shape"; return bp; }
     bp.ok = true;
     return bp;
   }

@@ -66,12 +66,11 @@ __device__ void write_se3(float* dst, const float* ar_, const float* ad_, const 
 }
 
 __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ PrologueParams p) {
-  const Program& P = p.prog;
   const int M = p.fr.M, B = p.desc.n_bones;
   float* cblock = p.workspace;
   if ((int)blockIdx.x == M) {
     // ---------------------------------------------------------------- constant block
-    const ConstLayout& C = P.cl;
+    const ConstLayout& C = p.cl;
     for (int i = threadIdx.x; i < C.n_floats; i += blockDim.x) cblock[i] = 0.f;
     __syncthreads();
     for (int l = 0; l < p.n_layers; ++l) {
@@ -106,10 +105,10 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
     return;
   }
   // ------------------------------------------------------------------ frame block
-  const FrameLayout& F = P.fl;
+  const FrameLayout& F = p.fl;
   const int f = blockIdx.x;
   const int fn = (M >= 2) ? (f ^ 1) : f;
-  float* fb = p.workspace + P.cl.n_floats + (size_t)f * F.n_floats;
+  float* fb = p.workspace + p.cl.n_floats + (size_t)f * F.n_floats;
   write_cam(fb + F.cam, p, f);
   write_cam(fb + F.cam_partner, p, fn);
   const float* codes[kNumCodes];
