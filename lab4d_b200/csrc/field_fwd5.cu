@@ -270,6 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd5_kernel(const __grid_co
     const uint32_t sc_s = cblk_s + 4u * CL.scalars;
     uint4* scr = p.scratch + ((size_t)blockIdx.x * kGroups + g) * (kTileRows * 32) + row;  // [32 uint4][128 rows]
 
+    // the prologue kernel (previous launch in the stream) wrote the workspace: wait for that grid to finish
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // stage the constant block once
     {
       const float4* src = reinterpret_cast<const float4*>(p.workspace);
@@ -756,13 +758,15 @@ static cudaError_t launch_one(const FieldKernelParams& p, int n_sm, cudaStream_t
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // overlap the set-up with the prologue kernel's tail
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 

@@ -1,13 +1,13 @@
 // Per-frame prologue: one launch builds the scratch the fused field kernel stages into shared memory.
 //
-//   block 0..M-1 : the frame block of frame f (program.h FrameLayout) -
+//   blocks 0..4M-1 : the frame block of frame f = block / 4 (program.h FrameLayout), four blocks per frame -
 //       cameras of the frame and of its flip_pair partner (nnutils/nerf.py:929-946),
 //       bias rows b + W[:, code columns] @ code[f] of the layers that see a per-frame code
 //       (instance / time / appearance codes are constant per frame: nnutils/base.py:140-146,
 //       nerf.py:200-204, skinning.py:109-116),
 //       bone tables: inverse bone transforms (utils/transforms.py:9-25) and the per-bone blend
 //       transforms rest (x) t^-1 / t (x) rest^-1 as dual quaternions (nnutils/warping.py:304-314).
-//   block M      : the constant block - plain bias rows, head weights, rest bone centres (utils/transforms.py:28-40), scalars.
+//   block 4M       : the constant block - plain bias rows, head weights, rest bone centres (utils/transforms.py:28-40), scalars.
 // M x B rows of quaternion algebra and a few (N x 32) mat-vecs: ~0.1 % of the step's FLOPs.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -65,10 +65,15 @@ __device__ void write_se3(float* dst, const float* ar_, const float* ad_, const 
   }
 }
 
+constexpr int kFrameParts = 4;  // blocks per frame: the bias rows are dealt round-robin, the bone tables by part
+
 __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ PrologueParams p) {
+  // let the field kernel (launched with programmatic stream serialization) start its set-up while this grid runs;
+  // it waits (griddepcontrol.wait) before it reads the workspace
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int M = p.fr.M, B = p.desc.n_bones;
   float* cblock = p.workspace;
-  if ((int)blockIdx.x == M) {
+  if ((int)blockIdx.x == kFrameParts * M) {
     // ---------------------------------------------------------------- constant block
     const ConstLayout& C = p.cl;
     for (int i = threadIdx.x; i < C.n_floats; i += blockDim.x) cblock[i] = 0.f;
@@ -104,13 +109,15 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
     }
     return;
   }
-  // ------------------------------------------------------------------ frame block
+  // ------------------------------------------------------------------ frame block, split over kFrameParts blocks
   const FrameLayout& F = p.fl;
-  const int f = blockIdx.x;
+  const int f = blockIdx.x / kFrameParts, part = blockIdx.x % kFrameParts;
   const int fn = (M >= 2) ? (f ^ 1) : f;
   float* fb = p.workspace + p.cl.n_floats + (size_t)f * F.n_floats;
-  write_cam(fb + F.cam, p, f);
-  write_cam(fb + F.cam_partner, p, fn);
+  if (part == 0) {
+    write_cam(fb + F.cam, p, f);
+    write_cam(fb + F.cam_partner, p, fn);
+  }
   const float* codes[kNumCodes];
   codes[CODE_INST_BASE] = p.fr.inst_base ? p.fr.inst_base + (size_t)f * 32 : nullptr;
   codes[CODE_INST_COLOR] = p.fr.inst_color ? p.fr.inst_color + (size_t)f * 32 : nullptr;
@@ -123,23 +130,32 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
   codes[CODE_DENSE_T_PARTNER] = p.fr.dense_t_embed ? p.fr.dense_t_embed + (size_t)fn * 128 : nullptr;
   codes[CODE_INST_DENSE_FWD] = p.fr.inst_dense_fwd ? p.fr.inst_dense_fwd + (size_t)f * 32 : nullptr;
   codes[CODE_INST_DENSE_BWD] = p.fr.inst_dense_bwd ? p.fr.inst_dense_bwd + (size_t)f * 32 : nullptr;
-  for (int ci = 0; ci < F.n_cond; ++ci) {
+  // all conditioned bias rows of the frame form one index space; this block takes every kFrameParts-th chunk of 256
+  int rows_total = 0;
+  for (int ci = 0; ci < F.n_cond; ++ci) rows_total += F.cond[ci].n;
+  for (int r = part * blockDim.x + threadIdx.x; r < rows_total; r += kFrameParts * blockDim.x) {
+    int ci = 0, n = r;
+    while (n >= F.cond[ci].n) { n -= F.cond[ci].n; ++ci; }
     const CondRow& c = F.cond[ci];
-    const float* Wm = p.par.weight[c.layer];
-    const float* bv = p.par.bias[c.layer];
-    for (int n = threadIdx.x; n < c.n; n += blockDim.x) {
-      float acc = bv[n];
-      for (int sgi = 0; sgi < c.n_seg; ++sgi) {
-        const float* code = codes[c.code[sgi]];
-        const float* wr = Wm + (size_t)n * c.in_dim + c.col0[sgi];
-        float a2 = 0.f;
-        for (int k = 0; k < c.width[sgi]; ++k) a2 += wr[k] * code[k];
-        acc += a2;
+    float acc = p.par.bias[c.layer][n];
+    for (int sgi = 0; sgi < c.n_seg; ++sgi) {
+      const float* code = codes[c.code[sgi]];
+      const float* wr = p.par.weight[c.layer] + (size_t)n * c.in_dim + c.col0[sgi];
+      const int wdt = c.width[sgi];
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int k = 0;
+      for (; k + 8 <= wdt; k += 8) {
+        a0 += wr[k] * code[k] + wr[k + 4] * code[k + 4];
+        a1 += wr[k + 1] * code[k + 1] + wr[k + 5] * code[k + 5];
+        a2 += wr[k + 2] * code[k + 2] + wr[k + 6] * code[k + 6];
+        a3 += wr[k + 3] * code[k + 3] + wr[k + 7] * code[k + 7];
       }
-      fb[c.frame_off + n] = acc;
+      for (; k < wdt; ++k) a0 += wr[k] * code[k];
+      acc += (a0 + a1) + (a2 + a3);
     }
+    fb[c.frame_off + n] = acc;
   }
-  if (B > 0) {
+  if (B > 0 && part >= 1) {
     __shared__ float ig[32 * 4];
     for (int b = threadIdx.x; b < B; b += blockDim.x)
       for (int c = 0; c < 3; ++c) {
@@ -149,17 +165,21 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
       }
     __syncthreads();
     const size_t o = (size_t)f * B * 4, on = (size_t)fn * B * 4;
-    write_binv(fb + F.binv_t, p.fr.t_art_qr + o, p.fr.t_art_qd + o, ig, B);
-    write_binv(fb + F.binv_rest, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, ig, B);
-    write_binv(fb + F.binv_rest_partner, p.fr.rest_art_qr + on, p.fr.rest_art_qd + on, ig, B);
-    write_se3(fb + F.se3_bwd, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, p.fr.t_art_qr + o, p.fr.t_art_qd + o, B);
-    write_se3(fb + F.se3_fwd, p.fr.t_art_qr + o, p.fr.t_art_qd + o, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, B);
-    write_se3(fb + F.se3_fwd_partner, p.fr.t_art_qr + on, p.fr.t_art_qd + on, p.fr.rest_art_qr + on, p.fr.rest_art_qd + on, B);
+    if (part == 1) {
+      write_binv(fb + F.binv_t, p.fr.t_art_qr + o, p.fr.t_art_qd + o, ig, B);
+      write_se3(fb + F.se3_bwd, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, p.fr.t_art_qr + o, p.fr.t_art_qd + o, B);
+    } else if (part == 2) {
+      write_binv(fb + F.binv_rest, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, ig, B);
+      write_se3(fb + F.se3_fwd, p.fr.t_art_qr + o, p.fr.t_art_qd + o, p.fr.rest_art_qr + o, p.fr.rest_art_qd + o, B);
+    } else {
+      write_binv(fb + F.binv_rest_partner, p.fr.rest_art_qr + on, p.fr.rest_art_qd + on, ig, B);
+      write_se3(fb + F.se3_fwd_partner, p.fr.t_art_qr + on, p.fr.t_art_qd + on, p.fr.rest_art_qr + on, p.fr.rest_art_qd + on, B);
+    }
   }
 }
 
 cudaError_t launch_prologue(const PrologueParams& p, cudaStream_t stream) {
-  prologue_kernel<<<p.fr.M + 1, 256, 0, stream>>>(p);
+  prologue_kernel<<<kFrameParts * p.fr.M + 1, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -58,10 +58,20 @@ for a in addrs:
     rng[role] += by[a]["c"]
     if a in wset: rngw[role] += by[a]["c"]
 print("by role (samples, of which mbarrier waits):", {k: (v, rngw[k]) for k, v in rng.items()})
-if len(sys.argv) > 3:
+if len(sys.argv) > 3 and sys.argv[3] in ("producer", "mma", "compute"):
     role = sys.argv[3]
     lo, hi = {"producer": (a_prod, a_mma), "mma": (a_mma, a_cmp), "compute": (a_cmp, addrs[-1] + 1)}[role]
     print("instructions of role", role, "with >= 0.05% samples")
     for a in addrs:
         if lo <= a < hi and by[a]["c"] >= max(1, tot // 2000):
             print(f"  {by[a]['c']:6d} @{a-base:#07x} {by[a]['t'][:70]:70s} {own_lines(a)[:3]}")
+if len(sys.argv) > 4:
+    # histogram of compute-role samples by the *innermost* own source line (last in list), bucketed by 10 lines
+    h = collections.Counter()
+    for a in addrs:
+        if a >= a_cmp:
+            ls = own_lines(a)
+            key = (ls[-1] // 10 * 10) if ls else -1
+            h[key] += by[a]["c"]
+    for k in sorted(h):
+        if h[k] >= tot // 500: print(f"  lines {k:4d}-{k+9:4d}: {h[k]:6d}  {src[k].strip()[:90] if k > 0 else ''}")
