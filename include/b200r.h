@@ -163,7 +163,7 @@ int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
                     void* workspace, size_t workspace_bytes, b200r_stream stream);
 
 /* ------------------------------------------------------------------ compositing (render_pixel) */
-#define B200R_MAX_CHANNELS 12
+#define B200R_MAX_CHANNELS 16
 /* how a per-sample array (R*D, nch) is reduced along the ray */
 #define B200R_CH_NORM 0       /* sum_k w_k/(mask+1e-6) v_k                 (rgb, depth, xyz, feature, ...) */
 #define B200R_CH_NORM_FROZEN 1 /* same, weights detached in backward         (cyc_dist, xyz_cam, skin_entropy) */

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200render.so")
 
 MAX_LAYERS = 32
-MAX_CHANNELS = 12
+MAX_CHANNELS = 16
 CH_NORM, CH_NORM_FROZEN, CH_MEAN, CH_FLOW, CH_WEIGHTSUM, CH_VIS = range(6)
 
 f32p = C.c_void_p  # device pointers are passed as integers

@@ -306,8 +306,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd5_kernel(const __grid_co
 #pragma unroll
       for (int g4 = 0; g4 < 8; ++g4) {
         const float4 b = lds128(bias + 16u * g4);
-        o[2 * g4] = Op::pack2_relu(__uint_as_float(ra[4 * g4 + 0]) + b.x, __uint_as_float(ra[4 * g4 + 1]) + b.y);
-        o[2 * g4 + 1] = Op::pack2_relu(__uint_as_float(ra[4 * g4 + 2]) + b.z, __uint_as_float(ra[4 * g4 + 3]) + b.w);
+        // packed fp32 adds (FADD2): two columns per instruction
+        const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(ra[4 * g4 + 0]), __uint_as_float(ra[4 * g4 + 1])), make_float2(b.x, b.y));
+        const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(ra[4 * g4 + 2]), __uint_as_float(ra[4 * g4 + 3])), make_float2(b.z, b.w));
+        o[2 * g4] = Op::pack2_relu(s0.x, s0.y);
+        o[2 * g4 + 1] = Op::pack2_relu(s1.x, s1.y);
       }
     };
     // finished GEMM of n (<= 128) columns: relu(acc + bias) -> activations [0, n)
