@@ -20,16 +20,7 @@ struct b200r_handle {
   bool slices_valid;
 };
 
-// Field-kernel generation: 5 = two tiles in flight per CTA (field_fwd5.cu), 4 = one tile per CTA (field_fwd.cu).
-// Process-wide (packing and launch must agree); B200R_KERNEL=4 selects the older kernel for A/B measurements.
-static int kernel_version() {
-  static const int v = [] {
-    const char* e = getenv("B200R_KERNEL");
-    return (e && e[0] == '4') ? 4 : 5;
-  }();
-  return v;
-}
-static b200r::BuiltProgram build(const b200r_field_desc& d) { return b200r::build_program(d, kernel_version()); }
+static b200r::BuiltProgram build(const b200r_field_desc& d) { return b200r::build_program(d); }
 
 static int fail(b200r_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
@@ -123,7 +114,7 @@ size_t b200r_workspace_bytes(const b200r_field_desc* desc, int32_t M) {
   if (!desc || M < 1) return 0;
   b200r::BuiltProgram bp = build(*desc);
   if (!bp.ok) return 0;
-  return kernel_version() >= 5 ? b200r::workspace_bytes_v5(bp.prog, M) : b200r::workspace_floats(bp.prog, M) * sizeof(float);
+  return b200r::workspace_bytes_total(bp.prog, M);
 }
 
 int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
@@ -189,12 +180,8 @@ int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
   kp.tiles_per_frame = (kp.ND + b200r::kTileRows - 1) / b200r::kTileRows;
   kp.n_tiles = M * kp.tiles_per_frame;
   kp.Lmax = desc->L_xyz + 2 > 10 ? 12 : 10;
-  if (kernel_version() >= 5) {
-    kp.scratch = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(workspace) + b200r::scratch_offset_bytes(bp.prog, M));
-    e = b200r::launch_field_fwd5(kp, h->n_sm, stream);
-  } else {
-    e = b200r::launch_field_fwd(kp, h->n_sm, stream);
-  }
+  kp.scratch = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(workspace) + b200r::scratch_offset_bytes(bp.prog, M));
+  e = b200r::launch_field_fwd(kp, h->n_sm, stream);
   if (e != cudaSuccess) return fail_cuda(h, e, "field_fwd kernel");
   return B200R_OK;
 }

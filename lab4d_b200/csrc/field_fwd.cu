@@ -1,23 +1,23 @@
-// Fused per-ray-sample forward of one Lab4D field (training-mode query_field) for sm_100a.
+// Fused per-ray-sample forward of one Lab4D field (training-mode query_field) for sm_100a:
+// TWO 128-sample tiles in flight per CTA.
 //
-// Persistent kernel, one CTA per SM, CTAs paired in clusters of 2 that share every weight chunk
-// through TMA multicast.  Each CTA walks 128-sample tiles (all samples of a tile belong to one frame).
-// Warp roles (320 threads):
-//   warps 0-7 : compute / epilogue.  Two threads per sample: warp w owns TMEM lanes 32*(w%4).. and
-//               the column half (w/4) of every accumulator; bones and Fourier frequencies are split
-//               the same way.  They place the sample on its ray, move it camera -> field space, run
-//               dual-quaternion blend skinning, write 16-bit operand rows into swizzled shared memory
-//               and run every layer's epilogue straight out of TMEM.
-//   warp 8    : TMA producer - streams its half of each pre-packed weight chunk (cp.async.bulk,
-//               multicast to both CTAs of the cluster) through a 3-stage ring of 32 KB.
-//   warp 9    : tcgen05.mma issuer (one elected lane) + TMEM owner; walks the MmaStep list of program.h.
-// The 256-wide chains (basefield, colorfield) are software-pipelined: every layer is issued as two
-// N-halves into two TMEM accumulators, warps 0-3 / 4-7 run the epilogue of half 0 / 1 and write the
-// 16-bit activations back to TMEM, where the next layer's MMAs read them as the A operand (TS form),
-// so the epilogue of one half overlaps the MMAs of the other and of the next layer.
-// Per-frame tables (cameras, bias rows with the per-frame codes folded in, bone transforms) and the
-// constant block (plain biases, head weights) are staged in shared memory; hidden activations never
-// leave the SM; HBM sees O(100 B) per sample of outputs.
+// Persistent kernel, one CTA per SM, CTAs paired in clusters of 2 that share every weight chunk through
+// TMA multicast.  Warp roles (320 threads):
+//   warps 0-3 : tile group 0, warps 4-7 : tile group 1.  One thread per sample (thread = tile row = TMEM lane):
+//               sample placement, camera -> field, dual-quaternion blend skinning (+ DenseWarp), Fourier embedding
+//               into swizzled shared memory, and every layer's epilogue straight out of TMEM.
+//   warp 8    : TMA producer - streams pre-packed weight chunks (cp.async.bulk, multicast to both CTAs of the
+//               cluster) through a 3-stage ring of 32 KB.
+//   warp 9    : tcgen05.mma issuer (one elected lane) + TMEM owner.  Walks the MmaStep list of program.h block by
+//               block (a block = one GEMM or one N-half of a 256-wide layer), issuing every block for group 0 and
+//               then for group 1: while one group runs an epilogue or its SIMT geometry, the tensor pipe works on
+//               the other group's tile, so the round-trip latencies of the 40-odd dependent GEMMs of a tile overlap.
+// TMEM (512 columns): per group 128 fp32 accumulator columns + 128 columns holding 256 16-bit activations.  All
+// hidden activations live in TMEM and feed the next layer as the A operand (TS form); the 256-wide layers run as
+// two N-halves on the same accumulator: the epilogue of half 0 drains it into registers while half 1 is being
+// multiplied, and both halves are written back in place once the layer's MMAs have read their input.
+// Shared memory holds only the embedding operand chunks (2 x 16 KB per group), the weight ring, the constant
+// block and one per-frame block per group.  HBM sees O(100 B) per sample of outputs.
 //
 // Restates (not ports) lab4d/nnutils/{nerf,deformable,feature,warping,skinning,embedding,visibility}.py
 // and lab4d/utils/{render_utils,geom_utils,quat_transform}.py - see include/b200r.h for file:line.
@@ -35,39 +35,31 @@
 #endif
 
 namespace b200r {
+namespace fwd {
 
 constexpr int kCluster = B200R_CLUSTER;
 constexpr int kNumStages = 3;
-constexpr int kComputeWarps = 8;
-constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kThreads = kComputeThreads + 64;
-constexpr int kSmemArena = kArenaChunks * kAChunkBytes;  //  96 KB
-constexpr int kSmemRing = kNumStages * kWStageBytes;     //  96 KB
+constexpr int kGroups = 2;
+constexpr int kGroupThreads = 128;
+constexpr int kComputeThreads = kGroups * kGroupThreads;
+constexpr int kThreads = kComputeThreads + 128;  // warpgroup 2 = producer warp, MMA warp, two idle warps (register donors)
+constexpr int kRegsCompute = 208, kRegsAux = 88;        // setmaxnreg: 2 x 128 x 208 + 128 x 88 = 64512 <= 65536
+constexpr int kArenaGroup = 2 * kAChunkBytes;           // CH_PE, CH_EXTRA
+constexpr int kSmemArena = kGroups * kArenaGroup;        // 64 KB
+constexpr int kSmemRing = kNumStages * kWStageBytes;     // 96 KB
+constexpr int kTmemAcc = 0, kTmemAct = 256, kTmemGroup = 128;
 
-// ---------------------------------------------------------------------------------- small math
 struct Q4 { float w, x, y, z; };
 __device__ __forceinline__ Q4 qmul(const Q4& a, const Q4& b) {
   return {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
           a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w};
 }
 __device__ __forceinline__ Q4 qconj(const Q4& a) { return {a.w, -a.x, -a.y, -a.z}; }
-// quaternion_apply: (q (0,p) q*)_xyz
-__device__ __forceinline__ float3 qrot(const Q4& q, const float3& p) {
+__device__ __forceinline__ float3 qrot(const Q4& q, const float3& p) {  // quaternion_apply
   Q4 t = qmul(q, Q4{0.f, p.x, p.y, p.z});
   Q4 r = qmul(t, qconj(q));
   return make_float3(r.x, r.y, r.z);
 }
-__device__ __forceinline__ Q4 ldq(const float* p) {
-  float4 v = *reinterpret_cast<const float4*>(p);
-  return {v.x, v.y, v.z, v.w};
-}
-template <class Op>
-__device__ __forceinline__ void store_group(uint8_t* chunk, uint32_t row, uint32_t g, const float* v) {
-  *reinterpret_cast<uint4*>(chunk + sw128_off(row, g)) =
-      make_uint4(Op::pack2(v[0], v[1]), Op::pack2(v[2], v[3]), Op::pack2(v[4], v[5]), Op::pack2(v[6], v[7]));
-}
-
-// explicit shared-window accessors (32-bit addresses from smem_u32)
 __device__ __forceinline__ float4 lds128(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
@@ -78,46 +70,44 @@ __device__ __forceinline__ float lds32(uint32_t a) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32u(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ void sts128f(uint32_t a, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts16(uint32_t a, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
-template <class Op>
-__device__ __forceinline__ void sts_group(uint32_t a, const float* v) {
-  sts128(a, make_uint4(Op::pack2(v[0], v[1]), Op::pack2(v[2], v[3]), Op::pack2(v[4], v[5]), Op::pack2(v[6], v[7])));
-}
 
 template <int V>
 using IC = std::integral_constant<int, V>;
 
-// ---------------------------------------------------------------------------------- the kernel
-template <class Op, int B, int LMAX, bool DENSE>
+template <class Op, int B, int LMAX, bool DENSE, int WIDTH>
 __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_constant__ FieldKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* arena = smem;
   uint8_t* ring = smem + kSmemArena;
   float* cblk = reinterpret_cast<float*>(ring + kSmemRing);
-  float* fblk = cblk + p.prog.cl.n_floats;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fblk + p.prog.fl.n_floats);
+  float* fblk = cblk + p.prog.cl.n_floats;  // one frame block per tile group
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fblk + kGroups * p.prog.fl.n_floats);
   uint64_t* full_bar = bars;                  // [kNumStages]
   uint64_t* empty_bar = bars + kNumStages;    // [kNumStages]
-  uint64_t* c2m = bars + 2 * kNumStages;      // [4] compute warps -> MMA thread, indexed by BAR_*
-  uint64_t* m2c = bars + 2 * kNumStages + 4;  // [4] MMA thread (tcgen05.commit) -> compute warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumStages + 8);
+  uint64_t* c2m = bars + 2 * kNumStages;      // [group][4] compute warps -> MMA thread, indexed by BAR_*
+  uint64_t* m2c = bars + 2 * kNumStages + 8;  // [group][4] MMA thread (tcgen05.commit) -> compute warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumStages + 16);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], kCluster); }
-    // one arrival per compute warp (lane 0 after __syncwarp), not per thread: 32x less mbarrier traffic
-    mbar_init(&c2m[BAR_ALL], kComputeWarps);
-    mbar_init(&c2m[BAR_H0], kComputeWarps);
-    mbar_init(&c2m[BAR_H1], kComputeWarps);
-    for (int i = 1; i < 4; ++i) mbar_init(&m2c[i], 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(&c2m[i], 4); mbar_init(&m2c[i], 1); }  // one arrival per warp of the group
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, kTmemCols);
@@ -125,136 +115,171 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();  // peer barriers are initialised before any multicast can land
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  if (*tmem_slot != 0) __trap();        // the CTA allocates all 512 columns, so the allocation starts at column 0
+  constexpr uint32_t tmem_base = 0;
   const Program& P = p.prog;
-  const int iters = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;  // identical in both CTAs of a cluster
+  const int pair_stride = 2 * (int)gridDim.x;
+  const int iters = (p.n_tiles + pair_stride - 1) / pair_stride;  // identical in both CTAs of a cluster
   const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0;
   const uint16_t cmask = (uint16_t)((1u << kCluster) - 1);
 
+  if (warp >= 8) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));
   if (warp == 8) {
     // =============================================================== TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < iters; ++it) {
-        for (int st = 0; st < P.n_steps; ++st) {
-          const MmaStep& S = P.steps[st];
-          const uint32_t bytes = (uint32_t)S.n * 128u * S.n_sub;
-          const uint32_t part = bytes / kCluster;
-          mbar_wait(&empty_bar[stage], phase ^ 1);  // both CTAs' MMAs are done with this slot
-          mbar_arrive_expect_tx(&full_bar[stage], bytes);
-          const uint8_t* src = p.packed + S.w_off + cta_rank * part;
-          uint8_t* dst = ring + stage * kWStageBytes + cta_rank * part;
-          if (kCluster > 1) tma_bulk_g2s_mcast(dst, src, part, &full_bar[stage], cmask);
-          else tma_bulk_g2s(dst, src, part, &full_bar[stage]);
-          if (++stage == kNumStages) { stage = 0; phase ^= 1; }
+        int st = 0;
+        while (st < P.n_steps) {
+          int end = st;
+          while (P.steps[end].commit == 0) ++end;
+          ++end;
+          for (int g = 0; g < kGroups; ++g) {
+            for (int s = st; s < end; ++s) {
+              const MmaStep& S = P.steps[s];
+              const uint32_t bytes = (uint32_t)S.n * 128u * S.n_sub;
+              const uint32_t part = bytes / kCluster;
+              mbar_wait(&empty_bar[stage], phase ^ 1);  // both CTAs' MMAs are done with this slot
+              mbar_arrive_expect_tx(&full_bar[stage], bytes);
+              const uint8_t* src = p.packed + S.w_off + cta_rank * part;
+              uint8_t* dst = ring + stage * kWStageBytes + cta_rank * part;
+              if (kCluster > 1) tma_bulk_g2s_mcast(dst, src, part, &full_bar[stage], cmask);
+              else tma_bulk_g2s(dst, src, part, &full_bar[stage]);
+              if (++stage == kNumStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          st = end;
         }
       }
     }
-  } else if (warp == 9) {
-    // =============================================================== MMA issuer
-    // The whole warp walks the step list converged (all lanes poll the barriers); one elected lane issues.
-    // Descriptors are base + small integer offsets (same swizzle/stride fields), so a step costs a handful of
-    // integer adds besides the barrier polls; the common shapes (4 or 4+4 k-steps) are fully unrolled.
-    {
-      uint32_t stage = 0, phase = 0;
-      uint32_t bar_phase = 0;  // bit i = parity of c2m[i]
-      const uint64_t adesc0 = umma_desc_k_sw128(smem_u32(arena)), bdesc0 = umma_desc_k_sw128(smem_u32(ring));
-      for (int it = 0; it < iters; ++it) {
+  } else if (warp == 9 || warp == 10) {
+    // =============================================================== MMA issuers: warp 9 -> tile group 0, warp 10 -> group 1.
+    // Ring slots are filled in the global order [block b, group 0][block b, group 1][block b+1, group 0]...; each
+    // issuer consumes its own group's slots and steps over the other's.  Everything here is warp-uniform and comes
+    // from the kernel parameters (MmaBlock), so descriptors and addresses stay in uniform registers.
+    const int g = warp - 9;
+    uint32_t stage = 0, phase = 0;
+    uint32_t bar_phase = 0;  // bit i = parity of c2m[g][i]
+    const uint32_t desc_hi = (uint32_t)(umma_desc_k_sw128(0) >> 32);
+    const uint32_t bd_lo0 = (uint32_t)umma_desc_k_sw128(smem_u32(ring));
+    const uint32_t ad_lo0 = (uint32_t)umma_desc_k_sw128(smem_u32(arena)) + (uint32_t)g * (kArenaGroup >> 4);
+    const uint32_t d = kTmemAcc + kTmemGroup * g;      // TMEM base is 0 (checked above): the CTA owns all 512 columns
+    const uint32_t act0 = kTmemAct + kTmemGroup * g;
+    uint64_t* c2m_g = c2m + 4 * g;
+    uint64_t* m2c_g = m2c + 4 * g;
+    auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
+    auto advance = [&]() { if (++stage == kNumStages) { stage = 0; phase ^= 1; } };
+    // Step over the other group's slots.  Their fill is still observed: a parity wait cannot tell "fill n+1 done" from
+    // "fill n not yet done", so an issuer must never wait for a stage's next fill before it has seen the previous one.
+    auto skip = [&](uint32_t cnt) {
+      for (uint32_t j = 0; j < cnt; ++j) {
+        mbar_wait(&full_bar[stage], phase);
+        advance();
+      }
+    };
+    auto release = [&]() {  // frees the ring slot (in both CTAs) once the MMAs issued so far have read it
+      if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);
+      else umma_commit(&empty_bar[stage]);
+    };
+    const int n_blocks = P.n_blocks;
+    for (int it = 0; it < iters; ++it) {
 #pragma unroll 1
-        for (int st = 0; st < P.n_steps; ++st) {
-          const MmaStep& S = P.steps[st];
-          const uint32_t idesc = umma_idesc_f16(Op::kFmt, S.n);
-          const uint32_t wt = S.wait;
-          if (wt) {
-            mbar_wait(&c2m[wt], (bar_phase >> wt) & 1u);
-            bar_phase ^= 1u << wt;
-          }
+      for (int b = 0; b < n_blocks; ++b) {
+        const MmaBlock& Bk = P.blocks[b];
+        const uint32_t n = (uint32_t)Bk.n16 << 4, ss = Bk.ss, ts_slots = Bk.ts_slots, cnt = (ss ? 1u : 0u) + ts_slots;
+        const uint32_t idesc = umma_idesc_f16(Op::kFmt, 0) | ((n >> 3) << 17);
+        const uint32_t tile2 = n << 3;  // descriptor offset of a slot's second weight tile (n rows x 128 B)
+        if (g == 1) skip(cnt);
+        const uint32_t wt = Bk.wait, cm = Bk.commit;
+        if (wt) {
+          mbar_wait(&c2m_g[wt], (bar_phase >> wt) & 1u);
+          bar_phase ^= 1u << wt;
+        }
+        uint32_t acc = 0;
+        if (ss) {  // embedding chunk(s) from shared memory
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          const uint64_t bd = bdesc0 + (uint64_t)(stage * (kWStageBytes >> 4));
-          const uint64_t bd2 = bd + (uint64_t)((uint32_t)S.n << 3);  // second tile: n * 128 B further
-          const uint32_t d = tmem_base + S.d_col;
-          const uint32_t acc0 = S.accumulate, ks = S.ksteps, ks2 = S.ksteps2;
+          const uint32_t bd = bd_lo0 + stage * (kWStageBytes >> 4);
           if (elect_one()) {
-            if (S.a_kind == 0) {
-              const uint64_t ad = adesc0 + (uint64_t)((uint32_t)S.a_chunk * (kAChunkBytes >> 4));
-              const uint64_t ad2 = adesc0 + (uint64_t)((uint32_t)S.a_chunk2 * (kAChunkBytes >> 4));
-              if (ks == 4) {
-                umma_f16_ss(d, ad, bd, idesc, acc0);
-                umma_f16_ss(d, ad + 2, bd + 2, idesc, 1u);
-                umma_f16_ss(d, ad + 4, bd + 4, idesc, 1u);
-                umma_f16_ss(d, ad + 6, bd + 6, idesc, 1u);
-              } else {
-                for (uint32_t k = 0; k < ks; ++k) umma_f16_ss(d, ad + 2 * k, bd + 2 * k, idesc, k ? 1u : acc0);
-              }
-              if (ks2 == 4) {
-                umma_f16_ss(d, ad2, bd2, idesc, 1u);
-                umma_f16_ss(d, ad2 + 2, bd2 + 2, idesc, 1u);
-                umma_f16_ss(d, ad2 + 4, bd2 + 4, idesc, 1u);
-                umma_f16_ss(d, ad2 + 6, bd2 + 6, idesc, 1u);
-              } else {
-                for (uint32_t k = 0; k < ks2; ++k) umma_f16_ss(d, ad2 + 2 * k, bd2 + 2 * k, idesc, 1u);
-              }
-            } else {
-              const uint32_t a = tmem_base + S.a_tmem_col;  // 16 halves per k-step = 8 TMEM columns
-              umma_f16_ts(d, a, bd, idesc, acc0);
-              umma_f16_ts(d, a + 8, bd + 2, idesc, 1u);
-              umma_f16_ts(d, a + 16, bd + 4, idesc, 1u);
-              umma_f16_ts(d, a + 24, bd + 6, idesc, 1u);
-              if (ks2) {
-                umma_f16_ts(d, a + 32, bd2, idesc, 1u);
-                umma_f16_ts(d, a + 40, bd2 + 2, idesc, 1u);
-                umma_f16_ts(d, a + 48, bd2 + 4, idesc, 1u);
-                umma_f16_ts(d, a + 56, bd2 + 6, idesc, 1u);
-              }
-            }
-            // frees the ring slot (in both CTAs) once these MMAs have read it
-            if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);
-            else umma_commit(&empty_bar[stage]);
-            if (S.commit) umma_commit(&m2c[S.commit]);
+            const uint32_t ks = ss & 7u, ks2 = (ss >> 3) & 7u;
+            const uint32_t a0 = ad_lo0 + (uint32_t)(Bk.ss_chunks & 15) * (kAChunkBytes >> 4);
+            const uint32_t a1 = ad_lo0 + (uint32_t)(Bk.ss_chunks >> 4) * (kAChunkBytes >> 4);
+            for (uint32_t k = 0; k < ks; ++k) umma_f16_ss(d, mk(a0 + 2 * k), mk(bd + 2 * k), idesc, k ? 1u : 0u);
+            for (uint32_t k = 0; k < ks2; ++k) umma_f16_ss(d, mk(a1 + 2 * k), mk(bd + tile2 + 2 * k), idesc, 1u);
+            release();
+            if (cm && ts_slots == 0) umma_commit(&m2c_g[cm]);
           }
           __syncwarp();
-          if (++stage == kNumStages) { stage = 0; phase ^= 1; }
+          advance();
+          acc = 1;
         }
+        uint32_t a = act0;
+#pragma unroll 1
+        for (uint32_t j = 0; j < ts_slots; ++j) {  // activations from TMEM, 64 columns (128 values) per slot
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t bd = bd_lo0 + stage * (kWStageBytes >> 4), bd2 = bd + tile2;
+          const bool last = j + 1 == ts_slots;
+          if (elect_one()) {
+            umma_f16_ts(d, a, mk(bd), idesc, acc);
+            umma_f16_ts(d, a + 8, mk(bd + 2), idesc, 1u);
+            umma_f16_ts(d, a + 16, mk(bd + 4), idesc, 1u);
+            umma_f16_ts(d, a + 24, mk(bd + 6), idesc, 1u);
+            if (!last || Bk.ts_ks2_last == 4) {
+              umma_f16_ts(d, a + 32, mk(bd2), idesc, 1u);
+              umma_f16_ts(d, a + 40, mk(bd2 + 2), idesc, 1u);
+              umma_f16_ts(d, a + 48, mk(bd2 + 4), idesc, 1u);
+              umma_f16_ts(d, a + 56, mk(bd2 + 6), idesc, 1u);
+            } else {
+              for (uint32_t k = 0; k < Bk.ts_ks2_last; ++k) umma_f16_ts(d, a + 32 + 8 * k, mk(bd2 + 2 * k), idesc, 1u);
+            }
+            release();
+            if (last && cm) umma_commit(&m2c_g[cm]);
+          }
+          __syncwarp();
+          advance();
+          acc = 1;
+          a += 64;
+        }
+        if (g == 0) skip(cnt);
       }
     }
+  }
   } else {
     // =============================================================== compute / epilogue warps
-    const int q = warp & 3, hsel = warp >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
+    const int g = warp >> 2, q = warp & 3;
+    const int gtid = threadIdx.x & (kGroupThreads - 1);
     const uint32_t row = (uint32_t)(q * 32 + lane);  // tile row == TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t all_phase = 0, half_phase = 0;  // parity of m2c[BAR_ALL]; bit n of half_phase = parity of m2c[BAR_H0 + n]
-    const int W = p.desc.W, HN = W / 2;
-    // canonical layer ids (same enumeration as program.h layer_ids)
+    const uint32_t tD = t_lane + kTmemAcc + kTmemGroup * g;  // this group's accumulator
+    const uint32_t tA = t_lane + kTmemAct + kTmemGroup * g;  // this group's 16-bit activations (2 per column)
+    uint64_t* c2m_g = c2m + 4 * g;
+    uint64_t* m2c_g = m2c + 4 * g;
+    uint32_t all_phase = 0, half_phase = 0;
+    constexpr int HN = WIDTH / 2, NBLK = HN / 32;  // N-half of the wide layers; 32-column blocks per half
     const int lid_delta = 0, lid_vis = B > 0 ? 3 : 0, lid_base = lid_vis + 2, lid_rgb0 = lid_base + p.desc.D + 1,
               lid_color = lid_rgb0 + 1, lid_feat = lid_color + 3, lid_dense = lid_feat + (p.desc.has_feature ? 6 : 0);
     const ConstLayout& CL = P.cl;
     const FrameLayout& FL = P.fl;
-    // 32-bit shared-window addresses (explicit ld/st.shared keeps the hot loops off the generic path)
-    const uint32_t arena_s = smem_u32(arena), cblk_s = smem_u32(cblk), fblk_s = smem_u32(fblk);
-    const uint32_t rowx = row * 128u + ((row & 7u) << 4);  // row base with the swizzle phase folded in:
-                                                           // group g of this row lives at chunk + (rowx ^ (g << 4))
+    float* fblk_g = fblk + g * FL.n_floats;
+    const uint32_t cblk_s = smem_u32(cblk), fblk_s = smem_u32(fblk_g);
+    const uint32_t pe_s = smem_u32(arena) + g * kArenaGroup, extra_s = pe_s + kAChunkBytes;
+    const uint32_t rowx = row * 128u + ((row & 7u) << 4);  // 16-B group gq of this row lives at chunk + (rowx ^ (gq << 4))
     const uint32_t sc_s = cblk_s + 4u * CL.scalars;
+    uint4* scr = p.scratch + ((size_t)blockIdx.x * kGroups + g) * (kTileRows * 32) + row;  // [32 uint4][128 rows]
 
-    // stage the constant block once (made visible by the first named barrier of the tile loop)
+    // the prologue kernel (previous launch in the stream) wrote the workspace: wait for that grid to finish
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // stage the constant block once
     {
       const float4* src = reinterpret_cast<const float4*>(p.workspace);
       float4* dst = reinterpret_cast<float4*>(cblk);
       for (int i = threadIdx.x; i < CL.n_floats / 4; i += kComputeThreads) dst[i] = __ldg(src + i);
     }
+    named_bar_sync(3, kComputeThreads);
 
-    // Exchange between the two threads of a row: 12 floats per thread inside the unused part of the
-    // CH_EXTRA rows (the MMA only reads their first 32 B).  Every exchange round uses its own floats
-    // and rounds that reuse an address are separated by a run_gemm() (a barrier of all compute threads).
-    const uint32_t extra_s = arena_s + CH_EXTRA * kAChunkBytes;
-    const uint32_t my_x0 = extra_s + (rowx ^ ((2u + 3u * hsel) << 4)), my_x1 = extra_s + (rowx ^ ((3u + 3u * hsel) << 4)),
-                   my_x2 = extra_s + (rowx ^ ((4u + 3u * hsel) << 4));
-    const uint32_t pr_x0 = extra_s + (rowx ^ ((2u + 3u * (hsel ^ 1)) << 4)), pr_x1 = extra_s + (rowx ^ ((3u + 3u * (hsel ^ 1)) << 4)),
-                   pr_x2 = extra_s + (rowx ^ ((4u + 3u * (hsel ^ 1)) << 4));
-    auto pair_sync = [&]() { named_bar_sync(1 + q, 64); };
-
-    // hand the operands to the MMA warp, then wait for the layer's accumulator
-    // every lane orders its own writes (generic -> async proxy, tcgen05), the warp converges, lane 0 signals
     auto warp_arrive = [&](uint64_t* bar) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar);
@@ -262,123 +287,155 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     auto arrive_all = [&]() {
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      warp_arrive(&c2m[BAR_ALL]);
+      warp_arrive(&c2m_g[BAR_ALL]);
     };
     auto wait_all = [&]() {
-      mbar_wait(&m2c[BAR_ALL], all_phase);
+      mbar_wait(&m2c_g[BAR_ALL], all_phase);
       all_phase ^= 1;
       tc_fence_after_sync();
     };
-    auto run_gemm = [&]() { arrive_all(); wait_all(); };
-    auto bias_s = [&](int layer) -> uint32_t { return (P.bias[layer].frame ? fblk_s : cblk_s) + 4u * P.bias[layer].off; };
-    // relu(acc + bias) -> 16-bit operand rows; this thread covers its half of the columns.
-    auto epi_relu_store = [&](uint32_t bias, int n_pad, int dst_chunk) {
-      const int ncols = n_pad >> 1, cb = hsel * ncols, nblk = ncols >> 5;
-      const uint32_t t0 = t_lane + kTmemD0 + cb;
-      auto process = [&](uint32_t (&r)[32], int c0) {
-        const uint32_t chunk = arena_s + (uint32_t)(dst_chunk + (c0 >> 6)) * kAChunkBytes;
-        const uint32_t gbase = (uint32_t)(c0 & 63) >> 3;
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const float4 b0 = lds128(bias + 4u * (c0 + g8 * 8));
-          const float4 b1 = lds128(bias + 4u * (c0 + g8 * 8 + 4));
-          uint4 o;
-          o.x = Op::pack2_relu(__uint_as_float(r[g8 * 8 + 0]) + b0.x, __uint_as_float(r[g8 * 8 + 1]) + b0.y);
-          o.y = Op::pack2_relu(__uint_as_float(r[g8 * 8 + 2]) + b0.z, __uint_as_float(r[g8 * 8 + 3]) + b0.w);
-          o.z = Op::pack2_relu(__uint_as_float(r[g8 * 8 + 4]) + b1.x, __uint_as_float(r[g8 * 8 + 5]) + b1.y);
-          o.w = Op::pack2_relu(__uint_as_float(r[g8 * 8 + 6]) + b1.z, __uint_as_float(r[g8 * 8 + 7]) + b1.w);
-          sts128(chunk + (rowx ^ ((gbase + g8) << 4)), o);
-        }
-      };
-#pragma unroll 1
-      for (int blk = 0; blk < nblk; ++blk) {
-        uint32_t ra[32];
-        tmem_ld32_issue(t0 + 32 * blk, ra);
-        tmem_ld_wait32(ra);
-        process(ra, cb + 32 * blk);
-      }
-    };
-    // Pipelined chain: epilogue of N-half `nh` (accumulator D<nh>, HN columns) of one layer.  All 8 warps take
-    // part: this thread covers HN/2 of the half's columns for its row.  relu(acc + bias) -> 16-bit activations ->
-    // TMEM buffer `wbuf`, then signal the MMA thread that D<nh> is free and this part of the operand is written.
+    auto gemm = [&]() { arrive_all(); wait_all(); };
     auto wait_half = [&](int nh) {
-      mbar_wait(&m2c[BAR_H0 + nh], (half_phase >> nh) & 1u);
+      mbar_wait(&m2c_g[BAR_H0 + nh], (half_phase >> nh) & 1u);
       half_phase ^= 1u << nh;
       tc_fence_after_sync();
     };
-    auto epi_half_to_tmem = [&](int layer, int wbuf, int nh) {
-      wait_half(nh);
-      const int c_lo = hsel * (HN >> 1);                // first column (inside the half) of this thread
-      const int feat0 = nh * HN + c_lo;                 // same, as a feature index of the W-wide layer
-      const uint32_t bias = bias_s(layer) + 4u * (uint32_t)feat0;
-      const uint32_t tsrc = t_lane + (nh ? kTmemD1 : kTmemD0) + (uint32_t)c_lo;
-      const uint32_t tdst = t_lane + (wbuf ? kTmemA1 : kTmemA0) + (uint32_t)(feat0 >> 1);
-      auto pack_store = [&](uint32_t (&ra)[32], int blk) {
-        uint32_t o[16];
+    auto bias_s = [&](int layer) -> uint32_t { return (P.bias[layer].frame ? fblk_s : cblk_s) + 4u * P.bias[layer].off; };
+    // 32 accumulator columns + bias -> relu -> 16 packed columns
+    auto relu_pack32 = [&](const uint32_t (&ra)[32], uint32_t bias, uint32_t (&o)[16]) {
 #pragma unroll
-        for (int g4 = 0; g4 < 8; ++g4) {
-          const float4 b = lds128(bias + 4u * (32 * blk + 4 * g4));
-          o[2 * g4] = Op::pack2_relu(__uint_as_float(ra[4 * g4 + 0]) + b.x, __uint_as_float(ra[4 * g4 + 1]) + b.y);
-          o[2 * g4 + 1] = Op::pack2_relu(__uint_as_float(ra[4 * g4 + 2]) + b.z, __uint_as_float(ra[4 * g4 + 3]) + b.w);
-        }
-        tmem_st16(tdst + 16 * blk, o);
-      };
-      if (HN == 128) {  // 64 columns per thread: both TMEM loads in flight before the first wait
-        uint32_t ra[32], rb[32];
-        tmem_ld32_issue(tsrc, ra);
-        tmem_ld32_issue(tsrc + 32, rb);
+      for (int g4 = 0; g4 < 8; ++g4) {
+        const float4 b = lds128(bias + 16u * g4);
+        // packed fp32 adds (FADD2): two columns per instruction
+        const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(ra[4 * g4 + 0]), __uint_as_float(ra[4 * g4 + 1])), make_float2(b.x, b.y));
+        const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(ra[4 * g4 + 2]), __uint_as_float(ra[4 * g4 + 3])), make_float2(b.z, b.w));
+        o[2 * g4] = Op::pack2_relu(s0.x, s0.y);
+        o[2 * g4 + 1] = Op::pack2_relu(s1.x, s1.y);
+      }
+    };
+    // finished GEMM of n (<= 128) columns: relu(acc + bias) -> activations [0, n)
+    auto epi_relu_act = [&](uint32_t bias, int n) {
+#pragma unroll 1
+      for (int blk = 0; blk < (n >> 5); ++blk) {
+        uint32_t ra[32], o[16];
+        tmem_ld32_issue(tD + 32 * blk, ra);
         tmem_ld_wait32(ra);
-        pack_store(ra, 0);
-        tmem_ld_wait32(rb);
-        pack_store(rb, 1);
-      } else {
-        uint32_t ra[32];
-        tmem_ld32_issue(tsrc, ra);
-        tmem_ld_wait32(ra);
-        pack_store(ra, 0);
+        relu_pack32(ra, bias + 128u * blk, o);
+        tmem_st16(tA + 16 * blk, o);
       }
       tmem_st_wait();
+    };
+    // One 2*hn-wide layer issued as two N-halves on this group's accumulator (program.h pipe5).
+    //   MODE 0: relu(acc + bias) -> activations (in place: half 0 is held in registers until the layer's MMAs are done)
+    //   MODE 1: basefield.linear_final: relu features -> packed into the per-row scratch, fp32 dot with sdf.weight
+    //   MODE 2: colorfield.linear_final: relu(acc + bias) + base features (scratch) -> activations (input of rgb.0)
+    float sdf_acc = 0.f;
+    auto chain_layer = [&](auto mode_tag, uint32_t bias) {
+      constexpr int MODE = decltype(mode_tag)::value;
+      uint32_t hold[NBLK][16];
+      auto math = [&](const uint32_t (&ra)[32], int col0, uint32_t (&o)[16]) {  // col0: first feature of these 32 columns
+        const uint32_t ba = bias + 4u * (uint32_t)col0;
+        if (MODE == 0) {
+          relu_pack32(ra, ba, o);
+        } else if (MODE == 1) {
+          const uint32_t wa = cblk_s + 4u * (CL.sdf_w + col0);
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int g4 = 0; g4 < 8; ++g4) {
+            const float4 b = lds128(ba + 16u * g4), w = lds128(wa + 16u * g4);
+            const float y0 = fmaxf(__uint_as_float(ra[4 * g4 + 0]) + b.x, 0.f), y1 = fmaxf(__uint_as_float(ra[4 * g4 + 1]) + b.y, 0.f);
+            const float y2 = fmaxf(__uint_as_float(ra[4 * g4 + 2]) + b.z, 0.f), y3 = fmaxf(__uint_as_float(ra[4 * g4 + 3]) + b.w, 0.f);
+            s0 += y0 * w.x + y2 * w.z;
+            s1 += y1 * w.y + y3 * w.w;
+            o[2 * g4] = Op::pack2(y0, y1);
+            o[2 * g4 + 1] = Op::pack2(y2, y3);
+          }
+          sdf_acc += s0 + s1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) scr[(size_t)((col0 >> 3) + j) * kTileRows] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 bf = scr[(size_t)((col0 >> 3) + j) * kTileRows];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int g4 = 2 * j + hh;
+              const float4 b = lds128(ba + 16u * g4);
+              const float2 f0 = Op::unpack2(hh ? bf.z : bf.x), f1 = Op::unpack2(hh ? bf.w : bf.y);
+              o[2 * g4] = Op::pack2(fmaxf(__uint_as_float(ra[4 * g4 + 0]) + b.x, 0.f) + f0.x, fmaxf(__uint_as_float(ra[4 * g4 + 1]) + b.y, 0.f) + f0.y);
+              o[2 * g4 + 1] = Op::pack2(fmaxf(__uint_as_float(ra[4 * g4 + 2]) + b.z, 0.f) + f1.x, fmaxf(__uint_as_float(ra[4 * g4 + 3]) + b.w, 0.f) + f1.y);
+            }
+          }
+        }
+      };
+      // ---- N-half 0: drain the accumulator so the MMAs of half 1 can start
+      wait_half(0);
+#pragma unroll
+      for (int blk = 0; blk < NBLK; ++blk) {
+        uint32_t ra[32];
+        tmem_ld32_issue(tD + 32 * blk, ra);
+        tmem_ld_wait32(ra);
+        math(ra, 32 * blk, hold[blk]);
+      }
       tc_fence_before_sync();
-      warp_arrive(&c2m[BAR_H0 + nh]);
+      warp_arrive(&c2m_g[BAR_H0]);
+      // ---- N-half 1: the layer's input has been read, activations can be overwritten
+      wait_half(1);
+      if (MODE != 1) {
+#pragma unroll
+        for (int blk = 0; blk < NBLK; ++blk) tmem_st16(tA + 16 * blk, hold[blk]);
+      }
+#pragma unroll
+      for (int blk = 0; blk < NBLK; ++blk) {
+        uint32_t ra[32], o[16];
+        tmem_ld32_issue(tD + 32 * blk, ra);
+        tmem_ld_wait32(ra);
+        math(ra, HN + 32 * blk, o);
+        if (MODE != 1) tmem_st16(tA + (HN >> 1) + 16 * blk, o);
+      }
+      if (MODE != 1) tmem_st_wait();
+      tc_fence_before_sync();
+      warp_arrive(&c2m_g[BAR_H1]);
     };
 
-    // 16-bit element `c` (0..63) of this row in operand chunk `chunk_s`
+    // 16-bit element `c` (0..63) of this row in an operand chunk
     auto put16 = [&](uint32_t chunk_s, int c, float val) { sts16(chunk_s + (rowx ^ ((uint32_t)(c >> 3) << 4)) + 2u * (c & 7), Op::cvt(val)); };
-    // DenseWarp.forward (nnutils/warping.py:143-170): x + 0.1 * CondMLP([PE6(x), t, inst]).  The time / instance codes
-    // are folded into the linear_1 bias row `bias1`; lid0 = canonical id of the map's linear_1.  Both threads of a
-    // row compute the same result.
-    auto dense_warp = [&](const float3& x, uint32_t bias1, int lid0) -> float3 {
-      const uint32_t pe_s = arena_s + CH_PE * kAChunkBytes;
-      if (hsel == 0) { put16(pe_s, 0, x.x); put16(pe_s, 1, x.y); put16(pe_s, 2, x.z); }
-      else {
-        put16(pe_s, 39, 0.f);  // 39 embedding columns; the third k-step reads up to column 47
-        sts128(pe_s + (rowx ^ (5u << 4)), make_uint4(0u, 0u, 0u, 0u));
-      }
-      float fr = hsel == 0 ? 1.0f : 8.0f;
+    // Fourier features of x: column e < 3 -> x_e, else frequency (e-3)/6, sin for (e-3)%6 < 3 (PosEmbedding.forward,
+    // nnutils/embedding.py:69-125).  Columns 0..62 live in CH_PE, 63.. in CH_EXTRA.
+    auto embed = [&](const float3& x, int nfreq) {
+      auto put = [&](int e, float val) { put16(e < 63 ? pe_s : extra_s, e < 63 ? e : e - 63, val); };
+      put(0, x.x); put(1, x.y); put(2, x.z);
+      float fr = 1.0f;
 #pragma unroll 1
-      for (int kf = 3 * hsel; kf < 3 * hsel + 3; ++kf) {
-        float sv[3], cv[3];
-        sincosf(fr * x.x, &sv[0], &cv[0]);
-        sincosf(fr * x.y, &sv[1], &cv[1]);
-        sincosf(fr * x.z, &sv[2], &cv[2]);
+      for (int kf = 0; kf < nfreq; ++kf) {
+        float s0, s1, s2, c0, c1, c2;
+        sincosf(fr * x.x, &s0, &c0);
+        sincosf(fr * x.y, &s1, &c1);
+        sincosf(fr * x.z, &s2, &c2);
         const int e0 = 3 + 6 * kf;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { put16(pe_s, e0 + c, sv[c]); put16(pe_s, e0 + 3 + c, cv[c]); }
+        put(e0, s0); put(e0 + 1, s1); put(e0 + 2, s2);
+        put(e0 + 3, c0); put(e0 + 4, c1); put(e0 + 5, c2);
         fr *= 2.0f;
       }
-      run_gemm();
-      epi_relu_store(bias1, 256, CH_H0);
-      run_gemm();
-      epi_relu_store(bias_s(lid0 + 1), 256, CH_H0);
-      run_gemm();
+    };
+    // DenseWarp.forward (nnutils/warping.py:143-170): x + 0.1 * CondMLP([PE6(x), t, inst]); the per-frame codes are
+    // folded into the linear_1 bias row `bias1`; lid0 = canonical id of the map's linear_1.
+    auto dense_warp = [&](const float3& x, uint32_t bias1, int lid0) -> float3 {
+      embed(x, 6);
+      put16(pe_s, 39, 0.f);  // 39 embedding columns; the third k-step reads up to column 47
+      sts128(pe_s + (rowx ^ (5u << 4)), make_uint4(0u, 0u, 0u, 0u));
+      arrive_all();
+#pragma unroll 1
+      for (int l = 0; l < 2; ++l) chain_layer(IC<0>{}, l == 0 ? bias1 : bias_s(lid0 + 1));
+      wait_all();
       float m[16];
-      tmem_ld16(t_lane + kTmemD0, m);
+      tmem_ld16(tD, m);
       const uint32_t b3 = bias_s(lid0 + 2);
       return make_float3(x.x + 0.1f * (m[0] + lds32(b3)), x.y + 0.1f * (m[1] + lds32(b3 + 4)), x.z + 0.1f * (m[2] + lds32(b3 + 8)));
     };
 
     for (int it = 0; it < iters; ++it) {
-      const int tile_raw = it * (int)gridDim.x + (int)blockIdx.x;
+      const int tile_raw = (2 * it + g) * (int)gridDim.x + (int)blockIdx.x;
       const bool dead_tile = tile_raw >= p.n_tiles;
       const int tile = dead_tile ? p.n_tiles - 1 : tile_raw;
       const int f = tile / p.tiles_per_frame;
@@ -390,18 +447,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       const size_t s = (size_t)f * p.ND + r_in;
 
       // ------------------------------------------------ stage this frame's block in shared memory
-      named_bar_sync(5, kComputeThreads);  // everyone is done with the previous block
+      named_bar_sync(1 + g, kGroupThreads);  // the group is done with the previous block
       {
         const float4* src = reinterpret_cast<const float4*>(p.workspace + CL.n_floats + (size_t)f * FL.n_floats);
-        float4* dst = reinterpret_cast<float4*>(fblk);
-        for (int i = threadIdx.x; i < FL.n_floats / 4; i += kComputeThreads) dst[i] = __ldg(src + i);
+        float4* dst = reinterpret_cast<float4*>(fblk_g);
+        for (int i = gtid; i < FL.n_floats / 4; i += kGroupThreads) dst[i] = __ldg(src + i);
       }
-      named_bar_sync(5, kComputeThreads);
+      named_bar_sync(1 + g, kGroupThreads);
 
       // ------------------------------------------------ sample placement (sample_cam_rays)
       const float* hx = p.rays.hxy + ((size_t)f * p.rays.N + n) * 3;
       const float h0 = __ldg(hx), h1 = __ldg(hx + 1), h2 = __ldg(hx + 2);
-      const float* cam = fblk + FL.cam;
+      const float* cam = fblk_g + FL.cam;
       float3 d = make_float3(h0 * cam[0] + h1 * cam[1] + h2 * cam[2], h0 * cam[3] + h1 * cam[4] + h2 * cam[5],
                              h0 * cam[6] + h1 * cam[7] + h2 * cam[8]);
       const float dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
@@ -424,85 +481,66 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       const float3 dir_f = qrot(qi, dir_cam);
 
       // ------------------------------------------------ skinning warps (SkinningWarp.forward), three per sample:
-      //   w = 0 backward warp (time-t -> canonical), w = 1 forward warp with the pair partner's
-      //   articulation (flow), w = 2 forward warp with the frame's own articulation (cycle).
+      //   w = 0 backward warp (time-t -> canonical), w = 1 forward warp with the pair partner's articulation (flow),
+      //   w = 2 forward warp with the frame's own articulation (cycle).
       // bone coordinates -> delta MLP on the tensor pipe -> softmax -> dual-quaternion blend.
-      // Half 0 owns bones [0,BS), half 1 bones [BS,B); operand groups are split at a 16-B boundary.
-      constexpr int BS = B == 25 ? 13 : (B == 18 ? 8 : 0);
-      constexpr int XTRA = (8 - (3 * BS) % 8) % 8;  // values of bone BS that complete half 0's last group
-      constexpr int I0 = 3 * BS + XTRA;             // first operand column written by half 1
-      constexpr int BH = BS > B - BS ? BS : B - BS;
-      auto skin_warp = [&](auto half_tag, const float3& x, uint32_t binv, uint32_t se3, uint32_t bias1, float& entropy,
-                           float& delta_skin) -> float3 {
-        constexpr int HALF = decltype(half_tag)::value;
-        constexpr int b_lo = HALF == 0 ? 0 : BS;
-        constexpr int b_hi = HALF == 0 ? BS : B;
-        constexpr int NB = b_hi - b_lo;
-        constexpr int NV = HALF == 0 ? 3 * BS + XTRA : 3 * (B - BS);
-        float dist2[BH > 0 ? BH : 1];
+      constexpr int NP = B > 0 ? (3 * B + 15) / 16 * 8 : 1;  // packed pairs of the zero-padded bone-coordinate row
+      auto skin_warp = [&](const float3& x, uint32_t binv, uint32_t se3, uint32_t bias1, float& entropy, float& delta_skin) -> float3 {
+        float dist2[B > 0 ? B : 1];
         {
-          float v[NV > 0 ? NV : 1];
+          uint32_t u[NP];
 #pragma unroll
-          for (int j = 0; j < (NV + 2) / 3; ++j) {
-            const uint32_t ba = binv + 48u * (b_lo + j);
-            const float4 r0 = lds128(ba), r1 = lds128(ba + 16), r2 = lds128(ba + 32);
-            const float xb0 = r0.x * x.x + r0.y * x.y + r0.z * x.z + r0.w;
-            const float xb1 = r1.x * x.x + r1.y * x.y + r1.z * x.z + r1.w;
-            const float xb2 = r2.x * x.x + r2.y * x.y + r2.z * x.z + r2.w;
-            if (j < NB) dist2[j] = xb0 * xb0 + xb1 * xb1 + xb2 * xb2;
-            if (3 * j < NV) v[3 * j] = xb0;
-            if (3 * j + 1 < NV) v[3 * j + 1] = xb1;
-            if (3 * j + 2 < NV) v[3 * j + 2] = xb2;
-          }
-          if (HALF == 0) {
+          for (int i = 0; i < NP; ++i) u[i] = 0u;
 #pragma unroll
-            for (int g = 0; g < NV / 8; ++g) sts_group<Op>(arena_s + CH_H0 * kAChunkBytes + (rowx ^ (g << 4)), v + 8 * g);
-          } else {
-            constexpr int END = (3 * B + 15) / 16 * 16;  // zero-padded to whole UMMA_K steps
+          for (int b2 = 0; b2 < (B + 1) / 2; ++b2) {
+            float v[6];
 #pragma unroll
-            for (int idx = I0; idx < END; idx += 8) {
-              float w8[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) w8[j] = (idx + j < 3 * B) ? v[(idx + j < 3 * B) ? idx + j - 3 * BS : 0] : 0.f;
-              sts_group<Op>(arena_s + (idx < 64 ? CH_H0 : CH_H1) * kAChunkBytes + (rowx ^ (((idx & 63) >> 3) << 4)), w8);
+            for (int j = 0; j < 2; ++j) {
+              const int b = 2 * b2 + j;
+              if (b < B) {
+                const uint32_t ba = binv + 48u * b;
+                const float4 r0 = lds128(ba), r1 = lds128(ba + 16), r2 = lds128(ba + 32);
+                v[3 * j + 0] = r0.x * x.x + r0.y * x.y + r0.z * x.z + r0.w;
+                v[3 * j + 1] = r1.x * x.x + r1.y * x.y + r1.z * x.z + r1.w;
+                v[3 * j + 2] = r2.x * x.x + r2.y * x.y + r2.z * x.z + r2.w;
+                dist2[b] = v[3 * j] * v[3 * j] + v[3 * j + 1] * v[3 * j + 1] + v[3 * j + 2] * v[3 * j + 2];
+              } else {
+                v[3 * j] = v[3 * j + 1] = v[3 * j + 2] = 0.f;
+              }
             }
+            u[3 * b2] = Op::pack2(v[0], v[1]);
+            u[3 * b2 + 1] = Op::pack2(v[2], v[3]);
+            u[3 * b2 + 2] = Op::pack2(v[4], v[5]);
           }
+          tmem_st32(tA, u);
+          if (NP > 32) tmem_st8(tA + 32, u + (NP > 32 ? 32 : 0));
+          tmem_st_wait();
         }
         // delta_field.linear_1 / linear_2 (ReLU) and linear_final
-        run_gemm();
-        epi_relu_store(bias1, 64, CH_H2);
-        run_gemm();
-        epi_relu_store(bias_s(lid_delta + 1), 64, CH_H2);
-        run_gemm();
+        gemm();
+        epi_relu_act(bias1, 64);
+        gemm();
+        epi_relu_act(bias_s(lid_delta + 1), 64);
+        gemm();
         float dl[32];
-        tmem_ld32(t_lane + kTmemD0, dl);
+        tmem_ld32(tD, dl);
         const uint32_t b3 = bias_s(lid_delta + 2);
         float mx = -INFINITY, dsum = 0.f;
         int amax = 0;
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          const float dv = 0.1f * fmaxf(dl[b_lo + j] + lds32(b3 + 4u * (b_lo + j)), 0.f);
+        for (int j = 0; j < B; ++j) {
+          const float dv = 0.1f * fmaxf(dl[j] + lds32(b3 + 4u * j), 0.f);
           dsum += dv * dv;
           const float lg = -(dist2[j] + dv);
           dist2[j] = lg;
-          if (lg > mx) { mx = lg; amax = b_lo + j; }
-        }
-        // round 1: global max / anchor bone (first maximum wins, like argmax)
-        sts32(my_x0 + 8, mx);
-        sts32(my_x0 + 12, __int_as_float(amax));
-        pair_sync();
-        {
-          const float omx = lds32(pr_x0 + 8);
-          const int oam = __float_as_int(lds32(pr_x0 + 12));
-          const bool take = HALF == 0 ? (omx > mx) : (omx >= mx);
-          if (take) { mx = omx; amax = oam; }
+          if (lg > mx) { mx = lg; amax = j; }  // first maximum wins, like argmax
         }
         const float4 qa = lds128(se3 + 32u * amax);
         float se = 0.f;
         float4 qr = make_float4(0.f, 0.f, 0.f, 0.f), qd = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          const uint32_t sa = se3 + 32u * (b_lo + j);
+        for (int j = 0; j < B; ++j) {
+          const uint32_t sa = se3 + 32u * j;
           const float e = __expf(dist2[j] - mx);
           se += e;
           const float4 r = lds128(sa), dq = lds128(sa + 16);
@@ -510,26 +548,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           const float wgt = dot > 0.f ? e : -e;  // the softmax denominator cancels in the normalisation below
           qr.x += wgt * r.x; qr.y += wgt * r.y; qr.z += wgt * r.z; qr.w += wgt * r.w;
           qd.x += wgt * dq.x; qd.y += wgt * dq.y; qd.z += wgt * dq.z; qd.w += wgt * dq.w;
-        }
-        // round 2: partial sums
-        sts32(my_x0, se);
-        sts32(my_x0 + 4, dsum);
-        sts128f(my_x1, qr);
-        sts128f(my_x2, qd);
-        pair_sync();
-        {
-          const float ose = lds32(pr_x0), ods = lds32(pr_x0 + 4);
-          const float4 o1 = lds128(pr_x1), o2 = lds128(pr_x2);
-          // add in bone order (half 0 first) so both threads of the row get bit-identical results
-          if (HALF == 0) {
-            se = se + ose; dsum = dsum + ods;
-            qr = make_float4(qr.x + o1.x, qr.y + o1.y, qr.z + o1.z, qr.w + o1.w);
-            qd = make_float4(qd.x + o2.x, qd.y + o2.y, qd.z + o2.z, qd.w + o2.w);
-          } else {
-            se = ose + se; dsum = ods + dsum;
-            qr = make_float4(o1.x + qr.x, o1.y + qr.y, o1.z + qr.z, o1.w + qr.w);
-            qd = make_float4(o2.x + qd.x, o2.y + qd.y, o2.z + qd.z, o2.w + qd.w);
-          }
         }
         entropy = __logf(se);  // logsumexp - max  (cross_entropy_skin_loss)
         delta_skin = dsum / (float)(B > 0 ? B : 1);
@@ -564,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           const uint32_t se3 = fblk_s + 4u * (w == 0 ? FL.se3_bwd : (w == 1 ? FL.se3_fwd_partner : FL.se3_fwd));
           const uint32_t bias1 = w == 0 ? bias_s(lid_delta) : fblk_s + 4u * FL.delta1_fwd;  // forward warps: mean time code
           float e, dk;
-          const float3 o = hsel == 0 ? skin_warp(IC<0>{}, src, binv, se3, bias1, e, dk) : skin_warp(IC<1>{}, src, binv, se3, bias1, e, dk);
+          const float3 o = skin_warp(src, binv, se3, bias1, e, dk);
           if (w == 0) { cur = o; xyz = o; ent_b = e; dsk_b = dk; }
           else if (w == 1) { x_next = o; }
           else {
@@ -578,156 +596,120 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         x_next = xyz;
       }
 
-      // ------------------------------------------------ positional embedding (PosEmbedding.forward)
-      // Column e of the embedding: e < 3 -> x_e, else frequency (e-3)/6, sin for (e-3)%6 < 3.  Columns 0..62 live in
-      // CH_PE (column 63 = 0), columns 63.. in CH_EXTRA.  Half 0 writes frequencies 0..LMAX/2-1, half 1 the rest.
+      // ------------------------------------------------ outputs that are final before the MLPs run
+      auto st3 = [&](float* dst, float a, float b, float c) { if (dst && live) { dst[s * 3] = a; dst[s * 3 + 1] = b; dst[s * 3 + 2] = c; } };
+      auto st1 = [&](float* dst, float a) { if (dst && live) dst[s] = a; };
       {
-        const uint32_t pe_s = arena_s + CH_PE * kAChunkBytes;
-        auto put = [&](int e, float val) { put16(e < 63 ? pe_s : extra_s, e < 63 ? e : e - 63, val); };  // embedding column e
-        if (hsel == 0) { put(0, xyz.x); put(1, xyz.y); put(2, xyz.z); }
-        else {
-          sts16(pe_s + (rowx ^ (7u << 4)) + 14u, (uint16_t)0);  // zero pad column 63 of CH_PE
-          if (LMAX > 10) {  // CH_EXTRA holds 12 values; its k-step reads 16 columns
-            sts32(extra_s + (rowx ^ (1u << 4)) + 8u, 0.f);
-            sts32(extra_s + (rowx ^ (1u << 4)) + 12u, 0.f);
+        // field_to_cam with the partner frame's camera, pinhole projection, flow (nerf.py:948-997)
+        const float* cn = fblk_g + FL.cam_partner;
+        const Q4 qn = {cn[11], cn[12], cn[13], cn[14]};
+        float3 xc = qrot(qn, x_next);
+        xc.x += cn[15]; xc.y += cn[16]; xc.z += cn[17];
+        const float k0 = cn[0], k1 = cn[4], k2 = cn[2], k3 = cn[5];
+        const float fx = 1.0f / k0, fy = 1.0f / k1, cx = -k2 / k0, cy = -k3 / k1;
+        const float hxn = (fx * xc.x + cx * xc.z) / (xc.z + 1e-6f);
+        const float hyn = (fy * xc.y + cy * xc.z) / (xc.z + 1e-6f);
+        const float fl0 = hxn - h0, fl1 = hyn - h1;
+        bool valid = xc.z > 1e-6f;
+        if (p.rays.flow_thresh >= 0.f) valid = valid && (sqrtf(fl0 * fl0 + fl1 * fl1) < p.rays.flow_thresh);
+        st3(p.out.flow, fl0, fl1, valid ? 1.f : 0.f);
+        // Gaussian bone density (compute_gauss_density): max_b exp(-d2_b / 2) = exp(-min_b d2_b / 2)
+        if constexpr (B > 0) {
+          float best = INFINITY;
+          const uint32_t ctr = cblk_s + 4u * CL.center;
+#pragma unroll 5
+          for (int b = 0; b < B; ++b) {
+            const float4 c = lds128(ctr + 16u * b);
+            const float dx = xyz.x - c.x, dy = xyz.y - c.y, dz = xyz.z - c.z;
+            best = fminf(best, dx * dx + dy * dy + dz * dz);
           }
+          st1(p.out.gauss_density, expf(-0.5f * (best / (0.01f * 0.01f))) * lds32(sc_s + 4u * SC_WARP_IBETA));
         }
-        const int k0 = hsel == 0 ? 0 : LMAX / 2, k1 = hsel == 0 ? LMAX / 2 : LMAX;
-        float fr = hsel == 0 ? 1.0f : (float)(1 << (LMAX / 2));
-#pragma unroll 1
-        for (int kf = k0; kf < k1; ++kf) {
-          float sv[3], cv[3];
-          sincosf(fr * xyz.x, &sv[0], &cv[0]);
-          sincosf(fr * xyz.y, &sv[1], &cv[1]);
-          sincosf(fr * xyz.z, &sv[2], &cv[2]);
-          const int e0 = 3 + 6 * kf;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) { put(e0 + c, sv[c]); put(e0 + 3 + c, cv[c]); }
-          fr *= 2.0f;
-        }
+        st3(p.out.xyz, xyz.x, xyz.y, xyz.z);
+        st3(p.out.xyz_cam, xyz_cam.x, xyz_cam.y, xyz_cam.z);
+        st3(p.out.xyz_t, xyz_t.x, xyz_t.y, xyz_t.z);
+        st3(p.out.dir, dir_f.x, dir_f.y, dir_f.z);
+        st1(p.out.depth, depth * lds32(sc_s + 4u * SC_INV_SCALE));
+        st1(p.out.deltas, delta);
+        st1(p.out.cyc_dist, cyc);
+        st1(p.out.delta_skin, dsk_out);
+        st1(p.out.skin_entropy, ent_out);
+      }
+
+      // ------------------------------------------------ positional embedding of the canonical point
+      embed(xyz, LMAX);
+      sts16(pe_s + (rowx ^ (7u << 4)) + 14u, (uint16_t)0);  // zero pad column 63 of CH_PE
+      if (LMAX > 10) {  // CH_EXTRA holds 12 values (columns 63..74); its k-step reads 16 columns
+        sts32(extra_s + (rowx ^ (1u << 4)) + 8u, 0.f);
+        sts32(extra_s + (rowx ^ (1u << 4)) + 12u, 0.f);
       }
 
       // ------------------------------------------------ visibility MLP (VisField.forward)
-      run_gemm();
-      epi_relu_store(bias_s(lid_vis), 64, CH_H0);
-      run_gemm();
-      float vis_out;
+      gemm();
+      epi_relu_act(bias_s(lid_vis), 64);
+      gemm();
       {
-        const uint32_t b2 = bias_s(lid_vis + 1) + 128u * hsel, vw = cblk_s + 4u * CL.vis_w + 128u * hsel;
-        float v[32];
-        tmem_ld32(t_lane + kTmemD0 + 32 * hsel, v);
+        const uint32_t b2 = bias_s(lid_vis + 1), vw = cblk_s + 4u * CL.vis_w;
         float a0 = 0.f, a1 = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          float v[32];
+          tmem_ld32(tD + c0, v);
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const float4 ba = lds128(b2 + 4u * j), bb = lds128(b2 + 4u * j + 16), wa = lds128(vw + 4u * j), wb = lds128(vw + 4u * j + 16);
-          a0 += fmaxf(v[j] + ba.x, 0.f) * wa.x; a1 += fmaxf(v[j + 1] + ba.y, 0.f) * wa.y;
-          a0 += fmaxf(v[j + 2] + ba.z, 0.f) * wa.z; a1 += fmaxf(v[j + 3] + ba.w, 0.f) * wa.w;
-          a0 += fmaxf(v[j + 4] + bb.x, 0.f) * wb.x; a1 += fmaxf(v[j + 5] + bb.y, 0.f) * wb.y;
-          a0 += fmaxf(v[j + 6] + bb.z, 0.f) * wb.z; a1 += fmaxf(v[j + 7] + bb.w, 0.f) * wb.w;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 ba = lds128(b2 + 4u * (c0 + j)), wa = lds128(vw + 4u * (c0 + j));
+            a0 += fmaxf(v[j] + ba.x, 0.f) * wa.x + fmaxf(v[j + 2] + ba.z, 0.f) * wa.z;
+            a1 += fmaxf(v[j + 1] + ba.y, 0.f) * wa.y + fmaxf(v[j + 3] + ba.w, 0.f) * wa.w;
+          }
         }
-        const float accv = a0 + a1;
-        sts32(my_x0, accv);
-        pair_sync();
-        const float other = lds32(pr_x0);
-        vis_out = (hsel == 0 ? accv + other : other + accv) + lds32(sc_s + 4u * SC_VIS_B);
+        st1(p.out.vis, a0 + a1 + lds32(sc_s + 4u * SC_VIS_B));
       }
 
       // ------------------------------------------------ feature field (FeatureNeRF.compute_feat)
-      float feat[16];
       if (p.desc.has_feature) {
 #pragma unroll 1
         for (int i = 0; i < 5; ++i) {
-          run_gemm();
-          epi_relu_store(bias_s(lid_feat + i), 128, CH_H0);
+          gemm();
+          epi_relu_act(bias_s(lid_feat + i), 128);
         }
-        run_gemm();
-        if (hsel == 0) {  // warp-uniform: 16 outputs, one thread per row
-          float v16[16];
-          tmem_ld16(t_lane + kTmemD0, v16);
-          const uint32_t bf = bias_s(lid_feat + 5);
-          float nn = 0.f;
+        gemm();
+        float v16[16];
+        tmem_ld16(tD, v16);
+        const uint32_t bf = bias_s(lid_feat + 5);
+        float nn = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { feat[j] = v16[j] + lds32(bf + 4u * j); nn += feat[j] * feat[j]; }
-          const float inv = rsqrtf(nn);
+        for (int j = 0; j < 16; ++j) { v16[j] += lds32(bf + 4u * j); nn += v16[j] * v16[j]; }
+        const float inv = rsqrtf(nn);
+        if (p.out.feature && live) {
+          float4* fo = reinterpret_cast<float4*>(p.out.feature + s * 16);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) feat[j] *= inv;
+          for (int j = 0; j < 4; ++j) fo[j] = make_float4(v16[4 * j] * inv, v16[4 * j + 1] * inv, v16[4 * j + 2] * inv, v16[4 * j + 3] * inv);
         }
       }
 
-      // ------------------------------------------------ density + colour chains (NeRF.forward), pipelined:
-      // the MMA thread issues every W-wide layer as two N-halves; this thread finishes its half's epilogue
-      // (writing 16-bit activations to TMEM) while the other half's / the next layer's MMAs run.
-      arrive_all();  // embedding operands written, accumulators free
-      int buf = 0;   // TMEM activation buffer the current layer READS; its epilogue writes buf ^ 1
+      // ------------------------------------------------ density + colour chains (NeRF.forward, nnutils/nerf.py:167-215)
+      arrive_all();  // embedding operands written, accumulator and activations free
+      sdf_acc = 0.f;
 #pragma unroll 1
-      for (int j = 0; j < p.desc.D; ++j) {
-        epi_half_to_tmem(lid_base + j, buf ^ 1, 0);
-        epi_half_to_tmem(lid_base + j, buf ^ 1, 1);
-        buf ^= 1;
-      }
-      float sdf;
-      {
-        // basefield.linear_final: features go to shared memory (rgb.0 reads them at the very end), sdf head in fp32
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 1
-        for (int nh = 0; nh < 2; ++nh) {
-          wait_half(nh);
-          const int c_lo = hsel * (HN >> 1), feat0 = nh * HN + c_lo;
-          const uint32_t bb = bias_s(lid_base + p.desc.D) + 4u * (uint32_t)feat0, sw = cblk_s + 4u * CL.sdf_w + 4u * (uint32_t)feat0;
-          const uint32_t tsrc = t_lane + (nh ? kTmemD1 : kTmemD0) + (uint32_t)c_lo;
-#pragma unroll 1
-          for (int c0 = 0; c0 < (HN >> 1); c0 += 32) {
-            float v[32];
-            tmem_ld32(tsrc + c0, v);
-            const int col = feat0 + c0;  // column of the full W-wide feature
-            const uint32_t chunk = arena_s + (uint32_t)(CH_H0 + (col >> 6)) * kAChunkBytes;
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const float4 b0 = lds128(bb + 4u * (c0 + g8 * 8)), b1 = lds128(bb + 4u * (c0 + g8 * 8 + 4));
-              const float4 w0 = lds128(sw + 4u * (c0 + g8 * 8)), w1 = lds128(sw + 4u * (c0 + g8 * 8 + 4));
-              float y[8];
-              y[0] = fmaxf(v[g8 * 8 + 0] + b0.x, 0.f); y[1] = fmaxf(v[g8 * 8 + 1] + b0.y, 0.f);
-              y[2] = fmaxf(v[g8 * 8 + 2] + b0.z, 0.f); y[3] = fmaxf(v[g8 * 8 + 3] + b0.w, 0.f);
-              y[4] = fmaxf(v[g8 * 8 + 4] + b1.x, 0.f); y[5] = fmaxf(v[g8 * 8 + 5] + b1.y, 0.f);
-              y[6] = fmaxf(v[g8 * 8 + 6] + b1.z, 0.f); y[7] = fmaxf(v[g8 * 8 + 7] + b1.w, 0.f);
-              a0 += y[0] * w0.x; a1 += y[1] * w0.y; a2 += y[2] * w0.z; a3 += y[3] * w0.w;
-              a0 += y[4] * w1.x; a1 += y[5] * w1.y; a2 += y[6] * w1.z; a3 += y[7] * w1.w;
-              sts_group<Op>(chunk + (rowx ^ ((((uint32_t)(col & 63) >> 3) + g8) << 4)), y);
-            }
-          }
-          fence_proxy_async_smem();
-          tc_fence_before_sync();
-          warp_arrive(&c2m[BAR_H0 + nh]);  // D<nh> is free, this part of the features is in shared memory
-        }
-        buf ^= 1;
-        const float accs = (a0 + a1) + (a2 + a3);
-        sts32(my_x1, accs);
-        pair_sync();
-        const float other = lds32(pr_x1);
-        sdf = (hsel == 0 ? accs + other : other + accs) + lds32(sc_s + 4u * SC_SDF_B);
-      }
+      for (int j = 0; j < p.desc.D; ++j) chain_layer(IC<0>{}, bias_s(lid_base + j));
+      chain_layer(IC<1>{}, bias_s(lid_base + p.desc.D));
+      const float sdf = sdf_acc + lds32(sc_s + 4u * SC_SDF_B);
       const float ibeta = lds32(sc_s + 4u * SC_IBETA);
       const float sgn = sdf > 0.f ? 1.f : (sdf < 0.f ? -1.f : 0.f);
-      const float density = (0.5f + 0.5f * sgn * expm1f(-fabsf(sdf) * ibeta)) * ibeta;
-
-      // colorfield: three more pipelined layers (the first reads the embedding again)
+      st1(p.out.density, (0.5f + 0.5f * sgn * expm1f(-fabsf(sdf) * ibeta)) * ibeta);
+      st1(p.out.sdf, sdf);
 #pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
-        epi_half_to_tmem(lid_color + j, buf ^ 1, 0);
-        epi_half_to_tmem(lid_color + j, buf ^ 1, 1);
-        buf ^= 1;
-      }
-      // rgb.0 on (base features from shared memory) + (colour features from TMEM), then rgb.2 + sigmoid
+      for (int j = 0; j < 2; ++j) chain_layer(IC<0>{}, bias_s(lid_color + j));
+      chain_layer(IC<2>{}, bias_s(lid_color + 2));
+      // rgb.0 on (base + colour features), then rgb.2 + sigmoid
       wait_all();
-      float rgb[3];
       {
-        const int ncols = HN >> 1, cb = hsel * ncols;
         const uint32_t b0 = bias_s(lid_rgb0), w2 = cblk_s + 4u * CL.rgb2_w, wd = cblk_s + 4u * CL.dir_w;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll 1
-        for (int c0 = cb; c0 < cb + ncols; c0 += 32) {
+        for (int c0 = 0; c0 < HN; c0 += 32) {
           float v[32];
-          tmem_ld32(t_lane + kTmemD0 + c0, v);
+          tmem_ld32(tD + c0, v);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 bv = lds128(b0 + 4u * (c0 + j));
@@ -746,75 +728,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
             a2 += h0_ * wb.x + h1_ * wb.y + h2_ * wb.z + h3_ * wb.w;
           }
         }
-        sts128f(my_x2, make_float4(a0, a1, a2, 0.f));
-        pair_sync();
-        const float4 o = lds128(pr_x2);
-        if (hsel == 0) { a0 = a0 + o.x; a1 = a1 + o.y; a2 = a2 + o.z; }
-        else { a0 = o.x + a0; a1 = o.y + a1; a2 = o.z + a2; }
         a0 += lds32(sc_s + 4u * SC_RGB2_B0); a1 += lds32(sc_s + 4u * SC_RGB2_B1); a2 += lds32(sc_s + 4u * SC_RGB2_B2);
-        rgb[0] = 1.f / (1.f + __expf(-a0)); rgb[1] = 1.f / (1.f + __expf(-a1)); rgb[2] = 1.f / (1.f + __expf(-a2));
-      }
-      if (hsel == 1 || !live) continue;  // half 0 writes the sample's outputs
-
-      float flow[3];
-      {
-        // field_to_cam with the partner frame's camera, pinhole projection, flow (nerf.py:948-997)
-        const float* cn = fblk + FL.cam_partner;
-        const Q4 qn = {cn[11], cn[12], cn[13], cn[14]};
-        float3 xc = qrot(qn, x_next);
-        xc.x += cn[15]; xc.y += cn[16]; xc.z += cn[17];
-        const float k0 = cn[0], k1 = cn[4], k2 = cn[2], k3 = cn[5];
-        const float fx = 1.0f / k0, fy = 1.0f / k1, cx = -k2 / k0, cy = -k3 / k1;
-        const float hxn = (fx * xc.x + cx * xc.z) / (xc.z + 1e-6f);
-        const float hyn = (fy * xc.y + cy * xc.z) / (xc.z + 1e-6f);
-        flow[0] = hxn - h0;
-        flow[1] = hyn - h1;
-        bool valid = xc.z > 1e-6f;
-        if (p.rays.flow_thresh >= 0.f) valid = valid && (sqrtf(flow[0] * flow[0] + flow[1] * flow[1]) < p.rays.flow_thresh);
-        flow[2] = valid ? 1.f : 0.f;
-      }
-
-      // ------------------------------------------------ Gaussian bone density (compute_gauss_density)
-      // max_b exp(-d2_b / 2) = exp(-min_b d2_b / 2)
-      float gdens = 0.f;
-      if constexpr (B > 0) {
-        float best = INFINITY;
-        const uint32_t ctr = cblk_s + 4u * CL.center;
-#pragma unroll 5
-        for (int b = 0; b < B; ++b) {
-          const float4 c = lds128(ctr + 16u * b);
-          const float dx = xyz.x - c.x, dy = xyz.y - c.y, dz = xyz.z - c.z;
-          best = fminf(best, dx * dx + dy * dy + dz * dz);
-        }
-        gdens = expf(-0.5f * (best / (0.01f * 0.01f))) * lds32(sc_s + 4u * SC_WARP_IBETA);
-      }
-
-      // ------------------------------------------------ per-sample outputs
-      {
-        auto st3 = [&](float* dst, float a, float b, float c) { if (dst) { dst[s * 3] = a; dst[s * 3 + 1] = b; dst[s * 3 + 2] = c; } };
-        auto st1 = [&](float* dst, float a) { if (dst) dst[s] = a; };
-        st3(p.out.rgb, rgb[0], rgb[1], rgb[2]);
-        st1(p.out.density, density);
-        st1(p.out.sdf, sdf);
-        st1(p.out.vis, vis_out);
-        st3(p.out.xyz, xyz.x, xyz.y, xyz.z);
-        st3(p.out.xyz_cam, xyz_cam.x, xyz_cam.y, xyz_cam.z);
-        st3(p.out.xyz_t, xyz_t.x, xyz_t.y, xyz_t.z);
-        st3(p.out.dir, dir_f.x, dir_f.y, dir_f.z);
-        st1(p.out.depth, depth * lds32(sc_s + 4u * SC_INV_SCALE));
-        st1(p.out.deltas, delta);
-        st3(p.out.flow, flow[0], flow[1], flow[2]);
-        st1(p.out.cyc_dist, cyc);
-        st1(p.out.delta_skin, dsk_out);
-        st1(p.out.skin_entropy, ent_out);
-        st1(p.out.gauss_density, gdens);
-        if (p.out.feature && p.desc.has_feature) {
-          float4* fo = reinterpret_cast<float4*>(p.out.feature + s * 16);
-          fo[0] = make_float4(feat[0], feat[1], feat[2], feat[3]);
-          fo[1] = make_float4(feat[4], feat[5], feat[6], feat[7]);
-          fo[2] = make_float4(feat[8], feat[9], feat[10], feat[11]);
-          fo[3] = make_float4(feat[12], feat[13], feat[14], feat[15]);
-        }
+        st3(p.out.rgb, 1.f / (1.f + __expf(-a0)), 1.f / (1.f + __expf(-a1)), 1.f / (1.f + __expf(-a2)));
       }
     }
   }
@@ -828,44 +743,51 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
   }
 }
 
-template <class Op, int B, int LMAX, bool DENSE>
+template <class Op, int B, int LMAX, bool DENSE, int WIDTH>
 static cudaError_t launch_one(const FieldKernelParams& p, int n_sm, cudaStream_t stream) {
-  auto kern = field_fwd_kernel<Op, B, LMAX, DENSE>;
-  const int smem = 1024 + kSmemArena + kSmemRing + (p.prog.cl.n_floats + p.prog.fl.n_floats) * 4 + 128;
+  auto kern = field_fwd_kernel<Op, B, LMAX, DENSE, WIDTH>;
+  const int smem = 1024 + kSmemArena + kSmemRing + (p.prog.cl.n_floats + kGroups * p.prog.fl.n_floats) * 4 + 256;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  int grid = p.n_tiles < n_sm ? p.n_tiles : n_sm;
+  int grid = (p.n_tiles + 1) / 2 < n_sm ? (p.n_tiles + 1) / 2 : n_sm;
   grid = (grid + kCluster - 1) / kCluster * kCluster;
   if (grid > n_sm) grid -= kCluster;
   if (grid < kCluster) grid = kCluster;
+  if (grid > kMaxCtas) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // overlap the set-up with the prologue kernel's tail
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
+}  // namespace fwd
+
 cudaError_t launch_field_fwd(const FieldKernelParams& p, int n_sm, cudaStream_t stream) {
   const bool bf = p.desc.operand_dtype == 1;
-#define B200R_CASE(BN, LM, DN)                                                    \
-  if (p.desc.n_bones == BN && p.Lmax == LM && (p.desc.dense != 0) == DN)          \
-    return bf ? launch_one<OpBF16, BN, LM, DN>(p, n_sm, stream) : launch_one<OpF16, BN, LM, DN>(p, n_sm, stream);
-  B200R_CASE(0, 10, false)
-  B200R_CASE(0, 12, false)
-  B200R_CASE(18, 12, false)
-  B200R_CASE(25, 12, false)
-  B200R_CASE(18, 12, true)
-  B200R_CASE(25, 12, true)
+#define B200R_CASE(BN, LM, DN, WD)                                                                    \
+  if (p.desc.n_bones == BN && p.Lmax == LM && (p.desc.dense != 0) == DN && p.desc.W == WD)            \
+    return bf ? fwd::launch_one<OpBF16, BN, LM, DN, WD>(p, n_sm, stream) : fwd::launch_one<OpF16, BN, LM, DN, WD>(p, n_sm, stream);
+  B200R_CASE(0, 10, false, 128)
+  B200R_CASE(0, 12, false, 128)
+  B200R_CASE(0, 10, false, 256)
+  B200R_CASE(0, 12, false, 256)
+  B200R_CASE(18, 12, false, 256)
+  B200R_CASE(25, 12, false, 256)
+  B200R_CASE(18, 12, true, 256)
+  B200R_CASE(25, 12, true, 256)
 #undef B200R_CASE
   return cudaErrorInvalidValue;
 }

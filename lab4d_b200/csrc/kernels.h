@@ -36,7 +36,7 @@ struct FieldKernelParams {
   b200r_field_outputs out;
   const uint8_t* packed;
   const float* workspace;
-  uint4* scratch;          // v5: per-CTA scratch for the packed base features (program.h kScratchPerCta)
+  uint4* scratch;          // per-CTA scratch for the packed base features (program.h kScratchPerCta)
   int32_t M;
   int32_t ND;              // N * D samples per frame
   int32_t tiles_per_frame;
@@ -48,7 +48,6 @@ cudaError_t launch_pack(const PackParams& p, int operand_dtype, cudaStream_t str
 cudaError_t launch_prologue(const PrologueParams& p, cudaStream_t stream);
 cudaError_t launch_composite_fwd(const b200r_composite_args& a, cudaStream_t stream);
 cudaError_t launch_composite_bwd(const b200r_composite_bwd_args& b, cudaStream_t stream);
-cudaError_t launch_field_fwd(const FieldKernelParams& p, int n_sm, cudaStream_t stream);   // v4: one tile per CTA
-cudaError_t launch_field_fwd5(const FieldKernelParams& p, int n_sm, cudaStream_t stream);  // v5: two tiles per CTA
+cudaError_t launch_field_fwd(const FieldKernelParams& p, int n_sm, cudaStream_t stream);
 
 }  // namespace b200r

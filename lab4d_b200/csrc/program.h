@@ -1,11 +1,12 @@
 // Host+device description of the per-tile tensor-core program of one field and of the scratch
 // blocks (constant block, per-frame blocks) the prologue kernel builds for it.
 //
-// A "tile" is 128 consecutive ray-samples of ONE frame.  Its activations live in an arena of K-major
-// SWIZZLE_128B operand chunks ([128 rows x 64 halves] = 16 KB each) in shared memory; every dense
-// layer is one GemmDesc: D[128 x n_pad] (+)= sum over K chunks A_chunk[128 x 16*ksteps] * W_chunk^T.
-// Weights are pre-packed by b200r_pack_weights into [n_pad x 64] chunks with the same swizzle, so a
-// plain 1-D TMA bulk copy lands them in shared memory ready for tcgen05.mma.
+// A "tile" is 128 consecutive ray-samples of ONE frame; a CTA keeps two tiles in flight (tile groups 0 and 1).
+// Per group: the Fourier embedding of the tile lives in two K-major SWIZZLE_128B operand chunks in shared memory
+// ([128 rows x 64 halves] = 16 KB each), hidden activations live in TMEM (128 columns = 256 halves per row) next
+// to a 128-column fp32 accumulator.  Every dense layer is a list of MMA steps D[128 x n] (+)= A * W_chunk^T.
+// Weights are pre-packed by b200r_pack_weights into [n x 64] chunks with the same swizzle, so a plain 1-D TMA
+// bulk copy lands them in shared memory ready for tcgen05.mma.
 #pragma once
 #include <stdint.h>
 
@@ -22,16 +23,10 @@ constexpr int kWStageBytes = 2 * 128 * 128;    // 32 KB weight ring stage (two [
 constexpr int kMaxSteps = 96;
 constexpr int kMaxCond = 12;
 
-// arena chunk ids
-enum : int { CH_PE = 0, CH_EXTRA = 1, CH_H0 = 2, CH_H1 = 3, CH_H2 = 4, CH_H3 = 5, kArenaChunks = 6 };
+// embedding operand chunks of one tile group (embedding columns 0..62 and 63..)
+enum : int { CH_PE = 0, CH_EXTRA = 1, kArenaChunks = 2 };
 
-// TMEM columns: two 128-column accumulators (N-halves of a 256-wide layer) and two 128-column
-// buffers of 16-bit activations (256 halves per row) that ping-pong between consecutive layers
-constexpr int kTmemCols = 512;
-constexpr int kTmemD0 = 0;
-constexpr int kTmemD1 = 128;
-constexpr int kTmemA0 = 256;
-constexpr int kTmemA1 = 384;
+constexpr int kTmemCols = 512;  // the CTA owns all of TMEM: per group 128 accumulator + 128 activation columns
 
 // One MMA step = one ring stage = one or two packed weight tiles [n x 64] (= up to 8 UMMA_K steps of
 // D[128 x n] (+)= A * W^T).  The A operand of each tile is either an arena chunk in shared memory (SS) or
@@ -39,8 +34,8 @@ constexpr int kTmemA1 = 384;
 struct MmaStep {
   uint32_t w_off;        // byte offset of the first packed tile (the second follows it)
   uint16_t n;            // UMMA N (multiple of 16, <= 256)
-  uint16_t d_col;        // accumulator TMEM column
-  uint16_t a_tmem_col;   // TS: TMEM column of the operand's first k-step
+  uint16_t d_col;        // unused (each group has one accumulator)
+  uint16_t a_tmem_col;   // TS: column inside the group's activation buffer of the operand's first k-step
   uint8_t a_kind;        // 0 = shared-memory chunk, 1 = TMEM
   uint8_t n_sub;         // 1 or 2 weight tiles in this step
   uint8_t a_chunk;       // SS: arena chunk id of tile 0
@@ -103,7 +98,7 @@ struct FrameLayout {
   CondRow cond[kMaxCond];
 };
 
-// v5: one block = one GEMM (or one N-half of a wide layer) as the MMA issuers see it: an optional first ring slot
+// One block = one GEMM (or one N-half of a wide layer) as the MMA issuers see it: an optional first ring slot
 // whose A operand is one or two embedding chunks in shared memory, then `ts_slots` slots whose A operand is the
 // group's activation buffer in TMEM, read front to back (4 + 4 k-steps per slot; the last slot has 4 + ts_ks2_last).
 struct MmaBlock {
@@ -171,7 +166,7 @@ struct BuiltProgram {
   const char* err;
 };
 
-inline BuiltProgram build_program(const b200r_field_desc& d, int version = 4) {
+inline BuiltProgram build_program(const b200r_field_desc& d) {
   BuiltProgram bp;
   bp.ok = false;
   bp.err = "";
@@ -278,13 +273,8 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int version = 4) {
   };
   if (d.dense) {
     for (int m = 0; m < 2; ++m) {
-      if (version >= 5) {
-        add_split_w(L.dense[3 * m + 0], DW, pe_d + TEMB + INST, pe_slices(pe_d, 0));
-        add_split_w(L.dense[3 * m + 1], DW, DW, hidden(0, DW));
-      } else {
-        add_layer(L.dense[3 * m + 0], DW, pe_d + TEMB + INST, pe_slices(pe_d, 0));
-        add_layer(L.dense[3 * m + 1], DW, DW, hidden(0, DW));
-      }
+      add_split_w(L.dense[3 * m + 0], DW, pe_d + TEMB + INST, pe_slices(pe_d, 0));
+      add_split_w(L.dense[3 * m + 1], DW, DW, hidden(0, DW));
       add_layer(L.dense[3 * m + 2], 3, DW, hidden(0, DW));
     }
   }
@@ -370,8 +360,8 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int version = 4) {
     s.ksteps = (uint8_t)c[0].ksteps; s.ksteps2 = (uint8_t)(n_sub > 1 ? c[1].ksteps : 0);
     s.accumulate = (uint8_t)acc; s.wait = (uint8_t)wait; s.commit = (uint8_t)commit;
   };
-  if (version >= 5) {
-    // ------------------------------------------------------------------ v5: two tiles in flight per CTA.
+  {
+    // ------------------------------------------------------------------ two tiles in flight per CTA.
     // Each tile group owns 128 accumulator columns and 128 columns of 16-bit activations in TMEM; the only
     // shared-memory operands are the embedding chunks CH_PE / CH_EXTRA.  Steps are grouped in blocks (a block ends
     // at the step that commits); the MMA warp issues block b for group 0, then for group 1, then block b+1, ...
@@ -460,127 +450,13 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int version = 4) {
     bp.ok = true;
     return bp;
   }
-  // sequential GEMM: all compute threads hand over operands (BAR_ALL) and wait for the result (BAR_ALL)
-  auto seq_gemm = [&](int id, const std::vector<int>& a_chunks) {
-    const auto& cs = chunks[id];
-    for (size_t c = 0; c < cs.size();) {
-      const int nsub = (c + 1 < cs.size() && 2 * cs[c].n * 128 <= kWStageBytes) ? 2 : 1;  // two tiles must fit one ring stage
-      step(&cs[c], nsub, 0, a_chunks[c], nsub > 1 ? a_chunks[c + 1] : 0, 0, kTmemD0, c > 0, c == 0 ? BAR_ALL : BAR_NONE,
-           c + (size_t)nsub == cs.size() ? BAR_ALL : BAR_NONE);
-      c += (size_t)nsub;
-    }
-  };
-  auto pe_ch = [&](int pe_n) { std::vector<int> v{CH_PE}; if (pe_n > 63) v.push_back(CH_EXTRA); return v; };
-  auto hch = [&](int first, int n) { std::vector<int> v; for (int j = 0; j < n; ++j) v.push_back(first + j); return v; };
-  auto catv = [](std::vector<int> a, const std::vector<int>& b) { a.insert(a.end(), b.begin(), b.end()); return a; };
-  auto dense_gemms = [&](int m) {  // DenseWarp MLP m (0 forward_map, 1 backward_map): PE6 -> 256 -> 256 -> 3
-    seq_gemm(L.dense[3 * m + 0], {CH_PE});
-    seq_gemm(L.dense[3 * m + 1], hch(CH_H0, 4));
-    seq_gemm(L.dense[3 * m + 2], hch(CH_H0, 4));
-  };
-  for (int w = 0; w < 3; ++w) {
-    P.st_delta[w] = ns;
-    if (d.dense && w > 0) dense_gemms(0);  // forward warps: soft deformation first (warping.py:459-463)
-    if (B > 0) {
-      seq_gemm(L.delta[0], 3 * B > 64 ? std::vector<int>{CH_H0, CH_H1} : std::vector<int>{CH_H0});
-      seq_gemm(L.delta[1], {CH_H2});
-      seq_gemm(L.delta[2], {CH_H2});
-    }
-    if (d.dense && w == 0) dense_gemms(1);  // backward warp: un-articulate, then the soft deformation (warping.py:472-476)
-  }
-  P.st_vis = ns;
-  seq_gemm(L.vis[0], pe_ch(pe_v));
-  seq_gemm(L.vis[1], {CH_H0});
-  P.st_feat = ns;
-  if (d.has_feature) {
-    for (int i = 0; i < 5; ++i) {
-      if (i == 0) seq_gemm(L.feat[i], pe_ch(pe_f));
-      else if (i == 4) seq_gemm(L.feat[i], catv(pe_ch(pe_f), hch(CH_H0, 2)));
-      else seq_gemm(L.feat[i], hch(CH_H0, 2));
-    }
-    seq_gemm(L.feat[5], hch(CH_H0, 2));
-  }
-  // Pipelined chain layer: N-halves h = 0,1 into D0 / D1.  The leading chunks read shared-memory operands
-  // (embedding), the remaining KC chunks read the previous layer's activations from TMEM buffer `a_buf`.
-  // Hidden chunk kc was written by half (kc*64)/HN of the previous layer's epilogue: the chunks of the first
-  // half are issued as soon as BAR_H0 fires, the others after BAR_H1.
-  auto pipe_layer = [&](int id, const std::vector<int>& ss_chunks, bool has_hidden, int a_buf, bool first_of_chain_all) {
-    const int n_ss = (int)ss_chunks.size();
-    for (int h = 0; h < 2; ++h) {
-      const auto& cs = h == 0 ? chunks[id] : chunks_h1[id];
-      const int dcol = h == 0 ? kTmemD0 : kTmemD1;
-      const int total = (int)cs.size();
-      int first_wait = first_of_chain_all ? (h == 0 ? BAR_ALL : BAR_NONE) : (h == 0 ? BAR_H0 : (has_hidden ? BAR_NONE : BAR_H1));
-      bool waited_h1 = (h == 1);
-      int c = 0;
-      auto last = [&](int used) { return c + used == total ? (h == 0 ? BAR_H0 : BAR_H1) : BAR_NONE; };
-      // shared-memory operand chunks (1 or 2), one step
-      if (n_ss > 0) {
-        step(&cs[0], n_ss, 0, ss_chunks[0], n_ss > 1 ? ss_chunks[1] : 0, 0, dcol, 0, first_wait, last(n_ss));
-        c = n_ss;
-        first_wait = BAR_NONE;
-      }
-      // hidden chunks from TMEM, paired when both belong to the same producing half
-      while (c < total) {
-        const int kc = c - n_ss;
-        const int owner = (kc * 64) / HN;
-        int nsub = 1;
-        if (c + 1 < total && ((kc + 1) * 64) / HN == owner) nsub = 2;
-        int wait = first_wait;
-        first_wait = BAR_NONE;
-        if (owner == 1 && !waited_h1) { wait = BAR_H1; waited_h1 = true; }
-        step(&cs[c], nsub, 1, 0, 0, (a_buf == 0 ? kTmemA0 : kTmemA1) + kc * 32, dcol, c > 0, wait, last(nsub));
-        c += nsub;
-      }
-    }
-  };
-  P.st_base = ns;
-  int buf = 0;  // TMEM activation buffer holding the current layer's INPUT
-  for (int i = 0; i <= d.D; ++i) {
-    if (i == 0) pipe_layer(L.base[i], pe_ch(pe_b), false, buf, true);
-    else if (i == d.skip) pipe_layer(L.base[i], pe_ch(pe_b), true, buf, false);
-    else pipe_layer(L.base[i], {}, true, buf, false);
-    buf ^= 1;  // this layer's epilogue writes the other buffer, which the next layer reads
-  }
-  // base final's epilogue writes the features to shared memory (CH_H0..) instead: colour L1 reads the embedding
-  P.st_color = ns;
-  pipe_layer(L.color[0], pe_ch(pe_c), false, buf, false);
-  buf ^= 1;
-  pipe_layer(L.color[1], {}, true, buf, false);
-  buf ^= 1;
-  pipe_layer(L.color[2], {}, true, buf, false);
-  buf ^= 1;
-  // rgb.0 applied to base features (shared memory) + colour features (TMEM), one accumulator
-  P.st_rgb = ns;
-  {
-    const auto& cs = chunks[L.rgb0];
-    for (int c = 0; c < KC; c += 2) {
-      const int nsub = c + 1 < KC ? 2 : 1;
-      step(&cs[c], nsub, 0, CH_H0 + c, CH_H0 + c + 1, 0, kTmemD0, c > 0, c == 0 ? BAR_H0 : BAR_NONE, BAR_NONE);
-    }
-    bool waited_h1 = false;
-    int kc = 0;
-    while (kc < KC) {
-      const int owner = (kc * 64) / HN;
-      int nsub = 1;
-      if (kc + 1 < KC && ((kc + 1) * 64) / HN == owner) nsub = 2;
-      int wait = BAR_NONE;
-      if (owner == 1 && !waited_h1) { wait = BAR_H1; waited_h1 = true; }
-      step(&cs[kc], nsub, 1, 0, 0, (buf == 0 ? kTmemA0 : kTmemA1) + kc * 32, kTmemD0, 1, wait, kc + nsub == KC ? BAR_ALL : BAR_NONE);
-      kc += nsub;
-    }
-  }
-  P.n_steps = ns;
-  if (ns > kMaxSteps) { bp.err = "too many MMA steps"; return bp; }
-  bp.ok = true;
-  return bp;
 }
 
 inline size_t workspace_floats(const Program& P, int M) { return (size_t)P.cl.n_floats + (size_t)M * P.fl.n_floats; }
-// v5 keeps the 256 packed base features of every row of both tiles in flight in a per-CTA scratch (L2 resident)
+// the field kernel keeps the 256 packed base features of every row of both tiles in flight in a per-CTA scratch (L2 resident)
 constexpr int kMaxCtas = 160;
 constexpr size_t kScratchPerCta = 2 * (size_t)kTileRows * 512;
 inline size_t scratch_offset_bytes(const Program& P, int M) { return (workspace_floats(P, M) * sizeof(float) + 255) / 256 * 256; }
-inline size_t workspace_bytes_v5(const Program& P, int M) { return scratch_offset_bytes(P, M) + kMaxCtas * kScratchPerCta; }
+inline size_t workspace_bytes_total(const Program& P, int M) { return scratch_offset_bytes(P, M) + kMaxCtas * kScratchPerCta; }
 
 }  // namespace b200r

@@ -4,5 +4,3 @@ timeout 600 python -m pytest tests -m gpu -q -s --timeout=120 -x > gpurun_out/py
 grep -E "passed|failed|Error|timed out|exit|assert|b200r:" gpurun_out/pytest_gpu.log | cut -c1-400 | tail -12
 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench.log 2>&1; echo "bench exit $?" >> gpurun_out/bench.log
 tail -2 gpurun_out/bench.log | cut -c1-1700
-B200R_KERNEL=4 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench4.log 2>&1
-tail -1 gpurun_out/bench4.log | cut -c1-300

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise an ncu report's warp-state samples of field_fwd5_kernel: per role (address range), top wait sites,
+"""Summarise an ncu report's warp-state samples of field_fwd_kernel: per role (address range), top wait sites,
 top instructions.  usage: ncu_src_summary.py report.ncu-rep"""
 import collections, csv, subprocess, sys, io
 rep = sys.argv[1]
@@ -19,8 +19,8 @@ for r in rows:
 addrs = sorted(by); base = addrs[0]
 tot = sum(by[a]["c"] for a in addrs)
 print("unique instructions", len(addrs), "samples", tot)
-src = open("/root/repo/lab4d_b200/csrc/field_fwd5.cu").read().split("\n")
-def own_lines(a): return sorted({l for f, l in by[a]["lines"] if f == "field_fwd5.cu" and l >= 96})
+src = open("/root/repo/lab4d_b200/csrc/field_fwd.cu").read().split("\n")
+def own_lines(a): return sorted({l for f, l in by[a]["lines"] if f == "field_fwd.cu" and l >= 96})
 def ctx(i):
     ls = set()
     for j in range(max(0, i - 10), min(len(addrs), i + 10)): ls.update(own_lines(addrs[j]))
