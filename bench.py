@@ -276,7 +276,7 @@ def main():
                     "d2h_bytes_per_step": out_host.numel() * 4},
             "gpu_launches": n_launch,
             "roofline": {"bound": "tensor", "kernel": "field_fwd_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": 3.74e6, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_final.md)",
+                         "frac": achieved / peak_tf, "traffic": 15.7e6, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_final.md)",
                          "kernel_ms": kms, "kernel_scope": "prologue_kernel + field_fwd_kernel (one C-ABI call)",
                          "flop_per_sample": FLOP_PER_SAMPLE_FWD, "peak_source": how + " bf16 dense burst"},
             "clocks": clocks, "wall_s_timed_region": t_wall,
