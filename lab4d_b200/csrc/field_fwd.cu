@@ -98,15 +98,17 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
   float* cblk = reinterpret_cast<float*>(ring + kSmemRing);
   float* fblk = cblk + p.prog.cl.n_floats;  // one frame block per tile group
   uint64_t* bars = reinterpret_cast<uint64_t*>(fblk + kGroups * p.prog.fl.n_floats);
-  uint64_t* full_bar = bars;                  // [kNumStages]
-  uint64_t* empty_bar = bars + kNumStages;    // [kNumStages]
-  uint64_t* c2m = bars + 2 * kNumStages;      // [group][4] compute warps -> MMA thread, indexed by BAR_*
-  uint64_t* m2c = bars + 2 * kNumStages + 8;  // [group][4] MMA thread (tcgen05.commit) -> compute warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumStages + 16);
+  // full barriers are per (group, stage): every barrier is then waited on by exactly one issuer, phase after phase,
+  // so a parity wait can never alias with a fill that belongs to the other group's use of the same stage
+  uint64_t* full_bar = bars;                  // [group][kNumStages]
+  uint64_t* empty_bar = bars + 2 * kNumStages;  // [kNumStages]
+  uint64_t* c2m = bars + 3 * kNumStages;      // [group][4] compute warps -> MMA thread, indexed by BAR_*
+  uint64_t* m2c = bars + 3 * kNumStages + 8;  // [group][4] MMA thread (tcgen05.commit) -> compute warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kNumStages + 16);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNumStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], kCluster); }
+    for (int i = 0; i < kNumStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&full_bar[kNumStages + i], 1); mbar_init(&empty_bar[i], kCluster); }
     for (int i = 0; i < 8; ++i) { mbar_init(&c2m[i], 4); mbar_init(&m2c[i], 1); }  // one arrival per warp of the group
     fence_barrier_init();
   }
@@ -140,12 +142,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
               const MmaStep& S = P.steps[s];
               const uint32_t bytes = (uint32_t)S.n * 128u * S.n_sub;
               const uint32_t part = bytes / kCluster;
+              uint64_t* fb = &full_bar[g * kNumStages + stage];
               mbar_wait(&empty_bar[stage], phase ^ 1);  // both CTAs' MMAs are done with this slot
-              mbar_arrive_expect_tx(&full_bar[stage], bytes);
+              mbar_arrive_expect_tx(fb, bytes);
               const uint8_t* src = p.packed + S.w_off + cta_rank * part;
               uint8_t* dst = ring + stage * kWStageBytes + cta_rank * part;
-              if (kCluster > 1) tma_bulk_g2s_mcast(dst, src, part, &full_bar[stage], cmask);
-              else tma_bulk_g2s(dst, src, part, &full_bar[stage]);
+              if (kCluster > 1) tma_bulk_g2s_mcast(dst, src, part, fb, cmask);
+              else tma_bulk_g2s(dst, src, part, fb);
               if (++stage == kNumStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -156,11 +159,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
   } else if (warp == 9 || warp == 10) {
     // =============================================================== MMA issuers: warp 9 -> tile group 0, warp 10 -> group 1.
     // Ring slots are filled in the global order [block b, group 0][block b, group 1][block b+1, group 0]...; each
-    // issuer consumes its own group's slots and steps over the other's.  Everything here is warp-uniform and comes
+    // issuer consumes its own group's slots (signalled on its own full barriers) and steps over the other's.  Everything here is warp-uniform and comes
     // from the kernel parameters (MmaBlock), so descriptors and addresses stay in uniform registers.
     const int g = warp - 9;
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0;
+    uint32_t full_par = 0;   // bit s = parity of this group's full barrier of stage s
     uint32_t bar_phase = 0;  // bit i = parity of c2m[g][i]
+    uint64_t* full_g = full_bar + g * kNumStages;
     const uint32_t desc_hi = (uint32_t)(umma_desc_k_sw128(0) >> 32);
     const uint32_t bd_lo0 = (uint32_t)umma_desc_k_sw128(smem_u32(ring));
     const uint32_t ad_lo0 = (uint32_t)umma_desc_k_sw128(smem_u32(arena)) + (uint32_t)g * (kArenaGroup >> 4);
@@ -169,14 +174,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     uint64_t* c2m_g = c2m + 4 * g;
     uint64_t* m2c_g = m2c + 4 * g;
     auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
-    auto advance = [&]() { if (++stage == kNumStages) { stage = 0; phase ^= 1; } };
-    // Step over the other group's slots.  Their fill is still observed: a parity wait cannot tell "fill n+1 done" from
-    // "fill n not yet done", so an issuer must never wait for a stage's next fill before it has seen the previous one.
-    auto skip = [&](uint32_t cnt) {
-      for (uint32_t j = 0; j < cnt; ++j) {
-        mbar_wait(&full_bar[stage], phase);
-        advance();
-      }
+    auto advance = [&]() { if (++stage == kNumStages) stage = 0; };
+    auto wait_full = [&]() {
+      mbar_wait(&full_g[stage], (full_par >> stage) & 1u);
+      full_par ^= 1u << stage;
+      tc_fence_after_sync();
+    };
+    auto skip = [&](uint32_t cnt) {  // step over the other group's slots (they have their own full barriers)
+      for (uint32_t j = 0; j < cnt; ++j) advance();
     };
     auto release = [&]() {  // frees the ring slot (in both CTAs) once the MMAs issued so far have read it
       if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], cmask);
@@ -198,8 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         }
         uint32_t acc = 0;
         if (ss) {  // embedding chunk(s) from shared memory
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after_sync();
+          wait_full();
           const uint32_t bd = bd_lo0 + stage * (kWStageBytes >> 4);
           if (elect_one()) {
             const uint32_t ks = ss & 7u, ks2 = (ss >> 3) & 7u;
@@ -217,8 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         uint32_t a = act0;
 #pragma unroll 1
         for (uint32_t j = 0; j < ts_slots; ++j) {  // activations from TMEM, 64 columns (128 values) per slot
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after_sync();
+          wait_full();
           const uint32_t bd = bd_lo0 + stage * (kWStageBytes >> 4), bd2 = bd + tile2;
           const bool last = j + 1 == ts_slots;
           if (elect_one()) {

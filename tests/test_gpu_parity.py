@@ -268,6 +268,44 @@ def test_query_field_skeleton18_with_symmetric_bones():
     assert rel_l2(render_pixel(feat, deltas)["rgb"].cpu(), O.render_pixel(ofeat, odel)["rgb"].cpu()) < 1e-3
 
 
+def _variant_cfg(name):
+    from lab4d_b200 import spec
+
+    if name == "w128_L10":  # narrow field with the 10-frequency embedding (12 for colour)
+        return spec.FieldConfig(category="bg", D=5, W=128, L_xyz=10, L_dir=0, appr_channels=0, motion="rigid", B=0, has_feature=False)
+    if name == "w256_L6":   # wide rigid field with a 6-frequency embedding (8 for colour)
+        return spec.FieldConfig(motion="rigid", B=0, L_xyz=6)
+    if name == "skel18_dense":
+        c = _skel18_cfg()
+        return spec.FieldConfig(motion="skel", B=18, symm_idx=c.symm_idx, dense=True)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["w128_L10", "w256_L6", "skel18_dense"])
+def test_other_kernel_variants_match_oracle(name):
+    """The remaining template instances of the field kernel (width x embedding size x bones x dense warp)."""
+    from lab4d_b200.render import render_pixel
+
+    cfg = _variant_cfg(name)
+    P = synth_params(cfg, 5, device=DEV)
+    M, N, D = 4, 12, 40
+    rays = {k: torch.from_numpy(v).to(DEV) for k, v in synth.synth_rays(M, N, seed=8).items()}
+    tab = synth_tables(cfg, M, DEV, seed=8, rays=rays, P=P)
+    r = _renderer(cfg, P)
+    feat, deltas = r.query_field(P, rays, tab, D)
+    torch.cuda.synchronize()
+    ofeat, odel = O.query_field(P, cfg.as_oracle_cfg(), rays, tab, D)
+    _report("oracle " + name, feat, ofeat)
+    for k, rv in ofeat.items():
+        if k in ("eikonal", "flow"):
+            continue
+        if k in ABS:
+            assert float((feat[k] - rv).abs().max()) <= ABS[k], k
+        else:
+            assert rel_l2(feat[k].cpu(), rv.cpu()) < REL[k], (k, rel_l2(feat[k].cpu(), rv.cpu()))
+    assert rel_l2(render_pixel(feat, deltas)["rgb"].cpu(), O.render_pixel(ofeat, odel)["rgb"].cpu()) < 1e-3
+
+
 @pytest.mark.parametrize("alpha", [0.3, 0.75])
 def test_annealing_window_folded_into_weights(alpha):
     """PosEmbedding coarse-to-fine window (nnutils/embedding.py:112-125): the CUDA path folds it into the packed
