@@ -32,6 +32,33 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class HostStage:
+    """Host-resident inputs of a step (ray batch + per-frame tables) in ONE pinned arena with a device mirror: a step's
+    host->device transfer is a single asynchronous copy instead of one per tensor.  `host` / `dev` are dicts of views
+    into the two arenas with the caller's keys, shapes and dtypes."""
+
+    def __init__(self, tensors, device):
+        offs, total = {}, 0
+        for k, v in tensors.items():
+            offs[k] = total
+            total += (v.numel() * v.element_size() + 255) // 256 * 256
+        self.host_arena = torch.empty(max(total, 256), dtype=torch.uint8).pin_memory()
+        self.dev_arena = torch.empty(max(total, 256), dtype=torch.uint8, device=device)
+        self.nbytes = sum(v.numel() * v.element_size() for v in tensors.values())
+
+        def views(arena):
+            return {k: arena[offs[k]:offs[k] + v.numel() * v.element_size()].view(v.dtype).view(v.shape) for k, v in tensors.items()}
+
+        self.host, self.dev = views(self.host_arena), views(self.dev_arena)
+        for k, v in tensors.items():
+            self.host[k].copy_(v)
+
+    def upload(self):
+        """Enqueue the host->device copy on the current stream; returns the device views."""
+        self.dev_arena.copy_(self.host_arena, non_blocking=True)
+        return self.dev
+
+
 class FieldRenderer:
     """One field (fg or bg).  Holds the packed tensor-core operands; everything else is per call."""
 
@@ -318,8 +345,8 @@ def render_pixel(field_dict, deltas):
         out[k] = v
     # per-batch normalisers (tiny (M,N) tensors)
     if "vis" in out:
-        v = out["vis"]
-        out["vis"] = (-(v[..., :1] / D) / (v[..., 1].detach().sum() / (R * D)))
+        v = out["vis"]  # -(v0 / D) / (sum(v1) / (R D)) with the scalar folded first: three small kernels instead of five
+        out["vis"] = v[..., :1] * (-float(R) / v[..., 1].detach().sum())
     for k in ("eikonal", "delta_skin"):
         if k in out:
             out[k] = out[k][..., 0]
@@ -327,7 +354,7 @@ def render_pixel(field_dict, deltas):
         out["gauss_mask"] = out.pop("gauss_density")
     dkeys = [k for k in out if k.startswith("density_")]
     if dkeys:
-        dsum = torch.cat([out[k] for k in dkeys], -1).sum(-1, keepdim=True) + 1e-6
+        dsum = (out[dkeys[0]] if len(dkeys) == 1 else torch.cat([out[k] for k in dkeys], -1).sum(-1, keepdim=True)) + 1e-6
         for k in dkeys:
             out[k.replace("density_", "mask_")] = out.pop(k) / dsum
     if "normal" in out:

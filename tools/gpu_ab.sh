@@ -1,6 +1,6 @@
 #!/bin/bash
+# A/B of a build flag: tools/gpu_ab.sh "<ENV=VAL ...>" (rebuilds on the box, benches, restores nothing: the box is scratch)
 mkdir -p gpurun_out
-echo "== cluster=2 (prebuilt)"; timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'])"
-B200R_CLUSTER=1 python lab4d_b200/build.py --force > gpurun_out/build_c1.log 2>&1
-echo "== cluster=1"; timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'])"
-timeout 300 python -m pytest tests -m gpu -q --timeout=300 2>&1 | tail -2
+timeout 200 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/bench_A.log 2>&1; grep -o '"kernel_ms": [0-9.]*' gpurun_out/bench_A.log
+env $1 python -m lab4d_b200.build --force > gpurun_out/build_B.log 2>&1; tail -1 gpurun_out/build_B.log
+timeout 200 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/bench_B.log 2>&1; grep -o '"kernel_ms": [0-9.]*' gpurun_out/bench_B.log; grep -m3 "b200r:\|Error" gpurun_out/bench_B.log
