@@ -1,9 +1,9 @@
 // Alpha compositing along rays (render_pixel / compute_weights / integrate,
 // lab4d/utils/render_utils.py:59-184) and its hand-derived backward.
 //
-// HBM-bound: one warp per ray, lanes across samples, warp-shuffle inclusive scan of the optical
-// depth with a running carry, per-ray weights kept in shared memory while the value channels are
-// reduced.  Algorithmic traffic = 4 B x (2 + sum of channel widths) per sample read + O(c) per ray.
+// HBM/L2-bound.  Forward: one 128-thread block per ray (block scan of the optical depth, flat coalesced walks
+// over the value arrays); backward: one warp per ray, lanes across samples, warp-shuffle inclusive scan with a
+// running carry.  Per-ray weights stay in shared memory while the value channels are reduced.  Algorithmic traffic = 4 B x (2 + sum of channel widths) per sample read + O(c) per ray.
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -12,7 +12,6 @@
 namespace b200r {
 
 constexpr int kWarpsPerBlock = 8;
-constexpr int kWarpsPerRayFwd = 1;  // (tried 4 warps per ray with the channels spread out: no gain on B200)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -50,80 +49,156 @@ __device__ __forceinline__ float ray_weights(const float* __restrict__ dens, con
   return warp_sum(msum);
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_fwd_kernel(const b200r_composite_args a) {
-  extern __shared__ float sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int D = a.D;
-  float* w_s = sm + (size_t)warp * 3 * D;
-  float* T_s = w_s + D;
-  float* g_s = T_s + D;  // scratch weights (gauss)
-  const int r = blockIdx.x * (kWarpsPerBlock / kWarpsPerRayFwd) + warp / kWarpsPerRayFwd;
-  const int cw = warp % kWarpsPerRayFwd;  // this warp's share of the channels; the weights are recomputed per warp
-  if (r >= a.R) return;
-  const size_t base = (size_t)r * D;
-  const float mask = ray_weights(a.density + base, a.deltas + base, D, lane, w_s, T_s);
-  __syncwarp();
-  if (cw == 0) {
-    if (lane == 0 && a.mask) a.mask[r] = mask;
-    if (a.weights)
-      for (int k = lane; k < D; k += 32) a.weights[base + k] = w_s[k];
-    if (a.transmit)
-      for (int k = lane; k < D; k += 32) a.transmit[base + k] = T_s[k];
+// ---- forward: one 128-thread block per ray.  Every per-sample array of the ray is walked as one flat, fully
+// coalesced run of D * nch floats (thread t takes elements t, t + 128, ...), so a ray's 37 floats per sample are in
+// flight at once instead of 4 strided channels per pass.
+constexpr int kFwdThreads = 128;
+constexpr int kFwdWarps = kFwdThreads / 32;
+
+struct FwdSmem {
+  float* w;    // [D] weights
+  float* T;    // [D] transmittance after each sample
+  float* red;  // [kFwdWarps * 32] reduction scratch
+};
+
+// sum over the block; every thread gets the result.  `red` must hold kFwdWarps floats per value.
+__device__ __forceinline__ float block_sum(float v, float* red, int warp, int lane) {
+  v = warp_sum(v);
+  __syncthreads();  // previous users of red are done
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < kFwdWarps; ++i) t += red[i];
+  return t;
+}
+
+// weights of one ray with the block: sample k = c0 + tid; returns sum_k w_k (all threads)
+__device__ __forceinline__ float block_ray_weights(const float* __restrict__ dens, const float* __restrict__ dl, int D, int warp,
+                                                   int lane, float* w_s, float* T_s, float* red) {
+  float carry = 0.f, msum = 0.f;
+  for (int c0 = 0; c0 < D; c0 += kFwdThreads) {
+    const int k = c0 + (int)threadIdx.x;
+    const float tau = k < D ? dens[k] * dl[k] : 0.f;
+    const float incl_w = warp_incl_scan(tau, lane);
+    float prev_w = __shfl_up_sync(0xffffffffu, incl_w, 1);
+    if (lane == 0) prev_w = 0.f;
+    __syncthreads();
+    if (lane == 31) red[warp] = incl_w;  // warp totals
+    __syncthreads();
+    float off = carry, tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kFwdWarps; ++i) {
+      if (i < warp) off += red[i];
+      tot += red[i];
+    }
+    const float w = (1.f - expf(-tau)) * expf(-(prev_w + off));
+    if (k < D) {
+      w_s[k] = w;
+      if (T_s) T_s[k] = expf(-(incl_w + off));
+      msum += w;
+    }
+    carry += tot;
   }
+  return block_sum(msum, red, warp, lane);
+}
+
+__global__ void __launch_bounds__(kFwdThreads) composite_fwd_kernel(const b200r_composite_args a) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int D = a.D;
+  float* w_s = sm;
+  float* T_s = sm + D;
+  float* g_s = sm + 2 * D;                 // scratch weights (gauss)
+  float* red = sm + 3 * D;                 // kFwdWarps * 32 floats
+  const int r = blockIdx.x;
+  const size_t base = (size_t)r * D;
+  const float mask = block_ray_weights(a.density + base, a.deltas + base, D, warp, lane, w_s, T_s, red);
+  __syncthreads();  // w_s / T_s visible to every thread
+  if (tid == 0 && a.mask) a.mask[r] = mask;
+  if (a.weights)
+    for (int k = tid; k < D; k += kFwdThreads) a.weights[base + k] = w_s[k];
+  if (a.transmit)
+    for (int k = tid; k < D; k += kFwdThreads) a.transmit[base + k] = T_s[k];
   const float inv = 1.0f / (mask + 1e-6f);
 
-  for (int c = cw; c < a.n_channels; c += kWarpsPerRayFwd) {
+  for (int c = 0; c < a.n_channels; ++c) {
     const int nch = a.nch[c], mode = a.mode[c];
     const float* __restrict__ src = a.src[c] + base * nch;
     float* dst = a.dst[c];
+    const int n_el = D * nch;
     if (mode == B200R_CH_NORM || mode == B200R_CH_NORM_FROZEN) {
-      for (int j0 = 0; j0 < nch; j0 += 4) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = lane; k < D; k += 32) {
-          const float wn = w_s[k] * inv;
+      if (nch <= 32 && (32 % nch) == 0) {
+        // channel of a thread is fixed: j = tid % nch
+        float acc = 0.f;
+        const int sh = __ffs(nch) - 1;  // nch is a power of two here
+        for (int e = tid; e < n_el; e += kFwdThreads) acc += w_s[e >> sh] * src[e];
+        for (int o = nch; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        __syncthreads();
+        if (lane < nch) red[warp * 32 + lane] = acc;
+        __syncthreads();
+        if (tid < nch) {
+          float t = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j0 + j < nch) acc[j] += wn * src[(size_t)k * nch + j0 + j];
+          for (int i = 0; i < kFwdWarps; ++i) t += red[i * 32 + tid];
+          dst[(size_t)r * nch + tid] = t * inv;
         }
+      } else if (nch == 3) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int e = tid; e < n_el; e += kFwdThreads) {
+          const int k = e / 3, j = e - 3 * k;
+          const float v = w_s[k] * src[e];
+          if (j == 0) a0 += v; else if (j == 1) a1 += v; else a2 += v;
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+        __syncthreads();
+        if (lane == 0) { red[warp * 32] = a0; red[warp * 32 + 1] = a1; red[warp * 32 + 2] = a2; }
+        __syncthreads();
+        if (tid < 3) {
+          float t = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float t = warp_sum(acc[j]);
-          if (lane == 0 && j0 + j < nch) dst[(size_t)r * nch + j0 + j] = t;
+          for (int i = 0; i < kFwdWarps; ++i) t += red[i * 32 + tid];
+          dst[(size_t)r * 3 + tid] = t * inv;
+        }
+      } else {  // any other width: one channel at a time
+        for (int j = 0; j < nch; ++j) {
+          float acc = 0.f;
+          for (int k = tid; k < D; k += kFwdThreads) acc += w_s[k] * src[(size_t)k * nch + j];
+          const float t = block_sum(acc, red, warp, lane);
+          if (tid == 0) dst[(size_t)r * nch + j] = t * inv;
         }
       }
     } else if (mode == B200R_CH_MEAN) {
       float acc = 0.f;
-      for (int e = lane; e < D * nch; e += 32) acc += src[e];
-      acc = warp_sum(acc);
-      if (lane == 0) dst[r] = acc / (float)(D * nch);
+      for (int e = tid; e < n_el; e += kFwdThreads) acc += src[e];
+      const float t = block_sum(acc, red, warp, lane);
+      if (tid == 0) dst[r] = t / (float)n_el;
     } else if (mode == B200R_CH_FLOW) {
-      float sw = 0.f, sx = 0.f, sy = 0.f;
-      for (int k = lane; k < D; k += 32) {
-        const float wf = w_s[k] * src[(size_t)k * 3 + 2];
-        sw += wf;
-      }
-      sw = warp_sum(sw);
+      float sw = 0.f;
+      for (int k = tid; k < D; k += kFwdThreads) sw += w_s[k] * src[(size_t)k * 3 + 2];
+      sw = block_sum(sw, red, warp, lane);
       const float invf = 1.0f / (sw + 1e-6f);
-      for (int k = lane; k < D; k += 32) {
+      float sx = 0.f, sy = 0.f;
+      for (int k = tid; k < D; k += kFwdThreads) {
         const float wf = w_s[k] * src[(size_t)k * 3 + 2] * invf;
         sx += wf * src[(size_t)k * 3];
         sy += wf * src[(size_t)k * 3 + 1];
       }
-      sx = warp_sum(sx);
-      sy = warp_sum(sy);
-      if (lane == 0) { dst[(size_t)r * 2] = sx; dst[(size_t)r * 2 + 1] = sy; }
+      sx = block_sum(sx, red, warp, lane);
+      sy = block_sum(sy, red, warp, lane);
+      if (tid == 0) { dst[(size_t)r * 2] = sx; dst[(size_t)r * 2 + 1] = sy; }
     } else if (mode == B200R_CH_WEIGHTSUM) {
-      const float m2 = ray_weights(src, a.deltas + base, D, lane, g_s, nullptr);
-      if (lane == 0) dst[r] = m2;
+      const float m2 = block_ray_weights(src, a.deltas + base, D, warp, lane, g_s, nullptr, red);
+      if (tid == 0) dst[r] = m2;
     } else if (mode == B200R_CH_VIS) {
       float s0 = 0.f, s1 = 0.f;
-      for (int k = lane; k < D; k += 32) {
+      for (int k = tid; k < D; k += kFwdThreads) {
         s0 += log_sigmoid(src[k]) * T_s[k];
         s1 += T_s[k];
       }
-      s0 = warp_sum(s0);
-      s1 = warp_sum(s1);
-      if (lane == 0) { dst[(size_t)r * 2] = s0; dst[(size_t)r * 2 + 1] = s1; }
+      s0 = block_sum(s0, red, warp, lane);
+      s1 = block_sum(s1, red, warp, lane);
+      if (tid == 0) { dst[(size_t)r * 2] = s0; dst[(size_t)r * 2 + 1] = s1; }
     }
   }
 }
@@ -263,13 +338,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_bwd_kernel(cons
 }
 
 cudaError_t launch_composite_fwd(const b200r_composite_args& a, cudaStream_t stream) {
-  const size_t smem = (size_t)kWarpsPerBlock * 3 * a.D * sizeof(float);
+  const size_t smem = ((size_t)3 * a.D + kFwdWarps * 32) * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int rays_per_block = kWarpsPerBlock / kWarpsPerRayFwd;
-  const int blocks = (a.R + rays_per_block - 1) / rays_per_block;
-  composite_fwd_kernel<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a);
+  composite_fwd_kernel<<<a.R, kFwdThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
