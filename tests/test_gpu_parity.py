@@ -365,6 +365,32 @@ def test_minimal_and_ragged_shapes(M, N, D):
         assert rel_l2(feat[k].cpu(), ofeat[k].cpu()) < REL[k], k
 
 
+@pytest.mark.parametrize("M,N,D", [(1, 5, 33), (320, 2, 16), (2, 6, 256)])
+def test_single_frame_many_frames_long_rays(M, N, D):
+    """M = 1 (a frame is its own flow partner), more frame blocks than the prologue grid holds in one wave, and rays
+    longer than a tile / than the compositing block (D = 256)."""
+    from lab4d_b200 import spec
+    from lab4d_b200.render import render_pixel
+
+    cfg = spec.FG_BOB
+    P = synth_params(cfg, 2, device=DEV)
+    rays = {k: torch.from_numpy(v).to(DEV) for k, v in synth.synth_rays(M, N, seed=11).items()}
+    tab = synth_tables(cfg, M, DEV, seed=11, rays=rays, P=P)
+    feat, deltas = _renderer(cfg, P).query_field(P, rays, tab, D)
+    torch.cuda.synchronize()
+    ofeat, odel = O.query_field(P, cfg.as_oracle_cfg(), rays, tab, D)
+    for k in ("rgb", "vis", "xyz", "depth", "feature", "skin_entropy"):
+        assert rel_l2(feat[k].cpu(), ofeat[k].cpu()) < REL[k], (k, rel_l2(feat[k].cpu(), ofeat[k].cpu()))
+    assert float((feat["cyc_dist"] - ofeat["cyc_dist"]).abs().max()) <= ABS["cyc_dist"]
+    rend, orend = render_pixel(feat, deltas), O.render_pixel(ofeat, odel)
+    for k in ("rgb", "mask", "depth", "xyz"):
+        assert rel_l2(rend[k].cpu(), orend[k].cpu()) < 5e-3, k
+    # compositing alone on the oracle's samples: D = 256 walks the block scan twice
+    rend2 = render_pixel({k: v.contiguous() for k, v in ofeat.items()}, odel.contiguous())
+    for k, v in orend.items():
+        assert rel_l2(rend2[k].cpu(), v.cpu()) < 5e-5, k
+
+
 def test_bad_arguments_are_rejected_not_crashed():
     from lab4d_b200 import spec
     from lab4d_b200.render import FieldRenderer
