@@ -198,6 +198,24 @@ typedef struct {
 
 int b200r_composite_bwd(b200r_handle* h, const b200r_composite_bwd_args* args, b200r_stream stream);
 
+/* ------------------------------------------------------------------ compose_fields (two fields -> one sample list)
+ * MultiFields.compose_fields (lab4d/nnutils/multifields.py:339-398): the samples of field A (first in field order) and
+ * field B along every ray are merged by depth (A first on ties); every per-sample array is gathered into the merged
+ * order.  A NULL source means the field lacks that key and contributes zeros.  More than two fields: merge pairwise. */
+typedef struct {
+  int32_t R, Da, Db;          /* rays, samples per ray of field A / B; inputs sorted by depth along the ray */
+  int32_t n_channels;
+  const float* depth_a;       /* (R*Da) */
+  const float* depth_b;       /* (R*Db) */
+  int32_t* perm;              /* (R*(Da+Db)) optional: index into the concatenation [A; B] of every output sample */
+  const float* src_a[B200R_MAX_CHANNELS];  /* (R*Da, nch) or NULL */
+  const float* src_b[B200R_MAX_CHANNELS];  /* (R*Db, nch) or NULL */
+  float* dst[B200R_MAX_CHANNELS];          /* (R*(Da+Db), nch) */
+  int32_t nch[B200R_MAX_CHANNELS];
+} b200r_compose_args;
+
+int b200r_compose_fwd(b200r_handle* h, const b200r_compose_args* args, b200r_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

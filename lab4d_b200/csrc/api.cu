@@ -227,4 +227,22 @@ int b200r_composite_bwd(b200r_handle* h, const b200r_composite_bwd_args* b, b200
   return B200R_OK;
 }
 
+int b200r_compose_fwd(b200r_handle* h, const b200r_compose_args* a, b200r_stream stream) {
+  if (!h) return B200R_E_INVALID;
+  if (!a) return fail(h, B200R_E_INVALID, "compose: null argument");
+  if (a->R < 1 || a->Da < 1 || a->Db < 1) return fail(h, B200R_E_INVALID, "compose: need R, Da, Db >= 1");
+  if (a->Da + a->Db > 8192) return fail(h, B200R_E_INVALID, "compose: more than 8192 samples per ray unsupported");
+  if (!a->depth_a || !a->depth_b) return fail(h, B200R_E_INVALID, "compose: missing depths");
+  if (a->n_channels < 0 || a->n_channels > B200R_MAX_CHANNELS) return fail(h, B200R_E_INVALID, "compose: bad channel count");
+  for (int c = 0; c < a->n_channels; ++c) {
+    if (!a->dst[c]) return fail(h, B200R_E_INVALID, "compose: null channel destination");
+    if (!a->src_a[c] && !a->src_b[c]) return fail(h, B200R_E_INVALID, "compose: channel without any source");
+    if (a->nch[c] < 1) return fail(h, B200R_E_INVALID, "compose: bad channel width");
+  }
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
+  if ((e = b200r::launch_compose_fwd(*a, (cudaStream_t)stream)) != cudaSuccess) return fail_cuda(h, e, "compose kernel");
+  return B200R_OK;
+}
+
 }  // extern "C"

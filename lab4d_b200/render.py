@@ -362,22 +362,46 @@ def render_pixel(field_dict, deltas):
     return out
 
 
+def _merge_pair(h, device, fa, fb, da, db):
+    """b200r_compose_fwd over the union of keys of two fields (dicts key -> (M,N,D,c)); deltas travel as one more key."""
+    depth_a, depth_b = _f32c(fa["depth"]), _f32c(fb["depth"])
+    M, N, Da = depth_a.shape[:3]
+    Db = depth_b.shape[2]
+    R = M * N
+    fa, fb = dict(fa, __deltas=da), dict(fb, __deltas=db)
+    keys = [k for k in fa] + [k for k in fb if k not in fa]
+    out, keep = {}, [depth_a, depth_b]
+    for c0 in range(0, len(keys), _lib.MAX_CHANNELS):
+        part = keys[c0:c0 + _lib.MAX_CHANNELS]
+        a = _lib.ComposeArgs()
+        a.R, a.Da, a.Db, a.n_channels = R, Da, Db, len(part)
+        a.depth_a, a.depth_b = depth_a.data_ptr(), depth_b.data_ptr()
+        for i, k in enumerate(part):
+            ta = _f32c(fa[k]) if k in fa else None
+            tb = _f32c(fb[k]) if k in fb else None
+            nch = (ta if ta is not None else tb).shape[-1]
+            keep += [ta, tb]
+            a.src_a[i] = ta.data_ptr() if ta is not None else None
+            a.src_b[i] = tb.data_ptr() if tb is not None else None
+            a.nch[i] = nch
+            out[k] = torch.empty(M, N, Da + Db, nch, device=device)
+            a.dst[i] = out[k].data_ptr()
+        h.check(h.lib.b200r_compose_fwd(h.h, C.byref(a), _stream(device)), "b200r_compose_fwd")
+    deltas = out.pop("__deltas")
+    return out, deltas
+
+
 @torch.no_grad()
 def compose_fields(feats, deltas_list):
-    """MultiFields.compose_fields (nnutils/multifields.py:339-398): concatenate the fields' samples
-    along the ray and depth-sort every key.  feats: list of dicts in field order."""
-    keys = []
-    for f in feats:
-        for k in f:
-            if k not in keys:
-                keys.append(k)
-    out = {}
-    for k in keys:
-        ref = next(f[k] for f in feats if k in f)
-        out[k] = torch.cat([f[k] if k in f else torch.zeros_like(ref) for f in feats], 2)
-    deltas = torch.cat(deltas_list, 2)
-    if len(feats) > 1:
-        idx = out["depth"].argsort(2)
-        out = {k: torch.gather(v, 2, idx.expand_as(v)) for k, v in out.items()}
-        deltas = torch.gather(deltas, 2, idx.expand_as(deltas))
+    """MultiFields.compose_fields (nnutils/multifields.py:339-398): merge the fields' samples along every ray by
+    depth and carry every key (zeros where a field lacks it).  feats: list of dicts in field order; every field's
+    samples are sorted by depth (uniform placement), so the reference's concatenate + argsort + gather is a merge,
+    done by the depth-merge kernel (csrc/compose.cu); more than two fields are merged pairwise in field order."""
+    if len(feats) == 1:
+        return dict(feats[0]), deltas_list[0]
+    device = feats[0]["depth"].device
+    h = _lib.handle_for(device)
+    out, deltas = feats[0], deltas_list[0]
+    for f, d in zip(feats[1:], deltas_list[1:]):
+        out, deltas = _merge_pair(h, device, out, f, deltas, d)
     return out, deltas

@@ -159,6 +159,35 @@ def synth_tables(cfg, M, device, seed, rays, P):
     return tab
 
 
+def test_compose_kernel_matches_sort_and_gather():
+    """Depth-merge kernel against the reference's own formulation (cat + argsort + gather, multifields.py:339-398) on
+    random sorted depths: bit-exact; keys only one field has read as zeros; ties keep field order."""
+    from lab4d_b200.render import compose_fields
+
+    g = torch.Generator(device="cpu").manual_seed(3)
+    M, N, Da, Db = 3, 37, 48, 80
+    mk = lambda *s: torch.rand(*s, generator=g).to(DEV)
+    fa = {"depth": mk(M, N, Da, 1).sort(2).values, "rgb": mk(M, N, Da, 3), "density": mk(M, N, Da, 1), "feature": mk(M, N, Da, 16)}
+    fb = {"depth": mk(M, N, Db, 1).sort(2).values, "rgb": mk(M, N, Db, 3), "density": mk(M, N, Db, 1), "flow": mk(M, N, Db, 3)}
+    fb["depth"][0, 0, :5] = fa["depth"][0, 0, :5]  # exact ties: field A's sample comes first
+    da, db = mk(M, N, Da, 1), mk(M, N, Db, 1)
+    out, dl = compose_fields([fa, fb], [da, db])
+    keys = ["depth", "rgb", "density", "feature", "flow"]
+    cat = {k: torch.cat([f[k] if k in f else torch.zeros(*f["depth"].shape[:3], (fa.get(k, fb.get(k))).shape[-1], device=DEV)
+                         for f in (fa, fb)], 2) for k in keys}
+    idx = cat["depth"].argsort(dim=2, stable=True)
+    assert set(out) == set(keys)
+    for k in keys:
+        assert torch.equal(out[k], torch.gather(cat[k], 2, idx.expand_as(cat[k]))), k
+    assert torch.equal(dl, torch.gather(torch.cat([da, db], 2), 2, idx))
+    # three fields: pairwise merge
+    fc = {"depth": mk(M, N, 9, 1).sort(2).values, "rgb": mk(M, N, 9, 3)}
+    out3, _ = compose_fields([fa, fb, fc], [da, db, mk(M, N, 9, 1)])
+    cat3 = torch.cat([fa["depth"], fb["depth"], fc["depth"]], 2)
+    assert torch.equal(out3["depth"], cat3.sort(2).values)
+    assert out3["rgb"].shape == (M, N, Da + Db + 9, 3)
+
+
 def test_two_field_scene_matches_reference():
     """bg + fg fields rendered separately, merged by compose_fields (multifields.py:339-398) and composited:
     against the reference's own composed output."""
