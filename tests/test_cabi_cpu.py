@@ -25,6 +25,38 @@ def test_library_exports_declared_symbols():
         assert hasattr(lib, n), n
 
 
+def test_header_is_plain_c_and_struct_sizes_match_ctypes(tmp_path):
+    """include/b200r.h compiles as C99 (no C++ or torch types in the ABI), a C program links against the library, and
+    the ctypes mirrors in lab4d_b200/_lib.py have the same sizes as the C structs."""
+    import shutil
+    import subprocess
+
+    from lab4d_b200 import _lib, build
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    build.build()
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "b200r.h"\n'
+        "int main(void) {\n"
+        "  b200r_field_desc d = {0};\n"
+        '  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b200r_field_desc), sizeof(b200r_field_params), sizeof(b200r_frame_tables),\n'
+        "         sizeof(b200r_ray_batch), sizeof(b200r_field_outputs), sizeof(b200r_composite_args), sizeof(b200r_composite_bwd_args),\n"
+        "         sizeof(b200r_compose_args), (size_t)b200r_layer_count(&d));\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "lab4d_b200")
+    cuda_lib = "/usr/local/cuda/lib64"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libb200render.so", f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{cuda_lib}", f"-Wl,-rpath-link,{cuda_lib}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    sizes = [int(x) for x in out[:8]]
+    mirrors = [_lib.FieldDesc, _lib.FieldParams, _lib.FrameTables, _lib.RayBatch, _lib.FieldOutputs, _lib.CompositeArgs,
+               _lib.CompositeBwdArgs, _lib.ComposeArgs]
+    assert sizes == [C.sizeof(m) for m in mirrors]
+
+
 def test_layer_counts_and_packed_sizes():
     from lab4d_b200 import _lib, spec
 
