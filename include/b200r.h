@@ -162,6 +162,22 @@ int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
                     const b200r_frame_tables* frames, const b200r_ray_batch* rays, const b200r_field_outputs* out,
                     void* workspace, size_t workspace_bytes, b200r_stream stream);
 
+/* NeRF.forward on given points (lab4d/nnutils/nerf.py:167-215), the boundary the reference's flat-point callers use
+ * (geometry_init nerf.py:277, extract_canonical_mesh :328, eval-mode query_nerf :794-805): canonical points in, rgb /
+ * density / sdf out.  Only the basefield, colorfield, sdf and rgb heads run (no ray placement, warps, visibility or
+ * feature field); `frames` needs M and the instance / appearance code rows only.  Outputs other than rgb, density,
+ * sdf and xyz (echo) must be NULL. */
+typedef struct {
+  int32_t P;           /* points per frame row */
+  int32_t pad_;
+  const float* xyz;    /* (M,P,3) points in the field's canonical space */
+  const float* dir;    /* (M,P,3) view directions in field space, or NULL (L_dir = -1 or density only) */
+} b200r_point_batch;
+
+int b200r_points_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* params,
+                     const b200r_frame_tables* frames, const b200r_point_batch* points, const b200r_field_outputs* out,
+                     void* workspace, size_t workspace_bytes, b200r_stream stream);
+
 /* ------------------------------------------------------------------ compositing (render_pixel) */
 #define B200R_MAX_CHANNELS 16
 /* how a per-sample array (R*D, nch) is reduced along the ray */

@@ -57,6 +57,10 @@ class CompositeBwdArgs(C.Structure):
                 ("g_src", f32p * MAX_CHANNELS)]
 
 
+class PointBatch(C.Structure):
+    _fields_ = [("P", C.c_int32), ("pad_", C.c_int32), ("xyz", f32p), ("dir", f32p)]
+
+
 class ComposeArgs(C.Structure):
     _fields_ = [("R", C.c_int32), ("Da", C.c_int32), ("Db", C.c_int32), ("n_channels", C.c_int32), ("depth_a", f32p),
                 ("depth_b", f32p), ("perm", C.c_void_p), ("src_a", f32p * MAX_CHANNELS), ("src_b", f32p * MAX_CHANNELS),
@@ -65,7 +69,7 @@ class ComposeArgs(C.Structure):
 
 EXPORTS = ["b200r_layer_count", "b200r_packed_bytes", "b200r_create", "b200r_destroy", "b200r_last_error",
            "b200r_pack_weights", "b200r_workspace_bytes", "b200r_field_fwd", "b200r_composite_fwd", "b200r_composite_bwd",
-           "b200r_compose_fwd"]
+           "b200r_compose_fwd", "b200r_points_fwd"]
 
 _lib = None
 
@@ -102,6 +106,10 @@ def load():
     lib.b200r_composite_fwd.restype = C.c_int
     lib.b200r_composite_bwd.argtypes = [C.c_void_p, C.POINTER(CompositeBwdArgs), C.c_void_p]
     lib.b200r_composite_bwd.restype = C.c_int
+    lib.b200r_points_fwd.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldParams),
+                                     C.POINTER(FrameTables), C.POINTER(PointBatch), C.POINTER(FieldOutputs), C.c_void_p,
+                                     C.c_size_t, C.c_void_p]
+    lib.b200r_points_fwd.restype = C.c_int
     lib.b200r_compose_fwd.argtypes = [C.c_void_p, C.POINTER(ComposeArgs), C.c_void_p]
     lib.b200r_compose_fwd.restype = C.c_int
     _lib = lib

@@ -117,38 +117,49 @@ size_t b200r_workspace_bytes(const b200r_field_desc* desc, int32_t M) {
   return b200r::workspace_bytes_total(bp.prog, M);
 }
 
-int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
-                    const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_field_outputs* out,
-                    void* workspace, size_t workspace_bytes, b200r_stream stream_) {
-  if (!h) return B200R_E_INVALID;
-  if (!desc || !packed || !par || !fr || !rays || !out || !workspace) return fail(h, B200R_E_INVALID, "field_fwd: null argument");
-  b200r::BuiltProgram bp = build(*desc);
-  if (!bp.ok) return fail(h, B200R_E_INVALID, std::string("field_fwd: ") + bp.err);
+// shared body of b200r_field_fwd (rays != NULL) and b200r_points_fwd (pts != NULL)
+static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
+                     const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_point_batch* pts,
+                     const b200r_field_outputs* out, void* workspace, size_t workspace_bytes, b200r_stream stream_) {
+  const char* who = pts ? "points_fwd" : "field_fwd";
+  auto bad = [&](const char* msg) { return fail(h, B200R_E_INVALID, std::string(who) + ": " + msg); };
+  if (!desc || !packed || !par || !fr || (!rays && !pts) || !out || !workspace) return bad("null argument");
+  b200r::BuiltProgram bp = b200r::build_program(*desc, pts != nullptr);
+  if (!bp.ok) return bad(bp.err);
   const int M = fr->M;
-  if (M < 1 || rays->N < 1 || rays->D < 2) return fail(h, B200R_E_INVALID, "field_fwd: need M,N >= 1 and D >= 2");
-  if ((long long)M * rays->N * rays->D > 0x7fffffffLL) return fail(h, B200R_E_INVALID, "field_fwd: too many samples");
-  if (M >= 2 && (M & 1)) return fail(h, B200R_E_INVALID, "field_fwd: frames must come in adjacent pairs (M even)");
-  if (!rays->hxy || !fr->Kinv || !fr->near_far || !fr->field2cam_q || !fr->field2cam_t)
-    return fail(h, B200R_E_INVALID, "field_fwd: missing ray/camera input");
-  if (!fr->inst_base || !fr->inst_color || !fr->inst_vis) return fail(h, B200R_E_INVALID, "field_fwd: missing instance codes");
-  if (desc->appr_channels > 0 && !fr->appr_code) return fail(h, B200R_E_INVALID, "field_fwd: missing appearance codes");
-  if (!par->sdf_w || !par->sdf_b || !par->rgb2_w || !par->rgb2_b || !par->vis_final_w || !par->vis_final_b || !par->logibeta ||
-      !par->logscale)
-    return fail(h, B200R_E_INVALID, "field_fwd: missing head weights");
+  const int N = pts ? pts->P : rays->N, D = pts ? 1 : rays->D;
+  if (M < 1 || N < 1 || (!pts && D < 2)) return bad("need M,N >= 1 and D >= 2");
+  if ((long long)M * N * D > 0x7fffffffLL) return bad("too many samples");
+  if (!pts) {
+    if (M >= 2 && (M & 1)) return bad("frames must come in adjacent pairs (M even)");
+    if (!rays->hxy || !fr->Kinv || !fr->near_far || !fr->field2cam_q || !fr->field2cam_t) return bad("missing ray/camera input");
+    if (!fr->inst_vis) return bad("missing instance codes");
+    if (!par->vis_final_w || !par->vis_final_b) return bad("missing head weights");
+  } else {
+    if (!pts->xyz) return bad("missing points");
+    if (desc->L_dir == 0 && !pts->dir && out->rgb) return bad("rgb needs view directions for this field");
+    if (out->vis || out->xyz_cam || out->xyz_t || out->dir || out->depth || out->deltas || out->feature || out->flow ||
+        out->cyc_dist || out->delta_skin || out->skin_entropy || out->gauss_density)
+      return bad("only rgb, density, sdf and xyz are produced");
+  }
+  if (!fr->inst_base || !fr->inst_color) return bad("missing instance codes");
+  if (desc->appr_channels > 0 && !fr->appr_code) return bad("missing appearance codes");
+  if (!par->sdf_w || !par->sdf_b || !par->rgb2_w || !par->rgb2_b || !par->logibeta || !par->logscale) return bad("missing head weights");
   const int nl = (int)bp.layer_out.size();
-  for (int i = 0; i < nl; ++i)
-    if (!par->weight[i] || !par->bias[i]) return fail(h, B200R_E_INVALID, "field_fwd: missing layer weight/bias");
-  if (desc->n_bones > 0) {
+  const b200r::LayerIds ids = b200r::layer_ids(*desc);
+  for (int i = 0; i < nl; ++i) {
+    const bool chain_layer = (i >= ids.base[0] && i <= ids.color[2]);  // basefield, rgb.0, colorfield are contiguous
+    if ((!pts || chain_layer) && (!par->weight[i] || !par->bias[i])) return bad("missing layer weight/bias");
+  }
+  if (desc->n_bones > 0 && !pts) {
     if (!fr->inst_skin || !fr->skin_t_embed || !fr->skin_t_embed_mean || !fr->t_art_qr || !fr->t_art_qd || !fr->rest_art_qr ||
         !fr->rest_art_qd || !par->warp_logibeta || !par->log_gauss)
-      return fail(h, B200R_E_INVALID, "field_fwd: missing skinning input");
+      return bad("missing skinning input");
   }
-  if (desc->dense && (!fr->dense_t_embed || !fr->inst_dense_fwd || !fr->inst_dense_bwd))
-    return fail(h, B200R_E_INVALID, "field_fwd: missing dense-warp codes");
-  if (reinterpret_cast<uintptr_t>(packed) & 15) return fail(h, B200R_E_INVALID, "field_fwd: packed must be 16-B aligned");
-  if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(h, B200R_E_INVALID, "field_fwd: workspace must be 16-B aligned");
-  if (workspace_bytes < b200r_workspace_bytes(desc, M))
-    return fail(h, B200R_E_INVALID, "field_fwd: workspace too small (see b200r_workspace_bytes)");
+  if (desc->dense && !pts && (!fr->dense_t_embed || !fr->inst_dense_fwd || !fr->inst_dense_bwd)) return bad("missing dense-warp codes");
+  if (reinterpret_cast<uintptr_t>(packed) & 15) return bad("packed must be 16-B aligned");
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) return bad("workspace must be 16-B aligned");
+  if (workspace_bytes < b200r_workspace_bytes(desc, M)) return bad("workspace too small (see b200r_workspace_bytes)");
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -162,21 +173,29 @@ int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
   pp.par = *par;
   pp.fr = *fr;
   pp.workspace = (float*)workspace;
+  pp.points_only = pts != nullptr;
   pp.n_layers = nl;
-  pp.rgb0_layer = b200r::layer_ids(*desc).rgb0;
+  pp.rgb0_layer = ids.rgb0;
   for (int i = 0; i < nl; ++i) { pp.layer_out[i] = (int16_t)bp.layer_out[i]; pp.layer_in[i] = (int16_t)bp.layer_in[i]; }
+  if (pts) {  // plain bias rows of layers that are not evaluated may be absent
+    for (int i = 0; i < nl; ++i)
+      if (!par->bias[i]) pp.cl.plain_off[i] = -1;
+  }
   if ((e = b200r::launch_prologue(pp, stream)) != cudaSuccess) return fail_cuda(h, e, "prologue kernel");
 
   b200r::FieldKernelParams kp;
   memset(&kp, 0, sizeof(kp));
   kp.prog = bp.prog;
   kp.desc = *desc;
-  kp.rays = *rays;
+  if (rays) kp.rays = *rays;
+  kp.rays.N = N;
+  kp.rays.D = D;
+  if (pts) { kp.points = pts->xyz; kp.point_dirs = pts->dir; kp.rays.flow_thresh = -1.f; }
   kp.out = *out;
   kp.packed = (const uint8_t*)packed;
   kp.workspace = (const float*)workspace;
   kp.M = M;
-  kp.ND = rays->N * rays->D;
+  kp.ND = N * D;
   kp.tiles_per_frame = (kp.ND + b200r::kTileRows - 1) / b200r::kTileRows;
   kp.n_tiles = M * kp.tiles_per_frame;
   kp.Lmax = desc->L_xyz + 2 > 10 ? 12 : 10;
@@ -184,6 +203,22 @@ int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
   e = b200r::launch_field_fwd(kp, h->n_sm, stream);
   if (e != cudaSuccess) return fail_cuda(h, e, "field_fwd kernel");
   return B200R_OK;
+}
+
+int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
+                    const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_field_outputs* out,
+                    void* workspace, size_t workspace_bytes, b200r_stream stream_) {
+  if (!h) return B200R_E_INVALID;
+  if (!rays) return fail(h, B200R_E_INVALID, "field_fwd: null argument");
+  return run_field(h, desc, packed, par, fr, rays, nullptr, out, workspace, workspace_bytes, stream_);
+}
+
+int b200r_points_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
+                     const b200r_frame_tables* fr, const b200r_point_batch* pts, const b200r_field_outputs* out,
+                     void* workspace, size_t workspace_bytes, b200r_stream stream_) {
+  if (!h) return B200R_E_INVALID;
+  if (!pts) return fail(h, B200R_E_INVALID, "points_fwd: null argument");
+  return run_field(h, desc, packed, par, fr, nullptr, pts, out, workspace, workspace_bytes, stream_);
 }
 
 static int check_composite(b200r_handle* h, const b200r_composite_args* a) {

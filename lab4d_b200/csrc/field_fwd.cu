@@ -468,29 +468,42 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       named_bar_sync(1 + g, kGroupThreads);
 
       // ------------------------------------------------ sample placement (sample_cam_rays)
-      const float* hx = p.rays.hxy + ((size_t)f * p.rays.N + n) * 3;
-      const float h0 = __ldg(hx), h1 = __ldg(hx + 1), h2 = __ldg(hx + 2);
-      const float* cam = fblk_g + FL.cam;
-      float3 d = make_float3(h0 * cam[0] + h1 * cam[1] + h2 * cam[2], h0 * cam[3] + h1 * cam[4] + h2 * cam[5],
-                             h0 * cam[6] + h1 * cam[7] + h2 * cam[8]);
-      const float dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
-      const float nearv = cam[9], farv = cam[10];
-      const int Dn = p.rays.D;
-      const float step = 1.0f / (float)(Dn - 1);
-      auto lin = [&](int i) { return i < Dn / 2 ? step * (float)i : 1.0f - step * (float)(Dn - 1 - i); };
-      auto depth_at = [&](int i) { float z = lin(i); return nearv * (1.0f - z) + farv * z; };
-      const float depth = depth_at(k);
-      const float delta = (k + 1 < Dn ? depth_at(k + 1) - depth : depth - depth_at(k - 1)) * dn;
-      const float3 xyz_cam = make_float3(d.x * depth, d.y * depth, d.z * depth);
-      const float3 dir_cam = make_float3(d.x / dn, d.y / dn, d.z / dn);
+      const bool pts = p.points != nullptr;  // b200r_points_fwd: canonical points are given, only NeRF.forward runs
+      float h0 = 0.f, h1 = 0.f, depth = 0.f, delta = 0.f;
+      float3 xyz_cam = make_float3(0.f, 0.f, 0.f), xyz_t = xyz_cam, dir_f = xyz_cam;
+      if (!pts) {
+        const float* hx = p.rays.hxy + ((size_t)f * p.rays.N + n) * 3;
+        h0 = __ldg(hx); h1 = __ldg(hx + 1);
+        const float h2 = __ldg(hx + 2);
+        const float* cam = fblk_g + FL.cam;
+        float3 d = make_float3(h0 * cam[0] + h1 * cam[1] + h2 * cam[2], h0 * cam[3] + h1 * cam[4] + h2 * cam[5],
+                               h0 * cam[6] + h1 * cam[7] + h2 * cam[8]);
+        const float dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+        const float nearv = cam[9], farv = cam[10];
+        const int Dn = p.rays.D;
+        const float step = 1.0f / (float)(Dn - 1);
+        auto lin = [&](int i) { return i < Dn / 2 ? step * (float)i : 1.0f - step * (float)(Dn - 1 - i); };
+        auto depth_at = [&](int i) { float z = lin(i); return nearv * (1.0f - z) + farv * z; };
+        depth = depth_at(k);
+        delta = (k + 1 < Dn ? depth_at(k + 1) - depth : depth - depth_at(k - 1)) * dn;
+        xyz_cam = make_float3(d.x * depth, d.y * depth, d.z * depth);
+        const float3 dir_cam = make_float3(d.x / dn, d.y / dn, d.z / dn);
 
-      // ------------------------------------------------ camera -> field (cam_to_field)
-      const Q4 qc = {cam[11], cam[12], cam[13], cam[14]};
-      const Q4 qi = qconj(qc);
-      const float3 ti = qrot(qi, make_float3(-cam[15], -cam[16], -cam[17]));
-      float3 xyz_t = qrot(qi, xyz_cam);
-      xyz_t.x += ti.x; xyz_t.y += ti.y; xyz_t.z += ti.z;
-      const float3 dir_f = qrot(qi, dir_cam);
+        // ---------------------------------------------- camera -> field (cam_to_field)
+        const Q4 qc = {cam[11], cam[12], cam[13], cam[14]};
+        const Q4 qi = qconj(qc);
+        const float3 ti = qrot(qi, make_float3(-cam[15], -cam[16], -cam[17]));
+        xyz_t = qrot(qi, xyz_cam);
+        xyz_t.x += ti.x; xyz_t.y += ti.y; xyz_t.z += ti.z;
+        dir_f = qrot(qi, dir_cam);
+      } else {
+        const float* px = p.points + s * 3;
+        xyz_t = make_float3(__ldg(px), __ldg(px + 1), __ldg(px + 2));
+        if (p.point_dirs) {
+          const float* pd = p.point_dirs + s * 3;
+          dir_f = make_float3(__ldg(pd), __ldg(pd + 1), __ldg(pd + 2));
+        }
+      }
 
       // ------------------------------------------------ skinning warps (SkinningWarp.forward), three per sample:
       //   w = 0 backward warp (time-t -> canonical), w = 1 forward warp with the pair partner's articulation (flow),
@@ -575,7 +588,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
 
       float3 xyz = xyz_t, x_next = xyz_t;
       float ent_b = 0.f, dsk_b = 0.f, ent_out = 0.f, dsk_out = 0.f, cyc = 0.f;
-      if constexpr (B > 0) {
+      if (pts) {
+        // canonical points are given
+      } else if constexpr (B > 0) {
         // ComposedWarp (warping.py:445-483) interleaves the DenseWarp soft deformation: backward = skin then dense,
         // forward = dense then skin.  One loop over stages keeps a single inlined copy of either body.
         constexpr int NST = DENSE ? 6 : 3;
@@ -611,7 +626,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       // ------------------------------------------------ outputs that are final before the MLPs run
       auto st3 = [&](float* dst, float a, float b, float c) { if (dst && live) { dst[s * 3] = a; dst[s * 3 + 1] = b; dst[s * 3 + 2] = c; } };
       auto st1 = [&](float* dst, float a) { if (dst && live) dst[s] = a; };
-      {
+      if (pts) {
+        st3(p.out.xyz, xyz.x, xyz.y, xyz.z);
+      } else {
         // field_to_cam with the partner frame's camera, pinhole projection, flow (nerf.py:948-997)
         const float* cn = fblk_g + FL.cam_partner;
         const Q4 qn = {cn[11], cn[12], cn[13], cn[14]};
@@ -657,6 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       }
 
       // ------------------------------------------------ visibility MLP (VisField.forward)
+      if (!pts) {
       gemm();
       epi_relu_act(bias_s(lid_vis), 64);
       gemm();
@@ -676,9 +694,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         }
         st1(p.out.vis, a0 + a1 + lds32(sc_s + 4u * SC_VIS_B));
       }
+      }
 
       // ------------------------------------------------ feature field (FeatureNeRF.compute_feat)
-      if (p.desc.has_feature) {
+      if (p.desc.has_feature && !pts) {
 #pragma unroll 1
         for (int i = 0; i < 5; ++i) {
           gemm();

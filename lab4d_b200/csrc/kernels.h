@@ -23,6 +23,7 @@ struct PrologueParams {
   b200r_field_params par;
   b200r_frame_tables fr;
   float* workspace;  // [const block][M frame blocks]
+  int32_t points_only;  // b200r_points_fwd: no cameras, no bone tables; bias rows whose codes are absent are skipped
   int32_t n_layers;
   int32_t rgb0_layer;
   int16_t layer_out[B200R_MAX_LAYERS];
@@ -36,6 +37,8 @@ struct FieldKernelParams {
   b200r_field_outputs out;
   const uint8_t* packed;
   const float* workspace;
+  const float* points;     // points mode (b200r_points_fwd): (M, ND, 3) canonical points, else NULL
+  const float* point_dirs; // points mode: (M, ND, 3) directions in field space or NULL
   uint4* scratch;          // per-CTA scratch for the packed base features (program.h kScratchPerCta)
   int32_t M;
   int32_t ND;              // N * D samples per frame

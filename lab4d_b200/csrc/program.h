@@ -166,7 +166,7 @@ struct BuiltProgram {
   const char* err;
 };
 
-inline BuiltProgram build_program(const b200r_field_desc& d) {
+inline BuiltProgram build_program(const b200r_field_desc& d, bool points_only = false) {
   BuiltProgram bp;
   bp.ok = false;
   bp.err = "";
@@ -416,17 +416,20 @@ inline BuiltProgram build_program(const b200r_field_desc& d) {
       pipe5(L.dense[3 * m + 1], tsn(4), BAR_H1);
       seq5(L.dense[3 * m + 2], tsn(4), BAR_H1);
     };
-    for (int w = 0; w < 3; ++w) {
+    // points_only (b200r_points_fwd): the same packed operands, but only the density + colour chains are issued
+    for (int w = 0; w < 3 && !points_only; ++w) {
       P.st_delta[w] = ns;
       if (d.dense && w > 0) dense5(0);
       if (B > 0) delta5();
       if (d.dense && w == 0) dense5(1);
     }
     P.st_vis = ns;
-    seq5(L.vis[0], pe5(pe_v));
-    seq5(L.vis[1], tsn(1));
+    if (!points_only) {
+      seq5(L.vis[0], pe5(pe_v));
+      seq5(L.vis[1], tsn(1));
+    }
     P.st_feat = ns;
-    if (d.has_feature) {
+    if (d.has_feature && !points_only) {
       seq5(L.feat[0], pe5(pe_f));
       for (int i = 1; i < 4; ++i) seq5(L.feat[i], tsn(2));
       seq5(L.feat[4], cat5(pe5(pe_f), tsn(2)));

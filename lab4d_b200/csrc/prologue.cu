@@ -85,13 +85,14 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
     const int W = p.desc.W, H = W / 2;
     for (int i = threadIdx.x; i < W; i += blockDim.x) cblock[C.sdf_w + i] = p.par.sdf_w[i];
     for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) cblock[C.rgb2_w + i] = p.par.rgb2_w[i];
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) cblock[C.vis_w + i] = p.par.vis_final_w[i];
+    if (p.par.vis_final_w)
+      for (int i = threadIdx.x; i < 64; i += blockDim.x) cblock[C.vis_w + i] = p.par.vis_final_w[i];
     if (p.desc.L_dir == 0) {
       const float* w0 = p.par.weight[p.rgb0_layer];
       const int in_dim = p.layer_in[p.rgb0_layer];
       for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) cblock[C.dir_w + i] = w0[(size_t)(i / 3) * in_dim + W + (i % 3)];
     }
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    for (int b = threadIdx.x; b < B && !p.points_only; b += blockDim.x) {
       const Q4 qr = ld4(p.fr.rest_art_qr + b * 4), qd = ld4(p.fr.rest_art_qd + b * 4);  // frame 0
       const Q4 t = qmul(qd, qconj(qr));
       cblock[C.center + b * 4 + 0] = 2.f * t.x;
@@ -102,10 +103,10 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
       float* s = cblock + C.scalars;
       s[SC_IBETA] = expf(p.par.logibeta[0]);
       s[SC_INV_SCALE] = 1.0f / expf(p.par.logscale[0]);
-      s[SC_WARP_IBETA] = B > 0 ? expf(p.par.warp_logibeta[0]) : 0.f;
+      s[SC_WARP_IBETA] = (B > 0 && p.par.warp_logibeta) ? expf(p.par.warp_logibeta[0]) : 0.f;
       s[SC_SDF_B] = p.par.sdf_b[0];
       s[SC_RGB2_B0] = p.par.rgb2_b[0]; s[SC_RGB2_B1] = p.par.rgb2_b[1]; s[SC_RGB2_B2] = p.par.rgb2_b[2];
-      s[SC_VIS_B] = p.par.vis_final_b[0];
+      s[SC_VIS_B] = p.par.vis_final_b ? p.par.vis_final_b[0] : 0.f;
     }
     return;
   }
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
   const int f = blockIdx.x / kFrameParts, part = blockIdx.x % kFrameParts;
   const int fn = (M >= 2) ? (f ^ 1) : f;
   float* fb = p.workspace + p.cl.n_floats + (size_t)f * F.n_floats;
-  if (part == 0) {
+  if (part == 0 && !p.points_only) {
     write_cam(fb + F.cam, p, f);
     write_cam(fb + F.cam_partner, p, fn);
   }
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
     int ci = 0, n = r;
     while (n >= F.cond[ci].n) { n -= F.cond[ci].n; ++ci; }
     const CondRow& c = F.cond[ci];
+    if (!codes[c.code[0]] || (c.n_seg > 1 && !codes[c.code[1]])) continue;  // points mode: layers that are not evaluated
     float acc = p.par.bias[c.layer][n];
     for (int sgi = 0; sgi < c.n_seg; ++sgi) {
       const float* code = codes[c.code[sgi]];
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
     }
     fb[c.frame_off + n] = acc;
   }
-  if (B > 0 && part >= 1) {
+  if (B > 0 && part >= 1 && !p.points_only) {
     __shared__ float ig[32 * 4];
     for (int b = threadIdx.x; b < B; b += blockDim.x)
       for (int c = 0; c < 3; ++c) {

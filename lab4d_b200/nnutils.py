@@ -97,6 +97,35 @@ def query_field(field, samples_dict, flow_thresh=None, n_depth=64):
     return feat, deltas, {}
 
 
+def nerf_forward(field, xyz, dir=None, frame_id=None, inst_id=None, get_density=True):
+    """Replacement body of NeRF.forward (nnutils/nerf.py:167-215) for inference callers (mesh extraction, geometry
+    queries, eval-mode query_nerf): xyz (M,N,D,3) with per-frame ids (M,), or flat (P,3) with ids None (mean instance
+    code) -> (rgb, density-or-sdf) when dir is given, else density-or-sdf, shaped like xyz[..., :1]."""
+    if torch.is_grad_enabled() and any(p.requires_grad for p in field.parameters()):
+        raise NotImplementedError("lab4d_b200: NeRF.forward is accelerated for inference only (call under torch.no_grad())")
+    cfg = config_from_module(field)
+    cache = field.__dict__.setdefault("_b200_renderer", {})
+    key = (cfg, str(xyz.device))
+    if key not in cache:
+        cache[key] = _render.FieldRenderer(cfg, xyz.device)
+    r = cache[key]
+    P = {k: v for k, v in field.named_parameters()}
+    r.pack(P, alpha=field.pos_embedding.alpha)
+    flat = xyz.dim() == 2
+    pts = xyz.reshape(1, -1, 3) if flat else xyz.reshape(xyz.shape[0], -1, 3)
+    M = pts.shape[0]
+    tab = {"inst_base": field.basefield.inst_embedding(inst_id).reshape(-1, 32).expand(M, -1),
+           "inst_color": field.colorfield.inst_embedding(inst_id).reshape(-1, 32).expand(M, -1)}
+    if field.appr_channels > 0 and dir is not None:
+        tab["appr_code"] = field.appr_embedding.get_vals(frame_id).reshape(-1, field.appr_channels).expand(M, -1)
+    want = ("density" if get_density else "sdf",) + (("rgb",) if dir is not None else ())
+    d = None if dir is None or cfg.L_dir != 0 else dir.reshape(M, -1, 3)
+    out = r.query_points(P, pts, tab, dir=d, want=want)
+    shape = xyz.shape[:-1]
+    val = out[want[0]].reshape(shape + (1,))
+    return (out["rgb"].reshape(shape + (3,)), val) if dir is not None else val
+
+
 def install(lab4d=None, n_depth=64):
     """Patch an imported reference package in place; returns a function that undoes the patch."""
     if lab4d is None:

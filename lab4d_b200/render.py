@@ -225,6 +225,45 @@ class FieldRenderer:
         return feat, deltas
 
 
+    # ------------------------------------------------------------------ NeRF.forward on points
+    @torch.no_grad()
+    def query_points(self, P, xyz, tab, dir=None, want=("rgb", "density", "sdf")):
+        """NeRF.forward (nnutils/nerf.py:167-215) on canonical points: xyz (M,P,3) [dir (M,P,3) in field space];
+        tab holds the per-frame code rows (inst_base, inst_color, appr_code).  Returns a dict with rgb (M,P,3),
+        density (M,P,1), sdf (M,P,1) as requested.  Only the basefield / colorfield / heads run."""
+        xyz = _f32c(xyz)
+        M, Pn = xyz.shape[:2]
+        par, keep = self._params(P)
+        keep.append(xyz)
+        fr = _lib.FrameTables()
+        fr.M = M
+        for field in ("inst_base", "inst_color", "appr_code"):
+            if tab.get(field) is not None:
+                t = _f32c(tab[field])
+                keep.append(t)
+                setattr(fr, field, t.data_ptr())
+        pb = _lib.PointBatch()
+        pb.P = Pn
+        pb.xyz = xyz.data_ptr()
+        if dir is not None:
+            d = _f32c(dir)
+            keep.append(d)
+            pb.dir = d.data_ptr()
+        out, oa = {}, _lib.FieldOutputs()
+        widths = dict(_lib.FIELD_OUTPUTS)
+        for name in want:
+            out[name] = torch.empty(M * Pn, widths[name], dtype=torch.float32, device=self.device)
+            setattr(oa, name, out[name].data_ptr())
+        wbytes = self.handle.lib.b200r_workspace_bytes(C.byref(self.desc), M)
+        if getattr(self, "_ws", None) is None or self._ws.numel() < wbytes:
+            self._ws = torch.empty(wbytes, dtype=torch.uint8, device=self.device)
+        rc = self.handle.lib.b200r_points_fwd(self.handle.h, C.byref(self.desc), _ptr(self.packed), C.byref(par), C.byref(fr),
+                                              C.byref(pb), C.byref(oa), _ptr(self._ws), self._ws.numel(), _stream(self.device))
+        self.handle.check(rc, "b200r_points_fwd")
+        self._keep_call = keep
+        return {k: v.view(M, Pn, -1) for k, v in out.items()}
+
+
 # ---------------------------------------------------------------------------------------- compositing
 KEY_SKIP = ("density", "vis", "flow", "eikonal", "xy_reproj", "xyz_reproj", "gauss_density")
 KEY_FREEZE = ("cyc_dist", "xyz_cam", "skin_entropy")
