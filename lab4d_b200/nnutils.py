@@ -114,8 +114,11 @@ def nerf_forward(field, xyz, dir=None, frame_id=None, inst_id=None, get_density=
     flat = xyz.dim() == 2
     pts = xyz.reshape(1, -1, 3) if flat else xyz.reshape(xyz.shape[0], -1, 3)
     M = pts.shape[0]
-    tab = {"inst_base": field.basefield.inst_embedding(inst_id).reshape(-1, 32).expand(M, -1),
-           "inst_color": field.colorfield.inst_embedding(inst_id).reshape(-1, 32).expand(M, -1)}
+    def code(mlp):  # CondMLP.forward: mean instance code when inst_id is None (nnutils/base.py:131-135)
+        c = mlp.inst_embedding.get_mean_embedding() if inst_id is None else mlp.inst_embedding(inst_id)
+        return c.reshape(-1, 32).expand(M, -1)
+
+    tab = {"inst_base": code(field.basefield), "inst_color": code(field.colorfield)}
     if field.appr_channels > 0 and dir is not None:
         tab["appr_code"] = field.appr_embedding.get_vals(frame_id).reshape(-1, field.appr_channels).expand(M, -1)
     want = ("density" if get_density else "sdf",) + (("rgb",) if dir is not None else ())
