@@ -178,6 +178,16 @@ int b200r_points_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* 
                      const b200r_frame_tables* frames, const b200r_point_batch* points, const b200r_field_outputs* out,
                      void* workspace, size_t workspace_bytes, b200r_stream stream);
 
+/* SkinningWarp.forward / ComposedWarp.forward on given points (lab4d/nnutils/warping.py:277-336, 445-483), the boundary
+ * of export.extract_deformation (lab4d/export.py:94-130) and soft_deform_loss (deformable.py:238-252).
+ * backward != 0: time-t space -> canonical (bone coordinates from t_articulation, the frame's time code);
+ * backward == 0: canonical -> time-t space with the frame's own articulation (mean time code, warping.py:313-314).
+ * `frames` needs M, the skinning (and dense-warp) code rows and the articulations; outputs: xyz (warped points),
+ * skin_entropy, delta_skin; everything else must be NULL.  Needs n_bones > 0. */
+int b200r_warp_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* params,
+                   const b200r_frame_tables* frames, const b200r_point_batch* points, int32_t backward,
+                   const b200r_field_outputs* out, void* workspace, size_t workspace_bytes, b200r_stream stream);
+
 /* ------------------------------------------------------------------ compositing (render_pixel) */
 #define B200R_MAX_CHANNELS 16
 /* how a per-sample array (R*D, nch) is reduced along the ray */

@@ -69,7 +69,7 @@ class ComposeArgs(C.Structure):
 
 EXPORTS = ["b200r_layer_count", "b200r_packed_bytes", "b200r_create", "b200r_destroy", "b200r_last_error",
            "b200r_pack_weights", "b200r_workspace_bytes", "b200r_field_fwd", "b200r_composite_fwd", "b200r_composite_bwd",
-           "b200r_compose_fwd", "b200r_points_fwd"]
+           "b200r_compose_fwd", "b200r_points_fwd", "b200r_warp_fwd"]
 
 _lib = None
 
@@ -110,6 +110,9 @@ def load():
                                      C.POINTER(FrameTables), C.POINTER(PointBatch), C.POINTER(FieldOutputs), C.c_void_p,
                                      C.c_size_t, C.c_void_p]
     lib.b200r_points_fwd.restype = C.c_int
+    lib.b200r_warp_fwd.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldParams), C.POINTER(FrameTables),
+                                   C.POINTER(PointBatch), C.c_int32, C.POINTER(FieldOutputs), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.b200r_warp_fwd.restype = C.c_int
     lib.b200r_compose_fwd.argtypes = [C.c_void_p, C.POINTER(ComposeArgs), C.c_void_p]
     lib.b200r_compose_fwd.restype = C.c_int
     _lib = lib

@@ -119,12 +119,13 @@ size_t b200r_workspace_bytes(const b200r_field_desc* desc, int32_t M) {
 
 // shared body of b200r_field_fwd (rays != NULL) and b200r_points_fwd (pts != NULL)
 static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
-                     const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_point_batch* pts,
+                     const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_point_batch* pts, int mode,
                      const b200r_field_outputs* out, void* workspace, size_t workspace_bytes, b200r_stream stream_) {
-  const char* who = pts ? "points_fwd" : "field_fwd";
+  const bool warp = mode == b200r::MODE_WARP_BWD || mode == b200r::MODE_WARP_FWD;
+  const char* who = warp ? "warp_fwd" : (pts ? "points_fwd" : "field_fwd");
   auto bad = [&](const char* msg) { return fail(h, B200R_E_INVALID, std::string(who) + ": " + msg); };
   if (!desc || !packed || !par || !fr || (!rays && !pts) || !out || !workspace) return bad("null argument");
-  b200r::BuiltProgram bp = b200r::build_program(*desc, pts != nullptr);
+  b200r::BuiltProgram bp = b200r::build_program(*desc, mode);
   if (!bp.ok) return bad(bp.err);
   const int M = fr->M;
   const int N = pts ? pts->P : rays->N, D = pts ? 1 : rays->D;
@@ -135,6 +136,11 @@ static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* 
     if (!rays->hxy || !fr->Kinv || !fr->near_far || !fr->field2cam_q || !fr->field2cam_t) return bad("missing ray/camera input");
     if (!fr->inst_vis) return bad("missing instance codes");
     if (!par->vis_final_w || !par->vis_final_b) return bad("missing head weights");
+  } else if (warp) {
+    if (!pts->xyz) return bad("missing points");
+    if (out->rgb || out->density || out->sdf || out->vis || out->xyz_cam || out->xyz_t || out->dir || out->depth || out->deltas ||
+        out->feature || out->flow || out->cyc_dist || out->gauss_density)
+      return bad("only xyz, skin_entropy and delta_skin are produced");
   } else {
     if (!pts->xyz) return bad("missing points");
     if (desc->L_dir == 0 && !pts->dir && out->rgb) return bad("rgb needs view directions for this field");
@@ -142,21 +148,25 @@ static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* 
         out->cyc_dist || out->delta_skin || out->skin_entropy || out->gauss_density)
       return bad("only rgb, density, sdf and xyz are produced");
   }
-  if (!fr->inst_base || !fr->inst_color) return bad("missing instance codes");
-  if (desc->appr_channels > 0 && !fr->appr_code) return bad("missing appearance codes");
+  if (!warp) {
+    if (!fr->inst_base || !fr->inst_color) return bad("missing instance codes");
+    if (desc->appr_channels > 0 && !fr->appr_code) return bad("missing appearance codes");
+  }
   if (!par->sdf_w || !par->sdf_b || !par->rgb2_w || !par->rgb2_b || !par->logibeta || !par->logscale) return bad("missing head weights");
   const int nl = (int)bp.layer_out.size();
   const b200r::LayerIds ids = b200r::layer_ids(*desc);
   for (int i = 0; i < nl; ++i) {
     const bool chain_layer = (i >= ids.base[0] && i <= ids.color[2]);  // basefield, rgb.0, colorfield are contiguous
-    if ((!pts || chain_layer) && (!par->weight[i] || !par->bias[i])) return bad("missing layer weight/bias");
+    const bool warp_layer = (desc->n_bones > 0 && i <= ids.delta[2]) || (desc->dense && i >= ids.dense[0]);
+    const bool needed = !pts || (warp ? warp_layer : chain_layer);
+    if (needed && (!par->weight[i] || !par->bias[i])) return bad("missing layer weight/bias");
   }
-  if (desc->n_bones > 0 && !pts) {
+  if (desc->n_bones > 0 && (!pts || warp)) {
     if (!fr->inst_skin || !fr->skin_t_embed || !fr->skin_t_embed_mean || !fr->t_art_qr || !fr->t_art_qd || !fr->rest_art_qr ||
         !fr->rest_art_qd || !par->warp_logibeta || !par->log_gauss)
       return bad("missing skinning input");
   }
-  if (desc->dense && !pts && (!fr->dense_t_embed || !fr->inst_dense_fwd || !fr->inst_dense_bwd)) return bad("missing dense-warp codes");
+  if (desc->dense && (!pts || warp) && (!fr->dense_t_embed || !fr->inst_dense_fwd || !fr->inst_dense_bwd)) return bad("missing dense-warp codes");
   if (reinterpret_cast<uintptr_t>(packed) & 15) return bad("packed must be 16-B aligned");
   if (reinterpret_cast<uintptr_t>(workspace) & 15) return bad("workspace must be 16-B aligned");
   if (workspace_bytes < b200r_workspace_bytes(desc, M)) return bad("workspace too small (see b200r_workspace_bytes)");
@@ -173,7 +183,8 @@ static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* 
   pp.par = *par;
   pp.fr = *fr;
   pp.workspace = (float*)workspace;
-  pp.points_only = pts != nullptr;
+  pp.skip_cams = pts != nullptr;
+  pp.skip_bones = pts != nullptr && !warp;
   pp.n_layers = nl;
   pp.rgb0_layer = ids.rgb0;
   for (int i = 0; i < nl; ++i) { pp.layer_out[i] = (int16_t)bp.layer_out[i]; pp.layer_in[i] = (int16_t)bp.layer_in[i]; }
@@ -190,7 +201,8 @@ static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* 
   if (rays) kp.rays = *rays;
   kp.rays.N = N;
   kp.rays.D = D;
-  if (pts) { kp.points = pts->xyz; kp.point_dirs = pts->dir; kp.rays.flow_thresh = -1.f; }
+  if (pts) { kp.points = pts->xyz; kp.point_dirs = warp ? nullptr : pts->dir; kp.rays.flow_thresh = -1.f; }
+  kp.warp_mode = warp ? mode : 0;
   kp.out = *out;
   kp.packed = (const uint8_t*)packed;
   kp.workspace = (const float*)workspace;
@@ -210,7 +222,7 @@ int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
                     void* workspace, size_t workspace_bytes, b200r_stream stream_) {
   if (!h) return B200R_E_INVALID;
   if (!rays) return fail(h, B200R_E_INVALID, "field_fwd: null argument");
-  return run_field(h, desc, packed, par, fr, rays, nullptr, out, workspace, workspace_bytes, stream_);
+  return run_field(h, desc, packed, par, fr, rays, nullptr, b200r::MODE_FIELD, out, workspace, workspace_bytes, stream_);
 }
 
 int b200r_points_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
@@ -218,7 +230,16 @@ int b200r_points_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* 
                      void* workspace, size_t workspace_bytes, b200r_stream stream_) {
   if (!h) return B200R_E_INVALID;
   if (!pts) return fail(h, B200R_E_INVALID, "points_fwd: null argument");
-  return run_field(h, desc, packed, par, fr, nullptr, pts, out, workspace, workspace_bytes, stream_);
+  return run_field(h, desc, packed, par, fr, nullptr, pts, b200r::MODE_POINTS, out, workspace, workspace_bytes, stream_);
+}
+
+int b200r_warp_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
+                   const b200r_frame_tables* fr, const b200r_point_batch* pts, int32_t backward, const b200r_field_outputs* out,
+                   void* workspace, size_t workspace_bytes, b200r_stream stream_) {
+  if (!h) return B200R_E_INVALID;
+  if (!pts) return fail(h, B200R_E_INVALID, "warp_fwd: null argument");
+  return run_field(h, desc, packed, par, fr, nullptr, pts, backward ? b200r::MODE_WARP_BWD : b200r::MODE_WARP_FWD, out, workspace,
+                   workspace_bytes, stream_);
 }
 
 static int check_composite(b200r_handle* h, const b200r_composite_args* a) {

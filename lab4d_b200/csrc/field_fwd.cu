@@ -588,15 +588,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
 
       float3 xyz = xyz_t, x_next = xyz_t;
       float ent_b = 0.f, dsk_b = 0.f, ent_out = 0.f, dsk_out = 0.f, cyc = 0.f;
-      if (pts) {
+      const int wm = p.warp_mode;  // b200r_warp_fwd: one warp of the given points, nothing else
+      if (pts && !wm) {
         // canonical points are given
       } else if constexpr (B > 0) {
         // ComposedWarp (warping.py:445-483) interleaves the DenseWarp soft deformation: backward = skin then dense,
         // forward = dense then skin.  One loop over stages keeps a single inlined copy of either body.
         constexpr int NST = DENSE ? 6 : 3;
+        constexpr int PER = DENSE ? 2 : 1;  // stages per warp
+        const int stg_lo = wm == MODE_WARP_FWD ? 2 * PER : 0, stg_hi = wm == MODE_WARP_BWD ? PER : NST;
         float3 cur = xyz_t;
 #pragma unroll 1
-        for (int stg = 0; stg < NST; ++stg) {
+        for (int stg = stg_lo; stg < stg_hi; ++stg) {
           const int w = DENSE ? (stg >> 1) : stg;
           if (DENSE && (stg == 1 || stg == 2 || stg == 4)) {
             const uint32_t bias1 = stg == 1 ? bias_s(lid_dense + 3) : (stg == 2 ? fblk_s + 4u * FL.dense1_partner : bias_s(lid_dense));
@@ -617,10 +620,19 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
             cyc = sqrtf(dx * dx + dy * dy + dz * dz);
             ent_out = 0.5f * (e + ent_b);
             dsk_out = 0.5f * (dk + dsk_b);
+            if (wm) { xyz = o; ent_b = e; dsk_b = dk; }  // warp entry, forward: the warped point and its own aux
           }
         }
       } else {
         x_next = xyz;
+      }
+      if (wm) {  // b200r_warp_fwd: warped point + the call's aux values, then on to the next tile
+        if (live) {
+          if (p.out.xyz) { p.out.xyz[s * 3] = xyz.x; p.out.xyz[s * 3 + 1] = xyz.y; p.out.xyz[s * 3 + 2] = xyz.z; }
+          if (p.out.skin_entropy) p.out.skin_entropy[s] = ent_b;
+          if (p.out.delta_skin) p.out.delta_skin[s] = dsk_b;
+        }
+        continue;
       }
 
       // ------------------------------------------------ outputs that are final before the MLPs run

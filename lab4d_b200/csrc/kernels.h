@@ -23,7 +23,8 @@ struct PrologueParams {
   b200r_field_params par;
   b200r_frame_tables fr;
   float* workspace;  // [const block][M frame blocks]
-  int32_t points_only;  // b200r_points_fwd: no cameras, no bone tables; bias rows whose codes are absent are skipped
+  int32_t skip_cams;    // point entries: no cameras; bias rows whose codes are absent are skipped
+  int32_t skip_bones;   // b200r_points_fwd: no bone tables
   int32_t n_layers;
   int32_t rgb0_layer;
   int16_t layer_out[B200R_MAX_LAYERS];
@@ -45,6 +46,7 @@ struct FieldKernelParams {
   int32_t tiles_per_frame;
   int32_t n_tiles;
   int32_t Lmax;            // frequencies of the shared embedding chunk(s): 10 or 12
+  int32_t warp_mode;       // 0, MODE_WARP_BWD or MODE_WARP_FWD: b200r_warp_fwd evaluates one warp on `points`
 };
 
 cudaError_t launch_pack(const PackParams& p, int operand_dtype, cudaStream_t stream);

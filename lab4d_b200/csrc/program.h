@@ -166,7 +166,10 @@ struct BuiltProgram {
   const char* err;
 };
 
-inline BuiltProgram build_program(const b200r_field_desc& d, bool points_only = false) {
+// what the per-tile step list evaluates (the packed operands are the same for every mode)
+enum : int { MODE_FIELD = 0, MODE_POINTS = 1, MODE_WARP_BWD = 2, MODE_WARP_FWD = 3 };
+
+inline BuiltProgram build_program(const b200r_field_desc& d, int mode = MODE_FIELD) {
   BuiltProgram bp;
   bp.ok = false;
   bp.err = "";
@@ -416,12 +419,22 @@ inline BuiltProgram build_program(const b200r_field_desc& d, bool points_only = 
       pipe5(L.dense[3 * m + 1], tsn(4), BAR_H1);
       seq5(L.dense[3 * m + 2], tsn(4), BAR_H1);
     };
-    // points_only (b200r_points_fwd): the same packed operands, but only the density + colour chains are issued
+    // MODE_POINTS (b200r_points_fwd): only the density + colour chains; MODE_WARP_* (b200r_warp_fwd): one warp only
+    const bool points_only = mode == MODE_POINTS, warp_only = mode == MODE_WARP_BWD || mode == MODE_WARP_FWD;
+    if (warp_only && B == 0) { bp.err = "warp entry needs a skinned field"; return bp; }
     for (int w = 0; w < 3 && !points_only; ++w) {
       P.st_delta[w] = ns;
+      if (warp_only && w != (mode == MODE_WARP_BWD ? 0 : 2)) continue;
       if (d.dense && w > 0) dense5(0);
       if (B > 0) delta5();
       if (d.dense && w == 0) dense5(1);
+    }
+    if (warp_only) {
+      P.n_steps = ns;
+      if (ns > kMaxSteps) { bp.err = "too many MMA steps"; return bp; }
+      if (!shape_ok) { bp.err = "internal: unsupported block shape"; return bp; }
+      bp.ok = true;
+      return bp;
     }
     P.st_vis = ns;
     if (!points_only) {

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
       const int in_dim = p.layer_in[p.rgb0_layer];
       for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) cblock[C.dir_w + i] = w0[(size_t)(i / 3) * in_dim + W + (i % 3)];
     }
-    for (int b = threadIdx.x; b < B && !p.points_only; b += blockDim.x) {
+    for (int b = threadIdx.x; b < B && !p.skip_bones; b += blockDim.x) {
       const Q4 qr = ld4(p.fr.rest_art_qr + b * 4), qd = ld4(p.fr.rest_art_qd + b * 4);  // frame 0
       const Q4 t = qmul(qd, qconj(qr));
       cblock[C.center + b * 4 + 0] = 2.f * t.x;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
   const int f = blockIdx.x / kFrameParts, part = blockIdx.x % kFrameParts;
   const int fn = (M >= 2) ? (f ^ 1) : f;
   float* fb = p.workspace + p.cl.n_floats + (size_t)f * F.n_floats;
-  if (part == 0 && !p.points_only) {
+  if (part == 0 && !p.skip_cams) {
     write_cam(fb + F.cam, p, f);
     write_cam(fb + F.cam_partner, p, fn);
   }
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
     }
     fb[c.frame_off + n] = acc;
   }
-  if (B > 0 && part >= 1 && !p.points_only) {
+  if (B > 0 && part >= 1 && !p.skip_bones) {
     __shared__ float ig[32 * 4];
     for (int b = threadIdx.x; b < B; b += blockDim.x)
       for (int c = 0; c < 3; ++c) {

@@ -264,6 +264,44 @@ class FieldRenderer:
         return {k: v.view(M, Pn, -1) for k, v in out.items()}
 
 
+    # ------------------------------------------------------------------ SkinningWarp / ComposedWarp on points
+    @torch.no_grad()
+    def warp_points(self, P, xyz, tab, backward):
+        """SkinningWarp.forward / ComposedWarp.forward (nnutils/warping.py:277-336, 445-483) on points xyz (M,P,3):
+        backward=True maps time-t space to canonical space, False canonical to time-t space with the frame's own
+        articulation.  tab: the skinning (and dense-warp) code rows and articulations of `query_field`.  Returns
+        (xyz' (M,P,3), {"skin_entropy", "delta_skin"} (M,P,1))."""
+        if self.cfg.motion == "rigid":
+            raise RuntimeError("warp_points: the field has no skinning warp")
+        xyz = _f32c(xyz)
+        M, Pn = xyz.shape[:2]
+        par, keep = self._params(P)
+        keep.append(xyz)
+        fr = _lib.FrameTables()
+        fr.M = M
+        for field, key in self._TAB_KEYS.items():
+            if key in tab and tab[key] is not None and not field.startswith("field2cam"):
+                t = _f32c(tab[key])
+                keep.append(t)
+                setattr(fr, field, t.data_ptr())
+        pb = _lib.PointBatch()
+        pb.P = Pn
+        pb.xyz = xyz.data_ptr()
+        out, oa = {}, _lib.FieldOutputs()
+        for name, nch in (("xyz", 3), ("skin_entropy", 1), ("delta_skin", 1)):
+            out[name] = torch.empty(M, Pn, nch, dtype=torch.float32, device=self.device)
+            setattr(oa, name, out[name].data_ptr())
+        wbytes = self.handle.lib.b200r_workspace_bytes(C.byref(self.desc), M)
+        if getattr(self, "_ws", None) is None or self._ws.numel() < wbytes:
+            self._ws = torch.empty(wbytes, dtype=torch.uint8, device=self.device)
+        rc = self.handle.lib.b200r_warp_fwd(self.handle.h, C.byref(self.desc), _ptr(self.packed), C.byref(par), C.byref(fr),
+                                            C.byref(pb), int(bool(backward)), C.byref(oa), _ptr(self._ws), self._ws.numel(),
+                                            _stream(self.device))
+        self.handle.check(rc, "b200r_warp_fwd")
+        self._keep_call = keep
+        return out["xyz"], {"skin_entropy": out["skin_entropy"], "delta_skin": out["delta_skin"]}
+
+
 # ---------------------------------------------------------------------------------------- compositing
 KEY_SKIP = ("density", "vis", "flow", "eikonal", "xy_reproj", "xyz_reproj", "gauss_density")
 KEY_FREEZE = ("cyc_dist", "xyz_cam", "skin_entropy")

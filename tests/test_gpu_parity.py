@@ -192,6 +192,38 @@ def test_points_entry_matches_nerf_forward(name):
     assert torch.equal(only["sdf"], got["sdf"])
 
 
+@pytest.mark.parametrize("name,backward", [("fg_bob", True), ("fg_bob", False), ("fg_compquad", True), ("fg_compquad", False)])
+def test_warp_entry_matches_warp_forward(name, backward):
+    """b200r_warp_fwd = SkinningWarp.forward / ComposedWarp.forward on points (warping.py:277-336, 445-483)."""
+    from lab4d_b200 import spec
+
+    cfg = {"fg_bob": spec.FG_BOB, "fg_compquad": spec.FG_COMP_QUAD}[name]
+    P = synth_params(cfg, 7, device=DEV)
+    M, Pn = 4, 333
+    rays = {k: torch.from_numpy(v).to(DEV) for k, v in synth.synth_rays(M, 4, seed=12).items()}
+    tab = synth_tables(cfg, M, DEV, seed=12, rays=rays, P=P)
+    g = torch.Generator().manual_seed(9)
+    xyz = ((torch.rand(M, Pn, 3, generator=g) - 0.5) * 0.5).to(DEV)
+    got, aux = _renderer(cfg, P).warp_points(P, xyz, tab, backward=backward)
+    torch.cuda.synchronize()
+    x4 = xyz.view(M, Pn, 1, 3)
+    t_art = (tab["t_articulation_qr"], tab["t_articulation_qd"])
+    r_art = (tab["rest_articulation_qr"], tab["rest_articulation_qd"])
+    wargs = (tab["skin_t_embed"], tab["skin_t_embed_mean"], tab["inst_skin"])
+    if backward:
+        ref, oaux = O.skinning_warp(P, x4, t_art, r_art, *wargs, backward=True, symm_idx=cfg.symm_idx and list(cfg.symm_idx))
+        if cfg.dense:
+            ref = O.dense_warp(P, ref, tab["dense_t_embed"], tab["inst_dense_bwd"], backward=True)
+    else:
+        x_in = O.dense_warp(P, x4, tab["dense_t_embed"], tab["inst_dense_fwd"], backward=False) if cfg.dense else x4
+        ref, oaux = O.skinning_warp(P, x_in, t_art, r_art, *wargs, backward=False, symm_idx=cfg.symm_idx and list(cfg.symm_idx))
+    e_xyz = rel_l2(got.cpu(), ref.view(M, Pn, 3).cpu())
+    e_ent = rel_l2(aux["skin_entropy"].cpu(), oaux["skin_entropy"].view(M, Pn, 1).cpu())
+    e_dsk = rel_l2(aux["delta_skin"].cpu(), oaux["delta_skin"].view(M, Pn, 1).cpu())
+    print(f"[parity] warp {name} backward={backward}: xyz={e_xyz:.2e} skin_entropy={e_ent:.2e} delta_skin={e_dsk:.2e}")
+    assert e_xyz < REL["xyz"] and e_ent < REL["skin_entropy"] and e_dsk < REL["delta_skin"]
+
+
 def test_compose_kernel_matches_sort_and_gather():
     """Depth-merge kernel against the reference's own formulation (cat + argsort + gather, multifields.py:339-398) on
     random sorted depths: bit-exact; keys only one field has read as zeros; ties keep field order."""
