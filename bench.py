@@ -285,7 +285,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0 at N = 1 only, ~10 s of CPU work
             threads = best_threads()
-            Ms, reps = 32, 20
+            Ms, reps = 8, 80  # 8-frame batches are the CPU path's fastest batch size (1.7e5 vs 0.7e5 samples/s at 32 frames)
             rate, dt = cpu_port_rate(Ms, N, D, threads, reps=reps)
             line["cpu_baseline"] = {"value": rate, "unit": "ray-samples/s", "cores": threads, "kind": "port",
                                     "sample": f"{reps} x ({Ms} of {M} frames x {N} rays x {D} samples), forward, fp32 oracle port, {reps * dt:.1f} s"}
