@@ -67,78 +67,16 @@ __device__ void write_se3(float* dst, const float* ar_, const float* ad_, const 
 
 constexpr int kFrameParts = 4;  // blocks per frame: the bias rows are dealt round-robin, the bone tables by part
 
-__global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ PrologueParams p) {
-  // let the field kernel (launched with programmatic stream serialization) start its set-up while this grid runs;
-  // it waits (griddepcontrol.wait) before it reads the workspace
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const int M = p.fr.M, B = p.desc.n_bones;
-  float* cblock = p.workspace;
-  if ((int)blockIdx.x == kFrameParts * M) {
-    // ---------------------------------------------------------------- constant block
-    const ConstLayout& C = p.cl;
-    for (int i = threadIdx.x; i < C.n_floats; i += blockDim.x) cblock[i] = 0.f;
-    __syncthreads();
-    for (int l = 0; l < p.n_layers; ++l) {
-      if (C.plain_off[l] < 0) continue;
-      for (int i = threadIdx.x; i < p.layer_out[l]; i += blockDim.x) cblock[C.plain_off[l] + i] = p.par.bias[l][i];
-    }
-    const int W = p.desc.W, H = W / 2;
-    for (int i = threadIdx.x; i < W; i += blockDim.x) cblock[C.sdf_w + i] = p.par.sdf_w[i];
-    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) cblock[C.rgb2_w + i] = p.par.rgb2_w[i];
-    if (p.par.vis_final_w)
-      for (int i = threadIdx.x; i < 64; i += blockDim.x) cblock[C.vis_w + i] = p.par.vis_final_w[i];
-    if (p.desc.L_dir == 0) {
-      const float* w0 = p.par.weight[p.rgb0_layer];
-      const int in_dim = p.layer_in[p.rgb0_layer];
-      for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) cblock[C.dir_w + i] = w0[(size_t)(i / 3) * in_dim + W + (i % 3)];
-    }
-    for (int b = threadIdx.x; b < B && !p.skip_bones; b += blockDim.x) {
-      const Q4 qr = ld4(p.fr.rest_art_qr + b * 4), qd = ld4(p.fr.rest_art_qd + b * 4);  // frame 0
-      const Q4 t = qmul(qd, qconj(qr));
-      cblock[C.center + b * 4 + 0] = 2.f * t.x;
-      cblock[C.center + b * 4 + 1] = 2.f * t.y;
-      cblock[C.center + b * 4 + 2] = 2.f * t.z;
-    }
-    if (threadIdx.x == 0) {
-      float* s = cblock + C.scalars;
-      s[SC_IBETA] = expf(p.par.logibeta[0]);
-      s[SC_INV_SCALE] = 1.0f / expf(p.par.logscale[0]);
-      s[SC_WARP_IBETA] = (B > 0 && p.par.warp_logibeta) ? expf(p.par.warp_logibeta[0]) : 0.f;
-      s[SC_SDF_B] = p.par.sdf_b[0];
-      s[SC_RGB2_B0] = p.par.rgb2_b[0]; s[SC_RGB2_B1] = p.par.rgb2_b[1]; s[SC_RGB2_B2] = p.par.rgb2_b[2];
-      s[SC_VIS_B] = p.par.vis_final_b ? p.par.vis_final_b[0] : 0.f;
-    }
-    return;
-  }
-  // ------------------------------------------------------------------ frame block, split over kFrameParts blocks
-  const FrameLayout& F = p.fl;
-  const int f = blockIdx.x / kFrameParts, part = blockIdx.x % kFrameParts;
-  const int fn = (M >= 2) ? (f ^ 1) : f;
-  float* fb = p.workspace + p.cl.n_floats + (size_t)f * F.n_floats;
-  if (part == 0 && !p.skip_cams) {
-    write_cam(fb + F.cam, p, f);
-    write_cam(fb + F.cam_partner, p, fn);
-  }
-  const float* codes[kNumCodes];
-  codes[CODE_INST_BASE] = p.fr.inst_base ? p.fr.inst_base + (size_t)f * 32 : nullptr;
-  codes[CODE_INST_COLOR] = p.fr.inst_color ? p.fr.inst_color + (size_t)f * 32 : nullptr;
-  codes[CODE_INST_VIS] = p.fr.inst_vis ? p.fr.inst_vis + (size_t)f * 32 : nullptr;
-  codes[CODE_APPR] = p.fr.appr_code ? p.fr.appr_code + (size_t)f * p.desc.appr_channels : nullptr;
-  codes[CODE_INST_SKIN] = p.fr.inst_skin ? p.fr.inst_skin + (size_t)f * 32 : nullptr;
-  codes[CODE_T_EMBED] = p.fr.skin_t_embed ? p.fr.skin_t_embed + (size_t)f * 128 : nullptr;
-  codes[CODE_T_EMBED_MEAN] = p.fr.skin_t_embed_mean;
-  codes[CODE_DENSE_T] = p.fr.dense_t_embed ? p.fr.dense_t_embed + (size_t)f * 128 : nullptr;
-  codes[CODE_DENSE_T_PARTNER] = p.fr.dense_t_embed ? p.fr.dense_t_embed + (size_t)fn * 128 : nullptr;
-  codes[CODE_INST_DENSE_FWD] = p.fr.inst_dense_fwd ? p.fr.inst_dense_fwd + (size_t)f * 32 : nullptr;
-  codes[CODE_INST_DENSE_BWD] = p.fr.inst_dense_bwd ? p.fr.inst_dense_bwd + (size_t)f * 32 : nullptr;
-  // all conditioned bias rows of the frame form one index space; this block takes every kFrameParts-th chunk of 256
+// bias rows b + sum_seg W[:, col0:col0+C] @ code_seg of one frame, rows dealt round-robin over the frame's blocks
+template <bool FILTER>
+__device__ __forceinline__ void frame_rows(const PrologueParams& p, const FrameLayout& F, const float* const* codes, float* fb, int part) {
   int rows_total = 0;
   for (int ci = 0; ci < F.n_cond; ++ci) rows_total += F.cond[ci].n;
   for (int r = part * blockDim.x + threadIdx.x; r < rows_total; r += kFrameParts * blockDim.x) {
     int ci = 0, n = r;
     while (n >= F.cond[ci].n) { n -= F.cond[ci].n; ++ci; }
     const CondRow& c = F.cond[ci];
-    if (!codes[c.code[0]] || (c.n_seg > 1 && !codes[c.code[1]])) continue;  // points mode: layers that are not evaluated
+    if (FILTER && (!codes[c.code[0]] || (c.n_seg > 1 && !codes[c.code[1]]))) continue;
     float acc = p.par.bias[c.layer][n];
     for (int sgi = 0; sgi < c.n_seg; ++sgi) {
       const float* code = codes[c.code[sgi]];
@@ -157,7 +95,80 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
     }
     fb[c.frame_off + n] = acc;
   }
-  if (B > 0 && part >= 1 && !p.skip_bones) {
+}
+
+
+// PT = point entries (b200r_points_fwd / b200r_warp_fwd): optional inputs may be absent.  The field entry compiles
+// every such check out (with them in, this latency-bound kernel takes 47 instead of 29 us).
+template <bool PT>
+__global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ PrologueParams p) {
+  // let the field kernel (launched with programmatic stream serialization) start its set-up while this grid runs;
+  // it waits (griddepcontrol.wait) before it reads the workspace
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int M = p.fr.M, B = p.desc.n_bones;
+  float* cblock = p.workspace;
+  if ((int)blockIdx.x == kFrameParts * M) {
+    // ---------------------------------------------------------------- constant block
+    const ConstLayout& C = p.cl;
+    for (int i = threadIdx.x; i < C.n_floats; i += blockDim.x) cblock[i] = 0.f;
+    __syncthreads();
+    for (int l = 0; l < p.n_layers; ++l) {
+      if (C.plain_off[l] < 0) continue;
+      for (int i = threadIdx.x; i < p.layer_out[l]; i += blockDim.x) cblock[C.plain_off[l] + i] = p.par.bias[l][i];
+    }
+    const int W = p.desc.W, H = W / 2;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) cblock[C.sdf_w + i] = p.par.sdf_w[i];
+    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) cblock[C.rgb2_w + i] = p.par.rgb2_w[i];
+    if (!PT || p.par.vis_final_w)
+      for (int i = threadIdx.x; i < 64; i += blockDim.x) cblock[C.vis_w + i] = p.par.vis_final_w[i];
+    if (p.desc.L_dir == 0) {
+      const float* w0 = p.par.weight[p.rgb0_layer];
+      const int in_dim = p.layer_in[p.rgb0_layer];
+      for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) cblock[C.dir_w + i] = w0[(size_t)(i / 3) * in_dim + W + (i % 3)];
+    }
+    for (int b = threadIdx.x; b < B && !(PT && p.skip_bones); b += blockDim.x) {
+      const Q4 qr = ld4(p.fr.rest_art_qr + b * 4), qd = ld4(p.fr.rest_art_qd + b * 4);  // frame 0
+      const Q4 t = qmul(qd, qconj(qr));
+      cblock[C.center + b * 4 + 0] = 2.f * t.x;
+      cblock[C.center + b * 4 + 1] = 2.f * t.y;
+      cblock[C.center + b * 4 + 2] = 2.f * t.z;
+    }
+    if (threadIdx.x == 0) {
+      float* s = cblock + C.scalars;
+      s[SC_IBETA] = expf(p.par.logibeta[0]);
+      s[SC_INV_SCALE] = 1.0f / expf(p.par.logscale[0]);
+      s[SC_WARP_IBETA] = (B > 0 && (!PT || p.par.warp_logibeta)) ? expf(p.par.warp_logibeta[0]) : 0.f;
+      s[SC_SDF_B] = p.par.sdf_b[0];
+      s[SC_RGB2_B0] = p.par.rgb2_b[0]; s[SC_RGB2_B1] = p.par.rgb2_b[1]; s[SC_RGB2_B2] = p.par.rgb2_b[2];
+      s[SC_VIS_B] = (!PT || p.par.vis_final_b) ? p.par.vis_final_b[0] : 0.f;
+    }
+    return;
+  }
+  // ------------------------------------------------------------------ frame block, split over kFrameParts blocks
+  const FrameLayout& F = p.fl;
+  const int f = blockIdx.x / kFrameParts, part = blockIdx.x % kFrameParts;
+  const int fn = (M >= 2) ? (f ^ 1) : f;
+  float* fb = p.workspace + p.cl.n_floats + (size_t)f * F.n_floats;
+  if (part == 0 && !(PT && p.skip_cams)) {
+    write_cam(fb + F.cam, p, f);
+    write_cam(fb + F.cam_partner, p, fn);
+  }
+  const float* codes[kNumCodes];
+  codes[CODE_INST_BASE] = p.fr.inst_base ? p.fr.inst_base + (size_t)f * 32 : nullptr;
+  codes[CODE_INST_COLOR] = p.fr.inst_color ? p.fr.inst_color + (size_t)f * 32 : nullptr;
+  codes[CODE_INST_VIS] = p.fr.inst_vis ? p.fr.inst_vis + (size_t)f * 32 : nullptr;
+  codes[CODE_APPR] = p.fr.appr_code ? p.fr.appr_code + (size_t)f * p.desc.appr_channels : nullptr;
+  codes[CODE_INST_SKIN] = p.fr.inst_skin ? p.fr.inst_skin + (size_t)f * 32 : nullptr;
+  codes[CODE_T_EMBED] = p.fr.skin_t_embed ? p.fr.skin_t_embed + (size_t)f * 128 : nullptr;
+  codes[CODE_T_EMBED_MEAN] = p.fr.skin_t_embed_mean;
+  codes[CODE_DENSE_T] = p.fr.dense_t_embed ? p.fr.dense_t_embed + (size_t)f * 128 : nullptr;
+  codes[CODE_DENSE_T_PARTNER] = p.fr.dense_t_embed ? p.fr.dense_t_embed + (size_t)fn * 128 : nullptr;
+  codes[CODE_INST_DENSE_FWD] = p.fr.inst_dense_fwd ? p.fr.inst_dense_fwd + (size_t)f * 32 : nullptr;
+  codes[CODE_INST_DENSE_BWD] = p.fr.inst_dense_bwd ? p.fr.inst_dense_bwd + (size_t)f * 32 : nullptr;
+  // all conditioned bias rows of the frame form one index space; this block takes every kFrameParts-th chunk of 256.
+  // Point entries pass only the codes of the layers they evaluate: their rows are filtered.
+  frame_rows<PT>(p, F, codes, fb, part);
+  if (B > 0 && part >= 1 && !(PT && p.skip_bones)) {
     __shared__ float ig[32 * 4];
     for (int b = threadIdx.x; b < B; b += blockDim.x)
       for (int c = 0; c < 3; ++c) {
@@ -181,7 +192,8 @@ __global__ void __launch_bounds__(256) prologue_kernel(const __grid_constant__ P
 }
 
 cudaError_t launch_prologue(const PrologueParams& p, cudaStream_t stream) {
-  prologue_kernel<<<kFrameParts * p.fr.M + 1, 256, 0, stream>>>(p);
+  if (p.skip_cams) prologue_kernel<true><<<kFrameParts * p.fr.M + 1, 256, 0, stream>>>(p);
+  else prologue_kernel<false><<<kFrameParts * p.fr.M + 1, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
