@@ -155,11 +155,6 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
   return d;
 }
-// advance along K inside the 128-B swizzle row: +32 B per UMMA_K=16 halves
-__device__ __forceinline__ uint64_t umma_desc_advance_k(uint64_t d, uint32_t kstep) {
-  return d + (uint64_t)((kstep * 32u) >> 4);
-}
-
 // kind::f16 instruction descriptor: D=f32, A/B = f16 (0) or bf16 (1), both K-major, M=128.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t ab_fmt, uint32_t N, uint32_t M = 128) {
   return (1u << 4)            // c_format = F32
@@ -190,46 +185,6 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
       "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Predicated forms for a warp-converged issue loop: every lane executes the (cheap, uniform) address
-// arithmetic, only the lane with issue != 0 actually issues.  Keeps the MMA warp free of divergence
-// bookkeeping (ELECT / R2UR.BROADCAST per instruction), which otherwise caps the issue rate.
-__device__ __forceinline__ void umma_f16_ss_pred(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                 uint32_t accumulate, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_ts_pred(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
-                                                 uint32_t accumulate, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
-      "r"(issue)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mcast_pred(uint64_t* bar, uint16_t mask, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %2, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
-          smem_u32(bar)),
-      "h"(mask), "r"(issue)
       : "memory");
 }
 // mbarrier arrives when all tcgen05 ops previously issued by this thread have completed.
@@ -290,13 +245,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), B200R_I8(r, 0) : "memory");
-}
-__device__ __forceinline__ void tmem_st16p(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      B200R_I8(r, 0), B200R_I8(r, 8)
-      : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
