@@ -129,6 +129,14 @@ def nerf_forward(field, xyz, dir=None, frame_id=None, inst_id=None, get_density=
     return (out["rgb"].reshape(shape + (3,)), val) if dir is not None else val
 
 
+def compose_fields(multifields_dict, deltas_dict):
+    """Replacement body of MultiFields.compose_fields (nnutils/multifields.py:339-398) for no-grad rendering: the
+    depth-merge kernel instead of cat + argsort + 15 gathers.  Same arguments (dicts keyed by field category, in field
+    order) and return value."""
+    cats = list(multifields_dict.keys())
+    return _render.compose_fields([multifields_dict[c] for c in cats], [deltas_dict[c] for c in cats])
+
+
 def install(lab4d=None, n_depth=64):
     """Patch an imported reference package in place; returns a function that undoes the patch."""
     if lab4d is None:
@@ -136,12 +144,13 @@ def install(lab4d=None, n_depth=64):
     import lab4d.engine.model as rmodel
     import lab4d.nnutils.deformable as rdef
     import lab4d.nnutils.feature as rfeat
+    import lab4d.nnutils.multifields as rmf
     import lab4d.nnutils.nerf as rnerf
     import lab4d.utils.render_utils as rru
 
     saved = [(rnerf.NeRF, "query_field", rnerf.NeRF.query_field), (rfeat.FeatureNeRF, "query_field", rfeat.FeatureNeRF.query_field),
              (rdef.Deformable, "query_field", rdef.Deformable.query_field), (rru, "render_pixel", rru.render_pixel),
-             (rmodel, "render_pixel", rmodel.render_pixel)]
+             (rmodel, "render_pixel", rmodel.render_pixel), (rmf.MultiFields, "compose_fields", rmf.MultiFields.__dict__["compose_fields"])]
 
     def _qf(self, samples_dict, flow_thresh=None):
         return query_field(self, samples_dict, flow_thresh=flow_thresh, n_depth=n_depth)
@@ -150,6 +159,14 @@ def install(lab4d=None, n_depth=64):
         cls.query_field = _qf
     rru.render_pixel = _render.render_pixel
     rmodel.render_pixel = _render.render_pixel
+    ref_compose = rmf.MultiFields.compose_fields
+
+    def _compose(multifields_dict, deltas_dict):
+        # the merge kernel has no backward: graphs that need gradients keep the reference's gather formulation
+        needs_grad = torch.is_grad_enabled() and any(v.requires_grad for f in multifields_dict.values() for v in f.values())
+        return ref_compose(multifields_dict, deltas_dict) if needs_grad else compose_fields(multifields_dict, deltas_dict)
+
+    rmf.MultiFields.compose_fields = staticmethod(_compose)
 
     def undo():
         for obj, name, val in saved:
