@@ -45,6 +45,8 @@ class FieldConfig:
 
 FG_BOB = FieldConfig()
 FG_RIGID = FieldConfig(motion="rigid", B=0)
+HUMAN_SYMM = (0, 1, 2, 3, 8, 9, 10, 11, 4, 5, 6, 7, 15, 16, 17, 12, 13, 14)
+FG_SKEL_HUMAN = FieldConfig(motion="skel", B=18, symm_idx=HUMAN_SYMM)  # configs[2]: skel-human
 QUAD_SYMM = (0, 1, 2, 3, 8, 9, 10, 11, 4, 5, 6, 7, 12, 13, 14, 15, 16, 21, 22, 23, 24, 17, 18, 19, 20)
 FG_COMP_QUAD = FieldConfig(motion="skel", B=25, symm_idx=QUAD_SYMM, dense=True)  # comp_skel-quad_dense
 BG = FieldConfig(category="bg", D=5, W=128, L_xyz=6, L_dir=0, appr_channels=0, motion="rigid", B=0, has_feature=False)

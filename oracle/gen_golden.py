@@ -104,3 +104,4 @@ if __name__ == "__main__":
     one("fg_bob_M2_N4_D128_thresh", "fg", "bob", 2, 4, 128, seed=1, flow_thresh=40.0)
     one("comp_bob_M2_N8_D16", "comp", "bob", 2, 8, 16, seed=0, with_grad=False)
     one("fg_compquad_M4_N8_D16", "fg", "comp_skel-quad_dense", 4, 8, 16, seed=3)
+    one("fg_skelhuman_M4_N8_D24", "fg", "skel-human", 4, 8, 24, seed=4)

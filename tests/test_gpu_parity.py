@@ -80,10 +80,10 @@ def test_query_field_matches_reference(path):
         assert torch.isfinite(g).all(), k
         if k == "eikonal":
             continue
-        if k in ABS:
+        if k == "flow":  # pixels: 0.15 px absolute, or 5e-4 of the flow field's norm where flows are hundreds of pixels
+            assert float((g - rv).abs().max()) <= ABS[k] or rel_l2(g, rv) < 5e-4, (k, float((g - rv).abs().max()), rel_l2(g, rv))
+        elif k in ABS:
             assert float((g - rv).abs().max()) <= ABS[k], k
-        elif k == "flow":
-            pass
         else:
             assert rel_l2(g, rv) < REL[k], (k, rel_l2(g, rv))
     if "flow" in ref:  # validity flags identical, flow vectors close in pixels

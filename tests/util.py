@@ -10,7 +10,8 @@ from lab4d_b200 import spec
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-CFG_OF = {"bg_rigid": spec.BG, "fg_rigid": spec.FG_RIGID, "fg_bob": spec.FG_BOB, "fg_compquad": spec.FG_COMP_QUAD}
+CFG_OF = {"bg_rigid": spec.BG, "fg_rigid": spec.FG_RIGID, "fg_bob": spec.FG_BOB, "fg_compquad": spec.FG_COMP_QUAD,
+          "fg_skelhuman": spec.FG_SKEL_HUMAN}
 
 
 def golden_files(prefix=""):
