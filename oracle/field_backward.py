@@ -1,5 +1,5 @@
-"""Hand-derived backward of the whole training-mode query_field of a skinned fg field (no dense warp, no eikonal),
-composed from oracle/skin_backward.py and oracle/nerf_backward.py plus the geometry / flow / cycle / visibility / feature /
+"""Hand-derived backward of the whole training-mode query_field of a skinned fg field (with or without the dense warp of
+a ComposedWarp; no eikonal), composed from oracle/skin_backward.py and oracle/nerf_backward.py plus the geometry / flow / cycle / visibility / feature /
 Gaussian-density stages.  TEST INFRASTRUCTURE: the per-sample part is written out by hand in the order the CUDA backward
 will run it; the per-frame part (tables <- articulations, folded bias rows <- codes) is left to autograd exactly as planned
 for the product.  tests/test_field_backward_cpu.py checks every parameter and per-frame input gradient
@@ -38,13 +38,26 @@ def _skin_tables(P, cfg, tab, M, which):
                 b2=P[pre + "linear_2.0.bias"], W3=P[pre + "linear_final.weight"], b3=P[pre + "linear_final.bias"])
 
 
+def _dense_fwd(P, x, t_embed, inst, backward):
+    """DenseWarp.forward (warping.py:143-170): x + 0.1 * CondMLP([PE6(x), t, inst]); returns (x', saved)."""
+    prefix = "warp.post_warp.backward_map." if backward else "warp.post_warp.forward_map."
+    m, sv = NB.mlp_forward_saved(P, prefix, NB.pe_forward(x, 6), torch.cat([t_embed, inst], -1), 2, final_act=False)
+    return x + 0.1 * m, dict(sv=sv, x=x, prefix=prefix)
+
+
+def _dense_bwd(P, saved, g_out, acc):
+    """Returns (g_x, g_t_embed (M,128), g_inst (M,32)); parameter gradients go to acc()."""
+    g_e, g_code, gp = NB.mlp_backward(P, saved["prefix"], saved["sv"], 0.1 * g_out, 2, final_act=False)
+    acc(gp)
+    return g_out + NB.pe_backward(saved["x"], 6, g_e), g_code[:, :128], g_code[:, 128:]
+
+
 def forward_saved(P, cfg, rays, tab, D):
     """Forward in the kernel's formulation; returns the outputs (M,S,c) with S = N*D and what the backward needs."""
     hxy, Kinv, near_far = rays["hxy"], rays["Kinv"], rays["near_far"]
     M, N = hxy.shape[:2]
     S = N * D
     d = torch.einsum("mni,mji->mnj", hxy, Kinv)
-    dn = d.norm(dim=-1, keepdim=True)
     z = torch.linspace(0, 1, D, dtype=hxy.dtype)
     depth = near_far[:, 0:1] * (1 - z) + near_far[:, 1:2] * z                      # (M,D)
     xyz_cam = (d[:, :, None, :] * depth[:, None, :, None]).reshape(M, S, 3)
@@ -53,9 +66,17 @@ def forward_saved(P, cfg, rays, tab, D):
     ti = O.qrot(qi, -t)
     xyz_t = O.qrot(qi[:, None].expand(M, S, 4), xyz_cam) + ti[:, None]
     T = [_skin_tables(P, cfg, tab, M, w) for w in range(3)]
-    xyz, ent0, dsk0, sv0 = SB.skin_forward_tables(xyz_t, **T[0])
-    x_next, _, _, sv1 = SB.skin_forward_tables(xyz, **T[1])
-    x_cyc, ent2, dsk2, sv2 = SB.skin_forward_tables(xyz, **T[2])
+    dense = bool(cfg.get("dense", False))
+    xs, ent0, dsk0, sv0 = SB.skin_forward_tables(xyz_t, **T[0])
+    dn = [None, None, None]
+    if dense:  # ComposedWarp (warping.py:445-483): backward = skin then dense, forward = dense then skin
+        xyz, dn[0] = _dense_fwd(P, xs, tab["dense_t_embed"], tab["inst_dense_bwd"], True)
+        x1, dn[1] = _dense_fwd(P, xyz, O.flip_pair(tab["dense_t_embed"]), tab["inst_dense_fwd"], False)
+        x2, dn[2] = _dense_fwd(P, xyz, tab["dense_t_embed"], tab["inst_dense_fwd"], False)
+    else:
+        xyz = x1 = x2 = xs
+    x_next, _, _, sv1 = SB.skin_forward_tables(x1, **T[1])
+    x_cyc, ent2, dsk2, sv2 = SB.skin_forward_tables(x2, **T[2])
     qn, tn, Kn = O.flip_pair(q), O.flip_pair(t), O.flip_pair(Kinv)
     xc = O.qrot(qn[:, None].expand(M, S, 4), x_next) + tn[:, None]
     Kmat = O.kmat_from_kinv(Kn)
@@ -74,7 +95,7 @@ def forward_saved(P, cfg, rays, tab, D):
     gd = torch.exp(-0.5 * dmin / 0.01 ** 2)[..., None] * wib
     out = dict(rgb=rgb, density=density, vis=vis, feature=fraw / fnorm, flow=flow, cyc_dist=cyc, xyz=xyz, xyz_cam=xyz_cam,
                delta_skin=0.5 * (dsk0 + dsk2)[..., None], skin_entropy=0.5 * (ent0 + ent2)[..., None], gauss_density=gd)
-    saved = dict(M=M, N=N, D=D, S=S, d=d, depth=depth, xyz_cam=xyz_cam, qi=qi, xyz_t=xyz_t, T=T, sv=(sv0, sv1, sv2), xyz=xyz,
+    saved = dict(dn=dn, x1=x1, x2=x2, M=M, N=N, D=D, S=S, d=d, depth=depth, xyz_cam=xyz_cam, qi=qi, xyz_t=xyz_t, T=T, sv=(sv0, sv1, sv2), xyz=xyz,
                  x_next=x_next, x_cyc=x_cyc, qn=qn, xc=xc, Kmat=Kmat, hn=hn, diff=diff, cyc=cyc, snerf=snerf, svis=svis, sfeat=sfeat,
                  fraw=fraw, fnorm=fnorm, ctr=ctr, amin=amin, gd=gd, wib=wib)
     return out, saved
@@ -119,8 +140,17 @@ def backward(P, cfg, rays, tab, saved, g):
     g_xyz_t = -g_diff
     T, (sv0, sv1, sv2) = v["T"], v["sv"]
     zero1 = torch.zeros(M, S, dtype=xyz.dtype)
-    b2 = SB.skin_backward_tables(xyz, **T[2], saved=sv2, g_xo=g_diff, g_ent=0.5 * g["skin_entropy"][..., 0], g_dsk=0.5 * g["delta_skin"][..., 0])
-    g_xyz = g_xyz + b2["x"]
+    dn = v["dn"]
+    g_dense = {"dense_t_embed": torch.zeros(M, 128, dtype=xyz.dtype), "inst_dense_fwd": torch.zeros(M, 32, dtype=xyz.dtype),
+               "inst_dense_bwd": torch.zeros(M, 32, dtype=xyz.dtype)}
+    b2 = SB.skin_backward_tables(v["x2"], **T[2], saved=sv2, g_xo=g_diff, g_ent=0.5 * g["skin_entropy"][..., 0], g_dsk=0.5 * g["delta_skin"][..., 0])
+    if dn[2] is not None:
+        gx, gt, gi = _dense_bwd(P, dn[2], b2["x"], acc)
+        g_xyz = g_xyz + gx
+        g_dense["dense_t_embed"] += gt
+        g_dense["inst_dense_fwd"] += gi
+    else:
+        g_xyz = g_xyz + b2["x"]
     # ---- flow: h = K xc, flow = h_xy / (h_z + 1e-6) - hxy;  xc = R(qn) x_next + tn
     hz = v["hn"][..., 2:] + 1e-6
     g_h = torch.cat([g["flow"] / hz, -(g["flow"] * v["hn"][..., :2]).sum(-1, keepdim=True) / hz.pow(2)], -1)
@@ -129,9 +159,19 @@ def backward(P, cfg, rays, tab, saved, g):
     g_tn = g_xc.sum(1)
     g_qn_s, g_xnext = _qrot_bwd(v["qn"][:, None].expand(M, S, 4), v["x_next"], g_xc)
     g_qn = g_qn_s.sum(1)
-    b1 = SB.skin_backward_tables(xyz, **T[1], saved=sv1, g_xo=g_xnext, g_ent=zero1, g_dsk=zero1)
-    g_xyz = g_xyz + b1["x"]
+    b1 = SB.skin_backward_tables(v["x1"], **T[1], saved=sv1, g_xo=g_xnext, g_ent=zero1, g_dsk=zero1)
+    if dn[1] is not None:
+        gx, gt, gi = _dense_bwd(P, dn[1], b1["x"], acc)
+        g_xyz = g_xyz + gx
+        g_dense["dense_t_embed"] += O.flip_pair(gt)  # the partner frame's time code
+        g_dense["inst_dense_fwd"] += gi
+    else:
+        g_xyz = g_xyz + b1["x"]
     # ---- backward warp
+    if dn[0] is not None:
+        g_xyz, gt, gi = _dense_bwd(P, dn[0], g_xyz, acc)
+        g_dense["dense_t_embed"] += gt
+        g_dense["inst_dense_bwd"] += gi
     b0 = SB.skin_backward_tables(v["xyz_t"], **T[0], saved=sv0, g_xo=g_xyz, g_ent=0.5 * g["skin_entropy"][..., 0], g_dsk=0.5 * g["delta_skin"][..., 0])
     g_xyz_t = g_xyz_t + b0["x"]
     # ---- camera -> field: xyz_t = R(qi) xyz_cam + ti
@@ -142,6 +182,6 @@ def backward(P, cfg, rays, tab, saved, g):
     # ---- sample placement: xyz_cam = (Kinv hxy) * depth
     g_d = (g_xyz_cam.reshape(M, N, D, 3) * v["depth"][:, None, :, None]).sum(2)
     g_Kinv = torch.einsum("mnj,mni->mji", g_d, rays["hxy"])
-    tables = dict(skin=(b0, b1, b2), g_ctr=g_ctr, g_qi=g_qi, g_ti=g_ti, g_qn=g_qn, g_tn=g_tn, g_Kmat=g_Kmat, g_Kinv=g_Kinv,
+    tables = dict(g_dense=g_dense, skin=(b0, b1, b2), g_ctr=g_ctr, g_qi=g_qi, g_ti=g_ti, g_qn=g_qn, g_tn=g_tn, g_Kmat=g_Kmat, g_Kinv=g_Kinv,
                   g_inst_vis=g_inst_vis, g_inst_base=gin["inst_base"], g_inst_color=gin["inst_color"], g_appr=gin["appr"])
     return grads, tables

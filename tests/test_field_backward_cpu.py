@@ -14,8 +14,8 @@ from util import synth_params
 KEYS = ("rgb", "density", "vis", "feature", "flow", "cyc_dist", "xyz", "xyz_cam", "delta_skin", "skin_entropy", "gauss_density")
 
 
-def _setup(dtype=torch.float64):
-    cfg = spec.FG_BOB
+def _setup(dtype=torch.float64, dense=False):
+    cfg = spec.FieldConfig(motion="bob", B=25, dense=True) if dense else spec.FG_BOB
     M, N, D = 2, 3, 5
     P = {k: v.requires_grad_(True) for k, v in synth_params(cfg, 1, dtype).items()}
     rays_np = synth.synth_rays(M, N, seed=3)
@@ -30,13 +30,19 @@ def _setup(dtype=torch.float64):
            "skin_t_embed": t_embed[:M].contiguous(), "skin_t_embed_mean": t_mean, "t_articulation_qr": t_art[0][:M].contiguous(),
            "t_articulation_qd": t_art[1][:M].contiguous(), "rest_articulation_qr": rest[0][:M].contiguous(),
            "rest_articulation_qd": rest[1][:M].contiguous()}
+    if dense:
+        tab.update({"dense_t_embed": f(M, 128), "inst_dense_fwd": f(M, 32, sc=0.5), "inst_dense_bwd": f(M, 32, sc=0.5)})
     for v in tab.values():
         v.requires_grad_(True)
     return cfg, P, rays, tab, M, N, D
 
 
-def test_forward_formulation_and_full_backward():
-    cfg, P, rays, tab, M, N, D = _setup()
+import pytest
+
+
+@pytest.mark.parametrize("dense", [False, True], ids=["skinning", "composed"])
+def test_forward_formulation_and_full_backward(dense):
+    cfg, P, rays, tab, M, N, D = _setup(dense=dense)
     ocfg = cfg.as_oracle_cfg()
     S = N * D
     feat, _ = O.query_field(P, ocfg, rays, tab, D)
@@ -80,6 +86,9 @@ def test_forward_formulation_and_full_backward():
     for n, gname in (("tab/inst_vis", "g_inst_vis"), ("tab/inst_base", "g_inst_base"), ("tab/inst_color", "g_inst_color"), ("tab/appr_code", "g_appr")):
         hand[n] = tb[gname] if hand[n] is None else hand[n] + tb[gname]
     hand["Kinv"] = tb["g_Kinv"] if hand["Kinv"] is None else hand["Kinv"] + tb["g_Kinv"]
+    if dense:
+        for k, gk in tb["g_dense"].items():
+            hand["tab/" + k] = gk if hand["tab/" + k] is None else hand["tab/" + k] + gk
 
     checked = 0
     for n in names:
