@@ -96,6 +96,31 @@ def one(name, field_type, motion, M, N, D, seed=0, flow_thresh=None, with_grad=T
           {c: (float(pack[f"{c}/rend/mask"].min()), float(pack[f"{c}/rend/mask"].max())) for c in cats})
 
 
+def one_importance(name, motion, M, N, D, seed=0):
+    """Eval-mode NeRF.importance_sampling (nnutils/nerf.py:686-738) of the unmodified reference: merged depths, deltas."""
+    torch.manual_seed(0)
+    mf = H.build_field("fg", motion, seed=seed)
+    rays = synth.synth_rays(M, N, seed=seed)
+    field = mf.field_params["fg"]
+    _, _, _, tabs, graph = H.run_field(mf, "fg", rays, D)   # training-mode pass: gives the per-frame tables / samples_dict
+    samples = graph[3]
+    field.eval()
+    with torch.no_grad():
+        xyz_cam, dir_cam, deltas, depth = field.importance_sampling(
+            samples["hxy"], samples["Kinv"], samples["near_far"], samples["field2cam"], samples["frame_id"], samples["inst_id"],
+            samples, n_depth=D)
+    field.train()
+    pack = {"meta/M": M, "meta/N": N, "meta/D": D, "meta/seed": seed}
+    for k, v in rays.items():
+        pack["rays/" + k] = v
+    for k, v in tabs.items():
+        pack["fg/tab/" + k] = v
+    pack.update({"imp/xyz_cam": xyz_cam.numpy(), "imp/dir": dir_cam.numpy(), "imp/deltas": deltas.numpy(), "imp/depth": depth.numpy()})
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **pack)
+    print(name, "->", os.path.getsize(path) // 1024, "KiB; depth range", float(depth.min()), float(depth.max()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     one("bg_rigid_M2_N16_D16", "bg", "rigid", 2, 16, 16)
@@ -105,3 +130,4 @@ if __name__ == "__main__":
     one("comp_bob_M2_N8_D16", "comp", "bob", 2, 8, 16, seed=0, with_grad=False)
     one("fg_compquad_M4_N8_D16", "fg", "comp_skel-quad_dense", 4, 8, 16, seed=3)
     one("fg_skelhuman_M4_N8_D24", "fg", "skel-human", 4, 8, 24, seed=4)
+    one_importance("imp_fg_bob_M2_N8_D32", "bob", 2, 8, 32, seed=5)

@@ -129,14 +129,17 @@ def _per_frame(code, ref):
 # --------------------------------------------------------------------------------------
 
 
-def sample_cam_rays(hxy, Kinv, near_far, D):
-    """utils/render_utils.py:8-56 with perturb=False, depth=None."""
+def sample_cam_rays(hxy, Kinv, near_far, D, depth=None):
+    """utils/render_utils.py:8-56 with perturb=False; depth (M,N,D,1) overrides the uniform placement."""
     d = torch.einsum("mni,mji->mnj", hxy, Kinv)
     dn = d.norm(dim=-1)
-    z = torch.linspace(0, 1, D, dtype=hxy.dtype, device=hxy.device)[None]
-    depth = near_far[:, 0:1] * (1 - z) + near_far[:, 1:2] * z  # (M,D)
     M, N = hxy.shape[:2]
-    depth = depth[:, None, :, None].expand(M, N, D, 1)
+    if depth is None:
+        z = torch.linspace(0, 1, D, dtype=hxy.dtype, device=hxy.device)[None]
+        depth = near_far[:, 0:1] * (1 - z) + near_far[:, 1:2] * z  # (M,D)
+        depth = depth[:, None, :, None].expand(M, N, D, 1)
+    else:
+        D = depth.shape[2]
     xyz = d[:, :, None, :] * depth
     dl = depth[:, :, 1:] - depth[:, :, :-1]
     dl = torch.cat([dl, dl[:, :, -1:]], 2) * dn[..., None, None]
@@ -428,6 +431,49 @@ def render_pixel(feat, deltas):
         gw, _ = compute_weights(feat["gauss_density"], deltas)
         out["gauss_mask"] = gw.sum(-1, keepdim=True)
     return out
+
+
+def sample_pdf(bins, weights, n_importance, eps=1e-5):
+    """sample_pdf (utils/render_utils.py:187-233), deterministic branch (u = linspace): inverse-CDF samples of the
+    piecewise-constant pdf `weights` (R, n) over the bin edges `bins` (R, n+1)."""
+    R, n = weights.shape
+    w = weights + eps
+    pdf = w / w.sum(-1, keepdim=True)
+    cdf = torch.cat([torch.zeros_like(pdf[:, :1]), torch.cumsum(pdf, -1)], -1)  # (R, n+1)
+    u = torch.linspace(0, 1, n_importance, dtype=bins.dtype, device=bins.device).expand(R, n_importance).contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    below, above = (inds - 1).clamp(min=0), inds.clamp(max=n)
+    cdf_lo, cdf_hi = torch.gather(cdf, 1, below), torch.gather(cdf, 1, above)
+    b_lo, b_hi = torch.gather(bins, 1, below), torch.gather(bins, 1, above)
+    denom = cdf_hi - cdf_lo
+    denom = torch.where(denom < eps, torch.ones_like(denom), denom)
+    return b_lo + (u - cdf_lo) / denom * (b_hi - b_lo)
+
+
+def importance_sampling(P, cfg, rays, tab, D):
+    """NeRF.importance_sampling in eval mode (nnutils/nerf.py:686-738): D/2 uniform samples -> density -> weights ->
+    D/2 inverse-CDF samples on the mid-points (weights[1:-1]) -> merged and sorted depths (M,N,D,1); returns
+    sample_cam_rays at those depths (xyz_cam, dir, deltas, depth)."""
+    hxy, Kinv, near_far = rays["hxy"], rays["Kinv"], rays["near_far"]
+    M, N = hxy.shape[:2]
+    Dc = D // 2
+    xyz_cam, dir_cam, deltas, depth = sample_cam_rays(hxy, Kinv, near_far, Dc)
+    xyz_t, _ = cam_to_field(xyz_cam, dir_cam, tab["field2cam_q"], tab["field2cam_t"])
+    if cfg["motion"] != "rigid":
+        t_art = (tab["t_articulation_qr"], tab["t_articulation_qd"])
+        r_art = (tab["rest_articulation_qr"], tab["rest_articulation_qd"])
+        xyz, _ = skinning_warp(P, xyz_t, t_art, r_art, tab["skin_t_embed"], tab["skin_t_embed_mean"], tab["inst_skin"],
+                               backward=True, symm_idx=cfg.get("symm_idx"))
+        if cfg.get("dense", False):
+            xyz = dense_warp(P, xyz, tab["dense_t_embed"], tab["inst_dense_bwd"], backward=True)
+    else:
+        xyz = xyz_t
+    density = nerf_forward(P, cfg, xyz, tab["inst_base"], tab["inst_color"])
+    weights, _ = compute_weights(density, deltas)
+    depth_mid = 0.5 * (depth[:, :, :-1] + depth[:, :, 1:]).reshape(-1, Dc - 1)
+    fine = sample_pdf(depth_mid, weights.reshape(-1, Dc)[:, 1:-1], Dc).reshape(M, N, Dc, 1)
+    merged, _ = torch.sort(torch.cat([depth, fine], -2), -2)
+    return sample_cam_rays(hxy, Kinv, near_far, D, depth=merged)
 
 
 def compose_fields(feats, deltas_list):

@@ -12,7 +12,7 @@ from util import cfg_for, golden_files, load_golden, rel_l2, sub, synth_params
 
 pytestmark = pytest.mark.gpu
 
-SINGLE = [p for p in golden_files() if not p.split("/")[-1].startswith("comp")]
+SINGLE = [p for p in golden_files() if not p.split("/")[-1].startswith(("comp", "imp"))]
 DEV = "cuda"
 
 # Tolerances.  The MLPs run with fp16 operands and fp32 accumulation (reference: fp32 everywhere);
