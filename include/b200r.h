@@ -126,6 +126,8 @@ typedef struct {
   float flow_thresh;   /* < 0: None */
   int32_t pad_;
   const float* hxy;    /* (M,N,3) homogeneous pixel coordinates */
+  const float* depth;  /* (M,N,D) sample depths along every ray, ascending (sample_cam_rays(depth=...), e.g. from
+                          b200r_importance_fwd), or NULL: uniform placement between the frame's near and far planes */
 } b200r_ray_batch;
 
 /* Per-sample outputs, (M*N*D, c) row-major fp32; any pointer may be NULL. */
@@ -223,6 +225,20 @@ typedef struct {
 } b200r_composite_bwd_args;
 
 int b200r_composite_bwd(b200r_handle* h, const b200r_composite_bwd_args* args, b200r_stream stream);
+
+/* ------------------------------------------------------------------ importance sampling (eval-mode sample placement)
+ * NeRF.importance_sampling (lab4d/nnutils/nerf.py:686-738) after the coarse pass: from the Dc coarse depths of every ray
+ * and their compositing weights (b200r_composite_fwd's `weights`), draw Dc deterministic inverse-CDF samples on the
+ * mid-points with weights[1:-1] (sample_pdf, lab4d/utils/render_utils.py:187-233, det=True) and merge them with the
+ * coarse depths: depth_out (R, 2*Dc) ascending, ready for b200r_ray_batch.depth. */
+typedef struct {
+  int32_t R, Dc;            /* rays, coarse samples per ray (Dc >= 4) */
+  const float* depth_c;     /* (R*Dc) coarse depths, ascending */
+  const float* weights;     /* (R*Dc) compositing weights of the coarse samples */
+  float* depth_out;         /* (R*2*Dc) */
+} b200r_importance_args;
+
+int b200r_importance_fwd(b200r_handle* h, const b200r_importance_args* args, b200r_stream stream);
 
 /* ------------------------------------------------------------------ compose_fields (two fields -> one sample list)
  * MultiFields.compose_fields (lab4d/nnutils/multifields.py:339-398): the samples of field A (first in field order) and

@@ -39,7 +39,7 @@ class FrameTables(C.Structure):
 
 
 class RayBatch(C.Structure):
-    _fields_ = [("N", C.c_int32), ("D", C.c_int32), ("flow_thresh", C.c_float), ("pad_", C.c_int32), ("hxy", f32p)]
+    _fields_ = [("N", C.c_int32), ("D", C.c_int32), ("flow_thresh", C.c_float), ("pad_", C.c_int32), ("hxy", f32p), ("depth", f32p)]
 
 
 class FieldOutputs(C.Structure):
@@ -61,6 +61,10 @@ class PointBatch(C.Structure):
     _fields_ = [("P", C.c_int32), ("pad_", C.c_int32), ("xyz", f32p), ("dir", f32p)]
 
 
+class ImportanceArgs(C.Structure):
+    _fields_ = [("R", C.c_int32), ("Dc", C.c_int32), ("depth_c", f32p), ("weights", f32p), ("depth_out", f32p)]
+
+
 class ComposeArgs(C.Structure):
     _fields_ = [("R", C.c_int32), ("Da", C.c_int32), ("Db", C.c_int32), ("n_channels", C.c_int32), ("depth_a", f32p),
                 ("depth_b", f32p), ("perm", C.c_void_p), ("src_a", f32p * MAX_CHANNELS), ("src_b", f32p * MAX_CHANNELS),
@@ -69,7 +73,7 @@ class ComposeArgs(C.Structure):
 
 EXPORTS = ["b200r_layer_count", "b200r_packed_bytes", "b200r_create", "b200r_destroy", "b200r_last_error",
            "b200r_pack_weights", "b200r_workspace_bytes", "b200r_field_fwd", "b200r_composite_fwd", "b200r_composite_bwd",
-           "b200r_compose_fwd", "b200r_points_fwd", "b200r_warp_fwd"]
+           "b200r_compose_fwd", "b200r_points_fwd", "b200r_warp_fwd", "b200r_importance_fwd"]
 
 _lib = None
 
@@ -113,6 +117,8 @@ def load():
     lib.b200r_warp_fwd.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldParams), C.POINTER(FrameTables),
                                    C.POINTER(PointBatch), C.c_int32, C.POINTER(FieldOutputs), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.b200r_warp_fwd.restype = C.c_int
+    lib.b200r_importance_fwd.argtypes = [C.c_void_p, C.POINTER(ImportanceArgs), C.c_void_p]
+    lib.b200r_importance_fwd.restype = C.c_int
     lib.b200r_compose_fwd.argtypes = [C.c_void_p, C.POINTER(ComposeArgs), C.c_void_p]
     lib.b200r_compose_fwd.restype = C.c_int
     _lib = lib

@@ -283,6 +283,17 @@ int b200r_composite_bwd(b200r_handle* h, const b200r_composite_bwd_args* b, b200
   return B200R_OK;
 }
 
+int b200r_importance_fwd(b200r_handle* h, const b200r_importance_args* a, b200r_stream stream) {
+  if (!h) return B200R_E_INVALID;
+  if (!a) return fail(h, B200R_E_INVALID, "importance: null argument");
+  if (a->R < 1 || a->Dc < 4 || a->Dc > 4096) return fail(h, B200R_E_INVALID, "importance: need R >= 1 and 4 <= Dc <= 4096");
+  if (!a->depth_c || !a->weights || !a->depth_out) return fail(h, B200R_E_INVALID, "importance: null buffer");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
+  if ((e = b200r::launch_importance_fwd(*a, (cudaStream_t)stream)) != cudaSuccess) return fail_cuda(h, e, "importance kernel");
+  return B200R_OK;
+}
+
 int b200r_compose_fwd(b200r_handle* h, const b200r_compose_args* a, b200r_stream stream) {
   if (!h) return B200R_E_INVALID;
   if (!a) return fail(h, B200R_E_INVALID, "compose: null argument");

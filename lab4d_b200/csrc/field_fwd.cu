@@ -484,8 +484,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         const float step = 1.0f / (float)(Dn - 1);
         auto lin = [&](int i) { return i < Dn / 2 ? step * (float)i : 1.0f - step * (float)(Dn - 1 - i); };
         auto depth_at = [&](int i) { float z = lin(i); return nearv * (1.0f - z) + farv * z; };
-        depth = depth_at(k);
-        delta = (k + 1 < Dn ? depth_at(k + 1) - depth : depth - depth_at(k - 1)) * dn;
+        if (p.rays.depth) {  // given sample depths (importance sampling): sample_cam_rays(depth=...)
+          const float* dp = p.rays.depth + ((size_t)f * p.rays.N + n) * Dn;
+          depth = __ldg(dp + k);
+          delta = (k + 1 < Dn ? __ldg(dp + k + 1) - depth : depth - __ldg(dp + k - 1)) * dn;
+        } else {
+          depth = depth_at(k);
+          delta = (k + 1 < Dn ? depth_at(k + 1) - depth : depth - depth_at(k - 1)) * dn;
+        }
         xyz_cam = make_float3(d.x * depth, d.y * depth, d.z * depth);
         const float3 dir_cam = make_float3(d.x / dn, d.y / dn, d.z / dn);
 

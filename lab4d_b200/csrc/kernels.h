@@ -53,6 +53,7 @@ cudaError_t launch_pack(const PackParams& p, int operand_dtype, cudaStream_t str
 cudaError_t launch_prologue(const PrologueParams& p, cudaStream_t stream);
 cudaError_t launch_composite_fwd(const b200r_composite_args& a, cudaStream_t stream);
 cudaError_t launch_composite_bwd(const b200r_composite_bwd_args& b, cudaStream_t stream);
+cudaError_t launch_importance_fwd(const b200r_importance_args& a, cudaStream_t stream);
 cudaError_t launch_compose_fwd(const b200r_compose_args& a, cudaStream_t stream);
 cudaError_t launch_field_fwd(const FieldKernelParams& p, int n_sm, cudaStream_t stream);
 

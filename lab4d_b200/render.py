@@ -59,6 +59,17 @@ class HostStage:
         return self.dev
 
 
+def importance_merge(handle, device, depth_c, weights):
+    """b200r_importance_fwd: coarse depths (R,Dc) + their compositing weights (R,Dc) -> merged ascending depths (R,2Dc)."""
+    R, Dc = depth_c.shape
+    out = torch.empty(R, 2 * Dc, device=device)
+    a = _lib.ImportanceArgs()
+    a.R, a.Dc = R, Dc
+    a.depth_c, a.weights, a.depth_out = depth_c.data_ptr(), weights.data_ptr(), out.data_ptr()
+    handle.check(handle.lib.b200r_importance_fwd(handle.h, C.byref(a), _stream(device)), "b200r_importance_fwd")
+    return out
+
+
 class FieldRenderer:
     """One field (fg or bg).  Holds the packed tensor-core operands; everything else is per call."""
 
@@ -158,11 +169,12 @@ class FieldRenderer:
 
     # ------------------------------------------------------------------ query_field
     @torch.no_grad()
-    def query_field(self, P, rays, tab, D, flow_thresh=None, want=None):
+    def query_field(self, P, rays, tab, D, flow_thresh=None, want=None, depth=None):
         """Training-mode query_field.  rays: hxy (M,N,3), Kinv (M,3,3), near_far (M,2);
         tab: per-frame tables (field2cam_q/t, codes, articulations).  Returns (feat_dict, deltas)
         with the reference's keys and (M,N,D,c) shapes.  `eikonal` is returned as zeros: its
-        second-order term stays on PyTorch autograd."""
+        second-order term stays on PyTorch autograd.  depth (M,N,D[,1]): given ascending sample
+        depths (e.g. from `importance_depths`) instead of the uniform placement."""
         c = self.cfg
         hxy = _f32c(rays["hxy"])
         M, N = hxy.shape[:2]
@@ -187,6 +199,10 @@ class FieldRenderer:
         rb.N, rb.D = N, int(D)
         rb.flow_thresh = -1.0 if flow_thresh is None else float(flow_thresh)
         rb.hxy = hxy.data_ptr()
+        if depth is not None:
+            dep = _f32c(depth.reshape(M, N, int(D)))
+            keep.append(dep)
+            rb.depth = dep.data_ptr()
         out, oa = {}, _lib.FieldOutputs()
         for name, nch in _lib.FIELD_OUTPUTS:
             if want is not None and name not in want:
@@ -224,6 +240,26 @@ class FieldRenderer:
             feat["eikonal"] = torch.zeros(M, N, D, 1, device=self.device)
         return feat, deltas
 
+
+    # ------------------------------------------------------------------ eval-mode importance sampling
+    @torch.no_grad()
+    def importance_depths(self, P, rays, tab, D):
+        """NeRF.importance_sampling (nnutils/nerf.py:686-738): D/2 uniform samples -> density -> compositing weights ->
+        D/2 deterministic inverse-CDF samples, merged: ascending depths (M,N,D,1) for `query_field(..., depth=...)`."""
+        Dc = int(D) // 2
+        feat, deltas = self.query_field(P, rays, tab, Dc, want=("density", "deltas"))
+        M, N = feat["density"].shape[:2]
+        R = M * N
+        nf = _f32c(rays["near_far"])
+        z = torch.linspace(0, 1, Dc, device=self.device)[None]
+        depth_c = (nf[:, 0:1] * (1 - z) + nf[:, 1:2] * z)[:, None, :].expand(M, N, Dc).reshape(R, Dc).contiguous()  # sample_cam_rays
+        dens, dl = _f32c(feat["density"]), _f32c(deltas)
+        w = torch.empty(R, Dc, device=self.device)
+        a = _lib.CompositeArgs()
+        a.R, a.D, a.n_channels = R, Dc, 0
+        a.density, a.deltas, a.weights = dens.data_ptr(), dl.data_ptr(), w.data_ptr()
+        self.handle.check(self.handle.lib.b200r_composite_fwd(self.handle.h, C.byref(a), _stream(self.device)), "b200r_composite_fwd")
+        return importance_merge(self.handle, self.device, depth_c, w).view(M, N, 2 * Dc, 1)
 
     # ------------------------------------------------------------------ NeRF.forward on points
     @torch.no_grad()

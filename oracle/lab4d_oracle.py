@@ -303,7 +303,7 @@ def kmat_from_kinv(Kinv):
 # --------------------------------------------------------------------------------------
 
 
-def query_field(P, cfg, rays, tab, D, flow_thresh=None, alpha=None, eikonal_rays=None):
+def query_field(P, cfg, rays, tab, D, flow_thresh=None, alpha=None, eikonal_rays=None, depth=None):
     """{NeRF,FeatureNeRF,Deformable}.query_field in training mode
     (nnutils/nerf.py:580-684, feature.py:89-133, deformable.py:300-356).
 
@@ -311,7 +311,7 @@ def query_field(P, cfg, rays, tab, D, flow_thresh=None, alpha=None, eikonal_rays
     oracle/ref_harness.frame_tables).  Returns (feat_dict, deltas)."""
     hxy, Kinv, near_far = rays["hxy"], rays["Kinv"], rays["near_far"]
     q, t = tab["field2cam_q"], tab["field2cam_t"]
-    xyz_cam, dir_cam, deltas, depth = sample_cam_rays(hxy, Kinv, near_far, D)
+    xyz_cam, dir_cam, deltas, depth = sample_cam_rays(hxy, Kinv, near_far, D, depth=depth)
     xyz_t, dirf = cam_to_field(xyz_cam, dir_cam, q, t)
     skel = cfg["motion"] != "rigid"
     feat = {}

@@ -41,9 +41,9 @@ def test_header_is_plain_c_and_struct_sizes_match_ctypes(tmp_path):
         '#include <stdio.h>\n#include "b200r.h"\n'
         "int main(void) {\n"
         "  b200r_field_desc d = {0};\n"
-        '  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b200r_field_desc), sizeof(b200r_field_params), sizeof(b200r_frame_tables),\n'
+        '  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b200r_field_desc), sizeof(b200r_field_params), sizeof(b200r_frame_tables),\n'
         "         sizeof(b200r_ray_batch), sizeof(b200r_field_outputs), sizeof(b200r_composite_args), sizeof(b200r_composite_bwd_args),\n"
-        "         sizeof(b200r_compose_args), sizeof(b200r_point_batch), (size_t)b200r_layer_count(&d));\n"
+        "         sizeof(b200r_compose_args), sizeof(b200r_point_batch), sizeof(b200r_importance_args), (size_t)b200r_layer_count(&d));\n"
         "  return 0;\n}\n")
     exe = tmp_path / "abi"
     libdir = os.path.join(ROOT, "lab4d_b200")
@@ -51,9 +51,9 @@ def test_header_is_plain_c_and_struct_sizes_match_ctypes(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                     "-L", libdir, "-l:libb200render.so", f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{cuda_lib}", f"-Wl,-rpath-link,{cuda_lib}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    sizes = [int(x) for x in out[:9]]
+    sizes = [int(x) for x in out[:10]]
     mirrors = [_lib.FieldDesc, _lib.FieldParams, _lib.FrameTables, _lib.RayBatch, _lib.FieldOutputs, _lib.CompositeArgs,
-               _lib.CompositeBwdArgs, _lib.ComposeArgs, _lib.PointBatch]
+               _lib.CompositeBwdArgs, _lib.ComposeArgs, _lib.PointBatch, _lib.ImportanceArgs]
     assert sizes == [C.sizeof(m) for m in mirrors]
 
 
