@@ -2,16 +2,22 @@
 // TWO 128-sample tiles in flight per CTA.
 //
 // Persistent kernel, one CTA per SM, CTAs paired in clusters of 2 that share every weight chunk through
-// TMA multicast.  Warp roles (320 threads):
+// TMA multicast.  Warp roles (384 threads, three warpgroups; setmaxnreg gives the two compute warpgroups 208 registers):
 //   warps 0-3 : tile group 0, warps 4-7 : tile group 1.  One thread per sample (thread = tile row = TMEM lane):
 //               sample placement, camera -> field, dual-quaternion blend skinning (+ DenseWarp), Fourier embedding
 //               into swizzled shared memory, and every layer's epilogue straight out of TMEM.
 //   warp 8    : TMA producer - streams pre-packed weight chunks (cp.async.bulk, multicast to both CTAs of the
-//               cluster) through a 3-stage ring of 32 KB.
-//   warp 9    : tcgen05.mma issuer (one elected lane) + TMEM owner.  Walks the MmaStep list of program.h block by
-//               block (a block = one GEMM or one N-half of a 256-wide layer), issuing every block for group 0 and
-//               then for group 1: while one group runs an epilogue or its SIMT geometry, the tensor pipe works on
-//               the other group's tile, so the round-trip latencies of the 40-odd dependent GEMMs of a tile overlap.
+//               cluster) through a 3-slot ring of 32 KB, in the order [block b, group 0][block b, group 1][block b+1, ...
+//               (a block = one GEMM or one N-half of a 256-wide layer).
+//   warps 9-10: tcgen05.mma issuers, one per tile group (one elected lane each; warp 9 owns the TMEM allocation).  Each
+//               walks the MmaBlock list of program.h out of the kernel parameters - every descriptor stays in uniform
+//               registers - and consumes its own group's ring slots: while one group runs an epilogue or its SIMT
+//               geometry, the tensor pipe works on the other group's tile, so the round-trip latencies of the 40-odd
+//               dependent GEMMs of a tile overlap.  Full barriers are per (group, slot): each is waited on by exactly
+//               one issuer, phase after phase (a shared barrier would alias parities between the groups).
+//   warp 11   : idle (register donor).
+// Other entries reuse the kernel with a shorter block list: b200r_points_fwd (NeRF.forward on given points) and
+// b200r_warp_fwd (one warp of given points); b200r_ray_batch.depth replaces the uniform sample placement.
 // TMEM (512 columns): per group 128 fp32 accumulator columns + 128 columns holding 256 16-bit activations.  All
 // hidden activations live in TMEM and feed the next layer as the A operand (TS form); the 256-wide layers run as
 // two N-halves on the same accumulator: the epilogue of half 0 drains it into registers while half 1 is being
