@@ -65,6 +65,11 @@ def forward_saved(P, cfg, rays, tab, D):
     qi = O.qconj(q)
     ti = O.qrot(qi, -t)
     xyz_t = O.qrot(qi[:, None].expand(M, S, 4), xyz_cam) + ti[:, None]
+    dir_cam = (d / d.norm(dim=-1, keepdim=True))[:, :, None, :].expand(M, N, D, 3).reshape(M, S, 3)
+    dir_f = O.qrot(qi[:, None].expand(M, S, 4), dir_cam)
+    if cfg["motion"] == "rigid":
+        return _forward_rigid(P, cfg, rays, tab, dict(M=M, N=N, D=D, S=S, d=d, depth=depth, xyz_cam=xyz_cam, qi=qi, xyz_t=xyz_t,
+                                                     dir_cam=dir_cam, dir_f=dir_f))
     T = [_skin_tables(P, cfg, tab, M, w) for w in range(3)]
     dense = bool(cfg.get("dense", False))
     xs, ent0, dsk0, sv0 = SB.skin_forward_tables(xyz_t, **T[0])
@@ -101,9 +106,64 @@ def forward_saved(P, cfg, rays, tab, D):
     return out, saved
 
 
+def _forward_rigid(P, cfg, rays, tab, v):
+    """Rigid field (IdentityWarp): canonical point = time-t point; flow through the partner camera only."""
+    M, S, N, D = v["M"], v["S"], v["N"], v["D"]
+    xyz = v["xyz_t"]
+    q, t = tab["field2cam_q"], tab["field2cam_t"]
+    qn, tn, Kn = O.flip_pair(q), O.flip_pair(t), O.flip_pair(rays["Kinv"])
+    xc = O.qrot(qn[:, None].expand(M, S, 4), xyz) + tn[:, None]
+    Kmat = O.kmat_from_kinv(Kn)
+    hn = torch.einsum("mij,msj->msi", Kmat, xc)
+    flow = hn[..., :2] / (hn[..., 2:] + 1e-6) - rays["hxy"][:, :, None, :2].expand(M, N, D, 2).reshape(M, S, 2)
+    dirs = v["dir_f"] if cfg["L_dir"] == 0 else None
+    rgb, density, sdf, snerf = NB.nerf_forward_saved(P, cfg, xyz, tab["inst_base"], tab["inst_color"], dirs, tab.get("appr_code"))
+    vis, svis = NB.mlp_forward_saved(P, "vis_mlp.basefield.", NB.pe_forward(xyz, 10), tab["inst_vis"], 2, final_act=False)
+    out = dict(rgb=rgb, density=density, vis=vis, flow=flow, xyz=xyz, xyz_cam=v["xyz_cam"])
+    v.update(rigid=True, xyz=xyz, qn=qn, xc=xc, Kmat=Kmat, hn=hn, snerf=snerf, svis=svis)
+    return out, v
+
+
+def _backward_rigid(P, cfg, rays, tab, v, g):
+    M, S, D, N = v["M"], v["S"], v["D"], v["N"]
+    grads = {}
+    xyz = v["xyz"]
+    g_xyz = g["xyz"].clone()
+    g_e, g_inst_vis, gp = NB.mlp_backward(P, "vis_mlp.basefield.", v["svis"], g["vis"], 2, final_act=False)
+    grads.update(gp)
+    g_xyz = g_xyz + NB.pe_backward(xyz, 10, g_e)
+    gin, gp = NB.nerf_backward(P, cfg, xyz, v["snerf"], g["rgb"], g["density"])
+    grads.update(gp)
+    g_xyz = g_xyz + gin["x"]
+    hz = v["hn"][..., 2:] + 1e-6
+    g_h = torch.cat([g["flow"] / hz, -(g["flow"] * v["hn"][..., :2]).sum(-1, keepdim=True) / hz.pow(2)], -1)
+    g_Kmat = torch.einsum("msi,msj->mij", g_h, v["xc"])
+    g_xc = torch.einsum("mij,msi->msj", v["Kmat"], g_h)
+    g_qn_s, g_x = _qrot_bwd(v["qn"][:, None].expand(M, S, 4), xyz, g_xc)
+    g_xyz = g_xyz + g_x
+    # camera -> field for the point and, when the field sees it, the view direction
+    qi_s = v["qi"][:, None].expand(M, S, 4)
+    g_qi_s, g_xyz_cam = _qrot_bwd(qi_s, v["xyz_cam"], g_xyz)
+    g_d = ((g_xyz_cam + g["xyz_cam"]).reshape(M, N, D, 3) * v["depth"][:, None, :, None]).sum(2)
+    if gin["dir"] is not None:
+        g_q2, g_dir_cam = _qrot_bwd(qi_s, v["dir_cam"], gin["dir"])
+        g_qi_s = g_qi_s + g_q2
+        dvec = v["d"]                                   # dir_cam = d / |d|
+        nrm = dvec.norm(dim=-1, keepdim=True)
+        u = dvec / nrm
+        gdc = g_dir_cam.reshape(M, N, D, 3).sum(2)
+        g_d = g_d + (gdc - u * (gdc * u).sum(-1, keepdim=True)) / nrm
+    tables = dict(g_qi=g_qi_s.sum(1), g_ti=g_xyz.sum(1), g_qn=g_qn_s.sum(1), g_tn=g_xc.sum(1), g_Kmat=g_Kmat,
+                  g_Kinv=torch.einsum("mnj,mni->mji", g_d, rays["hxy"]), g_inst_vis=g_inst_vis, g_inst_base=gin["inst_base"],
+                  g_inst_color=gin["inst_color"], g_appr=gin["appr"])
+    return grads, tables
+
+
 def backward(P, cfg, rays, tab, saved, g):
     """g: cotangent per output key (M,S,c).  Returns (param grads by name, table grads of the kernel-level tables)."""
     v = saved
+    if v.get("rigid"):
+        return _backward_rigid(P, cfg, rays, tab, v, g)
     M, S, D, N = v["M"], v["S"], v["D"], v["N"]
     grads = {}
 

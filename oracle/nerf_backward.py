@@ -108,6 +108,7 @@ def nerf_backward(P, cfg, x, saved, g_rgb, g_density):
     g_rin = g_z0 @ P["rgb.0.weight"]
     g_f2 = g_rin[..., :W]
     g_appr = g_rin[..., W + v["n_dir"]:].sum(1) if cfg["appr_channels"] > 0 else None
+    g_dir = g_rin[..., W:W + 3] if cfg["L_dir"] == 0 else None  # raw view direction (bg fields)
     # colorfield
     g_ec, g_inst_color, gc = mlp_backward(P, "colorfield.", v["sc"], g_f2, 2)
     grads.update(gc)
@@ -124,4 +125,4 @@ def nerf_backward(P, cfg, x, saved, g_rgb, g_density):
     g_eb, g_inst_base, gb = mlp_backward(P, "basefield.", v["sb"], g_feat, cfg["D"])
     grads.update(gb)
     g_x = pe_backward(x, cfg["L_xyz"], g_eb) + pe_backward(x, cfg["L_xyz"] + 2, g_ec)
-    return dict(x=g_x, inst_base=g_inst_base, inst_color=g_inst_color, appr=g_appr), grads
+    return dict(x=g_x, inst_base=g_inst_base, inst_color=g_inst_color, appr=g_appr, dir=g_dir), grads
