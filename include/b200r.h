@@ -53,7 +53,9 @@ typedef struct {
   int32_t skip;          /* skip-concat layer index (4) */
   int32_t n_bones;       /* 0 = rigid field, else SkinningWarp with B bones (18 or 25) */
   int32_t has_feature;   /* FeatureNeRF feature field present */
-  int32_t operand_dtype; /* tensor-core operand type: 0 = fp16, 1 = bf16 (fp32 accumulate) */
+  int32_t operand_dtype; /* tensor-core operand type (fp32 accumulate): 0 = fp16, 1 = bf16, 2 = fp16 head + tail
+                            (every operand split as x = fp16(x) + fp16(x - fp16(x)), three MMAs per k-step:
+                            ~22-bit operands, the mode that meets the 1e-4 rendered-RGB parity contract) */
   int32_t dense;         /* 1: ComposedWarp = SkinningWarp + DenseWarp(D=2, W=256, 6 xyz frequencies)
                             (nnutils/warping.py:104-170, 417-483); needs n_bones > 0 */
   int32_t pad_;

@@ -174,7 +174,7 @@ static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* 
   if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
   cudaStream_t stream = (cudaStream_t)stream_;
 
-  static_assert(sizeof(b200r::PrologueParams) <= 4096 && sizeof(b200r::FieldKernelParams) <= 4096, "kernel parameter space");
+  static_assert(sizeof(b200r::PrologueParams) <= 4096 && sizeof(b200r::FieldKernelParams) <= 16384, "kernel parameter space");
   b200r::PrologueParams pp;
   memset(&pp, 0, sizeof(pp));
   pp.cl = bp.prog.cl;

@@ -95,7 +95,12 @@ __device__ __forceinline__ void sts16(uint32_t a, uint16_t v) { asm volatile("st
 template <int V>
 using IC = std::integral_constant<int, V>;
 
-template <class Op, int B, int LMAX, bool DENSE, int WIDTH>
+// SPLIT (operand_dtype 2, "fp16x3"): every MMA operand is carried as an fp16 head plus the fp16 tail of its rounding
+// error and every product as head*head + tail*head + head*tail (fp32 accumulate): ~22-bit operands, the parity mode that
+// meets the 1e-4 rendered-RGB contract.  The tails take the TMEM / shared-memory / scratch space of tile group 1, so a CTA
+// then keeps ONE tile in flight (group 1's warps idle): activations tails in columns [384, 512), embedding tails in group
+// 1's arena chunks, N-half 0 of a wide layer is staged in columns [128, 256) instead of registers.
+template <class Op, int B, int LMAX, bool DENSE, int WIDTH, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_constant__ FieldKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -126,7 +131,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
   if (*tmem_slot != 0) __trap();        // the CTA allocates all 512 columns, so the allocation starts at column 0
   constexpr uint32_t tmem_base = 0;
   const Program& P = p.prog;
-  const int pair_stride = 2 * (int)gridDim.x;
+  constexpr int kActive = SPLIT ? 1 : kGroups;  // tile groups in flight
+  const int pair_stride = kActive * (int)gridDim.x;
   const int iters = (p.n_tiles + pair_stride - 1) / pair_stride;  // identical in both CTAs of a cluster
   const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0;
   const uint16_t cmask = (uint16_t)((1u << kCluster) - 1);
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           int end = st;
           while (P.steps[end].commit == 0) ++end;
           ++end;
-          for (int g = 0; g < kGroups; ++g) {
+          for (int g = 0; g < kActive; ++g) {
             for (int s = st; s < end; ++s) {
               const MmaStep& S = P.steps[s];
               const uint32_t bytes = (uint32_t)S.n * 128u * S.n_sub;
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 9 || warp == 10) {
+  } else if (warp == 9 || (warp == 10 && !SPLIT)) {
     // =============================================================== MMA issuers: warp 9 -> tile group 0, warp 10 -> group 1.
     // Ring slots are filled in the global order [block b, group 0][block b, group 1][block b+1, group 0]...; each
     // issuer consumes its own group's slots (signalled on its own full barriers) and steps over the other's.  Everything here is warp-uniform and comes
@@ -208,6 +214,52 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           bar_phase ^= 1u << wt;
         }
         uint32_t acc = 0;
+        if constexpr (SPLIT) {
+          // one ring slot per K chunk: [head tile][tail tile]; operand tails: embedding chunks of group 1's arena,
+          // activation columns + kTmemGroup.  D += Ah Wh + Al Wh + Ah Wl per k-step.
+          const uint32_t ks_ss[2] = {ss & 7u, (ss >> 3) & 7u};
+          const uint32_t n_ss = ss ? (ks_ss[1] ? 2u : 1u) : 0u;
+          for (uint32_t c = 0; c < n_ss; ++c) {
+            wait_full();
+            const uint32_t bd = bd_lo0 + stage * (kWStageBytes >> 4), bl = bd + tile2;
+            const bool last = c + 1 == n_ss && ts_slots == 0;
+            if (elect_one()) {
+              const uint32_t ah = ad_lo0 + (uint32_t)((Bk.ss_chunks >> (4 * c)) & 15) * (kAChunkBytes >> 4), al = ah + (kArenaGroup >> 4);
+              for (uint32_t k = 0; k < ks_ss[c]; ++k) {
+                umma_f16_ss(d, mk(ah + 2 * k), mk(bd + 2 * k), idesc, acc | k);
+                umma_f16_ss(d, mk(al + 2 * k), mk(bd + 2 * k), idesc, 1u);
+                umma_f16_ss(d, mk(ah + 2 * k), mk(bl + 2 * k), idesc, 1u);
+              }
+              release();
+              if (last && cm) umma_commit(&m2c_g[cm]);
+            }
+            __syncwarp();
+            advance();
+            acc = 1;
+          }
+          uint32_t a = act0;
+#pragma unroll 1
+          for (uint32_t j = 0; j < ts_slots; ++j) {
+            wait_full();
+            const uint32_t bd = bd_lo0 + stage * (kWStageBytes >> 4), bl = bd + tile2;
+            const bool last = j + 1 == ts_slots;
+            const uint32_t ks = last ? (uint32_t)Bk.ts_ks2_last : 4u;
+            if (elect_one()) {
+              for (uint32_t k = 0; k < ks; ++k) {
+                umma_f16_ts(d, a + 8 * k, mk(bd + 2 * k), idesc, acc | k);
+                umma_f16_ts(d, a + kTmemGroup + 8 * k, mk(bd + 2 * k), idesc, 1u);
+                umma_f16_ts(d, a + 8 * k, mk(bl + 2 * k), idesc, 1u);
+              }
+              release();
+              if (last && cm) umma_commit(&m2c_g[cm]);
+            }
+            __syncwarp();
+            advance();
+            acc = 1;
+            a += 32;
+          }
+          continue;
+        }
         if (ss) {  // embedding chunk(s) from shared memory
           wait_full();
           const uint32_t bd = bd_lo0 + stage * (kWStageBytes >> 4);
@@ -264,6 +316,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t tD = t_lane + kTmemAcc + kTmemGroup * g;  // this group's accumulator
     const uint32_t tA = t_lane + kTmemAct + kTmemGroup * g;  // this group's 16-bit activations (2 per column)
+    constexpr uint32_t kTail = kTmemGroup;                     // SPLIT: activation tails live in group 1's columns
+    const uint32_t tS = t_lane + kTmemAcc + kTmemGroup;        // SPLIT: staging of a wide layer's N-half 0 (group 1's accumulator)
     uint64_t* c2m_g = c2m + 4 * g;
     uint64_t* m2c_g = m2c + 4 * g;
     uint32_t all_phase = 0, half_phase = 0;
@@ -278,6 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     const uint32_t rowx = row * 128u + ((row & 7u) << 4);  // 16-B group gq of this row lives at chunk + (rowx ^ (gq << 4))
     const uint32_t sc_s = cblk_s + 4u * CL.scalars;
     uint4* scr = p.scratch + ((size_t)blockIdx.x * kGroups + g) * (kTileRows * 32) + row;  // [32 uint4][128 rows]
+    uint4* scr_t = scr + kTileRows * 32;                                                  // SPLIT: tails (group 1's scratch)
 
     // the prologue kernel (previous launch in the stream) wrote the workspace: wait for that grid to finish
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -310,26 +365,44 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       tc_fence_after_sync();
     };
     auto bias_s = [&](int layer) -> uint32_t { return (P.bias[layer].frame ? fblk_s : cblk_s) + 4u * P.bias[layer].off; };
-    // 32 accumulator columns + bias -> relu -> 16 packed columns
-    auto relu_pack32 = [&](const uint32_t (&ra)[32], uint32_t bias, uint32_t (&o)[16]) {
+    // (a, b) -> packed 16-bit heads and, in SPLIT mode, the packed tails a - head(a), b - head(b)
+    auto pack_ht = [&](float a, float b, uint32_t& hd, uint32_t& tl) {
+      hd = Op::pack2(a, b);
+      if constexpr (SPLIT) {
+        const float2 f = Op::unpack2(hd);
+        tl = Op::pack2(a - f.x, b - f.y);
+      }
+    };
+    // 32 accumulator columns + bias -> relu -> 16 packed columns (+ 16 packed tails)
+    auto relu_pack32 = [&](const uint32_t (&ra)[32], uint32_t bias, uint32_t (&o)[16], uint32_t (&ot)[16]) {
 #pragma unroll
       for (int g4 = 0; g4 < 8; ++g4) {
         const float4 b = lds128(bias + 16u * g4);
         // packed fp32 adds (FADD2): two columns per instruction
         const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(ra[4 * g4 + 0]), __uint_as_float(ra[4 * g4 + 1])), make_float2(b.x, b.y));
         const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(ra[4 * g4 + 2]), __uint_as_float(ra[4 * g4 + 3])), make_float2(b.z, b.w));
-        o[2 * g4] = Op::pack2_relu(s0.x, s0.y);
-        o[2 * g4 + 1] = Op::pack2_relu(s1.x, s1.y);
+        if constexpr (SPLIT) {
+          pack_ht(fmaxf(s0.x, 0.f), fmaxf(s0.y, 0.f), o[2 * g4], ot[2 * g4]);
+          pack_ht(fmaxf(s1.x, 0.f), fmaxf(s1.y, 0.f), o[2 * g4 + 1], ot[2 * g4 + 1]);
+        } else {
+          o[2 * g4] = Op::pack2_relu(s0.x, s0.y);
+          o[2 * g4 + 1] = Op::pack2_relu(s1.x, s1.y);
+        }
       }
     };
     // finished GEMM of n (<= 128) columns: relu(acc + bias) -> activations [0, n)
     auto epi_relu_act = [&](uint32_t bias, int n) {
 #pragma unroll 1
       for (int blk = 0; blk < (n >> 5); ++blk) {
-        uint32_t ra[32], o[16];
+        uint32_t ra[32], o[16], ot[SPLIT ? 16 : 1];
         tmem_ld32_issue(tD + 32 * blk, ra);
         tmem_ld_wait32(ra);
-        relu_pack32(ra, bias + 128u * blk, o);
+        if constexpr (SPLIT) {
+          relu_pack32(ra, bias + 128u * blk, o, ot);
+          tmem_st16(tA + kTail + 16 * blk, ot);
+        } else {
+          relu_pack32(ra, bias + 128u * blk, o, o);
+        }
         tmem_st16(tA + 16 * blk, o);
       }
       tmem_st_wait();
@@ -341,11 +414,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     float sdf_acc = 0.f;
     auto chain_layer = [&](auto mode_tag, uint32_t bias) {
       constexpr int MODE = decltype(mode_tag)::value;
-      uint32_t hold[NBLK][16];
-      auto math = [&](const uint32_t (&ra)[32], int col0, uint32_t (&o)[16]) {  // col0: first feature of these 32 columns
+      uint32_t hold[SPLIT ? 1 : NBLK][16];
+      auto math = [&](const uint32_t (&ra)[32], int col0, uint32_t (&o)[16], uint32_t (&ot)[16]) {  // col0: first feature of these 32 columns
         const uint32_t ba = bias + 4u * (uint32_t)col0;
         if (MODE == 0) {
-          relu_pack32(ra, ba, o);
+          relu_pack32(ra, ba, o, ot);
         } else if (MODE == 1) {
           const uint32_t wa = cblk_s + 4u * (CL.sdf_w + col0);
           float s0 = 0.f, s1 = 0.f;
@@ -356,23 +429,32 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
             const float y2 = fmaxf(__uint_as_float(ra[4 * g4 + 2]) + b.z, 0.f), y3 = fmaxf(__uint_as_float(ra[4 * g4 + 3]) + b.w, 0.f);
             s0 += y0 * w.x + y2 * w.z;
             s1 += y1 * w.y + y3 * w.w;
-            o[2 * g4] = Op::pack2(y0, y1);
-            o[2 * g4 + 1] = Op::pack2(y2, y3);
+            pack_ht(y0, y1, o[2 * g4], ot[2 * g4]);
+            pack_ht(y2, y3, o[2 * g4 + 1], ot[2 * g4 + 1]);
           }
           sdf_acc += s0 + s1;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) scr[(size_t)((col0 >> 3) + j) * kTileRows] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          for (int j = 0; j < 4; ++j) {
+            scr[(size_t)((col0 >> 3) + j) * kTileRows] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            if constexpr (SPLIT) scr_t[(size_t)((col0 >> 3) + j) * kTileRows] = make_uint4(ot[4 * j], ot[4 * j + 1], ot[4 * j + 2], ot[4 * j + 3]);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 bf = scr[(size_t)((col0 >> 3) + j) * kTileRows];
+            uint4 bt = make_uint4(0u, 0u, 0u, 0u);
+            if constexpr (SPLIT) bt = scr_t[(size_t)((col0 >> 3) + j) * kTileRows];
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const int g4 = 2 * j + hh;
               const float4 b = lds128(ba + 16u * g4);
-              const float2 f0 = Op::unpack2(hh ? bf.z : bf.x), f1 = Op::unpack2(hh ? bf.w : bf.y);
-              o[2 * g4] = Op::pack2(fmaxf(__uint_as_float(ra[4 * g4 + 0]) + b.x, 0.f) + f0.x, fmaxf(__uint_as_float(ra[4 * g4 + 1]) + b.y, 0.f) + f0.y);
-              o[2 * g4 + 1] = Op::pack2(fmaxf(__uint_as_float(ra[4 * g4 + 2]) + b.z, 0.f) + f1.x, fmaxf(__uint_as_float(ra[4 * g4 + 3]) + b.w, 0.f) + f1.y);
+              float2 f0 = Op::unpack2(hh ? bf.z : bf.x), f1 = Op::unpack2(hh ? bf.w : bf.y);
+              if constexpr (SPLIT) {
+                const float2 t0 = Op::unpack2(hh ? bt.z : bt.x), t1 = Op::unpack2(hh ? bt.w : bt.y);
+                f0.x += t0.x; f0.y += t0.y; f1.x += t1.x; f1.y += t1.y;
+              }
+              pack_ht(fmaxf(__uint_as_float(ra[4 * g4 + 0]) + b.x, 0.f) + f0.x, fmaxf(__uint_as_float(ra[4 * g4 + 1]) + b.y, 0.f) + f0.y, o[2 * g4], ot[2 * g4]);
+              pack_ht(fmaxf(__uint_as_float(ra[4 * g4 + 2]) + b.z, 0.f) + f1.x, fmaxf(__uint_as_float(ra[4 * g4 + 3]) + b.w, 0.f) + f1.y, o[2 * g4 + 1], ot[2 * g4 + 1]);
             }
           }
         }
@@ -384,22 +466,44 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         uint32_t ra[32];
         tmem_ld32_issue(tD + 32 * blk, ra);
         tmem_ld_wait32(ra);
-        math(ra, 32 * blk, hold[blk]);
+        if constexpr (SPLIT) {
+          uint32_t o[16], ot[16];
+          math(ra, 32 * blk, o, ot);
+          if (MODE != 1) { tmem_st16(tS + 16 * blk, o); tmem_st16(tS + 64 + 16 * blk, ot); }
+        } else {
+          math(ra, 32 * blk, hold[blk], hold[blk]);
+        }
       }
+      if (SPLIT && MODE != 1) tmem_st_wait();
       tc_fence_before_sync();
       warp_arrive(&c2m_g[BAR_H0]);
       // ---- N-half 1: the layer's input has been read, activations can be overwritten
       wait_half(1);
       if (MODE != 1) {
 #pragma unroll
-        for (int blk = 0; blk < NBLK; ++blk) tmem_st16(tA + 16 * blk, hold[blk]);
+        for (int blk = 0; blk < NBLK; ++blk) {
+          if constexpr (SPLIT) {  // staged heads and tails -> activation buffers
+            uint32_t t[16];
+            tmem_ld16u(tS + 16 * blk, t);
+            tmem_st16(tA + 16 * blk, t);
+            tmem_ld16u(tS + 64 + 16 * blk, t);
+            tmem_st16(tA + kTail + 16 * blk, t);
+          } else {
+            tmem_st16(tA + 16 * blk, hold[blk]);
+          }
+        }
       }
 #pragma unroll
       for (int blk = 0; blk < NBLK; ++blk) {
-        uint32_t ra[32], o[16];
+        uint32_t ra[32], o[16], ot[SPLIT ? 16 : 1];
         tmem_ld32_issue(tD + 32 * blk, ra);
         tmem_ld_wait32(ra);
-        math(ra, HN + 32 * blk, o);
+        if constexpr (SPLIT) {
+          math(ra, HN + 32 * blk, o, ot);
+          if (MODE != 1) tmem_st16(tA + kTail + (HN >> 1) + 16 * blk, ot);
+        } else {
+          math(ra, HN + 32 * blk, o, o);
+        }
         if (MODE != 1) tmem_st16(tA + (HN >> 1) + 16 * blk, o);
       }
       if (MODE != 1) tmem_st_wait();
@@ -408,7 +512,12 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     };
 
     // 16-bit element `c` (0..63) of this row in an operand chunk
-    auto put16 = [&](uint32_t chunk_s, int c, float val) { sts16(chunk_s + (rowx ^ ((uint32_t)(c >> 3) << 4)) + 2u * (c & 7), Op::cvt(val)); };
+    auto put16 = [&](uint32_t chunk_s, int c, float val) {
+      const uint32_t a = chunk_s + (rowx ^ ((uint32_t)(c >> 3) << 4)) + 2u * (c & 7);
+      const uint16_t hd = Op::cvt(val);
+      sts16(a, hd);
+      if constexpr (SPLIT) sts16(a + kArenaGroup, Op::cvt(val - Op::f32(hd)));  // tail chunk: group 1's arena
+    };
     // Fourier features of x: column e < 3 -> x_e, else frequency (e-3)/6, sin for (e-3)%6 < 3 (PosEmbedding.forward,
     // nnutils/embedding.py:69-125).  Columns 0..62 live in CH_PE, 63.. in CH_EXTRA.
     auto embed = [&](const float3& x, int nfreq) {
@@ -442,6 +551,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       embed(x, 6);
       put16(pe_s, 39, 0.f);  // 39 embedding columns; the third k-step reads up to column 47
       sts128(pe_s + (rowx ^ (5u << 4)), make_uint4(0u, 0u, 0u, 0u));
+      if constexpr (SPLIT) sts128(pe_s + kArenaGroup + (rowx ^ (5u << 4)), make_uint4(0u, 0u, 0u, 0u));
       arrive_all();
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) chain_layer(IC<0>{}, l == 0 ? bias1 : bias_s(lid0 + 1));
@@ -452,8 +562,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       return make_float3(x.x + 0.1f * (m[0] + lds32(b3)), x.y + 0.1f * (m[1] + lds32(b3 + 4)), x.z + 0.1f * (m[2] + lds32(b3 + 8)));
     };
 
-    for (int it = 0; it < iters; ++it) {
-      const int tile_raw = (2 * it + g) * (int)gridDim.x + (int)blockIdx.x;
+    for (int it = 0; it < (SPLIT && g == 1 ? 0 : iters); ++it) {  // SPLIT: group 1's resources hold the operand tails
+      const int tile_raw = (kActive * it + g) * (int)gridDim.x + (int)blockIdx.x;
       const bool dead_tile = tile_raw >= p.n_tiles;
       const int tile = dead_tile ? p.n_tiles - 1 : tile_raw;
       const int f = tile / p.tiles_per_frame;
@@ -525,9 +635,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       auto skin_warp = [&](const float3& x, uint32_t binv, uint32_t se3, uint32_t bias1, float& entropy, float& delta_skin) -> float3 {
         float dist2[B > 0 ? B : 1];
         {
-          uint32_t u[NP];
+          uint32_t u[NP], ut[SPLIT ? NP : 1];
 #pragma unroll
           for (int i = 0; i < NP; ++i) u[i] = 0u;
+          if constexpr (SPLIT) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) ut[i] = 0u;
+          }
 #pragma unroll
           for (int b2 = 0; b2 < (B + 1) / 2; ++b2) {
             float v[6];
@@ -545,12 +659,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
                 v[3 * j] = v[3 * j + 1] = v[3 * j + 2] = 0.f;
               }
             }
-            u[3 * b2] = Op::pack2(v[0], v[1]);
-            u[3 * b2 + 1] = Op::pack2(v[2], v[3]);
-            u[3 * b2 + 2] = Op::pack2(v[4], v[5]);
+            pack_ht(v[0], v[1], u[3 * b2], ut[SPLIT ? 3 * b2 : 0]);
+            pack_ht(v[2], v[3], u[3 * b2 + 1], ut[SPLIT ? 3 * b2 + 1 : 0]);
+            pack_ht(v[4], v[5], u[3 * b2 + 2], ut[SPLIT ? 3 * b2 + 2 : 0]);
           }
           tmem_st32(tA, u);
           if (NP > 32) tmem_st8(tA + 32, u + (NP > 32 ? 32 : 0));
+          if constexpr (SPLIT) {
+            tmem_st32(tA + kTail, ut);
+            if (NP > 32) tmem_st8(tA + kTail + 32, ut + (NP > 32 ? 32 : 0));
+          }
           tmem_st_wait();
         }
         // delta_field.linear_1 / linear_2 (ReLU) and linear_final
@@ -692,9 +810,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       // ------------------------------------------------ positional embedding of the canonical point
       embed(xyz, LMAX);
       sts16(pe_s + (rowx ^ (7u << 4)) + 14u, (uint16_t)0);  // zero pad column 63 of CH_PE
+      if constexpr (SPLIT) sts16(pe_s + kArenaGroup + (rowx ^ (7u << 4)) + 14u, (uint16_t)0);
       if (LMAX > 10) {  // CH_EXTRA holds 12 values (columns 63..74); its k-step reads 16 columns
         sts32(extra_s + (rowx ^ (1u << 4)) + 8u, 0.f);
         sts32(extra_s + (rowx ^ (1u << 4)) + 12u, 0.f);
+        if constexpr (SPLIT) {
+          sts32(extra_s + kArenaGroup + (rowx ^ (1u << 4)) + 8u, 0.f);
+          sts32(extra_s + kArenaGroup + (rowx ^ (1u << 4)) + 12u, 0.f);
+        }
       }
 
       // ------------------------------------------------ visibility MLP (VisField.forward)
@@ -798,14 +921,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
   }
 }
 
-template <class Op, int B, int LMAX, bool DENSE, int WIDTH>
+template <class Op, int B, int LMAX, bool DENSE, int WIDTH, bool SPLIT>
 static cudaError_t launch_one(const FieldKernelParams& p, int n_sm, cudaStream_t stream) {
-  auto kern = field_fwd_kernel<Op, B, LMAX, DENSE, WIDTH>;
+  auto kern = field_fwd_kernel<Op, B, LMAX, DENSE, WIDTH, SPLIT>;
+  constexpr int kPer = SPLIT ? 1 : 2;  // tiles in flight per CTA
   const int smem = 1024 + kSmemArena + kSmemRing + (p.prog.cl.n_floats + kGroups * p.prog.fl.n_floats) * 4 + 256;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  int grid = (p.n_tiles + 1) / 2 < n_sm ? (p.n_tiles + 1) / 2 : n_sm;
+  int grid = (p.n_tiles + kPer - 1) / kPer < n_sm ? (p.n_tiles + kPer - 1) / kPer : n_sm;
   grid = (grid + kCluster - 1) / kCluster * kCluster;
   if (grid > n_sm) grid -= kCluster;
   if (grid < kCluster) grid = kCluster;
@@ -831,10 +955,12 @@ static cudaError_t launch_one(const FieldKernelParams& p, int n_sm, cudaStream_t
 }  // namespace fwd
 
 cudaError_t launch_field_fwd(const FieldKernelParams& p, int n_sm, cudaStream_t stream) {
-  const bool bf = p.desc.operand_dtype == 1;
+  const int od = p.desc.operand_dtype;
 #define B200R_CASE(BN, LM, DN, WD)                                                                    \
   if (p.desc.n_bones == BN && p.Lmax == LM && (p.desc.dense != 0) == DN && p.desc.W == WD)            \
-    return bf ? fwd::launch_one<OpBF16, BN, LM, DN, WD>(p, n_sm, stream) : fwd::launch_one<OpF16, BN, LM, DN, WD>(p, n_sm, stream);
+    return od == 1 ? fwd::launch_one<OpBF16, BN, LM, DN, WD, false>(p, n_sm, stream)                  \
+                   : (od == 2 ? fwd::launch_one<OpF16, BN, LM, DN, WD, true>(p, n_sm, stream)        \
+                              : fwd::launch_one<OpF16, BN, LM, DN, WD, false>(p, n_sm, stream));
   B200R_CASE(0, 10, false, 128)
   B200R_CASE(0, 12, false, 128)
   B200R_CASE(0, 10, false, 256)

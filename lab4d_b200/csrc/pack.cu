@@ -9,7 +9,9 @@
 
 namespace b200r {
 
-template <class Op>
+// SPLIT: every [n_pad x 64] tile is followed by the tile of the fp16 rounding errors w - fp16(w) (operand_dtype 2):
+// the field kernel multiplies both, so the weight enters the product with ~22 mantissa bits.
+template <class Op, bool SPLIT>
 __global__ void pack_kernel(const __grid_constant__ PackParams p) {
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= p.total_groups) return;
@@ -18,7 +20,9 @@ __global__ void pack_kernel(const __grid_constant__ PackParams p) {
   for (int i = 1; i < p.n_slices; ++i)
     if (p.slices[i].dst_off <= byte) si = i;
   const PackSlice S = p.slices[si];
-  const uint32_t local = byte - S.dst_off;
+  uint32_t local = byte - S.dst_off;
+  bool tail = false;
+  if (SPLIT && local >= (uint32_t)S.n_pad * 128u) { tail = true; local -= (uint32_t)S.n_pad * 128u; }
   const uint32_t row = local / 128u;
   const uint32_t slot = (local % 128u) >> 4;   // physical 16-B slot in the row
   const uint32_t g = slot ^ (row & 7u);        // logical group (columns 8g..8g+7)
@@ -43,6 +47,7 @@ __global__ void pack_kernel(const __grid_constant__ PackParams p) {
           }
         }
       }
+      if (SPLIT && tail) x -= __half2float(__float2half_rn(x));
       v[h] = x;
     }
     w[j] = Op::pack2(v[0], v[1]);
@@ -53,8 +58,9 @@ __global__ void pack_kernel(const __grid_constant__ PackParams p) {
 cudaError_t launch_pack(const PackParams& p, int operand_dtype, cudaStream_t stream) {
   const int threads = 256;
   const int blocks = (int)((p.total_groups + threads - 1) / threads);
-  if (operand_dtype == 1) pack_kernel<OpBF16><<<blocks, threads, 0, stream>>>(p);
-  else pack_kernel<OpF16><<<blocks, threads, 0, stream>>>(p);
+  if (operand_dtype == 1) pack_kernel<OpBF16, false><<<blocks, threads, 0, stream>>>(p);
+  else if (operand_dtype == 2) pack_kernel<OpF16, true><<<blocks, threads, 0, stream>>>(p);
+  else pack_kernel<OpF16, false><<<blocks, threads, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -20,7 +20,7 @@ constexpr int kTileRows = 128;
 constexpr int kAChunkBytes = kTileRows * 128;  // 16 KB
 constexpr int kMaxN = 256;
 constexpr int kWStageBytes = 2 * 128 * 128;    // 32 KB weight ring stage (two [<=128 rows x 64] tiles)
-constexpr int kMaxSteps = 96;
+constexpr int kMaxSteps = 208;  // fg + dense warp in split mode: one ring slot per 64-wide K chunk
 constexpr int kMaxCond = 12;
 
 // embedding operand chunks of one tile group (embedding columns 0..62 and 63..)
@@ -101,6 +101,9 @@ struct FrameLayout {
 // One block = one GEMM (or one N-half of a wide layer) as the MMA issuers see it: an optional first ring slot
 // whose A operand is one or two embedding chunks in shared memory, then `ts_slots` slots whose A operand is the
 // group's activation buffer in TMEM, read front to back (4 + 4 k-steps per slot; the last slot has 4 + ts_ks2_last).
+// Split-operand mode (operand_dtype 2): every 64-wide K chunk is its own slot holding the weight tile's fp16 head
+// and tail ([n x 64] each); the embedding chunks are one slot each, ts_slots counts chunks and ts_ks2_last is the
+// number of k-steps of the LAST chunk.
 struct MmaBlock {
   uint8_t n16;          // UMMA N / 16
   uint8_t ss;           // 0: no shared-memory slot; else 0x80 | ksteps | ksteps2 << 3
@@ -184,7 +187,8 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int mode = MODE_FIE
   if (!(d.n_bones == 0 || d.n_bones == 18 || d.n_bones == 25)) { bp.err = "n_bones must be 0, 18 or 25"; return bp; }
   if (d.n_bones > 0 && d.L_xyz != 10) { bp.err = "skinned fields need L_xyz == 10"; return bp; }
   if (d.appr_channels < 0 || d.appr_channels > 64) { bp.err = "appr_channels out of range"; return bp; }
-  if (d.operand_dtype != 0 && d.operand_dtype != 1) { bp.err = "operand_dtype must be 0 or 1"; return bp; }
+  if (d.operand_dtype < 0 || d.operand_dtype > 2) { bp.err = "operand_dtype must be 0 (fp16), 1 (bf16) or 2 (fp16 head+tail)"; return bp; }
+  const bool split = d.operand_dtype == 2;  // every packed tile is followed by the fp16 tail of its rounding error
   if (d.dense != 0 && d.dense != 1) { bp.err = "dense must be 0 or 1"; return bp; }
   if (d.dense && d.n_bones == 0) { bp.err = "dense (ComposedWarp) needs a skinned field"; return bp; }
   const LayerIds L = layer_ids(d);
@@ -230,7 +234,7 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int mode = MODE_FIE
       s.in_dim = in_dim;
       s.dst_off = off;
       out.push_back({off, s.n_pad, (s.ncols + 15) / 16});
-      off += (uint32_t)s.n_pad * 128u;
+      off += (uint32_t)s.n_pad * 128u * (split ? 2u : 1u);
       bp.slices.push_back(s);
     }
   };
@@ -360,7 +364,7 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int mode = MODE_FIE
     s = MmaStep{};
     s.w_off = c[0].w_off; s.n = (uint16_t)c[0].n; s.d_col = (uint16_t)d_col; s.a_tmem_col = (uint16_t)a_tmem_col;
     s.a_kind = (uint8_t)a_kind; s.n_sub = (uint8_t)n_sub; s.a_chunk = (uint8_t)a_chunk; s.a_chunk2 = (uint8_t)a_chunk2;
-    s.ksteps = (uint8_t)c[0].ksteps; s.ksteps2 = (uint8_t)(n_sub > 1 ? c[1].ksteps : 0);
+    s.ksteps = (uint8_t)c[0].ksteps; s.ksteps2 = (uint8_t)(split ? c[0].ksteps : (n_sub > 1 ? c[1].ksteps : 0));
     s.accumulate = (uint8_t)acc; s.wait = (uint8_t)wait; s.commit = (uint8_t)commit;
   };
   {
@@ -383,6 +387,23 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int mode = MODE_FIE
       Bk.n16 = (uint8_t)(cs[0].n / 16); Bk.wait = (uint8_t)wait; Bk.commit = (uint8_t)commit;
       int next_col = 0;
       for (size_t c = 0; c < n;) {
+        if (split) {  // one chunk per slot: [head tile][tail tile]
+          step(&cs[c], 2, ops[c].kind, ops[c].kind == 0 ? ops[c].where : 0, 0, ops[c].kind == 1 ? ops[c].where : 0, 0, c > 0,
+               c == 0 ? wait : BAR_NONE, c + 1 == n ? commit : BAR_NONE);
+          const int ks = cs[c].ksteps;
+          if (ops[c].kind == 0) {  // embedding chunks: the first one or two slots of a block
+            shape_ok = shape_ok && c <= 1 && ks <= 7 && (c == 0 || ops[0].kind == 0);
+            if (c == 0) { Bk.ss = (uint8_t)(0x80 | ks); Bk.ss_chunks = (uint8_t)ops[c].where; }
+            else { Bk.ss |= (uint8_t)(ks << 3); Bk.ss_chunks |= (uint8_t)(ops[c].where << 4); }
+          } else {
+            shape_ok = shape_ok && ops[c].where == next_col && (ks == 4 || c + 1 == n);
+            next_col += 32;
+            Bk.ts_slots++;
+            Bk.ts_ks2_last = (uint8_t)ks;
+          }
+          c += 1;
+          continue;
+        }
         int nsub = 1;
         if (c + 1 < n && ops[c].kind == ops[c + 1].kind && 2 * cs[c].n * 128 <= kWStageBytes &&
             (ops[c].kind == 0 || ops[c + 1].where == ops[c].where + 8 * cs[c].ksteps))

@@ -247,6 +247,15 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), B200R_I8(r, 0) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16u(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : B200R_R8(r, 0), B200R_R8(r, 8)
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : B200R_W8(r, 0), B200R_W8(r, 8)::"memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -278,6 +287,7 @@ struct OpF16 {
     return *reinterpret_cast<uint16_t*>(&h);
   }
   __device__ static __forceinline__ float2 unpack2(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
+  __device__ static __forceinline__ float f32(uint16_t v) { return __half2float(*reinterpret_cast<__half*>(&v)); }
 };
 struct OpBF16 {
   static constexpr uint32_t kFmt = 1;
@@ -295,6 +305,7 @@ struct OpBF16 {
     return *reinterpret_cast<uint16_t*>(&h);
   }
   __device__ static __forceinline__ float2 unpack2(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v)); }
+  __device__ static __forceinline__ float f32(uint16_t v) { return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&v)); }
 };
 
 // Byte offset of the 16-byte group `g` (8 halves, g in [0,8)) of row `row` inside a

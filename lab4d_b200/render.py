@@ -71,7 +71,9 @@ def importance_merge(handle, device, depth_c, weights):
 
 
 class FieldRenderer:
-    """One field (fg or bg).  Holds the packed tensor-core operands; everything else is per call."""
+    """One field (fg or bg).  Holds the packed tensor-core operands; everything else is per call.
+    operand_dtype: "fp16x3" = split operands (fp16 head + tail, three MMAs per k-step, ~fp32 results: the parity mode),
+    "fp16" / "bf16" = single 16-bit operands (the fast modes)."""
 
     def __init__(self, cfg: FieldConfig, device="cuda", operand_dtype="fp16"):
         self.cfg = cfg
@@ -82,7 +84,7 @@ class FieldRenderer:
         self.desc = _lib.FieldDesc(category=0 if cfg.category == "fg" else 1, D=cfg.D, W=cfg.W, L_xyz=cfg.L_xyz,
                                    L_dir=cfg.L_dir, appr_channels=cfg.appr_channels, skip=cfg.skip,
                                    n_bones=cfg.B if cfg.motion != "rigid" else 0, has_feature=int(cfg.has_feature),
-                                   operand_dtype={"fp16": 0, "bf16": 1}[operand_dtype],
+                                   operand_dtype={"fp16": 0, "bf16": 1, "fp16x3": 2}[operand_dtype],
                                    dense=int(cfg.dense and cfg.motion != "rigid"))
         self.n_layers = self.handle.lib.b200r_layer_count(C.byref(self.desc))
         nbytes = self.handle.lib.b200r_packed_bytes(C.byref(self.desc))

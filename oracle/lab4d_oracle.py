@@ -364,7 +364,7 @@ def query_field(P, cfg, rays, tab, D, flow_thresh=None, alpha=None, eikonal_rays
 
     # eikonal on a given subset of rays (nnutils/nerf.py:416-453); zeros elsewhere
     M, N = hxy.shape[:2]
-    eik = torch.zeros(M * N, D, dtype=xyz.dtype)
+    eik = torch.zeros(M * N, D, dtype=xyz.dtype, device=xyz.device)
     if eikonal_rays is not None:
         with torch.enable_grad():
             xs = xyz.reshape(M * N, D, 3)[eikonal_rays].detach().requires_grad_(True)

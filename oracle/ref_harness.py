@@ -83,19 +83,24 @@ def frame_tables(field, rays):
     return {k: v.detach().numpy() for k, v in tabs.items()}
 
 
+def make_batch(field, rays, device="cpu"):
+    """(Kinv, batch) of one field from a synthetic ray dict, on `device` (the module must live there too)."""
+    batch = {
+        "hxy": torch.from_numpy(rays["hxy"]).to(device),
+        "frameid": torch.from_numpy(rays["frame_id"]).to(device),
+        "dataid": torch.from_numpy(rays["inst_id"]).to(device),
+        "field2cam": torch.from_numpy(rays["field2cam"]).to(device),
+    }
+    field.near_far.data = torch.from_numpy(rays["near_far"])[:1].repeat(field.near_far.shape[0], 1).to(device)
+    return torch.from_numpy(rays["Kinv"]).to(device), batch
+
+
 def run_field(mf, category, rays, D, flow_thresh=None, record_eikonal=True):
     """get_samples -> query_field -> render_pixel on one field; returns numpy dicts."""
     set_n_depth(D)
     field = mf.field_params[category]
     M = rays["hxy"].shape[0]
-    batch = {
-        "hxy": torch.from_numpy(rays["hxy"]),
-        "frameid": torch.from_numpy(rays["frame_id"]),
-        "dataid": torch.from_numpy(rays["inst_id"]),
-        "field2cam": torch.from_numpy(rays["field2cam"]),
-    }
-    field.near_far.data = torch.from_numpy(rays["near_far"])[:1].repeat(field.near_far.shape[0], 1)
-    Kinv = torch.from_numpy(rays["Kinv"])
+    Kinv, batch = make_batch(field, rays)
     picked = {}
     orig_multinomial = torch.multinomial
 

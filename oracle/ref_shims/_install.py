@@ -13,7 +13,17 @@ import types
 import numpy as np
 import torch
 
-REF_ROOT = "/root/reference"
+import os
+
+# The reference checkout when it exists (build container), else the git-ignored copy that travels to the GPU box
+# (baseline/_ref, written by tools/make_ref.py / __graft_entry__.build()).
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REF_COPY = os.path.normpath(os.path.join(_HERE, "..", "..", "baseline", "_ref"))
+REF_ROOT = os.environ.get("LAB4D_REF_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/lab4d") else _REF_COPY)
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "lab4d"))
 
 
 def _mod(name, **attrs):
@@ -90,6 +100,10 @@ def install():
     mpl.pyplot.cm = mpl.cm
     mpl.pyplot.get_cmap = mpl.cm.get_cmap
     _mod("imageio")
+    if not os.path.isdir(os.path.join(REF_ROOT, "preprocess", "third_party", "vcnplus", "flowutils")):
+        # visualisation helper of the preprocessing tree (lab4d/utils/vis_utils.py:11-16); absent from the travelling copy
+        fu = _mod("flowutils")
+        fu.flowlib = _mod("flowutils.flowlib", flow_to_image=lambda *a, **k: None)
     _mod("quaternion", quaternion_mul=_quaternion_mul, quaternion_conjugate=_quaternion_conjugate)
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)

@@ -1,4 +1,6 @@
 #!/bin/bash
+# usage: tools/gpu_k.sh <test file or empty> "<-k expr>" [log name]
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -s --timeout=120 -k "$1" > gpurun_out/pytest_k.log 2>&1; echo "pytest exit $?"
-grep -E "passed|failed|Error|assert|b200r" gpurun_out/pytest_k.log | head -12 | cut -c1-300
+LOG=gpurun_out/${3:-pytest_k}.log
+timeout 900 python -m pytest ${1:-tests} -m gpu -q -s --timeout=300 ${2:+-k "$2"} > $LOG 2>&1; echo "pytest exit $?" >> $LOG
+grep -E "^\[|passed|failed|Error|error|timed out|exit|assert|b200r:" $LOG | cut -c1-330 | tail -${4:-60}
