@@ -150,7 +150,25 @@ typedef struct {
   float* skin_entropy;  /* 1 */
   float* gauss_density; /* 1 */
   float* sdf;           /* 1 */
+  float* feat_norm;     /* 1: 1 / |feature| before normalisation (kept by the training forward for the backward) */
 } b200r_field_outputs;
+
+/* Cotangents of the per-sample outputs of one query_field call, (M*N*D, c) row-major fp32 like b200r_field_outputs;
+ * NULL = zero.  What b200r_composite_bwd (or autograd of the caller's own reductions) hands to b200r_field_bwd. */
+typedef struct {
+  const float* rgb;           /* 3 */
+  const float* density;       /* 1 */
+  const float* vis;           /* 1 */
+  const float* feature;       /* 16 */
+  const float* xyz;           /* 3 */
+  const float* xyz_cam;       /* 3 */
+  const float* depth;         /* 1 */
+  const float* flow;          /* 3 (the validity flag's entry is ignored) */
+  const float* cyc_dist;      /* 1 */
+  const float* delta_skin;    /* 1 */
+  const float* skin_entropy;  /* 1 */
+  const float* gauss_density; /* 1 */
+} b200r_field_grads;
 
 /* alpha: PosEmbedding annealing window (nnutils/embedding.py:112-125) folded into the packed weights
  * of basefield / colorfield; negative = None.  Call after every optimiser step / set_alpha. */
@@ -165,6 +183,74 @@ size_t b200r_workspace_bytes(const b200r_field_desc* desc, int32_t M);
 int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* params,
                     const b200r_frame_tables* frames, const b200r_ray_batch* rays, const b200r_field_outputs* out,
                     void* workspace, size_t workspace_bytes, b200r_stream stream);
+
+/* ------------------------------------------------------------------ training: forward with a tape, backward
+ * Replaces `total_loss.mean().backward()` through query_field (lab4d/engine/trainer.py:344-345; autograd of
+ * nnutils/nerf.py:580-684, warping.py:277-336, skinning.py:89-153, third_party/quaternion/src/quaternion.cu:67-199).
+ * The training forward records, per 128-sample tile, every tensor-core operand it produced (16-bit chunks) and the
+ * ReLU signs; b200r_field_bwd turns the cotangents of the per-sample outputs into
+ *   - the gradient of every layer's weight (columns fed by per-sample operands) in one flat fp32 buffer,
+ *   - the gradient of the constant block (plain bias rows, head weights, rest bone centres, scalars),
+ *   - the gradient of the M per-frame blocks (cameras, bias rows that carry per-frame codes, bone tables),
+ * whose layouts b200r_get_block_layout describes; the host side chains the two blocks to the per-frame inputs
+ * (M rows of quaternion algebra and code mat-vecs, lab4d_b200/prologue_grad.py). */
+typedef struct {
+  void* a;      /* forward-written operand chunks, a_bytes (1024-B aligned) */
+  void* g;      /* backward-written gradient chunks, g_bytes (1024-B aligned) */
+  void* mask;   /* ReLU sign words, mask_bytes */
+  size_t a_bytes, g_bytes, mask_bytes;
+} b200r_tape;
+
+/* Bytes of the three tape buffers for M frames x N rays x D samples. */
+int b200r_tape_sizes(const b200r_field_desc* desc, int32_t M, int32_t N, int32_t D, size_t* a_bytes, size_t* g_bytes,
+                     size_t* mask_bytes);
+
+/* b200r_field_fwd that also fills tape->a and tape->mask.  `out` must keep xyz, rgb, sdf (and feature, feat_norm). */
+int b200r_field_fwd_train(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* params,
+                          const b200r_frame_tables* frames, const b200r_ray_batch* rays, const b200r_field_outputs* out,
+                          const b200r_tape* tape, void* workspace, size_t workspace_bytes, b200r_stream stream);
+
+/* Transposed operand tiles (W^T) for the backward's data-gradient GEMMs; same conventions as b200r_pack_weights. */
+size_t b200r_packed_t_bytes(const b200r_field_desc* desc);
+int b200r_pack_weights_t(b200r_handle* h, const b200r_field_desc* desc, const b200r_field_params* params, float alpha,
+                         void* packed_t, size_t packed_bytes, b200r_stream stream);
+
+/* Float offsets inside the constant block and inside one frame block (-1 = absent). */
+#define B200R_MAX_COND 12
+typedef struct {
+  int32_t const_floats, frame_floats;
+  /* constant block */
+  int32_t c_plain_bias[B200R_MAX_LAYERS]; /* bias row of layer i when it carries no per-frame code */
+  int32_t c_sdf_w, c_rgb2_w, c_vis_w, c_dir_w; /* sdf.weight (W), rgb.2.weight (3, W/2), vis final weight (64), rgb.0 direction columns (W/2, 3) */
+  int32_t c_center;                       /* rest bone centres (B, 4) */
+  int32_t c_scalars;                      /* 8 scalars; gradients: [0] d/d logibeta, [2] d/d warp.logibeta, [1] d/d logscale (rendered depth only),
+                                             [3] sdf.bias, [4..6] rgb.2.bias, [7] vis final bias */
+  /* frame block */
+  int32_t f_cam, f_cam_partner;           /* 24 floats: Kinv[9], near, far, q[4], t[3]; GRADIENT slots 11..17 are w.r.t. the inverse
+                                             camera (q^-1, -q^-1 t q) for f_cam and w.r.t. (q, t) for f_cam_partner */
+  int32_t f_binv_t, f_se3_bwd, f_binv_rest, f_se3_fwd, f_binv_rest_partner, f_se3_fwd_partner; /* (B,12) / (B,8) */
+  int32_t n_cond;
+  struct {
+    int32_t layer, n, in_dim, frame_off, n_seg;
+    int32_t col0[2], width[2], code[2];   /* bias row = b + sum_seg W[:, col0:col0+width] @ code[frame]; code ids: 0 inst_base,
+                                             1 inst_color, 2 inst_vis, 3 appr, 4 inst_skin, 5 skin_t_embed, 6 skin_t_embed_mean, 7 dense_t,
+                                             8 dense_t (partner frame), 9 inst_dense_fwd, 10 inst_dense_bwd */
+  } cond[B200R_MAX_COND];
+} b200r_block_layout;
+int b200r_get_block_layout(const b200r_field_desc* desc, b200r_block_layout* out);
+
+typedef struct {
+  float* weights;                           /* flat fp32 buffer, ACCUMULATED into (zero it first) */
+  int64_t weight_off[B200R_MAX_LAYERS];     /* float offset of layer i's (out_i, in_i) weight gradient inside `weights` */
+  float* const_block;                       /* (const_floats)      overwritten */
+  float* frame_block;                       /* (M, frame_floats)   overwritten */
+} b200r_param_grads;
+
+/* Backward of one b200r_field_fwd_train call (same desc, params, frames, rays; `saved` = its outputs; tape->g is scratch). */
+int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* params,
+                    const b200r_frame_tables* frames, const b200r_ray_batch* rays, const b200r_field_outputs* saved,
+                    const b200r_field_grads* grads, const b200r_tape* tape, const b200r_param_grads* out, void* workspace,
+                    size_t workspace_bytes, b200r_stream stream);
 
 /* NeRF.forward on given points (lab4d/nnutils/nerf.py:167-215), the boundary the reference's flat-point callers use
  * (geometry_init nerf.py:277, extract_canonical_mesh :328, eval-mode query_nerf :794-805): canonical points in, rgb /

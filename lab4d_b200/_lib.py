@@ -21,7 +21,7 @@ class FieldDesc(C.Structure):
 
 FIELD_OUTPUTS = [("rgb", 3), ("density", 1), ("vis", 1), ("xyz", 3), ("xyz_cam", 3), ("xyz_t", 3), ("dir", 3), ("depth", 1),
                  ("deltas", 1), ("feature", 16), ("flow", 3), ("cyc_dist", 1), ("delta_skin", 1), ("skin_entropy", 1),
-                 ("gauss_density", 1), ("sdf", 1)]
+                 ("gauss_density", 1), ("sdf", 1), ("feat_norm", 1)]
 
 
 class FieldParams(C.Structure):
@@ -71,7 +71,41 @@ class ComposeArgs(C.Structure):
                 ("dst", f32p * MAX_CHANNELS), ("nch", C.c_int32 * MAX_CHANNELS)]
 
 
-EXPORTS = ["b200r_layer_count", "b200r_packed_bytes", "b200r_create", "b200r_destroy", "b200r_last_error",
+GRAD_KEYS = ["rgb", "density", "vis", "feature", "xyz", "xyz_cam", "depth", "flow", "cyc_dist", "delta_skin", "skin_entropy",
+             "gauss_density"]
+
+
+class FieldGrads(C.Structure):
+    _fields_ = [(n, f32p) for n in GRAD_KEYS]
+
+
+class Tape(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("g", C.c_void_p), ("mask", C.c_void_p), ("a_bytes", C.c_size_t), ("g_bytes", C.c_size_t),
+                ("mask_bytes", C.c_size_t)]
+
+
+MAX_COND = 12
+
+
+class CondRow(C.Structure):
+    _fields_ = [("layer", C.c_int32), ("n", C.c_int32), ("in_dim", C.c_int32), ("frame_off", C.c_int32), ("n_seg", C.c_int32),
+                ("col0", C.c_int32 * 2), ("width", C.c_int32 * 2), ("code", C.c_int32 * 2)]
+
+
+class BlockLayout(C.Structure):
+    _fields_ = ([("const_floats", C.c_int32), ("frame_floats", C.c_int32), ("c_plain_bias", C.c_int32 * MAX_LAYERS)]
+                + [(n, C.c_int32) for n in ("c_sdf_w", "c_rgb2_w", "c_vis_w", "c_dir_w", "c_center", "c_scalars", "f_cam", "f_cam_partner",
+                                            "f_binv_t", "f_se3_bwd", "f_binv_rest", "f_se3_fwd", "f_binv_rest_partner",
+                                            "f_se3_fwd_partner", "n_cond")]
+                + [("cond", CondRow * MAX_COND)])
+
+
+class ParamGrads(C.Structure):
+    _fields_ = [("weights", f32p), ("weight_off", C.c_int64 * MAX_LAYERS), ("const_block", f32p), ("frame_block", f32p)]
+
+
+EXPORTS = ["b200r_tape_sizes", "b200r_field_fwd_train", "b200r_packed_t_bytes", "b200r_pack_weights_t", "b200r_get_block_layout",
+           "b200r_field_bwd", "b200r_layer_count", "b200r_packed_bytes", "b200r_create", "b200r_destroy", "b200r_last_error",
            "b200r_pack_weights", "b200r_workspace_bytes", "b200r_field_fwd", "b200r_composite_fwd", "b200r_composite_bwd",
            "b200r_compose_fwd", "b200r_points_fwd", "b200r_warp_fwd", "b200r_importance_fwd"]
 
@@ -121,6 +155,22 @@ def load():
     lib.b200r_importance_fwd.restype = C.c_int
     lib.b200r_compose_fwd.argtypes = [C.c_void_p, C.POINTER(ComposeArgs), C.c_void_p]
     lib.b200r_compose_fwd.restype = C.c_int
+    lib.b200r_tape_sizes.argtypes = [C.POINTER(FieldDesc), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                     C.POINTER(C.c_size_t)]
+    lib.b200r_tape_sizes.restype = C.c_int
+    lib.b200r_field_fwd_train.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldParams), C.POINTER(FrameTables),
+                                          C.POINTER(RayBatch), C.POINTER(FieldOutputs), C.POINTER(Tape), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.b200r_field_fwd_train.restype = C.c_int
+    lib.b200r_packed_t_bytes.argtypes = [C.POINTER(FieldDesc)]
+    lib.b200r_packed_t_bytes.restype = C.c_size_t
+    lib.b200r_pack_weights_t.argtypes = lib.b200r_pack_weights.argtypes
+    lib.b200r_pack_weights_t.restype = C.c_int
+    lib.b200r_get_block_layout.argtypes = [C.POINTER(FieldDesc), C.POINTER(BlockLayout)]
+    lib.b200r_get_block_layout.restype = C.c_int
+    lib.b200r_field_bwd.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldParams), C.POINTER(FrameTables),
+                                    C.POINTER(RayBatch), C.POINTER(FieldOutputs), C.POINTER(FieldGrads), C.POINTER(Tape),
+                                    C.POINTER(ParamGrads), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.b200r_field_bwd.restype = C.c_int
     _lib = lib
     return lib
 

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200render.so")
-SOURCES = ["api.cu", "field_fwd.cu", "prologue.cu", "pack.cu", "composite.cu", "compose.cu", "importance.cu"]
+SOURCES = ["api.cu", "api_train.cu", "field_fwd.cu", "field_fwd_train.cu", "field_bwd.cu", "wgrad.cu", "prologue.cu", "pack.cu", "composite.cu", "compose.cu", "importance.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-DB200R_CLUSTER=" + os.environ.get("B200R_CLUSTER", "2"), "-DB200R_WATCHDOG=" + os.environ.get("B200R_WATCHDOG", "1")]
 
@@ -22,14 +22,27 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    objs = []
-    for src in SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    lib_t = os.path.getmtime(LIB) if os.path.exists(LIB) else 0.0
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [os.path.join(HERE, "..", "include", "b200r.h")]
+    hdr_t = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = ["nvcc", *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-        if r.returncode != 0:
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), hdr_t):
+            return obj, 0, ""  # object is newer than its source and every header
+        r = subprocess.run(["nvcc", *FLAGS, "-c", path, "-o", obj], capture_output=True, text=True)
+        return obj, r.returncode, r.stdout + r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:  # translation units compile in parallel
+        results = list(ex.map(compile_one, SOURCES))
+    objs = []
+    for src, (obj, rc, log) in zip(SOURCES, results):
+        if verbose or rc != 0:
+            sys.stderr.write(log)
+        if rc != 0:
             raise RuntimeError("nvcc failed on " + src)
         objs.append(obj)
     cmd = ["nvcc", "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]

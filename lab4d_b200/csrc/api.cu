@@ -7,28 +7,9 @@
 #include <string>
 #include <vector>
 
-#include "kernels.h"
-
-struct b200r_handle {
-  int device;
-  int n_sm;
-  std::string err;
-  // device copy of the pack-slice table of the last descriptor packed
-  b200r::PackSlice* d_slices;
-  size_t d_slices_cap;
-  b200r_field_desc slices_desc;
-  bool slices_valid;
-};
+#include "api_util.h"
 
 static b200r::BuiltProgram build(const b200r_field_desc& d) { return b200r::build_program(d); }
-
-static int fail(b200r_handle* h, int code, const std::string& msg) {
-  if (h) h->err = msg;
-  return code;
-}
-static int fail_cuda(b200r_handle* h, cudaError_t e, const char* where) {
-  return fail(h, B200R_E_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
-}
 
 extern "C" {
 
@@ -53,52 +34,48 @@ int b200r_create(int device, b200r_handle** out) {
   b200r_handle* h = new b200r_handle();
   h->device = device;
   h->n_sm = prop.multiProcessorCount;
-  h->d_slices = nullptr;
-  h->d_slices_cap = 0;
-  h->slices_valid = false;
+  h->d_scale = nullptr;
+  cudaError_t e2 = cudaSetDevice(device);
+  if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&h->d_scale, 16);
+  if (e2 != cudaSuccess) { delete h; return B200R_E_CUDA; }
   *out = h;
   return B200R_OK;
 }
 
 void b200r_destroy(b200r_handle* h) {
   if (!h) return;
-  if (h->d_slices) cudaFree(h->d_slices);
+  for (auto& kv : h->tables)
+    if (kv.second.dev) cudaFree(kv.second.dev);
+  if (h->d_scale) cudaFree(h->d_scale);
   delete h;
 }
 
 const char* b200r_last_error(const b200r_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
-int b200r_pack_weights(b200r_handle* h, const b200r_field_desc* desc, const b200r_field_params* params, float alpha,
-                       void* packed, size_t packed_bytes, b200r_stream stream_) {
+static int pack_common(b200r_handle* h, const b200r_field_desc* desc, const b200r_field_params* params, float alpha, void* packed,
+                       size_t packed_bytes, b200r_stream stream_, bool transposed) {
   if (!h) return B200R_E_INVALID;
   if (!desc || !params || !packed) return fail(h, B200R_E_INVALID, "pack_weights: null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  b200r::BuiltProgram bp = build(*desc);
+  b200r_field_desc dsc = *desc;
+  if (transposed && dsc.operand_dtype == 2) dsc.operand_dtype = 0;  // the backward runs on single fp16 operands
+  b200r::BuiltProgram bp = transposed ? b200r::build_bwd_program(dsc) : build(dsc);
   if (!bp.ok) return fail(h, B200R_E_INVALID, std::string("pack_weights: ") + bp.err);
   const int n_weights = (int)bp.layer_out.size();
   if (packed_bytes < bp.packed_bytes) return fail(h, B200R_E_INVALID, "pack_weights: packed buffer too small");
   if ((reinterpret_cast<uintptr_t>(packed) & 15) != 0) return fail(h, B200R_E_INVALID, "pack_weights: packed must be 16-B aligned");
   for (int i = 0; i < n_weights; ++i)
     if (!params->weight[i]) return fail(h, B200R_E_INVALID, "pack_weights: null weight pointer");
-  cudaError_t e = cudaSetDevice(h->device);
-  if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
-  const size_t sbytes = bp.slices.size() * sizeof(b200r::PackSlice);
-  if (!h->slices_valid || memcmp(&h->slices_desc, desc, sizeof(*desc)) != 0) {
-    if (sbytes > h->d_slices_cap) {
-      if (h->d_slices) cudaFree(h->d_slices);
-      h->d_slices = nullptr;
-      if ((e = cudaMalloc((void**)&h->d_slices, sbytes)) != cudaSuccess) return fail_cuda(h, e, "cudaMalloc");
-      h->d_slices_cap = sbytes;
-    }
-    // blocking copy of a few KB, once per descriptor (the table only depends on the architecture)
-    if ((e = cudaMemcpy(h->d_slices, bp.slices.data(), sbytes, cudaMemcpyHostToDevice)) != cudaSuccess)
-      return fail_cuda(h, e, "cudaMemcpy");
-    h->slices_desc = *desc;
-    h->slices_valid = true;
-  }
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  // the slice table only depends on the architecture: cached per descriptor, uploaded once on the caller's stream
+  cudaError_t e = cudaSuccess;
+  void* d_slices = b200r::cached_table(h, b200r::table_key(transposed ? "slicesT" : "slices", &dsc, sizeof(dsc)), bp.slices.data(),
+                                       bp.slices.size() * sizeof(b200r::PackSlice), stream, &e);
+  if (!d_slices) return fail_cuda(h, e, "slice table upload");
   b200r::PackParams pp;
   memset(&pp, 0, sizeof(pp));
-  pp.slices = h->d_slices;
+  pp.slices = (const b200r::PackSlice*)d_slices;
   for (int i = 0; i < n_weights; ++i) pp.weights[i] = params->weight[i];
   pp.n_slices = (int)bp.slices.size();
   pp.total_groups = (uint32_t)(bp.packed_bytes / 16);
@@ -106,8 +83,26 @@ int b200r_pack_weights(b200r_handle* h, const b200r_field_desc* desc, const b200
   pp.alpha = alpha;
   pp.L_base = desc->L_xyz;
   pp.L_color = desc->L_xyz + 2;
-  if ((e = b200r::launch_pack(pp, desc->operand_dtype, stream)) != cudaSuccess) return fail_cuda(h, e, "pack kernel");
+  if ((e = b200r::launch_pack(pp, dsc.operand_dtype, stream)) != cudaSuccess) return fail_cuda(h, e, "pack kernel");
   return B200R_OK;
+}
+
+int b200r_pack_weights(b200r_handle* h, const b200r_field_desc* desc, const b200r_field_params* params, float alpha,
+                       void* packed, size_t packed_bytes, b200r_stream stream) {
+  return pack_common(h, desc, params, alpha, packed, packed_bytes, stream, false);
+}
+
+size_t b200r_packed_t_bytes(const b200r_field_desc* desc) {
+  if (!desc) return 0;
+  b200r_field_desc dsc = *desc;
+  if (dsc.operand_dtype == 2) dsc.operand_dtype = 0;
+  b200r::BuiltProgram bp = b200r::build_bwd_program(dsc);
+  return bp.ok ? bp.packed_bytes : 0;
+}
+
+int b200r_pack_weights_t(b200r_handle* h, const b200r_field_desc* desc, const b200r_field_params* params, float alpha,
+                         void* packed_t, size_t packed_bytes, b200r_stream stream) {
+  return pack_common(h, desc, params, alpha, packed_t, packed_bytes, stream, true);
 }
 
 size_t b200r_workspace_bytes(const b200r_field_desc* desc, int32_t M) {
@@ -120,7 +115,8 @@ size_t b200r_workspace_bytes(const b200r_field_desc* desc, int32_t M) {
 // shared body of b200r_field_fwd (rays != NULL) and b200r_points_fwd (pts != NULL)
 static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
                      const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_point_batch* pts, int mode,
-                     const b200r_field_outputs* out, void* workspace, size_t workspace_bytes, b200r_stream stream_) {
+                     const b200r_field_outputs* out, void* workspace, size_t workspace_bytes, b200r_stream stream_,
+                     const b200r_tape* tape = nullptr) {
   const bool warp = mode == b200r::MODE_WARP_BWD || mode == b200r::MODE_WARP_FWD;
   const char* who = warp ? "warp_fwd" : (pts ? "points_fwd" : "field_fwd");
   auto bad = [&](const char* msg) { return fail(h, B200R_E_INVALID, std::string(who) + ": " + msg); };
@@ -170,8 +166,9 @@ static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* 
   if (reinterpret_cast<uintptr_t>(packed) & 15) return bad("packed must be 16-B aligned");
   if (reinterpret_cast<uintptr_t>(workspace) & 15) return bad("workspace must be 16-B aligned");
   if (workspace_bytes < b200r_workspace_bytes(desc, M)) return bad("workspace too small (see b200r_workspace_bytes)");
-  cudaError_t e = cudaSetDevice(h->device);
-  if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaError_t e = cudaSuccess;
   cudaStream_t stream = (cudaStream_t)stream_;
 
   static_assert(sizeof(b200r::PrologueParams) <= 4096 && sizeof(b200r::FieldKernelParams) <= 16384, "kernel parameter space");
@@ -212,9 +209,29 @@ static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* 
   kp.n_tiles = M * kp.tiles_per_frame;
   kp.Lmax = desc->L_xyz + 2 > 10 ? 12 : 10;
   kp.scratch = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(workspace) + b200r::scratch_offset_bytes(bp.prog, M));
-  e = b200r::launch_field_fwd(kp, h->n_sm, stream);
+  if (tape) {  // training forward: record the operand chunks and ReLU sign words
+    kp.tape = b200r::tape_layout(*desc);
+    size_t need_a = b200r::tape_a_bytes(kp.tape, kp.n_tiles), need_m = b200r::tape_mask_bytes(kp.tape, kp.n_tiles);
+    if (!tape->a || !tape->mask || tape->a_bytes < need_a || tape->mask_bytes < need_m) return bad("tape buffers missing or too small (b200r_tape_sizes)");
+    if ((reinterpret_cast<uintptr_t>(tape->a) & 1023) || (reinterpret_cast<uintptr_t>(tape->mask) & 15)) return bad("tape buffers must be 1024-B / 16-B aligned");
+    if (!out->xyz || !out->rgb || !out->sdf || (desc->has_feature && (!out->feature || !out->feat_norm))) return bad("the training forward must keep xyz, rgb, sdf (and feature, feat_norm)");
+    kp.tape_a = (uint8_t*)tape->a;
+    kp.tape_mask = (uint32_t*)tape->mask;
+    e = b200r::launch_field_fwd_train(kp, h->n_sm, stream);
+  } else {
+    e = b200r::launch_field_fwd(kp, h->n_sm, stream);
+  }
   if (e != cudaSuccess) return fail_cuda(h, e, "field_fwd kernel");
   return B200R_OK;
+}
+
+int b200r_field_fwd_train(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
+                          const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_field_outputs* out,
+                          const b200r_tape* tape, void* workspace, size_t workspace_bytes, b200r_stream stream_) {
+  if (!h) return B200R_E_INVALID;
+  if (!rays || !tape) return fail(h, B200R_E_INVALID, "field_fwd_train: null argument");
+  if (desc && desc->dense) return fail(h, B200R_E_INVALID, "field_fwd_train: the dense-warp backward is not built yet");
+  return run_field(h, desc, packed, par, fr, rays, nullptr, b200r::MODE_FIELD, out, workspace, workspace_bytes, stream_, tape);
 }
 
 int b200r_field_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
@@ -265,8 +282,9 @@ int b200r_composite_fwd(b200r_handle* h, const b200r_composite_args* a, b200r_st
   if (rc) return rc;
   for (int c = 0; c < a->n_channels; ++c)
     if (!a->dst[c]) return fail(h, B200R_E_INVALID, "composite_fwd: null channel destination");
-  cudaError_t e = cudaSetDevice(h->device);
-  if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaError_t e = cudaSuccess;
   if ((e = b200r::launch_composite_fwd(*a, (cudaStream_t)stream)) != cudaSuccess) return fail_cuda(h, e, "composite_fwd kernel");
   return B200R_OK;
 }
@@ -277,8 +295,9 @@ int b200r_composite_bwd(b200r_handle* h, const b200r_composite_bwd_args* b, b200
   int rc = check_composite(h, &b->fwd);
   if (rc) return rc;
   if (!b->g_density) return fail(h, B200R_E_INVALID, "composite_bwd: g_density required");
-  cudaError_t e = cudaSetDevice(h->device);
-  if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaError_t e = cudaSuccess;
   if ((e = b200r::launch_composite_bwd(*b, (cudaStream_t)stream)) != cudaSuccess) return fail_cuda(h, e, "composite_bwd kernel");
   return B200R_OK;
 }
@@ -288,8 +307,9 @@ int b200r_importance_fwd(b200r_handle* h, const b200r_importance_args* a, b200r_
   if (!a) return fail(h, B200R_E_INVALID, "importance: null argument");
   if (a->R < 1 || a->Dc < 4 || a->Dc > 4096) return fail(h, B200R_E_INVALID, "importance: need R >= 1 and 4 <= Dc <= 4096");
   if (!a->depth_c || !a->weights || !a->depth_out) return fail(h, B200R_E_INVALID, "importance: null buffer");
-  cudaError_t e = cudaSetDevice(h->device);
-  if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaError_t e = cudaSuccess;
   if ((e = b200r::launch_importance_fwd(*a, (cudaStream_t)stream)) != cudaSuccess) return fail_cuda(h, e, "importance kernel");
   return B200R_OK;
 }
@@ -306,8 +326,9 @@ int b200r_compose_fwd(b200r_handle* h, const b200r_compose_args* a, b200r_stream
     if (!a->src_a[c] && !a->src_b[c]) return fail(h, B200R_E_INVALID, "compose: channel without any source");
     if (a->nch[c] < 1) return fail(h, B200R_E_INVALID, "compose: bad channel width");
   }
-  cudaError_t e = cudaSetDevice(h->device);
-  if (e != cudaSuccess) return fail_cuda(h, e, "cudaSetDevice");
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaError_t e = cudaSuccess;
   if ((e = b200r::launch_compose_fwd(*a, (cudaStream_t)stream)) != cudaSuccess) return fail_cuda(h, e, "compose kernel");
   return B200R_OK;
 }

@@ -1,0 +1,316 @@
+// C ABI of the training path: tape sizes, block layouts, b200r_field_bwd (declarations: include/b200r.h).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "api_util.h"
+
+namespace b200r {
+
+// ---------------------------------------------------------------- gradient scale
+// max |g| over the cotangent arrays (the density's is weighted by |d density / d sdf| <= ibeta^2 / 2, the factor its
+// gradient picks up first) -> power-of-two scale that puts the largest entry at ~4 in the 16-bit gradient operands.
+struct ScaleParams {
+  const float* ptr[12];
+  long long n[12];
+  float weight[12];
+  const float* logibeta;
+  float* scale;  // [0] scale, [1] 1 / scale
+  unsigned int* amax_bits;
+  int bf16;
+};
+__global__ void absmax_kernel(const ScaleParams p) {
+  float m = 0.f;
+  for (int a = 0; a < 12; ++a) {
+    if (!p.ptr[a]) continue;
+    float w = p.weight[a];
+    if (w < 0.f) { const float ib = expf(p.logibeta[0]); w = 0.5f * ib * ib; }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n[a]; i += (long long)gridDim.x * blockDim.x) {
+      const float v = fabsf(p.ptr[a][i]) * w;
+      if (v < INFINITY) m = fmaxf(m, v);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(p.amax_bits, __float_as_uint(m));
+}
+__global__ void scale_kernel(const ScaleParams p) {
+  const float amax = __uint_as_float(*p.amax_bits);
+  float s = 1.0f;
+  if (!p.bf16 && amax > 0.f) s = exp2f(floorf(log2f(4.0f / amax)));
+  s = fminf(fmaxf(s, 1.0f / 16777216.0f), 1099511627776.0f);
+  p.scale[0] = s;
+  p.scale[1] = 1.0f / s;
+}
+
+// ---------------------------------------------------------------- weight-gradient job list
+enum : int { DST_WEIGHTS = 0, DST_FRAME = 1, DST_CONST = 2 };
+
+static std::vector<WgradJob> build_jobs(const b200r_field_desc& d, const BuiltProgram& bp, const TapeLayout& T, const int64_t* woff) {
+  std::vector<WgradJob> jobs;
+  const Program& P = bp.prog;
+  const LayerIds L = layer_ids(d);
+  const int B = d.n_bones, W = d.W, KC = W / 64, HN = W / 2;
+  const int pe_b = pe_dim(d.L_xyz), pe_c = pe_dim(d.L_xyz + 2), pe_v = pe_dim(10), pe_f = pe_dim(6);
+  std::vector<char> summed(512, 0);  // G operand (by first chunk id) whose columns were already summed
+  auto view = [](int row0, int col0, int rows, int cols, int ld, int kind, int64_t off) {
+    WgradView v;
+    v.row0 = row0; v.col0 = col0; v.rows = rows; v.cols = cols; v.ld = ld; v.per_frame = kind; v.dst_off = off;
+    return v;
+  };
+  // G (gradient tape) x A (operand from tape `a_src`): one view
+  auto job = [&](int g_chunk, int n_g, int a_chunk, int n_a, int a_src, const WgradView& v0) -> WgradJob& {
+    WgradJob j;
+    memset(&j, 0, sizeof(j));
+    j.g_chunk = (int16_t)g_chunk; j.n_g = (int16_t)n_g; j.a_chunk = (int16_t)a_chunk; j.n_a = (int16_t)n_a;
+    j.g_src = 1; j.a_src = (uint8_t)a_src;
+    j.n_views = 1; j.v[0] = v0;
+    j.per_frame = v0.per_frame == DST_FRAME;
+    jobs.push_back(j);
+    return jobs.back();
+  };
+  // weight gradient of `layer`, in-columns [c0, c0 + cols), and (once per G operand) its bias gradient
+  auto layer_job = [&](int layer, int g_chunk, int a_chunk, int n_a, int c0, int cols, int bias_frame_off = -1, int a_src = 0) {
+    const int n_out = bp.layer_out[layer], n_g = (n_out + 63) / 64;
+    WgradJob& j = job(g_chunk, n_g, a_chunk, n_a, a_src, view(0, 0, n_out, cols, bp.layer_in[layer], DST_WEIGHTS, woff[layer] + c0));
+    if (!summed[g_chunk]) {
+      summed[g_chunk] = 1;
+      const bool frame = bias_frame_off >= 0 || P.bias[layer].frame;
+      j.colsum = frame ? 2 : 1;
+      j.colsum_off = bias_frame_off >= 0 ? bias_frame_off : P.bias[layer].off;
+      j.colsum_n = n_out;
+    }
+  };
+  const int n_pe = pe_b < 63 ? pe_b : 63;
+  for (int w = 0; w < 3 && B > 0; ++w) {
+    layer_job(L.delta[0], T.g_z1[w], T.a_xb[w], (3 * B + 63) / 64, 0, 3 * B, w == 0 ? -1 : P.fl.delta1_fwd);
+    layer_job(L.delta[1], T.g_z2[w], T.a_h1[w], 1, 0, 64);
+    layer_job(L.delta[2], T.g_z[w], T.a_h2[w], 1, 0, 64);
+    // bone tables of the frame: [g_xb | ws]^T [x y z 1 | g_qhr g_qhd]
+    const int binv = w == 0 ? P.fl.binv_t : (w == 1 ? P.fl.binv_rest_partner : P.fl.binv_rest);
+    const int se3 = w == 0 ? P.fl.se3_bwd : (w == 1 ? P.fl.se3_fwd_partner : P.fl.se3_fwd);
+    WgradJob& j = job(T.g_xbw[w], 2, T.g_xg[w], 1, 1, view(0, 0, 3 * B, 4, 4, DST_FRAME, binv));
+    j.n_views = 2;
+    j.v[1] = view(96, 4, B, 8, 8, DST_FRAME, se3);
+  }
+  layer_job(L.vis[0], T.g_vis[0], T.a_pe, 1, 0, pe_v);
+  layer_job(L.vis[1], T.g_vis[1], T.a_vis[0], 1, 0, 64);
+  // heads: rows of the head chunk x their input operand
+  {
+    WgradJob& j = job(T.g_head, 1, T.a_vis[1], 1, 0, view(7, 0, 1, 64, 64, DST_CONST, P.cl.vis_w));
+    j.colsum = 1; j.colsum_off = P.cl.scalars; j.colsum_n = 8;  // sdf.bias, rgb.2.bias, vis final bias
+    job(T.g_head, 1, T.a_base[d.D], KC, 0, view(3, 0, 1, W, W, DST_CONST, P.cl.sdf_w));
+    job(T.g_head, 1, T.a_rgb0, KC / 2, 0, view(4, 0, 3, HN, HN, DST_CONST, P.cl.rgb2_w));
+  }
+  for (int i = 0; i <= d.D; ++i) {
+    if (i == 0) {
+      layer_job(L.base[i], T.g_base[i], T.a_pe, 1, 0, n_pe);
+    } else if (i == d.skip) {
+      layer_job(L.base[i], T.g_base[i], T.a_pe, 1, 0, n_pe);
+      layer_job(L.base[i], T.g_base[i], T.a_base[i - 1], KC, pe_b + 32, W);
+    } else {
+      layer_job(L.base[i], T.g_base[i], T.a_base[i - 1], KC, 0, W);
+    }
+  }
+  layer_job(L.rgb0, T.g_rgb0, T.a_f2, KC, 0, W);
+  if (d.L_dir == 0) layer_job(L.rgb0, T.g_rgb0, T.a_dir, 1, W, 3);
+  layer_job(L.color[0], T.g_col[0], T.a_pe, 1, 0, pe_c < 63 ? pe_c : 63);
+  if (pe_c > 63) layer_job(L.color[0], T.g_col[0], T.a_extra, 1, 63, pe_c - 63);
+  layer_job(L.color[1], T.g_col[1], T.a_col[0], KC, 0, W);
+  layer_job(L.color[2], T.g_col[2], T.a_col[1], KC, 0, W);
+  if (d.has_feature) {
+    layer_job(L.feat[0], T.g_feat[0], T.a_pe, 1, 0, pe_f);
+    for (int i = 1; i < 4; ++i) layer_job(L.feat[i], T.g_feat[i], T.a_feat[i - 1], 2, 0, 128);
+    layer_job(L.feat[4], T.g_feat[4], T.a_pe, 1, 0, pe_f);
+    layer_job(L.feat[4], T.g_feat[4], T.a_feat[3], 2, pe_f, 128);
+    layer_job(L.feat[5], T.g_feat[5], T.a_feat[4], 2, 0, 128);
+  }
+  return jobs;
+}
+
+// split the (job, tile) line evenly over `grid` CTAs
+static void build_work(const std::vector<WgradJob>& jobs, int n_tiles, int grid, std::vector<WgradWork>& work, std::vector<int32_t>& first) {
+  long long total = 0;
+  for (const auto& j : jobs) total += (long long)(j.n_g + j.n_a + 1) * n_tiles;
+  const long long per = (total + grid - 1) / grid;
+  work.clear();
+  first.assign(grid + 1, 0);
+  int cta = 0;
+  long long used = 0;  // cost already given to the current CTA
+  for (int ji = 0; ji < (int)jobs.size(); ++ji) {
+    const long long c = jobs[ji].n_g + jobs[ji].n_a + 1;
+    int t = 0;
+    while (t < n_tiles) {
+      long long room = per - used;
+      if (room < c && cta + 1 < grid) {  // next CTA
+        ++cta;
+        first[cta] = (int32_t)work.size();
+        used = 0;
+        continue;
+      }
+      long long take = room / c;
+      if (take < 1) take = 1;
+      if (cta + 1 == grid || take > n_tiles - t) take = (cta + 1 == grid) ? n_tiles - t : (take > n_tiles - t ? n_tiles - t : take);
+      work.push_back({ji, t, t + (int)take});
+      used += take * c;
+      t += (int)take;
+    }
+  }
+  for (int c2 = cta + 1; c2 <= grid; ++c2) first[c2] = (int32_t)work.size();
+}
+
+}  // namespace b200r
+
+extern "C" {
+
+int b200r_tape_sizes(const b200r_field_desc* desc, int32_t M, int32_t N, int32_t D, size_t* a_bytes, size_t* g_bytes, size_t* mask_bytes) {
+  if (!desc || M < 1 || N < 1 || D < 1) return B200R_E_INVALID;
+  const b200r::TapeLayout T = b200r::tape_layout(*desc);
+  const int tpf = (N * D + b200r::kTileRows - 1) / b200r::kTileRows, n_tiles = M * tpf;
+  if (a_bytes) *a_bytes = b200r::tape_a_bytes(T, n_tiles);
+  if (g_bytes) *g_bytes = b200r::tape_g_bytes(T, n_tiles + b200r::kMaxCtas);  // + scratch tiles of dead tile-pair halves
+  if (mask_bytes) *mask_bytes = b200r::tape_mask_bytes(T, n_tiles);
+  return B200R_OK;
+}
+
+int b200r_get_block_layout(const b200r_field_desc* desc, b200r_block_layout* out) {
+  if (!desc || !out) return B200R_E_INVALID;
+  b200r::BuiltProgram bp = b200r::build_program(*desc);
+  if (!bp.ok) return B200R_E_INVALID;
+  const b200r::ConstLayout& C = bp.prog.cl;
+  const b200r::FrameLayout& F = bp.prog.fl;
+  memset(out, 0, sizeof(*out));
+  out->const_floats = C.n_floats;
+  out->frame_floats = F.n_floats;
+  for (int i = 0; i < B200R_MAX_LAYERS; ++i) out->c_plain_bias[i] = C.plain_off[i];
+  out->c_sdf_w = C.sdf_w; out->c_rgb2_w = C.rgb2_w; out->c_vis_w = C.vis_w; out->c_dir_w = desc->L_dir == 0 ? C.dir_w : -1;
+  out->c_center = desc->n_bones > 0 ? C.center : -1;
+  out->c_scalars = C.scalars;
+  out->f_cam = F.cam; out->f_cam_partner = F.cam_partner;
+  const bool sk = desc->n_bones > 0;
+  out->f_binv_t = sk ? F.binv_t : -1; out->f_se3_bwd = sk ? F.se3_bwd : -1; out->f_binv_rest = sk ? F.binv_rest : -1;
+  out->f_se3_fwd = sk ? F.se3_fwd : -1; out->f_binv_rest_partner = sk ? F.binv_rest_partner : -1;
+  out->f_se3_fwd_partner = sk ? F.se3_fwd_partner : -1;
+  out->n_cond = F.n_cond;
+  for (int i = 0; i < F.n_cond && i < B200R_MAX_COND; ++i) {
+    const b200r::CondRow& c = F.cond[i];
+    out->cond[i].layer = c.layer; out->cond[i].n = c.n; out->cond[i].in_dim = c.in_dim; out->cond[i].frame_off = c.frame_off;
+    out->cond[i].n_seg = c.n_seg;
+    for (int s = 0; s < 2; ++s) { out->cond[i].col0[s] = c.col0[s]; out->cond[i].width[s] = c.width[s]; out->cond[i].code[s] = c.code[s]; }
+  }
+  return B200R_OK;
+}
+
+int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* par,
+                    const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_field_outputs* saved,
+                    const b200r_field_grads* grads, const b200r_tape* tape, const b200r_param_grads* out, void* workspace,
+                    size_t workspace_bytes, b200r_stream stream_) {
+  if (!h) return B200R_E_INVALID;
+  auto bad = [&](const char* msg) { return fail(h, B200R_E_INVALID, std::string("field_bwd: ") + msg); };
+  if (!desc || !packed_t || !par || !fr || !rays || !saved || !grads || !tape || !out || !workspace) return bad("null argument");
+  if (desc->dense) return bad("the dense-warp backward is not built yet");
+  b200r_field_desc dsc = *desc;
+  if (dsc.operand_dtype == 2) dsc.operand_dtype = 0;  // gradients run on single fp16 operands (scaled), whatever the forward used
+  b200r::BuiltProgram bp = b200r::build_bwd_program(dsc);
+  if (!bp.ok) return bad(bp.err);
+  const int M = fr->M, N = rays->N, D = rays->D;
+  if (M < 1 || N < 1 || D < 2) return bad("need M,N >= 1 and D >= 2");
+  if (M >= 2 && (M & 1)) return bad("frames must come in adjacent pairs (M even)");
+  if (!rays->hxy || !fr->Kinv || !fr->near_far || !fr->field2cam_q || !fr->field2cam_t) return bad("missing ray/camera input");
+  if (!saved->xyz || !saved->rgb || !saved->sdf || (desc->has_feature && (!saved->feature || !saved->feat_norm))) return bad("missing saved forward outputs");
+  if (!out->weights || !out->const_block || !out->frame_block) return bad("missing gradient outputs");
+  const b200r::TapeLayout T = b200r::tape_layout(*desc);
+  const int ND = N * D, tpf = (ND + b200r::kTileRows - 1) / b200r::kTileRows, n_tiles = M * tpf;
+  size_t na, ng, nm;
+  b200r_tape_sizes(desc, M, N, D, &na, &ng, &nm);
+  if (!tape->a || !tape->g || !tape->mask || tape->a_bytes < na || tape->g_bytes < ng || tape->mask_bytes < nm) return bad("tape buffers missing or too small");
+  if ((reinterpret_cast<uintptr_t>(tape->g) & 1023)) return bad("tape buffers must be 1024-B aligned");
+  if (workspace_bytes < b200r_workspace_bytes(desc, M)) return bad("workspace too small");
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cudaError_t e;
+
+  // per-frame blocks again (the workspace may have been reused since the forward)
+  const int nl = (int)bp.layer_out.size();
+  const b200r::LayerIds ids = b200r::layer_ids(*desc);
+  b200r::PrologueParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.cl = bp.prog.cl; pp.fl = bp.prog.fl; pp.desc = *desc; pp.par = *par; pp.fr = *fr;
+  pp.workspace = (float*)workspace;
+  pp.n_layers = nl; pp.rgb0_layer = ids.rgb0;
+  for (int i = 0; i < nl; ++i) { pp.layer_out[i] = (int16_t)bp.layer_out[i]; pp.layer_in[i] = (int16_t)bp.layer_in[i]; }
+  if ((e = b200r::launch_prologue(pp, stream)) != cudaSuccess) return fail_cuda(h, e, "prologue kernel");
+
+  // gradient scale
+  b200r::ScaleParams sp;
+  memset(&sp, 0, sizeof(sp));
+  const size_t S = (size_t)M * ND;
+  const float* gp[12] = {grads->rgb, grads->density, grads->vis, grads->feature, grads->xyz, grads->xyz_cam, grads->depth, grads->flow,
+                         grads->cyc_dist, grads->delta_skin, grads->skin_entropy, grads->gauss_density};
+  const int gw[12] = {3, 1, 1, 16, 3, 3, 1, 3, 1, 1, 1, 1};
+  for (int i = 0; i < 12; ++i) { sp.ptr[i] = gp[i]; sp.n[i] = (long long)S * gw[i]; sp.weight[i] = i == 1 ? -1.f : 1.f; }
+  sp.logibeta = par->logibeta;
+  sp.scale = h->d_scale;
+  sp.amax_bits = reinterpret_cast<unsigned int*>(h->d_scale + 2);
+  sp.bf16 = desc->operand_dtype == 1;
+  if ((e = cudaMemsetAsync(h->d_scale + 2, 0, 4, stream)) != cudaSuccess) return fail_cuda(h, e, "memset");
+  b200r::absmax_kernel<<<h->n_sm * 4, 256, 0, stream>>>(sp);
+  b200r::scale_kernel<<<1, 1, 0, stream>>>(sp);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail_cuda(h, e, "scale kernels");
+
+  if ((e = cudaMemsetAsync(out->const_block, 0, (size_t)bp.prog.cl.n_floats * 4, stream)) != cudaSuccess) return fail_cuda(h, e, "memset");
+  if ((e = cudaMemsetAsync(out->frame_block, 0, (size_t)M * bp.prog.fl.n_floats * 4, stream)) != cudaSuccess) return fail_cuda(h, e, "memset");
+
+  b200r::BwdKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.prog = bp.prog;
+  kp.tape = T;
+  kp.desc = dsc;
+  kp.rays = *rays;
+  kp.saved = *saved;
+  kp.g = *grads;
+  kp.packed_t = (const uint8_t*)packed_t;
+  kp.workspace = (const float*)workspace;
+  kp.tape_a = (const uint8_t*)tape->a;
+  kp.tape_g = (uint8_t*)tape->g;
+  kp.tape_mask = (const uint32_t*)tape->mask;
+  kp.g_cblk = out->const_block;
+  kp.g_fblk = out->frame_block;
+  kp.scale = h->d_scale;
+  kp.M = M; kp.ND = ND; kp.tiles_per_frame = tpf; kp.n_tiles = n_tiles;
+  if ((e = b200r::launch_field_bwd(kp, h->n_sm, stream)) != cudaSuccess) return fail_cuda(h, e, "field_bwd kernel");
+
+  // weight gradients
+  std::vector<b200r::WgradJob> jobs = b200r::build_jobs(dsc, bp, T, out->weight_off);
+  std::vector<b200r::WgradWork> work;
+  std::vector<int32_t> first;
+  const int grid = h->n_sm;
+  b200r::build_work(jobs, n_tiles, grid, work, first);
+  struct { b200r_field_desc d; int n_tiles, tpf, grid; } keyh = {dsc, n_tiles, tpf, grid};
+  const std::string key = b200r::table_key("wg", &keyh, sizeof(keyh), out->weight_off, sizeof(out->weight_off));
+  void* d_jobs = b200r::cached_table(h, key + "j", jobs.data(), jobs.size() * sizeof(b200r::WgradJob), stream, &e);
+  void* d_work = b200r::cached_table(h, key + "w", work.data(), work.size() * sizeof(b200r::WgradWork), stream, &e);
+  void* d_first = b200r::cached_table(h, key + "f", first.data(), first.size() * sizeof(int32_t), stream, &e);
+  if (!d_jobs || !d_work || !d_first) return fail_cuda(h, e, "job table upload");
+  b200r::WgradParams wp;
+  memset(&wp, 0, sizeof(wp));
+  wp.tape_a = (const uint8_t*)tape->a;
+  wp.tape_g = (const uint8_t*)tape->g;
+  wp.n_a = T.n_a; wp.n_g = T.n_g;
+  wp.jobs = (const b200r::WgradJob*)d_jobs;
+  wp.work = (const b200r::WgradWork*)d_work;
+  wp.cta_first = (const int32_t*)d_first;
+  wp.grad = out->weights;
+  wp.g_cblk = out->const_block;
+  wp.g_fblk = out->frame_block;
+  wp.frame_floats = bp.prog.fl.n_floats;
+  wp.tiles_per_frame = tpf;
+  wp.inv_scale = h->d_scale + 1;
+  if ((e = b200r::launch_wgrad(wp, grid, dsc.operand_dtype, stream)) != cudaSuccess) return fail_cuda(h, e, "wgrad kernel");
+  return B200R_OK;
+}
+
+}  // extern "C"

@@ -47,7 +47,57 @@ struct FieldKernelParams {
   int32_t n_tiles;
   int32_t Lmax;            // frequencies of the shared embedding chunk(s): 10 or 12
   int32_t warp_mode;       // 0, MODE_WARP_BWD or MODE_WARP_FWD: b200r_warp_fwd evaluates one warp on `points`
+  // training forward (b200r_field_fwd_train): tape buffers, else NULL
+  uint8_t* tape_a;
+  uint32_t* tape_mask;
+  TapeLayout tape;
 };
+
+// ---- backward of the field kernel (csrc/field_bwd.cu)
+struct BwdKernelParams {
+  Program prog;                // build_bwd_program: transposed-weight blocks, same constant / frame block layouts
+  TapeLayout tape;
+  b200r_field_desc desc;
+  b200r_ray_batch rays;
+  b200r_field_outputs saved;   // per-sample outputs of the training forward: xyz, rgb, sdf, feature, feat_norm
+  b200r_field_grads g;         // cotangents
+  const uint8_t* packed_t;
+  const float* workspace;      // constant block + frame blocks (rebuilt by the prologue kernel)
+  const uint8_t* tape_a;
+  uint8_t* tape_g;             // n_tiles + kMaxCtas tiles: dead tiles of a pair write to a scratch tile
+  const uint32_t* tape_mask;
+  float* g_cblk;               // gradient of the constant block (zeroed by the caller)
+  float* g_fblk;               // gradient of the frame blocks (zeroed by the caller)
+  const float* scale;          // device scalar: power-of-two gradient scale
+  int32_t M, ND, tiles_per_frame, n_tiles;
+};
+cudaError_t launch_field_bwd(const BwdKernelParams& p, int n_sm, cudaStream_t stream);
+
+// ---- weight-gradient kernel (csrc/wgrad.cu): D[row0 + r][col0 + c] of a job's accumulator is added to dst[r * ld + c]
+struct WgradView { int32_t row0, col0, rows, cols, ld, per_frame /* destination: 0 weights, 1 frame block, 2 constant block */; int64_t dst_off; };
+struct WgradJob {
+  int16_t g_chunk, n_g, a_chunk, n_a;  // operand chunk ranges of a tile: G (M = 64 n_g features) and A (N = 64 n_a features)
+  uint8_t g_src, a_src;                // which tape holds the operand: 0 = forward-written, 1 = backward-written
+  uint8_t n_views, colsum;             // colsum of the G operand: 0 none, 1 into the constant-block gradient, 2 per frame
+  int32_t per_frame;                   // flush the accumulators at every frame boundary
+  int32_t colsum_off, colsum_n;
+  WgradView v[2];
+};
+struct WgradWork { int32_t job, tile0, tile1; };
+struct WgradParams {
+  const uint8_t* tape_a;
+  const uint8_t* tape_g;
+  int32_t n_a, n_g;            // chunks per tile in each tape
+  const WgradJob* jobs;        // device
+  const WgradWork* work;       // device
+  const int32_t* cta_first;    // device, grid + 1 entries: work items of CTA b are [cta_first[b], cta_first[b + 1])
+  float* grad;                 // base of the flat weight-gradient buffer (views with per_frame == 0)
+  float* g_cblk;               // gradient of the constant block
+  float* g_fblk;               // gradient of the M frame blocks
+  int32_t frame_floats, tiles_per_frame;
+  const float* inv_scale;      // device scalar: 1 / grad_scale of the gradient chunks
+};
+cudaError_t launch_wgrad(const WgradParams& p, int grid, int operand_dtype, cudaStream_t stream);
 
 cudaError_t launch_pack(const PackParams& p, int operand_dtype, cudaStream_t stream);
 cudaError_t launch_prologue(const PrologueParams& p, cudaStream_t stream);
@@ -56,5 +106,6 @@ cudaError_t launch_composite_bwd(const b200r_composite_bwd_args& b, cudaStream_t
 cudaError_t launch_importance_fwd(const b200r_importance_args& a, cudaStream_t stream);
 cudaError_t launch_compose_fwd(const b200r_compose_args& a, cudaStream_t stream);
 cudaError_t launch_field_fwd(const FieldKernelParams& p, int n_sm, cudaStream_t stream);
+cudaError_t launch_field_fwd_train(const FieldKernelParams& p, int n_sm, cudaStream_t stream);
 
 }  // namespace b200r

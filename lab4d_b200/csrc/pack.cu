@@ -36,9 +36,10 @@ __global__ void pack_kernel(const __grid_constant__ PackParams p) {
       const int col = (int)g * 8 + j * 2 + h;
       float x = 0.f;
       if ((int)row < S.n && col < S.ncols) {
-        x = Wsrc[(size_t)(S.row0 + (int)row) * S.in_dim + S.col0 + col];
+        // forward tiles: rows = out-features; transposed (dgrad) tiles: rows = in-features, columns = out-features
+        x = S.transpose ? Wsrc[(size_t)(S.col0 + col) * S.in_dim + S.row0 + (int)row] : Wsrc[(size_t)(S.row0 + (int)row) * S.in_dim + S.col0 + col];
         if (S.pe_window != 0 && p.alpha >= 0.f) {
-          const int e = S.pe_col0 + col;  // index inside the positional embedding
+          const int e = S.pe_col0 + (S.transpose ? (int)row : col);  // index inside the positional embedding
           if (e >= 3) {
             const int L = S.pe_window == 1 ? p.L_base : p.L_color;
             const int kf = (e - 3) / 6;

@@ -139,6 +139,7 @@ struct PackSlice {
   int pe_col0;    // index of this slice's first column inside the positional embedding
   int row0;       // first output row of this chunk (N-halves of the pipelined layers)
   uint32_t dst_off;
+  int transpose;  // 1 (dgrad operands): tile element (row r, col c) = W[col0 + c][row0 + r] - rows are IN-features
 };
 
 inline int pe_dim(int L) { return L < 0 ? 0 : 3 * (2 * L + 1); }
@@ -487,6 +488,185 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int mode = MODE_FIE
     bp.ok = true;
     return bp;
   }
+}
+
+// ------------------------------------------------------------------------------------------------ training tape
+// A training-mode forward (b200r_field_fwd with a tape) records, per 128-sample tile, every MMA operand it produced
+// as [128 rows x 64] 16-bit chunks in the K-major SWIZZLE_128B image (16 KB each; row r at r * 128 B, 16-B group g at
+// ((g ^ (r & 7)) << 4)), plus one word of ReLU sign bits per (row, 32 columns).  The backward (b200r_field_bwd) adds
+// its masked gradients in the same format; the weight-gradient kernel then reads both straight into shared memory
+// with bulk copies and multiplies them as MN-major UMMA operands (reduction over the tile's rows).
+constexpr int kChunkBytes = kAChunkBytes;
+constexpr int kMaskWords = 8;  // sign words per (row, slot): up to 256 columns
+struct TapeLayout {
+  int16_t n_a, n_g, n_mask;  // chunks per tile written by the forward / by the backward; mask slots per row
+  // ---- forward-written operand chunks (first chunk id of each group, -1 = absent)
+  int16_t a_xb[3], a_h1[3], a_h2[3], a_z[3];  // skinning warps w = 0 (backward), 1 (flow), 2 (cycle): bone coords, delta MLP hidden, raw output
+  int16_t a_pe, a_extra;                       // Fourier embedding of the canonical point: columns 0..62, 63..74
+  int16_t a_vis[2], a_feat[5], a_base[10], a_col[2], a_f2, a_rgb0;  // hidden activations; a_base[D] = base features; a_f2 = input of rgb.0
+  int16_t a_dpe[3], a_dh1[3], a_dh2[3];        // dense warp stages (backward map, forward map partner, forward map own)
+  int16_t a_dir;                               // raw view direction (3 columns), L_dir == 0
+  // ---- sign-bit slots (bit = 1: pre-activation <= 0)
+  int16_t m_h1[3], m_h2[3], m_z[3], m_vis[2], m_feat[5], m_base[10], m_col[3], m_rgb0, m_dh1[3], m_dh2[3];
+  // ---- backward-written gradient chunks
+  int16_t g_z1[3], g_z2[3], g_z[3], g_xbw[3], g_xg[3];
+  int16_t g_vis[2], g_feat[6], g_base[10], g_col[3], g_rgb0, g_head;
+  int16_t g_d1[3], g_d2[3], g_d3[3];
+};
+// columns of the head chunk (g_head): gradients of the fp32 heads' pre-activations
+enum : int { GH_SDF = 0, GH_RGB = 1, GH_VIS = 4, kHeadCols = 16 };
+
+inline TapeLayout tape_layout(const b200r_field_desc& d) {
+  TapeLayout T;
+  int16_t* p = reinterpret_cast<int16_t*>(&T);
+  for (size_t i = 0; i < sizeof(T) / sizeof(int16_t); ++i) p[i] = -1;
+  const int B = d.n_bones, KC = d.W / 64;
+  int a = 0, g = 0, m = 0;
+  auto A = [&](int n) { int o = a; a += n; return (int16_t)o; };
+  auto G = [&](int n) { int o = g; g += n; return (int16_t)o; };
+  auto Mk = [&]() { return (int16_t)(m++); };
+  for (int w = 0; w < 3 && B > 0; ++w) {
+    T.a_xb[w] = A((3 * B + 63) / 64); T.a_h1[w] = A(1); T.a_h2[w] = A(1); T.a_z[w] = A(1);
+    T.m_h1[w] = Mk(); T.m_h2[w] = Mk(); T.m_z[w] = Mk();
+    T.g_z1[w] = G(1); T.g_z2[w] = G(1); T.g_z[w] = G(1); T.g_xbw[w] = G(2); T.g_xg[w] = G(1);
+    if (d.dense) {
+      T.a_dpe[w] = A(1); T.a_dh1[w] = A(4); T.a_dh2[w] = A(4);
+      T.m_dh1[w] = Mk(); T.m_dh2[w] = Mk();
+      T.g_d1[w] = G(4); T.g_d2[w] = G(4); T.g_d3[w] = G(1);
+    }
+  }
+  T.a_pe = A(1); T.a_extra = A(1);
+  if (d.L_dir == 0) T.a_dir = A(1);
+  for (int i = 0; i < 2; ++i) { T.a_vis[i] = A(1); T.m_vis[i] = Mk(); T.g_vis[i] = G(1); }
+  if (d.has_feature) {
+    for (int i = 0; i < 5; ++i) { T.a_feat[i] = A(2); T.m_feat[i] = Mk(); T.g_feat[i] = G(2); }
+    T.g_feat[5] = G(1);
+  }
+  for (int i = 0; i <= d.D; ++i) { T.a_base[i] = A(KC); T.m_base[i] = Mk(); T.g_base[i] = G(KC); }
+  for (int i = 0; i < 2; ++i) { T.a_col[i] = A(KC); T.m_col[i] = Mk(); T.g_col[i] = G(KC); }
+  T.m_col[2] = Mk(); T.g_col[2] = G(KC);
+  T.a_f2 = A(KC);
+  T.a_rgb0 = A(KC / 2); T.m_rgb0 = Mk(); T.g_rgb0 = G(KC / 2);
+  T.g_head = G(1);
+  T.n_a = (int16_t)a; T.n_g = (int16_t)g; T.n_mask = (int16_t)m;
+  return T;
+}
+inline size_t tape_a_bytes(const TapeLayout& T, int n_tiles) { return (size_t)n_tiles * T.n_a * kChunkBytes; }
+inline size_t tape_g_bytes(const TapeLayout& T, int n_tiles) { return (size_t)n_tiles * T.n_g * kChunkBytes; }
+inline size_t tape_mask_bytes(const TapeLayout& T, int n_tiles) { return (size_t)n_tiles * kTileRows * T.n_mask * kMaskWords * 4; }
+
+// ------------------------------------------------------------------------------------------------ backward (dgrad) program
+// The backward kernel walks the layers in reverse: G_{l-1} = (G_l W_l) * relu'.  Every GEMM reads its A operand (the
+// 16-bit gradient rows) from the group's activation columns in TMEM and its B operand from a TRANSPOSED packed tile
+// (rows = in-features of the layer, K = out-features), streamed through the same ring by the same producer / issuer
+// code as the forward.  Block order = the order of csrc/field_bwd.cu's phases:
+//   rgb.0, colorfield (final, 2, 1), basefield (final, D..1; the skip layer first returns its embedding columns),
+//   feature field, visibility MLP, then per skinning warp w = 2, 1, 0: [dense map], delta MLP (final, 2, 1).
+inline BuiltProgram build_bwd_program(const b200r_field_desc& d) {
+  BuiltProgram bp = build_program(d, MODE_FIELD);  // same constant / frame block layouts, same checks
+  if (!bp.ok) return bp;
+  bp.ok = false;
+  bp.slices.clear();
+  Program& P = bp.prog;
+  P.n_steps = 0;
+  P.n_blocks = 0;
+  const LayerIds L = layer_ids(d);
+  const int B = d.n_bones, W = d.W, HN = W / 2;
+  const int pe_b = pe_dim(d.L_xyz), pe_c = pe_dim(d.L_xyz + 2), pe_v = pe_dim(10), pe_f = pe_dim(6), pe_d = pe_dim(6);
+  uint32_t off = 0;
+  int ns = 0;
+  bool ok = true;
+  struct Chunk { uint32_t w_off; int n; int ksteps; };
+  // tiles of W_layer^T for in-features [r0, r0 + rows): one [pad16(rows) x 64] tile per 64 out-features
+  auto chunks_of = [&](int layer, int r0, int rows, int win) {
+    std::vector<Chunk> v;
+    const int n_out = bp.layer_out[layer];
+    for (int c0 = 0; c0 < n_out; c0 += 64) {
+      PackSlice s{};
+      s.layer = layer; s.transpose = 1;
+      s.n = rows; s.n_pad = pad16(rows); s.in_dim = bp.layer_in[layer];
+      s.col0 = c0; s.ncols = n_out - c0 < 64 ? n_out - c0 : 64;
+      s.row0 = r0; s.pe_window = win; s.pe_col0 = r0; s.dst_off = off;
+      v.push_back({off, s.n_pad, (s.ncols + 15) / 16});
+      off += (uint32_t)s.n_pad * 128u;
+      bp.slices.push_back(s);
+    }
+    return v;
+  };
+  auto block = [&](const std::vector<Chunk>& cs, int wait, int commit) {
+    if (P.n_blocks >= kMaxSteps) { ok = false; return; }
+    MmaBlock& Bk = P.blocks[P.n_blocks++];
+    Bk = MmaBlock{};
+    Bk.n16 = (uint8_t)(cs[0].n / 16); Bk.wait = (uint8_t)wait; Bk.commit = (uint8_t)commit;
+    for (size_t c = 0; c < cs.size();) {
+      const int nsub = (c + 1 < cs.size() && 2 * cs[c].n * 128 <= kWStageBytes && cs[c].ksteps == 4) ? 2 : 1;
+      if (ns >= kMaxSteps) { ok = false; return; }
+      MmaStep& S = P.steps[ns++];
+      S = MmaStep{};
+      S.w_off = cs[c].w_off; S.n = (uint16_t)cs[c].n; S.n_sub = (uint8_t)nsub; S.a_kind = 1;
+      S.ksteps = (uint8_t)cs[c].ksteps; S.ksteps2 = (uint8_t)(nsub > 1 ? cs[c + 1].ksteps : 0);
+      S.accumulate = c > 0; S.wait = (uint8_t)(c == 0 ? wait : BAR_NONE);
+      S.commit = (uint8_t)(c + (size_t)nsub == cs.size() ? commit : BAR_NONE);
+      // slots of activation operands: 4 k-steps per tile except in the last slot (field kernels' issuer contract)
+      ok = ok && (cs[c].ksteps == 4 || c + (size_t)nsub == cs.size());
+      Bk.ts_slots++;
+      Bk.ts_ks2_last = (uint8_t)(nsub > 1 ? cs[c + 1].ksteps : 0);
+      if (nsub == 1 && cs[c].ksteps != 4) {  // a lone short tile: encode its k-steps as "first tile" of the last slot
+        Bk.pad_ = (uint8_t)cs[c].ksteps;
+      }
+      c += (size_t)nsub;
+    }
+  };
+  auto seq = [&](int layer, int r0, int rows, int win = 0, int wait = BAR_ALL) { block(chunks_of(layer, r0, rows, win), wait, BAR_ALL); };
+  auto pipe = [&](int layer, int r0, int width, int first_wait) {
+    const auto h0 = chunks_of(layer, r0, width / 2, 0), h1 = chunks_of(layer, r0 + width / 2, width / 2, 0);
+    block(h0, first_wait, BAR_H0);
+    block(h1, BAR_H0, BAR_H1);
+  };
+  // ---- rgb.0 and the colour chain
+  pipe(L.rgb0, 0, W, BAR_ALL);
+  pipe(L.color[2], 0, W, BAR_H1);
+  pipe(L.color[1], 0, W, BAR_H1);
+  seq(L.color[0], 0, pe_c, 2, BAR_H1);
+  // ---- density chain
+  pipe(L.base[d.D], 0, W, BAR_ALL);
+  for (int i = d.D - 1; i >= 1; --i) {
+    if (i == d.skip) {
+      seq(L.base[i], 0, pe_b, 1, BAR_H1);
+      pipe(L.base[i], pe_b + 32, W, BAR_ALL);
+    } else {
+      pipe(L.base[i], 0, W, BAR_H1);
+    }
+  }
+  seq(L.base[0], 0, pe_b, 1, BAR_H1);
+  // ---- feature field
+  if (d.has_feature) {
+    seq(L.feat[5], 0, 128);
+    seq(L.feat[4], 0, pe_f);
+    seq(L.feat[4], pe_f, 128);
+    for (int i = 3; i >= 1; --i) seq(L.feat[i], 0, 128);
+    seq(L.feat[0], 0, pe_f);
+  }
+  // ---- visibility MLP
+  seq(L.vis[1], 0, 64);
+  seq(L.vis[0], 0, pe_v);
+  // ---- skinning warps, last first: cycle (w = 2), flow (w = 1), backward (w = 0)
+  for (int w = 2; w >= 0 && B > 0; --w) {
+    auto dense = [&](int m) {  // DenseWarp map m (0 forward_map, 1 backward_map): linear_2, linear_1 (the 3-wide head is SIMT)
+      pipe(L.dense[3 * m + 1], 0, 256, BAR_ALL);
+      seq(L.dense[3 * m + 0], 0, pe_d, 0, BAR_H1);
+    };
+    if (d.dense && w == 0) dense(1);
+    seq(L.delta[2], 0, 64);
+    seq(L.delta[1], 0, 64);
+    seq(L.delta[0], 0, 3 * B);
+    if (d.dense && w > 0) dense(0);
+  }
+  P.n_steps = ns;
+  bp.packed_bytes = off;
+  if (!ok) { bp.err = "internal: backward program does not fit"; return bp; }
+  bp.ok = true;
+  return bp;
 }
 
 inline size_t workspace_floats(const Program& P, int M) { return (size_t)P.cl.n_floats + (size_t)M * P.fl.n_floats; }

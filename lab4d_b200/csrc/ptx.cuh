@@ -288,6 +288,12 @@ struct OpF16 {
   }
   __device__ static __forceinline__ float2 unpack2(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
   __device__ static __forceinline__ float f32(uint16_t v) { return __half2float(*reinterpret_cast<__half*>(&v)); }
+  // saturating pack (gradient operands: an overflow clamps to +-65504 instead of becoming inf / NaN downstream)
+  __device__ static __forceinline__ uint32_t pack2_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  }
 };
 struct OpBF16 {
   static constexpr uint32_t kFmt = 1;
@@ -306,6 +312,11 @@ struct OpBF16 {
   }
   __device__ static __forceinline__ float2 unpack2(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v)); }
   __device__ static __forceinline__ float f32(uint16_t v) { return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&v)); }
+  __device__ static __forceinline__ uint32_t pack2_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  }
 };
 
 // Byte offset of the 16-byte group `g` (8 halves, g in [0,8)) of row `row` inside a

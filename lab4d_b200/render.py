@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .spec import FieldConfig, pe_dim
+from .spec import FieldConfig, field_param_shapes, pe_dim
 
 
 def _ptr(t):
@@ -209,7 +209,7 @@ class FieldRenderer:
         for name, nch in _lib.FIELD_OUTPUTS:
             if want is not None and name not in want:
                 continue
-            if name == "feature" and not c.has_feature:
+            if name in ("feature", "feat_norm") and not c.has_feature:
                 continue
             if name == "gauss_density" and c.motion == "rigid":
                 continue
@@ -233,15 +233,180 @@ class FieldRenderer:
         self._keep_call = keep
         feat = {k: v.view(M, N, D, -1) for k, v in out.items()}
         deltas = feat.pop("deltas", None)
-        for k in ("xyz_t", "dir", "sdf"):
+        for k in ("xyz_t", "dir", "sdf", "feat_norm"):
             feat.pop(k, None)
-        self.last_aux = {k: out[k].view(M, N, D, -1) for k in ("xyz_t", "dir", "sdf") if k in out}
+        self.last_aux = {k: out[k].view(M, N, D, -1) for k in ("xyz_t", "dir", "sdf", "feat_norm") if k in out}
         if "density" in feat:
             feat["density_" + c.category] = feat["density"]
         if want is None or "eikonal" in want:
             feat["eikonal"] = torch.zeros(M, N, D, 1, device=self.device)
         return feat, deltas
 
+
+    # ------------------------------------------------------------------ training: forward with a tape, backward
+    def _train_state(self):
+        """Flat weight-gradient buffer layout, block layouts and the transposed operand buffer (built once)."""
+        st = getattr(self, "_train", None)
+        if st is not None:
+            return st
+        lib, h = self.handle.lib, self.handle
+        layout = _lib.BlockLayout()
+        h.check(lib.b200r_get_block_layout(C.byref(self.desc), C.byref(layout)), "b200r_get_block_layout")
+        shapes = field_param_shapes(self.cfg)
+        offs, total = [], 0
+        for name, _ in self._layers:
+            offs.append(total)
+            n_out, n_in = shapes[name + ".weight"]
+            total += (n_out * n_in + 3) // 4 * 4
+        nbytes = lib.b200r_packed_t_bytes(C.byref(self.desc))
+        st = dict(layout=layout, offs=offs, total=total, shapes=shapes,
+                  packed_t=torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device))
+        self._train = st
+        return st
+
+    def pack_train(self, P, alpha=None):
+        """pack() plus the transposed (W^T) operand tiles the backward's data-gradient GEMMs read."""
+        self.pack(P, alpha)
+        st = self._train_state()
+        par, keep = self._params(P)
+        rc = self.handle.lib.b200r_pack_weights_t(self.handle.h, C.byref(self.desc), C.byref(par),
+                                                  C.c_float(-1.0 if alpha is None else float(alpha)), _ptr(st["packed_t"]),
+                                                  st["packed_t"].numel(), _stream(self.device))
+        self.handle.check(rc, "b200r_pack_weights_t")
+        self._keep_t = keep
+        self._alpha = alpha
+
+    def _tape(self, M, N, D):
+        a, g, m = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self.handle.check(self.handle.lib.b200r_tape_sizes(C.byref(self.desc), M, N, D, C.byref(a), C.byref(g), C.byref(m)), "b200r_tape_sizes")
+        need = (a.value, g.value, m.value)
+        bufs = getattr(self, "_tape_bufs", None)
+        if bufs is None or any(b.numel() < n for b, n in zip(bufs, need)):
+            bufs = tuple(torch.empty(n + 1024, dtype=torch.uint8, device=self.device) for n in need)
+            self._tape_bufs = bufs
+        t = _lib.Tape()
+        al = lambda b: (b.data_ptr() + 1023) // 1024 * 1024
+        t.a, t.g, t.mask = al(bufs[0]), al(bufs[1]), al(bufs[2])
+        t.a_bytes, t.g_bytes, t.mask_bytes = need
+        return t
+
+    def _frame_tables(self, rays, tab, keep):
+        fr = _lib.FrameTables()
+        fr.M = rays["hxy"].shape[0]
+
+        def put(name, t):
+            t = _f32c(t)
+            keep.append(t)
+            setattr(fr, name, t.data_ptr())
+
+        put("Kinv", rays["Kinv"])
+        put("near_far", rays["near_far"])
+        for field, key in self._TAB_KEYS.items():
+            if key in tab and tab[key] is not None:
+                put(field, tab[key])
+        return fr
+
+    @torch.no_grad()
+    def query_field_train(self, P, rays, tab, D, flow_thresh=None, depth=None):
+        """Training forward: query_field that also records the tape.  Returns (feat_dict, deltas, ctx); `ctx` goes to
+        `backward`.  One call may be in flight per renderer (the tape buffers belong to the renderer)."""
+        c = self.cfg
+        hxy = _f32c(rays["hxy"])
+        M, N = hxy.shape[:2]
+        S = M * N * int(D)
+        keep = [hxy]
+        par, kp = self._params(P)
+        keep += kp
+        fr = self._frame_tables(rays, tab, keep)
+        rb = _lib.RayBatch()
+        rb.N, rb.D = N, int(D)
+        rb.flow_thresh = -1.0 if flow_thresh is None else float(flow_thresh)
+        rb.hxy = hxy.data_ptr()
+        if depth is not None:
+            dep = _f32c(depth.reshape(M, N, int(D)))
+            keep.append(dep)
+            rb.depth = dep.data_ptr()
+        out, oa = {}, _lib.FieldOutputs()
+        for name, nch in _lib.FIELD_OUTPUTS:
+            if name in ("feature", "feat_norm") and not c.has_feature:
+                continue
+            if name == "gauss_density" and c.motion == "rigid":
+                continue
+            out[name] = torch.empty(S, nch, dtype=torch.float32, device=self.device)
+            setattr(oa, name, out[name].data_ptr())
+        wbytes = self.handle.lib.b200r_workspace_bytes(C.byref(self.desc), M)
+        if getattr(self, "_ws", None) is None or self._ws.numel() < wbytes:
+            self._ws = torch.empty(wbytes, dtype=torch.uint8, device=self.device)
+        tape = self._tape(M, N, int(D))
+        rc = self.handle.lib.b200r_field_fwd_train(self.handle.h, C.byref(self.desc), _ptr(self.packed), C.byref(par), C.byref(fr),
+                                                   C.byref(rb), C.byref(oa), C.byref(tape), _ptr(self._ws), self._ws.numel(),
+                                                   _stream(self.device))
+        self.handle.check(rc, "b200r_field_fwd_train")
+        feat = {k: v.view(M, N, int(D), -1) for k, v in out.items()}
+        deltas = feat.pop("deltas")
+        for k in ("xyz_t", "dir", "sdf", "feat_norm"):
+            feat.pop(k, None)
+        feat["density_" + c.category] = feat["density"]
+        feat["eikonal"] = torch.zeros(M, N, int(D), 1, device=self.device)
+        ctx = dict(out=out, par=par, fr=fr, rb=rb, tape=tape, keep=keep, M=M, N=N, D=int(D), P=P, tab=tab, rays=rays)
+        return feat, deltas, ctx
+
+    @torch.no_grad()
+    def backward(self, ctx, grads):
+        """grads: key -> cotangent of the per-sample output (M,N,D,c) (keys of _lib.GRAD_KEYS; missing = zero; `density_fg` /
+        `density_bg` are added to `density`).  Returns (param_grads, table_grads): name -> tensor."""
+        from . import prologue_grad
+
+        st = self._train_state()
+        M = ctx["M"]
+        keep = []
+        fg = _lib.FieldGrads()
+        gd = dict(grads)
+        for k in ("density_fg", "density_bg"):
+            if gd.get(k) is not None:
+                gd["density"] = gd[k] if gd.get("density") is None else gd["density"] + gd[k]
+        for k in _lib.GRAD_KEYS:
+            if gd.get(k) is not None:
+                t = _f32c(gd[k])
+                keep.append(t)
+                setattr(fg, k, t.data_ptr())
+        saved, out = _lib.FieldOutputs(), ctx["out"]
+        for k in ("xyz", "rgb", "sdf", "feature", "feat_norm"):
+            if k in out:
+                setattr(saved, k, out[k].data_ptr())
+        layout = st["layout"]
+        flat = torch.zeros(st["total"], device=self.device)
+        g_const = torch.empty(layout.const_floats, device=self.device)
+        g_frame = torch.empty(M, layout.frame_floats, device=self.device)
+        pgs = _lib.ParamGrads()
+        pgs.weights, pgs.const_block, pgs.frame_block = flat.data_ptr(), g_const.data_ptr(), g_frame.data_ptr()
+        for i, o in enumerate(st["offs"]):
+            pgs.weight_off[i] = o
+        rc = self.handle.lib.b200r_field_bwd(self.handle.h, C.byref(self.desc), _ptr(st["packed_t"]), C.byref(ctx["par"]), C.byref(ctx["fr"]),
+                                             C.byref(ctx["rb"]), C.byref(saved), C.byref(fg), C.byref(ctx["tape"]), C.byref(pgs),
+                                             _ptr(self._ws), self._ws.numel(), _stream(self.device))
+        self.handle.check(rc, "b200r_field_bwd")
+        names = [n for n, _ in self._layers]
+        wg = {}
+        for (name, _), o in zip(self._layers, st["offs"]):
+            shp = st["shapes"][name + ".weight"]
+            wg[name + ".weight"] = flat[o:o + shp[0] * shp[1]].view(shp)
+        alpha = getattr(self, "_alpha", None)
+        if alpha is not None:  # the annealing window is folded into the packed weights: dW = dW_eff * window
+            self._apply_window(wg, alpha)
+        pg, tg = prologue_grad.chain(layout, names, self.cfg, ctx["P"], ctx["tab"], ctx["rays"], g_const, g_frame, wg)
+        self.last_flat_grad = flat
+        self._keep_bwd = keep
+        return pg, tg
+
+    def _apply_window(self, wg, alpha):
+        import math
+
+        c = self.cfg
+        for name, L in (("basefield.linear_1.0", c.L_xyz), (f"basefield.linear_{c.skip + 1}.0", c.L_xyz), ("colorfield.linear_1.0", c.L_xyz + 2)):
+            k = torch.arange(L, device=self.device, dtype=torch.float32)
+            wdw = 0.5 * (1 + torch.cos(math.pi * torch.clamp(alpha * L - k, 0.0, 1.0) + math.pi))
+            wg[name + ".weight"][:, 3:3 + 6 * L] *= wdw.repeat_interleave(6)[None]
 
     # ------------------------------------------------------------------ eval-mode importance sampling
     @torch.no_grad()
