@@ -12,7 +12,8 @@ namespace b200r {
 
 // ---------------------------------------------------------------- gradient scale
 // max |g| over the cotangent arrays (the density's is weighted by |d density / d sdf| <= ibeta^2 / 2, the factor its
-// gradient picks up first) -> power-of-two scale that puts the largest entry at ~4 in the 16-bit gradient operands.
+// gradient picks up first) -> power-of-two scale that puts the largest entry at ~1024 in the 16-bit gradient operands
+// (entries 1e-7 of the largest still land in fp16's normal range).
 struct ScaleParams {
   const float* ptr[12];
   long long n[12];
@@ -39,7 +40,7 @@ __global__ void absmax_kernel(const ScaleParams p) {
 __global__ void scale_kernel(const ScaleParams p) {
   const float amax = __uint_as_float(*p.amax_bits);
   float s = 1.0f;
-  if (!p.bf16 && amax > 0.f) s = exp2f(floorf(log2f(4.0f / amax)));
+  if (!p.bf16 && amax > 0.f) s = exp2f(floorf(log2f(1024.0f / amax)));  // fp16 tops out at 65504: 64x headroom, saturating packs beyond
   s = fminf(fmaxf(s, 1.0f / 16777216.0f), 1099511627776.0f);
   p.scale[0] = s;
   p.scale[1] = 1.0f / s;
