@@ -1,14 +1,20 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: ray-samples/s/GPU on BASELINE.json configs[1]
-(fg-bob deformable field, 2048 rays x 128 samples per GPU, synthetic rays, synthetic "trained-like"
-weights, rays sharded data-parallel = weak scaling).
+"""Benchmark of the hot path: ray-samples/s on BASELINE.json's configs.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pass forward]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pass step|forward] [--config c2|c3|c4]
+                  [--precision fp16x3|fp16|bf16]
 
-One "step" = one pass of the hot path over one batch: weight packing (weights change every
-optimiser step in training), the fused query_field kernel and the compositing kernel.
-`value` times the step with inputs resident in HBM; `e2e` goes through the public API with pinned
-HOST buffers (H2D of rays + per-frame tables and D2H of the rendered pixels inside the timed region).
+Default = configs[1] (C2): fg-bob deformable field, 2048 rays x 128 samples per GPU, synthetic rays and synthetic
+"trained-like" weights, ONE TRAINING STEP of the renderer per "step":
+    weight packing (forward + transposed operands; weights change every optimiser step),
+    training forward (fused query_field kernel writing the tape), compositing (render_pixel),
+    loss = fixed linear functional of the rendered pixels, compositing backward, field backward (data-gradient kernel +
+    weight-gradient kernel + per-frame chain), flat gradient buffer, and for N > 1 ONE NCCL all-reduce (mean) of it.
+Rays shard data-parallel over the N GPUs (weak scaling: every rank renders its own batch).  `--pass forward` is the
+inference path (query_field + render_pixel, no tape).  `value` times the step with inputs resident in HBM; `e2e` goes
+through the same public API with the step's inputs in pinned HOST memory (H2D of rays + per-frame tables and D2H of the
+rendered RGB inside the timed region).  `--config c4` is the strong-scaling shape of configs[3]: 4096 rays x (128 fg +
+128 bg) samples split over the ranks (forward: the composed dense-warp field's backward is not built).
 """
 import argparse
 import json
@@ -26,62 +32,69 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 import numpy as np
 import torch
 
-# algorithmic FLOPs per ray-sample of what the fused forward computes (hook-measured on
-# the reference): F_query,fwd(fg-bob) = 1 914 380 incl. the 1/16-ray eikonal forward (71 616), which
-# stays on PyTorch -> 1 842 764.
-FLOP_PER_SAMPLE_FWD = 1_914_380 - 71_616
-WORKLOAD = dict(M=128, N=16, D=128)
+# algorithmic FLOPs per ray-sample (hook-measured on the reference): F_query,fwd incl. the 1/16-ray
+# eikonal forward (71 616 for fg fields), which this renderer does not compute.  Training step = 3 x forward (dgrad + wgrad).
+FLOP_FWD = {"fg_bob": 1_914_380 - 71_616, "fg_skelhuman": 1_903_572 - 71_616, "comp": 1_479_732 - 35_808}
+CONFIGS = {
+    "c2": dict(field="fg_bob", M=128, N=16, D=128, precision="fp16x3", desc="fg-bob 2048 rays x 128 samples per GPU (configs[1])"),
+    "c3": dict(field="fg_skelhuman", M=256, N=16, D=192, precision="bf16", desc="skel-human 4096 rays x 192 samples per GPU, bf16 operands (configs[2])"),
+    "c4": dict(field="comp", M=256, N=16, D=128, precision="fp16x3", desc="comp skel-quad+dense fg + bg, 4096 rays x 256 samples TOTAL, ray-sharded (configs[3])"),
+}
 
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return float(d["bf16_tflops"]), float(d["hbm_gbs"]), "measured"
-    return 1590.0, 6650.0, "fallback"
+        return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), float(d["hbm_gbs"]), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+def dram_traffic_from_profile(kernel):
+    """dram read+write bytes per launch of `kernel` from the committed ncu raw page (profiles/r02_*_raw.csv), else None."""
+    import csv
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_*raw*.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            head = rows[0]
+            ik, ir, iw = head.index("Kernel Name"), head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
+            units = rows[1]
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            vals = [float(r[ir].replace(",", "")) * mult.get(units[ir], 1.0) + float(r[iw].replace(",", "")) * mult.get(units[iw], 1.0)
+                    for r in rows[2:] if kernel in r[ik]]
+            if vals:
+                return float(np.mean(vals)), os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
 
 
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons DURING the timed region: NVML in-process (10 ms period), nvidia-smi as fallback."""
+    """SM clock + throttle reasons DURING the timed region, one nvidia-smi query loop (-lms) for the whole region."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.rows, self.proc = index, [], None
 
     def run(self):
-        try:
-            import pynvml as nv
-
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-            while not self._halt.is_set():
-                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits.values()])
-                self._halt.wait(0.01)
-            return
-        except Exception:
-            pass
-        self._run_smi()
-
-    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [x.strip() for x in line.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+        except Exception:
+            pass
 
     def stop(self):
-        self._halt.set()
+        time.sleep(0.25)  # let at least two samples land even for a short region
+        if self.proc is not None:
+            self.proc.terminate()
         self.join(timeout=5)
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
@@ -94,134 +107,232 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def make_problem(device, rank, M, N, D):
+def field_cfgs(name):
+    from lab4d_b200 import spec
+
+    return {"fg_bob": [spec.FG_BOB], "fg_skelhuman": [spec.FG_SKEL_HUMAN], "comp": [spec.BG, spec.FG_COMP_QUAD]}[name]
+
+
+def make_problem(device, rank, field, M, N, D):
+    """Per field: (cfg, params, rays, tables); synthetic 'trained-like' weights, seeded rays."""
     import synth
     from lab4d_b200 import spec
     from test_gpu_parity import synth_tables
 
-    cfg = spec.FG_BOB
-    st = synth.synth_state(spec.field_param_shapes(cfg), 0, "fg")
-    P = {k: torch.from_numpy(v).to(device) for k, v in st.items()}
+    out = []
     rays_np = synth.synth_rays(M, N, seed=10 + rank)
-    rays = {k: torch.from_numpy(v).to(device) for k, v in rays_np.items()}
-    tab = synth_tables(cfg, M, device, seed=10 + rank, rays=rays, P=P)
-    return cfg, P, rays, tab
+    for cfg in field_cfgs(field):
+        st = synth.synth_state(spec.field_param_shapes(cfg), 0, cfg.category)
+        P = {k: torch.from_numpy(v).to(device) for k, v in st.items()}
+        rays = {k: torch.from_numpy(v).to(device) for k, v in rays_np.items()}
+        if cfg.category == "bg" and field == "comp":
+            rays["near_far"] = rays["near_far"] * torch.tensor([[0.93, 1.11]], device=device)
+        tab = {k: v.clone() for k, v in synth_tables(cfg, M, device, seed=10 + rank, rays=rays, P=P).items()}
+        out.append((cfg, P, rays, tab))
+    return out
 
 
-def best_threads():
-    """All host cores is not the fastest setting for this op mix (hundreds of small torch ops): pick the
-    fastest thread count on a small sample so the CPU arm is not handicapped by oversubscription."""
-    import lab4d_oracle as O
-
-    ncpu = os.cpu_count() or 1
-    cfg, P, rays, tab = make_problem("cpu", 0, 2, 16, 32)
-    best, best_t = 1, 1e30
-    for th in sorted({t for t in (4, 8, 16, 32, 64, ncpu) if t <= ncpu}):
-        torch.set_num_threads(th)
-        with torch.no_grad():
-            O.query_field(P, cfg.as_oracle_cfg(), rays, tab, 32)
-            t0 = time.perf_counter()
-            O.query_field(P, cfg.as_oracle_cfg(), rays, tab, 32)
-            dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = th, dt
-    return best
-
-
-def cpu_port_rate(M, N, D, threads, reps=1):
-    """The oracle restatement (a port of the reference's PyTorch path) on the host cores."""
-    import lab4d_oracle as O
-
+# ------------------------------------------------------------------------------------------ CPU arm (reference's PyTorch path)
+def cpu_reference_rate(field, M, N, D, with_backward, reps, threads):
+    """The reference's CPU PyTorch implementation of the path on the host cores: the UNMODIFIED reference (baseline/_ref
+    through oracle/ref_shims) when the travelling copy is present, else the oracle port."""
     torch.set_num_threads(threads)
-    cfg, P, rays, tab = make_problem("cpu", 0, M, N, D)
-    with torch.no_grad():
-        O.render_pixel(*O.query_field(P, cfg.as_oracle_cfg(), rays, tab, D))  # warm-up
+    kind = "port"
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_shims"))
+        import _install
+
+        if not _install.available() or field != "fg_bob":
+            raise ImportError
+        import ref_harness as H
+        import synth
+        from lab4d.utils.render_utils import render_pixel as ref_render_pixel
+
+        mf = H.build_field("fg", "bob", seed=0)
+        fld = mf.field_params["fg"]
+        H.set_n_depth(D)
+        Kinv, batch = H.make_batch(fld, synth.synth_rays(M, N, seed=10))
+
+        def step():
+            fld.zero_grad()
+            s = fld.get_samples(Kinv, batch)
+            feat, deltas, _ = fld.query_field(s, flow_thresh=None)
+            r = ref_render_pixel(feat, deltas)
+            if with_backward:
+                (r["rgb"].sum() + r["mask"].sum() + 1e-3 * r["flow"].sum()).backward()
+        kind = "reference"
+    except Exception:
+        import lab4d_oracle as O
+
+        cfg, P, rays, tab = make_problem("cpu", 0, field, M, N, D)[-1]
+        if with_backward:
+            P = {k: v.requires_grad_(True) for k, v in P.items()}
+
+        def step():
+            feat, deltas = O.query_field(P, cfg.as_oracle_cfg(), rays, tab, D)
+            r = O.render_pixel(feat, deltas)
+            if with_backward:
+                for v in P.values():
+                    v.grad = None
+                (r["rgb"].sum() + r["mask"].sum() + 1e-3 * r["flow"].sum()).backward()
+    ctx = torch.enable_grad() if with_backward else torch.no_grad()
+    with ctx:
+        step()
         t0 = time.perf_counter()
         for _ in range(reps):
-            O.render_pixel(*O.query_field(P, cfg.as_oracle_cfg(), rays, tab, D))
+            step()
         dt = (time.perf_counter() - t0) / reps
-    return M * N * D / dt, dt
+    return M * N * D / dt, dt, kind
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU PyTorch path (oracle port) on the host cores, rank 0 only."""
+def cpu_policy():
+    """Fixed thread policy: all host cores (os.cpu_count()), capped at 32 - beyond that PyTorch's intra-op pool only adds
+    contention for this op mix of hundreds of small kernels."""
+    ncpu = os.cpu_count() or 1
+    return min(ncpu, 32), ncpu
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation on the host cores (rank 0 only), bounded sample per step."""
     if rank != 0:
         return
-    threads = best_threads()
-    Ms = 8  # bounded sample: 8 frames x 16 rays x 128 samples = 16 384 ray-samples per step
-    times = []
+    cfgd = CONFIGS[args.config]
+    threads, ncpu = cpu_policy()
+    Ms = 8
+    with_bwd = args.passes == "step"
+    times, kind = [], "port"
     for i in range(args.warmup + args.steps):
-        rate, dt = cpu_port_rate(Ms, WORKLOAD["N"], WORKLOAD["D"], threads)
+        rate, dt, kind = cpu_reference_rate(cfgd["field"] if cfgd["field"] != "comp" else "fg_bob", Ms, cfgd["N"], cfgd["D"], with_bwd, 1, threads)
         if i >= args.warmup:
             times.append(dt)
-    S = Ms * WORKLOAD["N"] * WORKLOAD["D"]
+    S = Ms * cfgd["N"] * cfgd["D"]
     val = S / float(np.mean(times))
-    sample = f"{Ms} of {WORKLOAD['M']} frames x {WORKLOAD['N']} rays x {WORKLOAD['D']} samples per step, forward, fp32"
+    sample = f"{Ms} of {cfgd['M']} frames x {cfgd['N']} rays x {cfgd['D']} samples per step, {'forward+backward' if with_bwd else 'forward'}, fp32"
     print(json.dumps({
         "impl": "reference", "metric": "ray-samples/s", "value": val, "unit": "ray-samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "fg-bob 2048 rays x 128 samples (configs[1]), forward", "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "ray-samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": cfgd["desc"] + (", training step" if with_bwd else ", forward"), "sample": sample, "pass": args.passes},
+        "cpu_baseline": {"value": val, "unit": "ray-samples/s", "cores": threads, "host_cores": ncpu, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class Step:
+    """One step of the chosen pass over one batch, through the public API (lab4d_b200.render / autograd / parallel)."""
+
+    def __init__(self, args, device, rank, world):
+        from lab4d_b200 import parallel
+        from lab4d_b200.render import FieldRenderer
+
+        cfgd = CONFIGS[args.config]
+        self.cfgd, self.args, self.device, self.world = cfgd, args, device, world
+        M = cfgd["M"]
+        if args.config == "c4":  # strong scaling: the 4096 rays are split over the ranks (frame pairs stay together)
+            lo, hi = parallel.shard_frames(M, rank, world)
+            M = hi - lo
+        self.M, self.N, self.D = M, cfgd["N"], cfgd["D"]
+        self.S = self.M * self.N * self.D * len(field_cfgs(cfgd["field"]))
+        self.fields = make_problem(device, rank, cfgd["field"], self.M, self.N, self.D)
+        self.precision = args.precision or cfgd["precision"]
+        self.renderers = [FieldRenderer(cfg, device, operand_dtype=self.precision) for cfg, *_ in self.fields]
+        self.train = args.passes == "step"
+        if self.train:
+            for _, P, _, _ in self.fields:
+                for v in P.values():
+                    v.requires_grad_(True)
+            g = torch.Generator().manual_seed(5)
+            R = self.M * self.N
+            self.coeff = {k: (torch.rand(self.M, self.N, c, generator=g) / R).to(device) for k, c in
+                          (("rgb", 3), ("mask", 1), ("depth", 1), ("flow", 2), ("feature", 16), ("vis", 1), ("xyz", 3), ("gauss_mask", 1))}
+        self.launches = 0
+        self.flat = None
+
+    def run(self, fields=None):
+        from lab4d_b200 import autograd as b2grad
+        from lab4d_b200 import parallel
+        from lab4d_b200.render import compose_fields, render_pixel
+
+        fields = fields or self.fields
+        feats, dls = [], []
+        for r, (cfg, P, rays, tab) in zip(self.renderers, fields):
+            if self.train:
+                r.pack_train(P)
+                feat, deltas = b2grad.query_field(r, P, rays, tab, self.D)
+                self.launches += 2 + 2  # pack, pack^T; prologue + field_fwd(train)
+            else:
+                r.pack(P)
+                feat, deltas = r.query_field(P, rays, tab, self.D)
+                self.launches += 1 + 2
+            feats.append(feat)
+            dls.append(deltas)
+        fd, dl = (feats[0], dls[0]) if len(feats) == 1 else compose_fields(feats, dls)
+        rend = render_pixel(fd, dl)
+        self.launches += 1 + (len(feats) > 1) * 2
+        if self.train:
+            loss = sum((self.coeff[k] * rend[k]).sum() for k in self.coeff if k in rend)
+            for _, P, _, _ in fields:
+                for v in P.values():
+                    v.grad = None
+            loss.backward()
+            self.launches += 1 + 5  # composite_bwd; prologue, absmax, scale, field_bwd, wgrad
+            self.flat = parallel.flat_grads([P for _, P, _, _ in fields])
+            parallel.allreduce_mean_(self.flat)
+        return rend
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--pass", dest="passes", default="step", choices=["step", "forward"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", default=None, choices=["fp16x3", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the step as a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.config == "c4":
+        args.passes = "forward"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
     import torch.distributed as dist
 
-    from lab4d_b200.render import FieldRenderer, render_pixel
+    from lab4d_b200.render import HostStage
 
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    M, N, D = WORKLOAD["M"], WORKLOAD["N"], WORKLOAD["D"]
-    S = M * N * D
-    cfg, P, rays, tab = make_problem(device, rank, M, N, D)
-    r = FieldRenderer(cfg, device)
+    step = Step(args, device, rank, world)
+    cfgd = step.cfgd
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
-    launches = {"n": 0}
 
-    def step():
-        r.pack(P)
-        feat, deltas = r.query_field(P, rays, tab, D)
-        rend = render_pixel(feat, deltas)
-        launches["n"] += 1 + 2 + 1  # pack; prologue + field_fwd; composite (14 channels in one launch)
-        return rend
-
-    # end-to-end arm: the step's inputs live in pinned host memory (one arena) and are copied every step
-    from lab4d_b200.render import HostStage
-
-    stage = HostStage({k: v.cpu() for k, v in {**rays, **tab}.items()}, device)
-    h2d = stage.nbytes
-    out_host = torch.empty(M, N, 3).pin_memory()
+    # end-to-end arm: the step's inputs (rays + per-frame tables of every field) live in ONE pinned host arena
+    host = {}
+    for fi, (_, _, rays, tab) in enumerate(step.fields):
+        for k, v in {**rays, **tab}.items():
+            host[f"{fi}/{k}"] = v.detach().cpu()
+    stage = HostStage(host, device)
+    rgb_host = torch.empty(step.M, step.N, 3).pin_memory()
 
     def step_e2e():
-        dev_in = stage.upload()
-        rr = {k: dev_in[k] for k in rays}
-        tt = {k: dev_in[k] for k in tab}
-        r.pack(P)
-        feat, deltas = r.query_field(P, rr, tt, D)
-        rend = render_pixel(feat, deltas)
-        out_host.copy_(rend["rgb"], non_blocking=True)
+        dev = stage.upload()
+        fields = []
+        for fi, (cfg, P, rays, tab) in enumerate(step.fields):
+            fields.append((cfg, P, {k: dev[f"{fi}/{k}"] for k in rays}, {k: dev[f"{fi}/{k}"] for k in tab}))
+        rend = step.run(fields)
+        rgb_host.copy_(rend["rgb"].detach(), non_blocking=True)
         return rend
 
-    def timed(fn, steps, kernel_events=None):
+    def timed(fn, steps):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for i in range(steps):
             flush.fill_(i & 0xFF)  # evict L2 between timed iterations
@@ -232,63 +343,111 @@ def main():
         return [a.elapsed_time(b) for a, b in ev]
 
     for _ in range(args.warmup):
-        step()
+        step.run()
         step_e2e()
     torch.cuda.synchronize()
+    # the step as one CUDA graph (static shapes): replaying keeps the host out of the timed region
+    run_fn, e2e_fn, graphed = step.run, step_e2e, False
+    if not args.no_graph:
+        try:
+            from lab4d_b200.graph import GraphedStep
+
+            g_run = GraphedStep(step.run, warmup=2, device=device)
+            g_e2e = GraphedStep(step_e2e, warmup=2, device=device)
+            run_fn, e2e_fn, graphed = g_run.replay, g_e2e.replay, True
+        except Exception as ex:  # stay on the eager path
+            print(f"bench: CUDA-graph capture failed ({type(ex).__name__}: {str(ex)[:200]}); eager launches", file=sys.stderr)
+            torch.cuda.synchronize()
+    launches_per_step = None
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    launches["n"] = 0
+    step.launches = 0
+    step.run()
+    launches_per_step = step.launches
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
-    ms = timed(step, args.steps)
-    n_launch = launches["n"]
+    ms = timed(run_fn, args.steps)
+    n_launch = launches_per_step * args.steps
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
-    ms_e2e = timed(step_e2e, args.steps)
-    # the dominant kernel alone (same stream, CUDA events around the C-ABI call only)
-    kern = []
-    for i in range(args.steps):
+    ms_e2e = timed(e2e_fn, args.steps)
+    # the phases alone (same stream, CUDA events around the public calls): forward kernel(s), backward call
+    phase = {"fwd_ms": [], "bwd_ms": []}
+    r0, (cfg0, P0, rays0, tab0) = step.renderers[-1], step.fields[-1]
+    for i in range(min(args.steps, 50)):
         flush.fill_(i & 0xFF)
-        r.time_next_launch = True
-        r.query_field(P, rays, tab, D)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        if step.train:
+            feat, deltas, ctx = r0.query_field_train(P0, rays0, tab0, step.D)
+        else:
+            feat, deltas = r0.query_field(P0, rays0, tab0, step.D)
+        e[1].record()
+        if step.train:
+            r0.backward(ctx, {"rgb": feat["rgb"], "density": feat["density"], "vis": feat["vis"], "xyz": feat["xyz"]})
+        e[2].record()
         torch.cuda.synchronize()
-        kern.append(r.last_kernel_ms)
+        phase["fwd_ms"].append(e[0].elapsed_time(e[1]))
+        phase["bwd_ms"].append(e[1].elapsed_time(e[2]))
     clocks = sampler.stop()
     tot = torch.tensor([sum(ms), sum(ms_e2e)], device=device, dtype=torch.float64)
+    Stot = torch.tensor([float(step.S)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        dist.all_reduce(Stot, op=dist.ReduceOp.SUM)
     ms_step = float(tot[0]) / args.steps
     ms_step_e2e = float(tot[1]) / args.steps
     if rank == 0:
-        peak_tf, peak_bw, how = peaks()
-        kms = float(np.mean(kern))
-        achieved = FLOP_PER_SAMPLE_FWD * S / (kms * 1e-3) / 1e12
+        peak_burst, peak_sust, peak_bw, how = peaks()
+        S_all = float(Stot[0])
+        flop_fwd = FLOP_FWD[cfgd["field"]]
+        fwd_ms = float(np.mean(phase["fwd_ms"]))
+        bwd_ms = float(np.mean(phase["bwd_ms"])) if step.train else 0.0
+        mult = 3 if step.train else 1
+        kern_ms = fwd_ms + bwd_ms
+        achieved = mult * flop_fwd * step.S / len(step.fields) / (kern_ms * 1e-3) / 1e12 if len(step.fields) == 1 else None
+        kname = "field_fwd_kernel"
+        traffic, tsrc = dram_traffic_from_profile(kname)
+        strong = args.config == "c4"
         line = {
-            "metric": "ray-samples/s", "value": world * S / (ms_step * 1e-3), "unit": "ray-samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
-            "config": {"workload": "fg-bob 2048 rays x 128 samples per GPU (configs[1]), forward query_field + render_pixel",
-                       "rays_per_gpu": M * N, "samples_per_ray": D, "bones": cfg.B, "l2": "flushed between iterations (256 MB write)",
-                       "pass": "forward", "per_gpu": "BASELINE metric ray-samples/s/GPU = value / n_gpus", "parallelism": f"dp{world} (rays sharded, no data-path collective in forward)"},
-            "e2e": {"value": world * S / (ms_step_e2e * 1e-3), "unit": "ray-samples/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": out_host.numel() * 4},
-            "gpu_launches": n_launch,
-            "roofline": {"bound": "tensor", "kernel": "field_fwd_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": 15.7e6, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_final.md)",
-                         "kernel_ms": kms, "kernel_scope": "prologue_kernel + field_fwd_kernel (one C-ABI call)",
-                         "flop_per_sample": FLOP_PER_SAMPLE_FWD, "peak_source": how + " bf16 dense burst"},
+            "metric": "ray-samples/s", "value": S_all / (ms_step * 1e-3), "unit": "ray-samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": {"fp16x3": "f16 head+tail operands (3 MMAs per k-step, ~fp32 results: meets the 1e-4 RGB contract) / f32 accumulate",
+                      "fp16": "f16 operands / f32 accumulate", "bf16": "bf16 operands / f32 accumulate"}[step.precision]
+                     + ("; backward GEMMs f16 (scaled) / f32 accumulate" if step.train else ""),
+            "data": "synthetic",
+            "config": {"workload": cfgd["desc"] + (", training step (fwd + bwd + grad all-reduce)" if step.train else ", forward query_field + render_pixel"),
+                       "pass": args.passes, "precision": step.precision, "rays_per_gpu": step.M * step.N, "samples_per_ray": step.D * len(step.fields),
+                       "l2": "flushed between iterations (256 MB write)", "per_gpu": "BASELINE metric ray-samples/s/GPU = value / n_gpus",
+                       "parallelism": f"dp{world}: rays sharded" + (", one NCCL all-reduce (mean) of the flat gradient buffer per step" if step.train else ", no data-path collective in forward")},
+            "e2e": {"value": S_all / (ms_step_e2e * 1e-3), "unit": "ray-samples/s", "h2d_bytes_per_step": stage.nbytes,
+                    "d2h_bytes_per_step": rgb_host.numel() * 4},
+            "gpu_launches": n_launch, "cuda_graph": graphed,
+            "phases_ms": {"forward_call": fwd_ms, "backward_call": bwd_ms, "step": ms_step,
+                          "note": "CUDA events around FieldRenderer.query_field[_train] (prologue + field kernel) and FieldRenderer.backward (prologue, scale, data-gradient kernel, weight-gradient kernel, per-frame chain)"},
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
-        if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0 at N = 1 only, ~10 s of CPU work
-            threads = best_threads()
-            Ms, reps = 8, 80  # 8-frame batches are the CPU path's fastest batch size (1.7e5 vs 0.7e5 samples/s at 32 frames)
-            rate, dt = cpu_port_rate(Ms, N, D, threads, reps=reps)
-            line["cpu_baseline"] = {"value": rate, "unit": "ray-samples/s", "cores": threads, "kind": "port",
-                                    "sample": f"{reps} x ({Ms} of {M} frames x {N} rays x {D} samples), forward, fp32 oracle port, {reps * dt:.1f} s"}
+        if achieved is not None:
+            line["roofline"] = {"bound": "tensor", "kernel": "field_fwd_kernel + field_bwd_kernel + wgrad_kernel" if step.train else "field_fwd_kernel",
+                                "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved / peak_burst,
+                                "frac_of_sustained": achieved / peak_sust, "traffic": traffic,
+                                "traffic_unit": f"DRAM bytes per field_fwd launch ({tsrc})" if tsrc else "no committed ncu capture found",
+                                "kernel_ms": kern_ms, "flop_per_sample": mult * flop_fwd,
+                                "peak_source": how + " bf16 dense burst (sustained also given)"}
+        if step.flat is not None:
+            line["grad_buffer_bytes"] = int(step.flat.numel() * 4)
+        if not args.no_cpu_baseline and world == 1 and args.config == "c2":  # reported baseline: rank 0 at N = 1, ~10-20 s of CPU work
+            threads, ncpu = cpu_policy()
+            Ms, reps = 8, (12 if step.train else 40)
+            rate, dt, kind = cpu_reference_rate(cfgd["field"], Ms, step.N, step.D, step.train, reps, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "ray-samples/s", "cores": threads, "host_cores": ncpu, "kind": kind,
+                                    "sample": f"{reps} x ({Ms} of {cfgd['M']} frames x {step.N} rays x {step.D} samples), "
+                                              f"{'forward+backward' if step.train else 'forward'}, fp32, {reps * dt:.1f} s"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

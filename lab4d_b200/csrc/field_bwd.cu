@@ -245,10 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
     const uint8_t* at_tile = nullptr;    // this tile's forward chunks
     const uint32_t* mask_row = nullptr;  // this row's ReLU sign words
     auto gtape_st32 = [&](int chunk, int col0, const uint32_t (&o)[16]) {
-      uint8_t* base = gt_tile + (size_t)(chunk + (col0 >> 6)) * kChunkBytes;
-      const uint32_t g0 = (uint32_t)(col0 & 63) >> 3;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(base + (rowx ^ ((g0 + j) << 4))) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      chunk_st32(gt_tile + (size_t)(chunk + (col0 >> 6)) * kChunkBytes, row, (uint32_t)(col0 & 63) >> 3, o);
     };
     auto gtape_zero_row = [&](int chunk) {
       uint8_t* base = gt_tile + (size_t)chunk * kChunkBytes + row * 128u;

@@ -343,10 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     auto tape_st32 = [&](int chunk, int col0, const uint32_t (&o)[16]) {
       if constexpr (SAVE) {
         if (tape_tile != nullptr && chunk >= 0) {
-          uint8_t* base = tape_tile + (size_t)(chunk + (col0 >> 6)) * kChunkBytes;
-          const uint32_t g0 = (uint32_t)(col0 & 63) >> 3;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(base + (rowx ^ ((g0 + j) << 4))) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          chunk_st32(tape_tile + (size_t)(chunk + (col0 >> 6)) * kChunkBytes, row, (uint32_t)(col0 & 63) >> 3, o);
         }
       }
     };

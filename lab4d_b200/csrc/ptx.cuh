@@ -269,6 +269,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---------------------------------------------------------------- tape stores
+// 32 operand columns (16 packed registers = four 16-B groups g0..g0+3, g0 in {0, 4}) of tile row `row` into a
+// [128 x 64] SWIZZLE_128B chunk image in global memory: group g lives in 16-B slot g ^ (row & 7) of the row's 128 B, so
+// groups (g, g+1) share one aligned 32-B sector (swapped when the row is odd) -> two 256-bit stores (STG.256) per call,
+// each a full sector.
+__device__ __forceinline__ void stg256(void* a, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t r5, uint32_t r6,
+                                       uint32_t r7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(a), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4), "r"(r5), "r"(r6), "r"(r7)
+               : "memory");
+}
+__device__ __forceinline__ void chunk_st32(uint8_t* chunk, uint32_t row, uint32_t g0, const uint32_t (&o)[16]) {
+  const uint32_t r = row & 7u;
+  const bool odd = (r & 1u) != 0;
+  uint8_t* rb = chunk + row * 128u;
+#pragma unroll
+  for (int pr = 0; pr < 2; ++pr) {
+    const uint32_t slot = ((g0 + 2u * pr) ^ r) & ~1u;
+    const uint32_t* a = o + 8 * pr;
+    stg256(rb + (slot << 4), odd ? a[4] : a[0], odd ? a[5] : a[1], odd ? a[6] : a[2], odd ? a[7] : a[3], odd ? a[0] : a[4], odd ? a[1] : a[5],
+           odd ? a[2] : a[6], odd ? a[3] : a[7]);
+  }
+}
+
 // ---------------------------------------------------------------- 16-bit operand formats
 struct OpF16 {
   static constexpr uint32_t kFmt = 0;

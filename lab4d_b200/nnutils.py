@@ -9,9 +9,11 @@ B200 renderer unchanged.  Parameters stay nn.Parameters of the reference modules
 param groups and DDP are untouched); per-frame codes / cameras / articulations are still produced by the
 reference's small per-frame MLPs and handed over as tables.
 
-Scope of this round: the forward pass.  query_field raises if autograd is recording and the caller did
-not ask for `forward_only=True` semantics (the field kernel's backward is the next milestone; the
-compositing backward is already native).
+Training (autograd recording): query_field goes through lab4d_b200.autograd.FieldFunction - training forward with the
+tape, hand-derived backward kernels, gradients delivered to the reference modules' own Parameters and, through the
+per-frame tables, to the camera / articulation / embedding modules.  Eval mode: importance sampling + bounding-box
+masking + the reference's normals.  global_match / forward_project (feature.py:152-226) and the eikonal term stay the
+reference's own torch code, evaluated on the kernels' xyz / feature outputs.
 """
 import functools
 
@@ -73,28 +75,79 @@ def tables_from_module(field, samples_dict):
     return tab
 
 
-def query_field(field, samples_dict, flow_thresh=None, n_depth=64):
-    """Replacement body of {NeRF,FeatureNeRF,Deformable}.query_field (training-mode path,
-    nnutils/nerf.py:580-684).  Returns (feat_dict, deltas, aux_dict) like the reference."""
-    if not field.training:
-        raise NotImplementedError("eval-mode query_field (importance sampling, aabb compaction, normals) is not accelerated yet")
-    if torch.is_grad_enabled() and any(p.requires_grad for p in field.parameters()):
-        raise NotImplementedError("lab4d_b200: the field kernel's backward is not implemented in this round; "
-                                  "call under torch.no_grad() for forward rendering")
-    if field.pos_embedding.alpha is not None and field.pos_embedding_color.alpha != field.pos_embedding.alpha:
-        raise NotImplementedError("different annealing windows for density and colour embeddings")
+def _renderer_for(field, device, operand_dtype):
     cfg = config_from_module(field)
     cache = field.__dict__.setdefault("_b200_renderer", {})
-    dev = samples_dict["hxy"].device
-    key = (cfg, str(dev))
+    key = (cfg, str(device), operand_dtype)
     if key not in cache:
-        cache[key] = _render.FieldRenderer(cfg, dev)
-    r = cache[key]
-    P = {k: v for k, v in field.named_parameters()}
-    r.pack(P, alpha=field.pos_embedding.alpha)
+        cache[key] = _render.FieldRenderer(cfg, device, operand_dtype=operand_dtype)
+    return cfg, cache[key]
+
+
+def _hot_params(field, cfg):
+    """name -> nn.Parameter of everything the per-sample kernels read (state_dict names, lab4d_b200/spec.py)."""
+    from .spec import field_param_shapes
+
+    named = dict(field.named_parameters())
+    return {k: named[k] for k in field_param_shapes(cfg)}
+
+
+def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype="fp16x3"):
+    """Replacement body of NeRF.query_field (nnutils/nerf.py:580-684) for NeRF / FeatureNeRF / Deformable modules.
+    Training mode: the fused kernels (with the tape and the hand-derived backward when autograd is recording); the
+    eikonal term stays the reference's own `compute_eikonal` (second-order autograd on 1/16 of the rays).
+    Eval mode (`lab4d/render.py` -> dvr_model.evaluate): importance sampling (nerf.py:686-738), samples outside the
+    bounding boxes zeroed like the reference's masked query_nerf (nerf.py:495-528, 769-819), normals from the
+    reference's `compute_normal`.  Returns (feat_dict, deltas, aux_dict) like the reference."""
+    if field.pos_embedding.alpha is not None and field.pos_embedding_color.alpha != field.pos_embedding.alpha:
+        raise NotImplementedError("different annealing windows for density and colour embeddings")
+    dev = samples_dict["hxy"].device
+    cfg, r = _renderer_for(field, dev, operand_dtype)
+    P = _hot_params(field, cfg)
+    alpha = field.pos_embedding.alpha
     rays = {"hxy": samples_dict["hxy"], "Kinv": samples_dict["Kinv"], "near_far": samples_dict["near_far"]}
-    feat, deltas = r.query_field(P, rays, tables_from_module(field, samples_dict), n_depth, flow_thresh=flow_thresh)
-    return feat, deltas, {}
+    inst_id = samples_dict["inst_id"]
+    if field.training:
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in P.values()) or samples_dict["Kinv"].requires_grad)
+        tab = tables_from_module(field, samples_dict)
+        if needs_grad:
+            if cfg.dense:
+                raise NotImplementedError("lab4d_b200: the backward of ComposedWarp (dense soft deformation) fields is not built yet")
+            from . import autograd as _ag
+
+            r.pack_train({k: v.detach() for k, v in P.items()}, alpha=alpha)
+            feat, deltas = _ag.query_field(r, P, rays, tab, n_depth, flow_thresh=flow_thresh)
+        else:
+            with torch.no_grad():
+                r.pack(P, alpha=alpha)
+                feat, deltas = r.query_field(P, rays, tab, n_depth, flow_thresh=flow_thresh)
+        feat["eikonal"] = field.compute_eikonal(feat["xyz"], inst_id=inst_id)  # reference: nerf.py:416-453
+    else:
+        with torch.no_grad():
+            tab = tables_from_module(field, samples_dict)
+            r.pack(P, alpha=alpha)
+            depth = r.importance_depths(P, rays, tab, n_depth)
+            want = ("rgb", "density", "vis", "xyz", "xyz_cam", "xyz_t", "depth", "deltas") + (("gauss_density",) if cfg.motion != "rigid" else ())
+            feat, deltas = r.query_field(P, rays, tab, n_depth, depth=depth, want=want)
+            xyz_t = r.last_aux["xyz_t"]
+            valid = field.get_valid_idx(feat["xyz"], xyz_t, feat["vis"], samples_dict)
+            if valid is not None:  # the reference evaluates only these samples and leaves zeros elsewhere
+                m = valid[..., None].to(feat["rgb"].dtype)
+                feat["rgb"], feat["density"] = feat["rgb"] * m, feat["density"] * m
+                feat["density_" + cfg.category] = feat["density"]
+        # normals: autograd of the SDF through the backward warp w.r.t. camera-space points (nerf.py:455-493)
+        hxy, Kinv = samples_dict["hxy"], samples_dict["Kinv"]
+        d = hxy @ Kinv.permute(0, 2, 1)
+        dir_cam = torch.nn.functional.normalize(d, 2, -1)[:, :, None].expand_as(feat["xyz_cam"])
+        feat["eikonal"], feat["normal"] = field.compute_normal(feat["xyz_cam"], dir_cam, samples_dict["field2cam"], samples_dict["frame_id"],
+                                                               inst_id, samples_dict)
+    aux = {}
+    if hasattr(field, "global_match") and "feature" in samples_dict and "feature" in feat:  # FeatureNeRF.query_field, feature.py:119-131
+        xyz_matches = field.global_match(samples_dict["feature"], feat["feature"], feat["xyz"])
+        xy_reproj, xyz_reproj = field.forward_project(xyz_matches, samples_dict["field2cam"], samples_dict["Kinv"], samples_dict["frame_id"],
+                                                       inst_id, samples_dict=samples_dict)
+        aux.update(xyz_matches=xyz_matches, xyz_reproj=xyz_reproj, xy_reproj=xy_reproj)
+    return feat, deltas, aux
 
 
 def nerf_forward(field, xyz, dir=None, frame_id=None, inst_id=None, get_density=True):
@@ -137,8 +190,9 @@ def compose_fields(multifields_dict, deltas_dict):
     return _render.compose_fields([multifields_dict[c] for c in cats], [deltas_dict[c] for c in cats])
 
 
-def install(lab4d=None, n_depth=64):
-    """Patch an imported reference package in place; returns a function that undoes the patch."""
+def install(lab4d=None, n_depth=64, operand_dtype="fp16x3"):
+    """Patch an imported reference package in place; returns a function that undoes the patch.
+    operand_dtype: "fp16x3" (parity mode, default), "fp16" or "bf16" (fast modes)."""
     if lab4d is None:
         import lab4d  # noqa: F401
     import lab4d.engine.model as rmodel
@@ -153,8 +207,10 @@ def install(lab4d=None, n_depth=64):
              (rmodel, "render_pixel", rmodel.render_pixel), (rmf.MultiFields, "compose_fields", rmf.MultiFields.__dict__["compose_fields"])]
 
     def _qf(self, samples_dict, flow_thresh=None):
-        return query_field(self, samples_dict, flow_thresh=flow_thresh, n_depth=n_depth)
+        return query_field(self, samples_dict, flow_thresh=flow_thresh, n_depth=n_depth, operand_dtype=operand_dtype)
 
+    # one body for the three classes: the kernels already produce what FeatureNeRF / Deformable add on top of NeRF
+    # (feature field, Gaussian bone density); the per-ray matching of FeatureNeRF runs inside query_field above
     for cls in (rnerf.NeRF, rfeat.FeatureNeRF, rdef.Deformable):
         cls.query_field = _qf
     rru.render_pixel = _render.render_pixel

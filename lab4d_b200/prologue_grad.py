@@ -54,6 +54,17 @@ def _se3(ar, ad, br, bd):
     return torch.cat((_qmul(ar, bir), _qmul(ar, bid) + _qmul(ad, bir)), -1)
 
 
+_SYMM = {}
+
+
+def _symm_index(symm_idx, device):
+    """Device index tensor of the left/right bone pairing, built once (a list index would copy from the host every call)."""
+    key = (tuple(symm_idx), str(device))
+    if key not in _SYMM:
+        _SYMM[key] = torch.tensor(list(symm_idx), dtype=torch.long, device=device)
+    return _SYMM[key]
+
+
 def chain(layout, layer_names, cfg, P, tab, rays, g_const, g_frame, weight_grads):
     """g_const (C,), g_frame (M, F): gradients of the blocks.  weight_grads: name -> (out, in) gradient views (the kernel
     filled the columns fed by per-sample operands; the code columns are added here).  Returns (param_grads, table_grads):
@@ -133,7 +144,7 @@ def chain(layout, layer_names, cfg, P, tab, rays, g_const, g_frame, weight_grads
             tqr, tqd, rqr, rqd = ins
             lgs = lg
             if cfg.symm_idx is not None:
-                lgs = 0.5 * (lg[list(cfg.symm_idx)] + lg)
+                lgs = 0.5 * (lg[_symm_index(cfg.symm_idx, lg.device)] + lg)
             ig = torch.exp(-lgs)
             tables = [(_binv(tqr, tqd, ig), layout.f_binv_t, 12), (_se3(rqr, rqd, tqr, tqd), layout.f_se3_bwd, 8),
                       (_binv(rqr, rqd, ig), layout.f_binv_rest, 12), (_se3(tqr, tqd, rqr, rqd), layout.f_se3_fwd, 8),
