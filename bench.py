@@ -259,7 +259,7 @@ class Step:
         for r, (cfg, P, rays, tab) in zip(self.renderers, fields):
             if self.train:
                 r.pack_train(P)
-                feat, deltas = b2grad.query_field(r, P, rays, tab, self.D)
+                feat, deltas = b2grad.query_field(r, P, rays, tab, self.D, bind_grads=True)
                 self.launches += 2 + 2  # pack, pack^T; prologue + field_fwd(train)
             else:
                 r.pack(P)
@@ -276,8 +276,9 @@ class Step:
                 for v in P.values():
                     v.grad = None
             loss.backward()
-            self.launches += 1 + 5  # composite_bwd; prologue, absmax, scale, field_bwd, wgrad
-            self.flat = parallel.flat_grads([P for _, P, _, _ in fields])
+            self.launches += 1 + 6  # composite_bwd; prologue, absmax, scale, field_bwd, wgrad, chain
+            # the parameters' .grad are views of the renderer's flat gradient buffer: the step's ONE all-reduce runs on it
+            self.flat = self.renderers[-1].grad_buffer()[0]
             parallel.allreduce_mean_(self.flat)
         return rend
 

@@ -240,17 +240,42 @@ typedef struct {
 int b200r_get_block_layout(const b200r_field_desc* desc, b200r_block_layout* out);
 
 typedef struct {
-  float* weights;                           /* flat fp32 buffer, ACCUMULATED into (zero it first) */
-  int64_t weight_off[B200R_MAX_LAYERS];     /* float offset of layer i's (out_i, in_i) weight gradient inside `weights` */
-  float* const_block;                       /* (const_floats)      overwritten */
-  float* frame_block;                       /* (M, frame_floats)   overwritten */
+  float* flat;                              /* flat fp32 gradient buffer of the field's hot-path parameters, ACCUMULATED into
+                                               (zero it for a fresh gradient); all offsets below are float offsets into it, -1 = absent */
+  int64_t weight_off[B200R_MAX_LAYERS];     /* layer i's (out_i, in_i) weight */
+  int64_t bias_off[B200R_MAX_LAYERS];       /* layer i's bias */
+  int64_t sdf_w, sdf_b, rgb2_w, rgb2_b, vis_final_w, vis_final_b, logibeta, logscale, warp_logibeta, log_gauss;
+  float* const_block;                       /* (const_floats)     scratch: gradient of the constant block, overwritten */
+  float* frame_block;                       /* (M, frame_floats)  scratch: gradient of the frame blocks, overwritten */
 } b200r_param_grads;
 
-/* Backward of one b200r_field_fwd_train call (same desc, params, frames, rays; `saved` = its outputs; tape->g is scratch). */
+/* Gradients of the per-frame inputs, shapes of b200r_frame_tables; OVERWRITTEN; any pointer may be NULL. */
+typedef struct {
+  float* Kinv;              /* (M,3,3) */
+  float* field2cam_q;       /* (M,4) */
+  float* field2cam_t;       /* (M,3) */
+  float* inst_base;         /* (M,32) */
+  float* inst_color;
+  float* inst_vis;
+  float* appr_code;         /* (M,appr_channels) */
+  float* inst_skin;
+  float* skin_t_embed;      /* (M,128) */
+  float* skin_t_embed_mean; /* (128) */
+  float* dense_t_embed;     /* (M,128) */
+  float* inst_dense_fwd;
+  float* inst_dense_bwd;
+  float* t_art_qr;          /* (M,B,4) */
+  float* t_art_qd;
+  float* rest_art_qr;
+  float* rest_art_qd;
+} b200r_frame_grads;
+
+/* Backward of one b200r_field_fwd_train call (same desc, params, frames, rays; `saved` = its outputs; tape->g is scratch):
+ * data-gradient kernel, weight-gradient kernel, then the backward of the per-frame prologue. */
 int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* params,
                     const b200r_frame_tables* frames, const b200r_ray_batch* rays, const b200r_field_outputs* saved,
-                    const b200r_field_grads* grads, const b200r_tape* tape, const b200r_param_grads* out, void* workspace,
-                    size_t workspace_bytes, b200r_stream stream);
+                    const b200r_field_grads* grads, const b200r_tape* tape, const b200r_param_grads* out,
+                    const b200r_frame_grads* frame_grads, void* workspace, size_t workspace_bytes, b200r_stream stream);
 
 /* NeRF.forward on given points (lab4d/nnutils/nerf.py:167-215), the boundary the reference's flat-point callers use
  * (geometry_init nerf.py:277, extract_canonical_mesh :328, eval-mode query_nerf :794-805): canonical points in, rgb /

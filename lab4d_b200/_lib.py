@@ -100,8 +100,20 @@ class BlockLayout(C.Structure):
                 + [("cond", CondRow * MAX_COND)])
 
 
+HEAD_GRADS = ["sdf_w", "sdf_b", "rgb2_w", "rgb2_b", "vis_final_w", "vis_final_b", "logibeta", "logscale", "warp_logibeta", "log_gauss"]
+
+
 class ParamGrads(C.Structure):
-    _fields_ = [("weights", f32p), ("weight_off", C.c_int64 * MAX_LAYERS), ("const_block", f32p), ("frame_block", f32p)]
+    _fields_ = ([("flat", f32p), ("weight_off", C.c_int64 * MAX_LAYERS), ("bias_off", C.c_int64 * MAX_LAYERS)]
+                + [(n, C.c_int64) for n in HEAD_GRADS] + [("const_block", f32p), ("frame_block", f32p)])
+
+
+FRAME_GRADS = ["Kinv", "field2cam_q", "field2cam_t", "inst_base", "inst_color", "inst_vis", "appr_code", "inst_skin", "skin_t_embed",
+               "skin_t_embed_mean", "dense_t_embed", "inst_dense_fwd", "inst_dense_bwd", "t_art_qr", "t_art_qd", "rest_art_qr", "rest_art_qd"]
+
+
+class FrameGrads(C.Structure):
+    _fields_ = [(n, f32p) for n in FRAME_GRADS]
 
 
 EXPORTS = ["b200r_tape_sizes", "b200r_field_fwd_train", "b200r_packed_t_bytes", "b200r_pack_weights_t", "b200r_get_block_layout",
@@ -169,7 +181,7 @@ def load():
     lib.b200r_get_block_layout.restype = C.c_int
     lib.b200r_field_bwd.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldParams), C.POINTER(FrameTables),
                                     C.POINTER(RayBatch), C.POINTER(FieldOutputs), C.POINTER(FieldGrads), C.POINTER(Tape),
-                                    C.POINTER(ParamGrads), C.c_void_p, C.c_size_t, C.c_void_p]
+                                    C.POINTER(ParamGrads), C.POINTER(FrameGrads), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.b200r_field_bwd.restype = C.c_int
     _lib = lib
     return lib

@@ -26,8 +26,24 @@ class FieldFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_deltas, *g_outs):
         grads = {k: g for k, g in zip(ctx.keys, g_outs) if g is not None and k in _lib.GRAD_KEYS}
-        pg, tg = ctx.renderer.backward(ctx.c, grads)
         meta = ctx.meta
+        params = meta.get("bind")  # name -> leaf Parameter whose .grad should BE the flat buffer's view (no per-tensor copies)
+        if params is not None:
+            # DDP's gradient_as_bucket_view arrangement: the kernels accumulate straight into the views
+            flat, views = ctx.renderer.grad_buffer()
+            if all(p.grad is None for p in params.values()):
+                flat.zero_()
+            for n, p in params.items():
+                if p.grad is None:
+                    p.grad = views[n]
+                elif p.grad.data_ptr() != views[n].data_ptr():  # another autograd path got there first: fold it in
+                    views[n].copy_(p.grad)
+                    p.grad = views[n]
+            _, tg = ctx.renderer.backward(ctx.c, grads, accumulate=True)
+            pg = {}
+        else:
+            pg, tg = ctx.renderer.backward(ctx.c, grads)
+            pg = {k: v.clone() for k, v in pg.items()}  # the flat buffer is reused by the next backward
         out = [None, None]
         for n in meta["p_names"]:
             out.append(pg.get(n))
@@ -38,12 +54,16 @@ class FieldFunction(torch.autograd.Function):
         return tuple(out)
 
 
-def query_field(renderer, P, rays, tab, D, flow_thresh=None, depth=None):
+def query_field(renderer, P, rays, tab, D, flow_thresh=None, depth=None, bind_grads=False):
     """Differentiable training-mode query_field: (feat_dict, deltas) like FieldRenderer.query_field, with autograd edges
-    to P's tensors, tab's tensors and rays['Kinv'].  Call renderer.pack_train(P, alpha) first (every optimiser step)."""
+    to P's tensors, tab's tensors and rays['Kinv'].  Call renderer.pack_train(P, alpha) first (every optimiser step).
+    bind_grads: P's tensors are leaf parameters; their .grad become views of the renderer's flat gradient buffer and the
+    backward kernels accumulate into it directly (no per-parameter gradient tensors, one buffer to all-reduce)."""
     p_names = [k for k in P]
     t_names = [k for k, v in tab.items() if torch.is_tensor(v)]
     meta = dict(p_names=p_names, t_names=t_names, rays={k: v for k, v in rays.items() if k != "Kinv"}, D=int(D), flow_thresh=flow_thresh, depth=depth)
+    if bind_grads:
+        meta["bind"] = {k: v for k, v in P.items() if v.requires_grad and v.is_leaf}
     res = FieldFunction.apply(renderer, meta, *[P[k] for k in p_names], *[tab[k] for k in t_names], rays["Kinv"])
     deltas, outs = res[0], res[1:]
     feat = dict(zip(meta["out_keys"], outs))

@@ -206,8 +206,8 @@ int b200r_get_block_layout(const b200r_field_desc* desc, b200r_block_layout* out
 
 int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* par,
                     const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_field_outputs* saved,
-                    const b200r_field_grads* grads, const b200r_tape* tape, const b200r_param_grads* out, void* workspace,
-                    size_t workspace_bytes, b200r_stream stream_) {
+                    const b200r_field_grads* grads, const b200r_tape* tape, const b200r_param_grads* out,
+                    const b200r_frame_grads* fgr, void* workspace, size_t workspace_bytes, b200r_stream stream_) {
   if (!h) return B200R_E_INVALID;
   auto bad = [&](const char* msg) { return fail(h, B200R_E_INVALID, std::string("field_bwd: ") + msg); };
   if (!desc || !packed_t || !par || !fr || !rays || !saved || !grads || !tape || !out || !workspace) return bad("null argument");
@@ -221,7 +221,7 @@ int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
   if (M >= 2 && (M & 1)) return bad("frames must come in adjacent pairs (M even)");
   if (!rays->hxy || !fr->Kinv || !fr->near_far || !fr->field2cam_q || !fr->field2cam_t) return bad("missing ray/camera input");
   if (!saved->xyz || !saved->rgb || !saved->sdf || (desc->has_feature && (!saved->feature || !saved->feat_norm))) return bad("missing saved forward outputs");
-  if (!out->weights || !out->const_block || !out->frame_block) return bad("missing gradient outputs");
+  if (!out->flat || !out->const_block || !out->frame_block) return bad("missing gradient outputs");
   const b200r::TapeLayout T = b200r::tape_layout(*desc);
   const int ND = N * D, tpf = (ND + b200r::kTileRows - 1) / b200r::kTileRows, n_tiles = M * tpf;
   size_t na, ng, nm;
@@ -304,13 +304,35 @@ int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
   wp.jobs = (const b200r::WgradJob*)d_jobs;
   wp.work = (const b200r::WgradWork*)d_work;
   wp.cta_first = (const int32_t*)d_first;
-  wp.grad = out->weights;
+  wp.grad = out->flat;
   wp.g_cblk = out->const_block;
   wp.g_fblk = out->frame_block;
   wp.frame_floats = bp.prog.fl.n_floats;
   wp.tiles_per_frame = tpf;
   wp.inv_scale = h->d_scale + 1;
   if ((e = b200r::launch_wgrad(wp, grid, dsc.operand_dtype, stream)) != cudaSuccess) return fail_cuda(h, e, "wgrad kernel");
+
+  // backward of the per-frame prologue: blocks -> parameters (flat buffer) and per-frame inputs
+  b200r::ChainParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.cl = bp.prog.cl; cp.fl = bp.prog.fl; cp.desc = *desc; cp.par = *par; cp.fr = *fr;
+  if (fgr) cp.gf = *fgr;
+  cp.off = *out;
+  cp.g_cblk = out->const_block; cp.g_fblk = out->frame_block; cp.grad = out->flat;
+  cp.n_layers = nl;
+  for (int i = 0; i < nl; ++i) cp.layer_out[i] = (int16_t)bp.layer_out[i];
+  if (fgr) {  // code gradients are accumulated with atomics (mean / partner codes, shared rows)
+    const size_t B4 = (size_t)desc->n_bones * 4;
+    struct { float* ptr; size_t n; } z[] = {
+        {fgr->inst_base, (size_t)M * 32}, {fgr->inst_color, (size_t)M * 32}, {fgr->inst_vis, (size_t)M * 32},
+        {fgr->appr_code, (size_t)M * desc->appr_channels}, {fgr->inst_skin, (size_t)M * 32}, {fgr->skin_t_embed, (size_t)M * 128},
+        {fgr->skin_t_embed_mean, 128}, {fgr->dense_t_embed, (size_t)M * 128}, {fgr->inst_dense_fwd, (size_t)M * 32},
+        {fgr->inst_dense_bwd, (size_t)M * 32}, {fgr->t_art_qr, M * B4}, {fgr->t_art_qd, M * B4}, {fgr->rest_art_qr, M * B4},
+        {fgr->rest_art_qd, M * B4}, {fgr->Kinv, (size_t)M * 9}, {fgr->field2cam_q, (size_t)M * 4}, {fgr->field2cam_t, (size_t)M * 3}};
+    for (auto& it : z)
+      if (it.ptr && it.n && (e = cudaMemsetAsync(it.ptr, 0, it.n * 4, stream)) != cudaSuccess) return fail_cuda(h, e, "memset");
+  }
+  if ((e = b200r::launch_chain(cp, stream)) != cudaSuccess) return fail_cuda(h, e, "chain kernel");
   return B200R_OK;
 }
 

@@ -768,8 +768,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
           seq_dgrad(64, TL.m_h1[w], TL.g_z1[w]);
           gemm();
           // accumulator: dL/d bone coordinates through the MLP; add the dist2 path, fold back onto the point
-#pragma unroll 1
-          for (int blk = 0; blk < 3; ++blk) {
+#pragma unroll
+          for (int blk = 0; blk < 3; ++blk) {  // unrolled: the bone of every column is then a compile-time index
             float v[32];
             uint32_t o[16];
             tmem_ld32(tD + 32 * blk, v);
@@ -780,10 +780,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
               if (c < 3 * B) {
                 const float4 rr = lds128(binv + 16u * c);
                 const float xb = rr.x * x.x + rr.y * x.y + rr.z * x.z + rr.w;
-                float gdb = 0.f;
-#pragma unroll
-                for (int b = 0; b < B; ++b) gdb = (c / 3 == b) ? gd2[b] : gdb;
-                gv = v[j] + 2.f * xb * gdb;
+                gv = v[j] + 2.f * xb * gd2[c / 3 < B ? c / 3 : 0];
                 g_x.x += rr.x * gv; g_x.y += rr.y * gv; g_x.z += rr.z * gv;
               }
               v[j] = gv;

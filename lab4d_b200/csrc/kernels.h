@@ -73,6 +73,23 @@ struct BwdKernelParams {
 };
 cudaError_t launch_field_bwd(const BwdKernelParams& p, int n_sm, cudaStream_t stream);
 
+// ---- backward of the per-frame prologue (csrc/chain.cu)
+struct ChainParams {
+  ConstLayout cl;
+  FrameLayout fl;
+  b200r_field_desc desc;
+  b200r_field_params par;
+  b200r_frame_tables fr;
+  b200r_frame_grads gf;
+  b200r_param_grads off;   // offsets (the pointers in it are not used by the kernel)
+  const float* g_cblk;
+  const float* g_fblk;
+  float* grad;             // flat gradient buffer
+  int32_t n_layers;
+  int16_t layer_out[B200R_MAX_LAYERS];
+};
+cudaError_t launch_chain(const ChainParams& p, cudaStream_t stream);
+
 // ---- weight-gradient kernel (csrc/wgrad.cu): D[row0 + r][col0 + c] of a job's accumulator is added to dst[r * ld + c]
 struct WgradView { int32_t row0, col0, rows, cols, ld, per_frame /* destination: 0 weights, 1 frame block, 2 constant block */; int64_t dst_off; };
 struct WgradJob {

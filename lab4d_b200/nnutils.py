@@ -92,7 +92,7 @@ def _hot_params(field, cfg):
     return {k: named[k] for k in field_param_shapes(cfg)}
 
 
-def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype="fp16x3"):
+def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False):
     """Replacement body of NeRF.query_field (nnutils/nerf.py:580-684) for NeRF / FeatureNeRF / Deformable modules.
     Training mode: the fused kernels (with the tape and the hand-derived backward when autograd is recording); the
     eikonal term stays the reference's own `compute_eikonal` (second-order autograd on 1/16 of the rays).
@@ -116,7 +116,7 @@ def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype
             from . import autograd as _ag
 
             r.pack_train({k: v.detach() for k, v in P.items()}, alpha=alpha)
-            feat, deltas = _ag.query_field(r, P, rays, tab, n_depth, flow_thresh=flow_thresh)
+            feat, deltas = _ag.query_field(r, P, rays, tab, n_depth, flow_thresh=flow_thresh, bind_grads=bind_grads)
         else:
             with torch.no_grad():
                 r.pack(P, alpha=alpha)
@@ -190,9 +190,12 @@ def compose_fields(multifields_dict, deltas_dict):
     return _render.compose_fields([multifields_dict[c] for c in cats], [deltas_dict[c] for c in cats])
 
 
-def install(lab4d=None, n_depth=64, operand_dtype="fp16x3"):
+def install(lab4d=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False):
     """Patch an imported reference package in place; returns a function that undoes the patch.
-    operand_dtype: "fp16x3" (parity mode, default), "fp16" or "bf16" (fast modes)."""
+    operand_dtype: "fp16x3" (parity mode, default), "fp16" or "bf16" (fast modes).
+    bind_grads: make the hot-path parameters' .grad views of the renderer's flat gradient buffer (no per-tensor gradient
+    copies; all-reduce the buffer yourself) - leave False under DistributedDataParallel, whose reducer waits for autograd's
+    per-parameter hooks (engine/trainer.py:110-115)."""
     if lab4d is None:
         import lab4d  # noqa: F401
     import lab4d.engine.model as rmodel
@@ -207,7 +210,7 @@ def install(lab4d=None, n_depth=64, operand_dtype="fp16x3"):
              (rmodel, "render_pixel", rmodel.render_pixel), (rmf.MultiFields, "compose_fields", rmf.MultiFields.__dict__["compose_fields"])]
 
     def _qf(self, samples_dict, flow_thresh=None):
-        return query_field(self, samples_dict, flow_thresh=flow_thresh, n_depth=n_depth, operand_dtype=operand_dtype)
+        return query_field(self, samples_dict, flow_thresh=flow_thresh, n_depth=n_depth, operand_dtype=operand_dtype, bind_grads=bind_grads)
 
     # one body for the three classes: the kernels already produce what FeatureNeRF / Deformable add on top of NeRF
     # (feature field, Gaussian bone density); the per-ray matching of FeatureNeRF runs inside query_field above

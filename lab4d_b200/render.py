@@ -244,8 +244,15 @@ class FieldRenderer:
 
 
     # ------------------------------------------------------------------ training: forward with a tape, backward
+    # state_dict name of the parameter behind every head offset of b200r_param_grads
+    _HEAD_NAMES = {"sdf_w": "sdf.weight", "sdf_b": "sdf.bias", "rgb2_w": "rgb.2.weight", "rgb2_b": "rgb.2.bias",
+                   "vis_final_w": "vis_mlp.basefield.linear_final.weight", "vis_final_b": "vis_mlp.basefield.linear_final.bias",
+                   "logibeta": "logibeta", "logscale": "logscale", "warp_logibeta": "warp.logibeta",
+                   "log_gauss": "warp.skinning_model.log_gauss"}
+
     def _train_state(self):
-        """Flat weight-gradient buffer layout, block layouts and the transposed operand buffer (built once)."""
+        """Layout of the flat gradient buffer (every hot-path parameter, in the order of spec.field_param_shapes; 16-B
+        aligned slots), block layouts and the transposed operand buffer (built once)."""
         st = getattr(self, "_train", None)
         if st is not None:
             return st
@@ -253,16 +260,28 @@ class FieldRenderer:
         layout = _lib.BlockLayout()
         h.check(lib.b200r_get_block_layout(C.byref(self.desc), C.byref(layout)), "b200r_get_block_layout")
         shapes = field_param_shapes(self.cfg)
-        offs, total = [], 0
-        for name, _ in self._layers:
-            offs.append(total)
-            n_out, n_in = shapes[name + ".weight"]
-            total += (n_out * n_in + 3) // 4 * 4
+        slots, total = {}, 0
+        for name, shp in shapes.items():
+            n = 1
+            for d in shp:
+                n *= d
+            slots[name] = (total, n, tuple(shp))
+            total += (n + 3) // 4 * 4
         nbytes = lib.b200r_packed_t_bytes(C.byref(self.desc))
-        st = dict(layout=layout, offs=offs, total=total, shapes=shapes,
+        st = dict(layout=layout, slots=slots, total=total, shapes=shapes,
                   packed_t=torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device))
         self._train = st
         return st
+
+    def grad_buffer(self):
+        """The renderer's persistent flat gradient buffer and name -> view (param-shaped) into it.  The backward ACCUMULATES
+        into it (DDP's gradient_as_bucket_view arrangement: parameters' .grad can be these views, the step's one all-reduce
+        runs on the flat buffer)."""
+        st = self._train_state()
+        if "flat" not in st:
+            st["flat"] = torch.zeros(st["total"], device=self.device)
+            st["views"] = {k: st["flat"][o:o + n].view(shp) for k, (o, n, shp) in st["slots"].items()}
+        return st["flat"], st["views"]
 
     def pack_train(self, P, alpha=None):
         """pack() plus the transposed (W^T) operand tiles the backward's data-gradient GEMMs read."""
@@ -352,12 +371,15 @@ class FieldRenderer:
         return feat, deltas, ctx
 
     @torch.no_grad()
-    def backward(self, ctx, grads):
+    def backward(self, ctx, grads, accumulate=False):
         """grads: key -> cotangent of the per-sample output (M,N,D,c) (keys of _lib.GRAD_KEYS; missing = zero; `density_fg` /
-        `density_bg` are added to `density`).  Returns (param_grads, table_grads): name -> tensor."""
-        from . import prologue_grad
-
+        `density_bg` are added to `density`).  One C-ABI call: data-gradient kernel, weight-gradient kernel, backward of the
+        per-frame prologue.  Parameter gradients land in the flat buffer (`grad_buffer()`; zeroed first unless
+        `accumulate`).  Returns (param_grads, table_grads): name -> view / tensor."""
         st = self._train_state()
+        flat, views = self.grad_buffer()
+        if not accumulate:
+            flat.zero_()
         M = ctx["M"]
         keep = []
         fg = _lib.FieldGrads()
@@ -374,39 +396,51 @@ class FieldRenderer:
         for k in ("xyz", "rgb", "sdf", "feature", "feat_norm"):
             if k in out:
                 setattr(saved, k, out[k].data_ptr())
-        layout = st["layout"]
-        flat = torch.zeros(st["total"], device=self.device)
+        layout, slots = st["layout"], st["slots"]
         g_const = torch.empty(layout.const_floats, device=self.device)
         g_frame = torch.empty(M, layout.frame_floats, device=self.device)
         pgs = _lib.ParamGrads()
-        pgs.weights, pgs.const_block, pgs.frame_block = flat.data_ptr(), g_const.data_ptr(), g_frame.data_ptr()
-        for i, o in enumerate(st["offs"]):
-            pgs.weight_off[i] = o
+        pgs.flat, pgs.const_block, pgs.frame_block = flat.data_ptr(), g_const.data_ptr(), g_frame.data_ptr()
+        for i in range(_lib.MAX_LAYERS):
+            pgs.weight_off[i], pgs.bias_off[i] = -1, -1
+        for i, (name, _) in enumerate(self._layers):
+            pgs.weight_off[i], pgs.bias_off[i] = slots[name + ".weight"][0], slots[name + ".bias"][0]
+        for fld, name in self._HEAD_NAMES.items():
+            setattr(pgs, fld, slots[name][0] if name in slots else -1)
+        # gradients of the per-frame inputs: one tensor per table the call received
+        tg, fgr, tab, rays = {}, _lib.FrameGrads(), ctx["tab"], ctx["rays"]
+        tg["Kinv"] = torch.empty(M, 3, 3, device=self.device)
+        fgr.Kinv = tg["Kinv"].data_ptr()
+        for field, key in self._TAB_KEYS.items():
+            if tab.get(key) is not None and field in _lib.FRAME_GRADS:
+                tg[key] = torch.empty(tab[key].shape, device=self.device)
+                setattr(fgr, field, tg[key].data_ptr())
+        alpha = getattr(self, "_alpha", None)
+        wnames = self._window_names() if alpha is not None else []
+        before = {nl: views[nl[0]].clone() for nl in wnames}
         rc = self.handle.lib.b200r_field_bwd(self.handle.h, C.byref(self.desc), _ptr(st["packed_t"]), C.byref(ctx["par"]), C.byref(ctx["fr"]),
-                                             C.byref(ctx["rb"]), C.byref(saved), C.byref(fg), C.byref(ctx["tape"]), C.byref(pgs),
+                                             C.byref(ctx["rb"]), C.byref(saved), C.byref(fg), C.byref(ctx["tape"]), C.byref(pgs), C.byref(fgr),
                                              _ptr(self._ws), self._ws.numel(), _stream(self.device))
         self.handle.check(rc, "b200r_field_bwd")
-        names = [n for n, _ in self._layers]
-        wg = {}
-        for (name, _), o in zip(self._layers, st["offs"]):
-            shp = st["shapes"][name + ".weight"]
-            wg[name + ".weight"] = flat[o:o + shp[0] * shp[1]].view(shp)
-        alpha = getattr(self, "_alpha", None)
-        if alpha is not None:  # the annealing window is folded into the packed weights: dW = dW_eff * window
-            self._apply_window(wg, alpha)
-        pg, tg = prologue_grad.chain(layout, names, self.cfg, ctx["P"], ctx["tab"], ctx["rays"], g_const, g_frame, wg)
-        self.last_flat_grad = flat
+        if alpha is not None:  # the annealing window is folded into the packed weights: this call's dW = dW_eff * window
+            self._apply_window(views, before, alpha)
+        self.last_blocks = (g_const, g_frame)
         self._keep_bwd = keep
-        return pg, tg
+        return views, tg
 
-    def _apply_window(self, wg, alpha):
+    def _window_names(self):
+        c = self.cfg
+        return [("basefield.linear_1.0.weight", c.L_xyz), (f"basefield.linear_{c.skip + 1}.0.weight", c.L_xyz), ("colorfield.linear_1.0.weight", c.L_xyz + 2)]
+
+    def _apply_window(self, views, before, alpha):
         import math
 
-        c = self.cfg
-        for name, L in (("basefield.linear_1.0", c.L_xyz), (f"basefield.linear_{c.skip + 1}.0", c.L_xyz), ("colorfield.linear_1.0", c.L_xyz + 2)):
+        for name, L in self._window_names():
             k = torch.arange(L, device=self.device, dtype=torch.float32)
             wdw = 0.5 * (1 + torch.cos(math.pi * torch.clamp(alpha * L - k, 0.0, 1.0) + math.pi))
-            wg[name + ".weight"][:, 3:3 + 6 * L] *= wdw.repeat_interleave(6)[None]
+            cols = slice(3, 3 + 6 * L)
+            delta = views[(name, L)[0]][:, cols] - before[(name, L)][:, cols]
+            views[name][:, cols] = before[(name, L)][:, cols] + delta * wdw.repeat_interleave(6)[None]
 
     # ------------------------------------------------------------------ eval-mode importance sampling
     @torch.no_grad()
