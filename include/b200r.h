@@ -151,6 +151,8 @@ typedef struct {
   float* gauss_density; /* 1 */
   float* sdf;           /* 1 */
   float* feat_norm;     /* 1: 1 / |feature| before normalisation (kept by the training forward for the backward) */
+  float* warp_pts;      /* 9: ComposedWarp fields, training forward: the skinned point before the soft deformation and the two
+                           softly deformed points that enter the forward skinning warps (flow partner, cycle) */
 } b200r_field_outputs;
 
 /* Cotangents of the per-sample outputs of one query_field call, (M*N*D, c) row-major fp32 like b200r_field_outputs;

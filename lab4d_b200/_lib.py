@@ -21,7 +21,7 @@ class FieldDesc(C.Structure):
 
 FIELD_OUTPUTS = [("rgb", 3), ("density", 1), ("vis", 1), ("xyz", 3), ("xyz_cam", 3), ("xyz_t", 3), ("dir", 3), ("depth", 1),
                  ("deltas", 1), ("feature", 16), ("flow", 3), ("cyc_dist", 1), ("delta_skin", 1), ("skin_entropy", 1),
-                 ("gauss_density", 1), ("sdf", 1), ("feat_norm", 1)]
+                 ("gauss_density", 1), ("sdf", 1), ("feat_norm", 1), ("warp_pts", 9)]
 
 
 class FieldParams(C.Structure):

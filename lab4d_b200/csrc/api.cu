@@ -214,7 +214,8 @@ static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* 
     size_t need_a = b200r::tape_a_bytes(kp.tape, kp.n_tiles), need_m = b200r::tape_mask_bytes(kp.tape, kp.n_tiles);
     if (!tape->a || !tape->mask || tape->a_bytes < need_a || tape->mask_bytes < need_m) return bad("tape buffers missing or too small (b200r_tape_sizes)");
     if ((reinterpret_cast<uintptr_t>(tape->a) & 1023) || (reinterpret_cast<uintptr_t>(tape->mask) & 15)) return bad("tape buffers must be 1024-B / 16-B aligned");
-    if (!out->xyz || !out->rgb || !out->sdf || (desc->has_feature && (!out->feature || !out->feat_norm))) return bad("the training forward must keep xyz, rgb, sdf (and feature, feat_norm)");
+    if (!out->xyz || !out->rgb || !out->sdf || (desc->has_feature && (!out->feature || !out->feat_norm)) || (desc->dense && !out->warp_pts))
+      return bad("the training forward must keep xyz, rgb, sdf (and feature, feat_norm; warp_pts for ComposedWarp fields)");
     kp.tape_a = (uint8_t*)tape->a;
     kp.tape_mask = (uint32_t*)tape->mask;
     e = b200r::launch_field_fwd_train(kp, h->n_sm, stream);
@@ -230,7 +231,6 @@ int b200r_field_fwd_train(b200r_handle* h, const b200r_field_desc* desc, const v
                           const b200r_tape* tape, void* workspace, size_t workspace_bytes, b200r_stream stream_) {
   if (!h) return B200R_E_INVALID;
   if (!rays || !tape) return fail(h, B200R_E_INVALID, "field_fwd_train: null argument");
-  if (desc && desc->dense) return fail(h, B200R_E_INVALID, "field_fwd_train: the dense-warp backward is not built yet");
   return run_field(h, desc, packed, par, fr, rays, nullptr, b200r::MODE_FIELD, out, workspace, workspace_bytes, stream_, tape);
 }
 

@@ -95,6 +95,13 @@ static std::vector<WgradJob> build_jobs(const b200r_field_desc& d, const BuiltPr
     WgradJob& j = job(T.g_xbw[w], 2, T.g_xg[w], 1, 1, view(0, 0, 3 * B, 4, 4, DST_FRAME, binv));
     j.n_views = 2;
     j.v[1] = view(96, 4, B, 8, 8, DST_FRAME, se3);
+    if (d.dense) {  // soft deformation of this stage: backward_map for w = 0, forward_map (partner / own time code) for w = 1, 2
+      const int m = w == 0 ? 1 : 0;
+      const int row1 = w == 1 ? P.fl.dense1_partner : -1;  // bias row with the partner frame's time code
+      layer_job(L.dense[3 * m + 0], T.g_d1[w], T.a_dpe[w], 1, 0, pe_dim(6), row1);
+      layer_job(L.dense[3 * m + 1], T.g_d2[w], T.a_dh1[w], 4, 0, 256);
+      layer_job(L.dense[3 * m + 2], T.g_d3[w], T.a_dh2[w], 4, 0, 256);
+    }
   }
   layer_job(L.vis[0], T.g_vis[0], T.a_pe, 1, 0, pe_v);
   layer_job(L.vis[1], T.g_vis[1], T.a_vis[0], 1, 0, 64);
@@ -211,7 +218,6 @@ int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
   if (!h) return B200R_E_INVALID;
   auto bad = [&](const char* msg) { return fail(h, B200R_E_INVALID, std::string("field_bwd: ") + msg); };
   if (!desc || !packed_t || !par || !fr || !rays || !saved || !grads || !tape || !out || !workspace) return bad("null argument");
-  if (desc->dense) return bad("the dense-warp backward is not built yet");
   b200r_field_desc dsc = *desc;
   if (dsc.operand_dtype == 2) dsc.operand_dtype = 0;  // gradients run on single fp16 operands (scaled), whatever the forward used
   b200r::BuiltProgram bp = b200r::build_bwd_program(dsc);
@@ -281,6 +287,11 @@ int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
   kp.g_cblk = out->const_block;
   kp.g_fblk = out->frame_block;
   kp.scale = h->d_scale;
+  if (desc->dense) {
+    if (!saved->warp_pts) return bad("missing saved forward outputs (warp_pts)");
+    kp.dense_w3[0] = par->weight[ids.dense[2]];
+    kp.dense_w3[1] = par->weight[ids.dense[5]];
+  }
   kp.M = M; kp.ND = ND; kp.tiles_per_frame = tpf; kp.n_tiles = n_tiles;
   if ((e = b200r::launch_field_bwd(kp, h->n_sm, stream)) != cudaSuccess) return fail_cuda(h, e, "field_bwd kernel");
 

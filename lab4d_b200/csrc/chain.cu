@@ -5,7 +5,7 @@
 //   * the per-frame inputs of query_field: codes, cameras, articulations (b200r_frame_grads).
 // M x B rows of quaternion calculus and a few (M x 32) mat-vecs, hand-derived from the table formulas of prologue.cu
 // (utils/transforms.py:9-25, nnutils/warping.py:304-314, nnutils/base.py:140-146); <0.1 % of the step, one launch.
-// tests/test_gpu_chain.py checks it against autograd of a torch restatement (oracle/chain_torch.py).
+// tests/test_gpu_backward.py checks it against autograd of a torch restatement of the tables (oracle/chain_torch.py).
 #include <cuda_runtime.h>
 #include <math.h>
 

@@ -73,7 +73,7 @@ __device__ __forceinline__ float lds32(uint32_t a) {
   return v;
 }
 
-template <class Op, int B, int WIDTH>
+template <class Op, int B, int WIDTH, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -581,6 +581,39 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
       }
 
       float3 g_xyz_t = make_float3(0.f, 0.f, 0.f);
+      // DenseWarp.forward backward (nnutils/warping.py:143-170): x' = x + 0.1 CondMLP([PE6(x), t, inst]); map m = 0 forward_map,
+      // 1 backward_map; w = tape slot of the stage.  Returns dL/dx for the cotangent g_out of x'.
+      auto dense_backward = [&](int m, int w, const float3& x_in, const float3& g_out) -> float3 {
+        const float gm0 = 0.1f * g_out.x, gm1 = 0.1f * g_out.y, gm2 = 0.1f * g_out.z;
+        gtape_zero_row(TL.g_d3[w]);
+        *reinterpret_cast<uint2*>(gt_tile + (size_t)TL.g_d3[w] * kChunkBytes + rowx) = make_uint2(Op::pack2_sat(gm0, gm1), Op::pack2_sat(gm2, 0.f));
+        const float* w3 = p.dense_w3[m];  // (3, 256) head weight, read through L1 (every row reads the same addresses)
+        const uint4 ma = __ldg(reinterpret_cast<const uint4*>(mask_row + TL.m_dh2[w] * kMaskWords));
+        const uint4 mb = __ldg(reinterpret_cast<const uint4*>(mask_row + TL.m_dh2[w] * kMaskWords) + 1);
+        const uint32_t mws[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+#pragma unroll 1
+        for (int blk = 0; blk < 8; ++blk) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(w3 + 32 * blk + j)), b = __ldg(reinterpret_cast<const float4*>(w3 + 256 + 32 * blk + j)),
+                         c = __ldg(reinterpret_cast<const float4*>(w3 + 512 + 32 * blk + j));
+            v[j] = gm0 * a.x + gm1 * b.x + gm2 * c.x; v[j + 1] = gm0 * a.y + gm1 * b.y + gm2 * c.y;
+            v[j + 2] = gm0 * a.z + gm1 * b.z + gm2 * c.z; v[j + 3] = gm0 * a.w + gm1 * b.w + gm2 * c.w;
+          }
+          uint32_t o[16];
+          mask_pack32(v, mws[blk], o);
+          tmem_st16(tA + 16 * blk, o);
+          gtape_st32(TL.g_d2[w], 32 * blk, o);
+        }
+        tmem_st_wait();
+        arrive_all();
+        wide_dgrad(std::integral_constant<int, 0>{}, TL.m_dh1[w], TL.g_d1[w]);  // linear_2
+        wait_all();                                                                // linear_1 -> embedding columns
+        float3 g_in = g_out;
+        pe_backward(x_in, 6, g_in);
+        return g_in;
+      };
       // partner camera: flow = project(K', R(qn) x_next + tn) - hxy  (nnutils/nerf.py:948-997)
       auto flow_backward = [&](const float3& x_next) -> float3 {
         const float* cn = fblk_g + FL.cam_partner;
@@ -630,9 +663,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
         }
         // ================================================================ skinning warps, last first
         const float g_ent = 0.5f * ld1(p.g.skin_entropy), g_dsk = 0.5f * ld1(p.g.delta_skin), g_cyc = ld1(p.g.cyc_dist);
+        float3 x_soft[3] = {xyz, xyz, xyz};  // ComposedWarp: [skinned point before the soft deformation, flow input, cycle input]
+        if constexpr (DENSE) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) x_soft[i] = make_float3(__ldg(p.saved.warp_pts + s * 9 + 3 * i), __ldg(p.saved.warp_pts + s * 9 + 3 * i + 1), __ldg(p.saved.warp_pts + s * 9 + 3 * i + 2));
+        }
 #pragma unroll 1
         for (int w = 2; w >= 0; --w) {
-          const float3 x = w == 0 ? xyz_t : xyz;
+          const float3 x = w == 0 ? xyz_t : (DENSE ? x_soft[w] : xyz);
           const uint32_t binv = fblk_s + 4u * (w == 0 ? FL.binv_t : (w == 1 ? FL.binv_rest_partner : FL.binv_rest));
           const uint32_t se3 = fblk_s + 4u * (w == 0 ? FL.se3_bwd : (w == 1 ? FL.se3_fwd_partner : FL.se3_fwd));
           // ---- recompute the blend (SkinningWarp.forward) from the taped delta-MLP outputs
@@ -700,6 +738,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
             ge = 0.f; gk = 0.f;
           } else {
             g_xo = g_xyz;
+            if constexpr (DENSE) g_xo = dense_backward(1, 0, x_soft[0], g_xyz);  // canonical = soft deformation of the skinned point
           }
           // ---- blend backward (oracle/skin_backward.py)
           const Q4 G = {0.f, g_xo.x, g_xo.y, g_xo.z}, Pq = {0.f, x.x, x.y, x.z};
@@ -789,8 +828,12 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
             for (int i = 0; i < 16; ++i) o[i] = Op::pack2_sat(v[2 * i], v[2 * i + 1]);
             gtape_st32(TL.g_xbw[w], 32 * blk, o);
           }
-          if (w == 0) { g_xyz_t.x += g_x.x; g_xyz_t.y += g_x.y; g_xyz_t.z += g_x.z; }
-          else { g_xyz.x += g_x.x; g_xyz.y += g_x.y; g_xyz.z += g_x.z; }
+          if (w == 0) {
+            g_xyz_t.x += g_x.x; g_xyz_t.y += g_x.y; g_xyz_t.z += g_x.z;
+          } else {
+            if constexpr (DENSE) g_x = dense_backward(0, w, xyz, g_x);  // forward warps deform the canonical point first
+            g_xyz.x += g_x.x; g_xyz.y += g_x.y; g_xyz.z += g_x.z;
+          }
         }
       } else {
         // rigid field: canonical point = time-t point; the flow sees it through the partner camera only
@@ -848,9 +891,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
   }
 }
 
-template <class Op, int B, int WIDTH>
+template <class Op, int B, int WIDTH, bool DENSE>
 static cudaError_t launch_one(const BwdKernelParams& p, int n_sm, cudaStream_t stream) {
-  auto kern = field_bwd_kernel<Op, B, WIDTH>;
+  auto kern = field_bwd_kernel<Op, B, WIDTH, DENSE>;
   const int smem = 1024 + kSmemRing + (p.prog.cl.n_floats + kGroups * p.prog.fl.n_floats) * 4 + 256;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -880,13 +923,15 @@ static cudaError_t launch_one(const BwdKernelParams& p, int n_sm, cudaStream_t s
 
 cudaError_t launch_field_bwd(const BwdKernelParams& p, int n_sm, cudaStream_t stream) {
   const bool bf = p.desc.operand_dtype == 1;
-#define B200R_CASE(BN, WD)                                \
-  if (p.desc.n_bones == BN && p.desc.W == WD)             \
-    return bf ? bwd::launch_one<OpBF16, BN, WD>(p, n_sm, stream) : bwd::launch_one<OpF16, BN, WD>(p, n_sm, stream);
-  B200R_CASE(0, 128)
-  B200R_CASE(0, 256)
-  B200R_CASE(18, 256)
-  B200R_CASE(25, 256)
+#define B200R_CASE(BN, WD, DN)                                                 \
+  if (p.desc.n_bones == BN && p.desc.W == WD && (p.desc.dense != 0) == DN)     \
+    return bf ? bwd::launch_one<OpBF16, BN, WD, DN>(p, n_sm, stream) : bwd::launch_one<OpF16, BN, WD, DN>(p, n_sm, stream);
+  B200R_CASE(0, 128, false)
+  B200R_CASE(0, 256, false)
+  B200R_CASE(18, 256, false)
+  B200R_CASE(25, 256, false)
+  B200R_CASE(18, 256, true)
+  B200R_CASE(25, 256, true)
 #undef B200R_CASE
   return cudaErrorInvalidValue;
 }

@@ -823,6 +823,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           const uint32_t bias1 = w == 0 ? bias_s(lid_delta) : fblk_s + 4u * FL.delta1_fwd;  // forward warps: mean time code
           float e, dk;
           const float3 o = skin_warp(src, binv, se3, bias1, e, dk, w);
+          if (SAVE && DENSE && live && p.out.warp_pts) {  // inputs of the dense maps / forward skinning warps (the backward recomputes from them)
+            float* wp = p.out.warp_pts + s * 9 + 3 * w;  // w = 0: skinned point before the soft deformation; 1, 2: deformed points
+            const float3 sv = w == 0 ? o : src;
+            wp[0] = sv.x; wp[1] = sv.y; wp[2] = sv.z;
+          }
           if (w == 0) { cur = o; xyz = o; ent_b = e; dsk_b = dk; }
           else if (w == 1) { x_next = o; }
           else {

@@ -69,6 +69,7 @@ struct BwdKernelParams {
   float* g_cblk;               // gradient of the constant block (zeroed by the caller)
   float* g_fblk;               // gradient of the frame blocks (zeroed by the caller)
   const float* scale;          // device scalar: power-of-two gradient scale
+  const float* dense_w3[2];    // ComposedWarp: post_warp.{forward_map, backward_map}.linear_final.weight (3, 256)
   int32_t M, ND, tiles_per_frame, n_tiles;
 };
 cudaError_t launch_field_bwd(const BwdKernelParams& p, int n_sm, cudaStream_t stream);

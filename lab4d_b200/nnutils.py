@@ -111,8 +111,6 @@ def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype
         needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in P.values()) or samples_dict["Kinv"].requires_grad)
         tab = tables_from_module(field, samples_dict)
         if needs_grad:
-            if cfg.dense:
-                raise NotImplementedError("lab4d_b200: the backward of ComposedWarp (dense soft deformation) fields is not built yet")
             from . import autograd as _ag
 
             r.pack_train({k: v.detach() for k, v in P.items()}, alpha=alpha)

@@ -213,6 +213,8 @@ class FieldRenderer:
                 continue
             if name == "gauss_density" and c.motion == "rigid":
                 continue
+            if name == "warp_pts":
+                continue
             out[name] = torch.empty(S, nch, dtype=torch.float32, device=self.device)
             setattr(oa, name, out[name].data_ptr())
         wbytes = self.handle.lib.b200r_workspace_bytes(C.byref(self.desc), M)
@@ -233,7 +235,7 @@ class FieldRenderer:
         self._keep_call = keep
         feat = {k: v.view(M, N, D, -1) for k, v in out.items()}
         deltas = feat.pop("deltas", None)
-        for k in ("xyz_t", "dir", "sdf", "feat_norm"):
+        for k in ("xyz_t", "dir", "sdf", "feat_norm", "warp_pts"):
             feat.pop(k, None)
         self.last_aux = {k: out[k].view(M, N, D, -1) for k in ("xyz_t", "dir", "sdf", "feat_norm") if k in out}
         if "density" in feat:
@@ -351,6 +353,8 @@ class FieldRenderer:
                 continue
             if name == "gauss_density" and c.motion == "rigid":
                 continue
+            if name == "warp_pts" and not (c.dense and c.motion != "rigid"):
+                continue
             out[name] = torch.empty(S, nch, dtype=torch.float32, device=self.device)
             setattr(oa, name, out[name].data_ptr())
         wbytes = self.handle.lib.b200r_workspace_bytes(C.byref(self.desc), M)
@@ -363,7 +367,7 @@ class FieldRenderer:
         self.handle.check(rc, "b200r_field_fwd_train")
         feat = {k: v.view(M, N, int(D), -1) for k, v in out.items()}
         deltas = feat.pop("deltas")
-        for k in ("xyz_t", "dir", "sdf", "feat_norm"):
+        for k in ("xyz_t", "dir", "sdf", "feat_norm", "warp_pts"):
             feat.pop(k, None)
         feat["density_" + c.category] = feat["density"]
         feat["eikonal"] = torch.zeros(M, N, int(D), 1, device=self.device)
@@ -393,7 +397,7 @@ class FieldRenderer:
                 keep.append(t)
                 setattr(fg, k, t.data_ptr())
         saved, out = _lib.FieldOutputs(), ctx["out"]
-        for k in ("xyz", "rgb", "sdf", "feature", "feat_norm"):
+        for k in ("xyz", "rgb", "sdf", "feature", "feat_norm", "warp_pts"):
             if k in out:
                 setattr(saved, k, out[k].data_ptr())
         layout, slots = st["layout"], st["slots"]

@@ -1,4 +1,4 @@
-"""Host side of the field backward: chains the gradients of the kernel-level blocks (constant block, M per-frame blocks:
+"""TEST INFRASTRUCTURE (checker of csrc/chain.cu): torch restatement of the backward of the per-frame prologue. Chains the gradients of the kernel-level blocks (constant block, M per-frame blocks:
 include/b200r.h b200r_block_layout) to the reference's parameters and to the per-frame inputs of query_field.
 
 The blocks are what csrc/prologue.cu builds every call from M rows of per-frame data - cameras, bias rows with the

@@ -24,7 +24,7 @@ GRAD_TOL_SMALL = 2e-2  # gradients that reach their tensor through dL/dx of the 
 LOOSE = ("warp.skinning_model.log_gauss", "logscale", "field2cam_q", "field2cam_t", "Kinv", "sdf.bias", "t_articulation_qr",
          "t_articulation_qd", "rest_articulation_qr", "rest_articulation_qd")
 
-TABLE_GRAD_KEYS = ["inst_base", "inst_color", "inst_vis", "appr_code", "inst_skin", "skin_t_embed", "skin_t_embed_mean", "field2cam_q",
+TABLE_GRAD_KEYS = ["dense_t_embed", "inst_dense_fwd", "inst_dense_bwd", "inst_base", "inst_color", "inst_vis", "appr_code", "inst_skin", "skin_t_embed", "skin_t_embed_mean", "field2cam_q",
                    "field2cam_t", "t_articulation_qr", "t_articulation_qd", "rest_articulation_qr", "rest_articulation_qd"]
 OUT_KEYS = ["rgb", "density", "vis", "feature", "xyz", "xyz_cam", "depth", "flow", "cyc_dist", "delta_skin", "skin_entropy", "gauss_density"]
 
@@ -32,7 +32,8 @@ OUT_KEYS = ["rgb", "density", "vis", "feature", "xyz", "xyz_cam", "depth", "flow
 def _cfgs():
     from lab4d_b200 import spec
 
-    return {"bg": spec.BG, "fg_rigid": spec.FG_RIGID, "fg_bob": spec.FG_BOB, "fg_skelhuman": spec.FG_SKEL_HUMAN}
+    return {"bg": spec.BG, "fg_rigid": spec.FG_RIGID, "fg_bob": spec.FG_BOB, "fg_skelhuman": spec.FG_SKEL_HUMAN, "fg_compquad": spec.FG_COMP_QUAD,
+            "fg_comphuman": spec.FieldConfig(motion="skel", B=18, symm_idx=spec.HUMAN_SYMM, dense=True)}
 
 
 def _problem(name, M, N, seed):
@@ -76,7 +77,8 @@ def _oracle_grads(cfg, P, rays, tab, D, cot, flow_thresh=None, dtype=torch.float
 
 
 @pytest.mark.parametrize("name,M,N,D,fwd_dtype", [("bg", 4, 24, 33, "fp16x3"), ("fg_rigid", 2, 16, 40, "fp16x3"), ("fg_bob", 4, 16, 48, "fp16x3"),
-                                                 ("fg_skelhuman", 4, 8, 24, "fp16x3"), ("fg_bob", 8, 16, 128, "fp16")])
+                                                 ("fg_skelhuman", 4, 8, 24, "fp16x3"), ("fg_bob", 8, 16, 128, "fp16"),
+                                                 ("fg_compquad", 4, 16, 32, "fp16x3"), ("fg_comphuman", 2, 16, 40, "fp16x3")])
 def test_field_backward_matches_oracle_autograd(name, M, N, D, fwd_dtype):
     from lab4d_b200.render import FieldRenderer
 
@@ -110,3 +112,50 @@ def test_field_backward_matches_oracle_autograd(name, M, N, D, fwd_dtype):
                 worst.append((k, e, floor))
     print(f"[backward] {name} {M}x{N}x{D} fwd={fwd_dtype} (ours vs fp64 / reference fp32 vs fp64): " + " ".join(rows))
     assert not worst, worst
+
+
+@pytest.mark.parametrize("name", ["fg_skelhuman", "bg"])
+def test_chain_kernel_matches_torch_restatement(name):
+    """csrc/chain.cu (backward of the per-frame prologue) against autograd of the torch restatement of the prologue's table
+    formulas (oracle/chain_torch.py) on the SAME block gradients: biases, code columns of the weights, per-frame codes,
+    cameras, articulations, Gaussian bone scales (with left/right symmetric bones)."""
+    import chain_torch
+    from lab4d_b200.render import FieldRenderer
+
+    M, N, D = 4, 8, 24
+    cfg, P, rays, tab = _problem(name, M, N, seed=33)
+    r = FieldRenderer(cfg, DEV, operand_dtype="fp16")
+    r.pack_train(P)
+    feat, deltas, ctx = r.query_field_train(P, rays, tab, D)
+    pg, tg = r.backward(ctx, _cotangents(feat, seed=9))
+    torch.cuda.synchronize()
+    g_const, g_frame = r.last_blocks
+    st = r._train_state()
+    names = [n for n, _ in r._layers]
+    zeros = {n + ".weight": torch.zeros(st["shapes"][n + ".weight"], device=DEV) for n in names}
+    tpg, ttg = chain_torch.chain(st["layout"], names, cfg, P, tab, rays, g_const, g_frame, zeros)
+    rows = []
+    for k, ref in sorted(ttg.items()):
+        e = rel_l2(tg[k].reshape(ref.shape).cpu(), ref.cpu())
+        rows.append(f"[{k}]={e:.1e}")
+        assert e < 1e-5, (k, e)
+    for k, ref in sorted(tpg.items()):
+        if k.endswith(".weight") and k[:-7] in names:  # compare the code columns only (the rest comes from the wgrad kernel)
+            lay = st["layout"]
+            for ci in range(lay.n_cond):
+                c = lay.cond[ci]
+                if names[c.layer] + ".weight" != k:
+                    continue
+                for sgi in range(c.n_seg):
+                    sl = slice(c.col0[sgi], c.col0[sgi] + c.width[sgi])
+                    if float(ref[:, sl].abs().max()) > 0:
+                        e = rel_l2(pg[k][:, sl].cpu(), ref[:, sl].cpu())
+                        rows.append(f"{k}[:,{sl.start}:{sl.stop}]={e:.1e}")
+                        assert e < 1e-5, (k, e)
+        elif not k.endswith(".weight") or k in ("sdf.weight", "rgb.2.weight", "vis_mlp.basefield.linear_final.weight"):
+            if float(ref.abs().max()) == 0:
+                continue
+            e = rel_l2(pg[k].reshape(ref.shape).cpu(), ref.cpu())
+            rows.append(f"{k}={e:.1e}")
+            assert e < 1e-5, (k, e)
+    print(f"[chain] {name}: " + " ".join(rows[:12]) + f" ... ({len(rows)} tensors)")
