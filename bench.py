@@ -14,7 +14,7 @@ Rays shard data-parallel over the N GPUs (weak scaling: every rank renders its o
 inference path (query_field + render_pixel, no tape).  `value` times the step with inputs resident in HBM; `e2e` goes
 through the same public API with the step's inputs in pinned HOST memory (H2D of rays + per-frame tables and D2H of the
 rendered RGB inside the timed region).  `--config c4` is the strong-scaling shape of configs[3]: 4096 rays x (128 fg +
-128 bg) samples split over the ranks (forward: the composed dense-warp field's backward is not built).
+128 bg) samples, composed by depth, split over the ranks.
 """
 import argparse
 import json
@@ -245,7 +245,8 @@ class Step:
             g = torch.Generator().manual_seed(5)
             R = self.M * self.N
             self.coeff = {k: (torch.rand(self.M, self.N, c, generator=g) / R).to(device) for k, c in
-                          (("rgb", 3), ("mask", 1), ("depth", 1), ("flow", 2), ("feature", 16), ("vis", 1), ("xyz", 3), ("gauss_mask", 1))}
+                          (("rgb", 3), ("mask", 1), ("depth", 1), ("flow", 2), ("feature", 16), ("vis", 1), ("xyz", 3), ("gauss_mask", 1),
+                           ("mask_fg", 1), ("cyc_dist", 1))}
         self.launches = 0
         self.flat = None
 
@@ -277,9 +278,11 @@ class Step:
                     v.grad = None
             loss.backward()
             self.launches += 1 + 6  # composite_bwd; prologue, absmax, scale, field_bwd, wgrad, chain
-            # the parameters' .grad are views of the renderer's flat gradient buffer: the step's ONE all-reduce runs on it
-            self.flat = self.renderers[-1].grad_buffer()[0]
-            parallel.allreduce_mean_(self.flat)
+            # the parameters' .grad are views of the renderers' flat gradient buffers: the step's all-reduce runs on them
+            # (one NCCL call per field: 1 for C2 / C3, 2 for the composed scene)
+            self.flat = [r.grad_buffer()[0] for r in self.renderers]
+            for fl in self.flat:
+                parallel.allreduce_mean_(fl)
         return rend
 
 
@@ -296,8 +299,6 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the step as a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.config == "c4":
-        args.passes = "forward"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -376,20 +377,41 @@ def main():
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
     ms_e2e = timed(e2e_fn, args.steps)
-    # the phases alone (same stream, CUDA events around the public calls): forward kernel(s), backward call
+    # the phases alone: the forward call and the backward call of the (last) field, each replayed as its own CUDA graph and
+    # timed with CUDA events on the launching stream
     phase = {"fwd_ms": [], "bwd_ms": []}
     r0, (cfg0, P0, rays0, tab0) = step.renderers[-1], step.fields[-1]
+    P0d = {k: v.detach() for k, v in P0.items()}
+    hold = {}
+
+    def ph_fwd():
+        if step.train:
+            hold["feat"], _, hold["ctx"] = r0.query_field_train(P0d, rays0, tab0, step.D)
+        else:
+            hold["feat"], _ = r0.query_field(P0d, rays0, tab0, step.D)
+
+    def ph_bwd():
+        f = hold["feat"]
+        r0.backward(hold["ctx"], {"rgb": f["rgb"], "density": f["density"], "vis": f["vis"], "xyz": f["xyz"]})
+
+    try:
+        from lab4d_b200.graph import GraphedStep
+
+        if args.no_graph:
+            raise RuntimeError("eager")
+        gf = GraphedStep(ph_fwd, warmup=2, device=device)
+        gb = GraphedStep(ph_bwd, warmup=2, device=device) if step.train else None
+        f_fn, b_fn = gf.replay, (gb.replay if gb else None)
+    except Exception:
+        f_fn, b_fn = ph_fwd, (ph_bwd if step.train else None)
     for i in range(min(args.steps, 50)):
         flush.fill_(i & 0xFF)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
-        if step.train:
-            feat, deltas, ctx = r0.query_field_train(P0, rays0, tab0, step.D)
-        else:
-            feat, deltas = r0.query_field(P0, rays0, tab0, step.D)
+        f_fn()
         e[1].record()
-        if step.train:
-            r0.backward(ctx, {"rgb": feat["rgb"], "density": feat["density"], "vis": feat["vis"], "xyz": feat["xyz"]})
+        if b_fn:
+            b_fn()
         e[2].record()
         torch.cuda.synchronize()
         phase["fwd_ms"].append(e[0].elapsed_time(e[1]))
@@ -410,7 +432,7 @@ def main():
         bwd_ms = float(np.mean(phase["bwd_ms"])) if step.train else 0.0
         mult = 3 if step.train else 1
         kern_ms = fwd_ms + bwd_ms
-        achieved = mult * flop_fwd * step.S / len(step.fields) / (kern_ms * 1e-3) / 1e12 if len(step.fields) == 1 else None
+        achieved = mult * flop_fwd * step.S / (kern_ms * 1e-3) / 1e12 if len(step.fields) == 1 else None
         kname = "field_fwd_kernel"
         traffic, tsrc = dram_traffic_from_profile(kname)
         strong = args.config == "c4"
@@ -441,7 +463,7 @@ def main():
                                 "kernel_ms": kern_ms, "flop_per_sample": mult * flop_fwd,
                                 "peak_source": how + " bf16 dense burst (sustained also given)"}
         if step.flat is not None:
-            line["grad_buffer_bytes"] = int(step.flat.numel() * 4)
+            line["grad_buffer_bytes"] = int(sum(fl.numel() for fl in step.flat) * 4)
         if not args.no_cpu_baseline and world == 1 and args.config == "c2":  # reported baseline: rank 0 at N = 1, ~10-20 s of CPU work
             threads, ncpu = cpu_policy()
             Ms, reps = 8, (12 if step.train else 40)
@@ -449,9 +471,19 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "ray-samples/s", "cores": threads, "host_cores": ncpu, "kind": kind,
                                     "sample": f"{reps} x ({Ms} of {cfgd['M']} frames x {step.N} rays x {step.D} samples), "
                                               f"{'forward+backward' if step.train else 'forward'}, fp32, {reps * dt:.1f} s"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    # tear-down: graphs that captured NCCL collectives must go before the process group does; a stuck communicator
+    # tear-down must never outlive the measurement (the line above is already out)
+    g_run = g_e2e = gf = gb = run_fn = e2e_fn = f_fn = b_fn = None
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -181,9 +181,9 @@ def nerf_forward(field, xyz, dir=None, frame_id=None, inst_id=None, get_density=
 
 
 def compose_fields(multifields_dict, deltas_dict):
-    """Replacement body of MultiFields.compose_fields (nnutils/multifields.py:339-398) for no-grad rendering: the
-    depth-merge kernel instead of cat + argsort + 15 gathers.  Same arguments (dicts keyed by field category, in field
-    order) and return value."""
+    """Replacement body of MultiFields.compose_fields (nnutils/multifields.py:339-398): the depth-merge kernel instead of
+    cat + argsort + 15 gathers, differentiable (inverse gather of the merge permutation).  Same arguments (dicts keyed by
+    field category, in field order) and return value."""
     cats = list(multifields_dict.keys())
     return _render.compose_fields([multifields_dict[c] for c in cats], [deltas_dict[c] for c in cats])
 
@@ -216,14 +216,7 @@ def install(lab4d=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False):
         cls.query_field = _qf
     rru.render_pixel = _render.render_pixel
     rmodel.render_pixel = _render.render_pixel
-    ref_compose = rmf.MultiFields.compose_fields
-
-    def _compose(multifields_dict, deltas_dict):
-        # the merge kernel has no backward: graphs that need gradients keep the reference's gather formulation
-        needs_grad = torch.is_grad_enabled() and any(v.requires_grad for f in multifields_dict.values() for v in f.values())
-        return ref_compose(multifields_dict, deltas_dict) if needs_grad else compose_fields(multifields_dict, deltas_dict)
-
-    rmf.MultiFields.compose_fields = staticmethod(_compose)
+    rmf.MultiFields.compose_fields = staticmethod(compose_fields)
 
     def undo():
         for obj, name, val in saved:

@@ -680,8 +680,9 @@ def render_pixel(field_dict, deltas):
     return out
 
 
-def _merge_pair(h, device, fa, fb, da, db):
-    """b200r_compose_fwd over the union of keys of two fields (dicts key -> (M,N,D,c)); deltas travel as one more key."""
+def _merge_pair(h, device, fa, fb, da, db, want_perm=False):
+    """b200r_compose_fwd over the union of keys of two fields (dicts key -> (M,N,D,c)); deltas travel as one more key.
+    want_perm: also return the (M*N, Da+Db) int32 index of every merged sample inside the concatenation [A; B]."""
     depth_a, depth_b = _f32c(fa["depth"]), _f32c(fb["depth"])
     M, N, Da = depth_a.shape[:3]
     Db = depth_b.shape[2]
@@ -689,11 +690,14 @@ def _merge_pair(h, device, fa, fb, da, db):
     fa, fb = dict(fa, __deltas=da), dict(fb, __deltas=db)
     keys = [k for k in fa] + [k for k in fb if k not in fa]
     out, keep = {}, [depth_a, depth_b]
+    perm = torch.empty(R, Da + Db, dtype=torch.int32, device=device) if want_perm else None
     for c0 in range(0, len(keys), _lib.MAX_CHANNELS):
         part = keys[c0:c0 + _lib.MAX_CHANNELS]
         a = _lib.ComposeArgs()
         a.R, a.Da, a.Db, a.n_channels = R, Da, Db, len(part)
         a.depth_a, a.depth_b = depth_a.data_ptr(), depth_b.data_ptr()
+        if perm is not None and c0 == 0:
+            a.perm = perm.data_ptr()
         for i, k in enumerate(part):
             ta = _f32c(fa[k]) if k in fa else None
             tb = _f32c(fb[k]) if k in fb else None
@@ -706,20 +710,67 @@ def _merge_pair(h, device, fa, fb, da, db):
             a.dst[i] = out[k].data_ptr()
         h.check(h.lib.b200r_compose_fwd(h.h, C.byref(a), _stream(device)), "b200r_compose_fwd")
     deltas = out.pop("__deltas")
-    return out, deltas
+    return (out, deltas, perm) if want_perm else (out, deltas)
 
 
-@torch.no_grad()
+class _Compose(torch.autograd.Function):
+    """compose_fields of two fields with the hand-derived backward: the merge is a permutation of the concatenated samples
+    (multifields.py:393-397), so every key's gradient is the inverse gather of the merged gradient."""
+
+    @staticmethod
+    def forward(ctx, keys_a, keys_b, da, db, *vals):
+        fa = dict(zip(keys_a, vals[:len(keys_a)]))
+        fb = dict(zip(keys_b, vals[len(keys_a):]))
+        device = da.device
+        out, deltas, perm = _merge_pair(_lib.handle_for(device), device, {k: v.detach() for k, v in fa.items()},
+                                        {k: v.detach() for k, v in fb.items()}, da.detach(), db.detach(), want_perm=True)
+        ctx.keys_a, ctx.keys_b, ctx.out_keys = keys_a, keys_b, list(out.keys())
+        ctx.Da, ctx.Db = fa["depth"].shape[2], fb["depth"].shape[2]
+        ctx.save_for_backward(perm)
+        ctx.mark_non_differentiable(deltas)
+        return (deltas, *[out[k] for k in ctx.out_keys])
+
+    @staticmethod
+    def backward(ctx, g_deltas, *g_outs):
+        (perm,) = ctx.saved_tensors
+        R, Dt = perm.shape
+        # inverse permutation: position of concatenated sample j in the merged list
+        inv = torch.empty(R, Dt, dtype=torch.int64, device=perm.device)
+        inv.scatter_(1, perm.long(), torch.arange(Dt, device=perm.device).expand(R, Dt))
+        g = dict(zip(ctx.out_keys, g_outs))
+        res = [None, None, None, None]
+        for keys, lo, hi in ((ctx.keys_a, 0, ctx.Da), (ctx.keys_b, ctx.Da, Dt)):
+            for k in keys:
+                go = g.get(k)
+                if go is None:
+                    res.append(None)
+                    continue
+                M, N, _, c = go.shape
+                idx = inv[:, lo:hi].reshape(M, N, hi - lo, 1).expand(M, N, hi - lo, c)
+                res.append(torch.gather(go, 2, idx))
+        return tuple(res)
+
+
 def compose_fields(feats, deltas_list):
     """MultiFields.compose_fields (nnutils/multifields.py:339-398): merge the fields' samples along every ray by
     depth and carry every key (zeros where a field lacks it).  feats: list of dicts in field order; every field's
     samples are sorted by depth (uniform placement), so the reference's concatenate + argsort + gather is a merge,
-    done by the depth-merge kernel (csrc/compose.cu); more than two fields are merged pairwise in field order."""
+    done by the depth-merge kernel (csrc/compose.cu); more than two fields are merged pairwise in field order.
+    Differentiable w.r.t. every per-sample array (the backward is the inverse gather of the merge permutation)."""
     if len(feats) == 1:
         return dict(feats[0]), deltas_list[0]
     device = feats[0]["depth"].device
     h = _lib.handle_for(device)
     out, deltas = feats[0], deltas_list[0]
     for f, d in zip(feats[1:], deltas_list[1:]):
-        out, deltas = _merge_pair(h, device, out, f, deltas, d)
+        needs_grad = torch.is_grad_enabled() and any(v.requires_grad for v in list(out.values()) + list(f.values()))
+        if needs_grad:
+            ka, kb = list(out.keys()), list(f.keys())
+            res = _Compose.apply(ka, kb, deltas, d, *[out[k] for k in ka], *[f[k] for k in kb])
+            deltas = res[0]
+            merged_keys = ka + [k for k in kb if k not in ka]
+            out = dict(zip(merged_keys, res[1:]))
+        else:
+            with torch.no_grad():
+                out, deltas = _merge_pair(h, device, out, f, deltas, d)
     return out, deltas

@@ -159,3 +159,39 @@ def test_chain_kernel_matches_torch_restatement(name):
             rows.append(f"{k}={e:.1e}")
             assert e < 1e-5, (k, e)
     print(f"[chain] {name}: " + " ".join(rows[:12]) + f" ... ({len(rows)} tensors)")
+
+
+def test_compose_fields_backward_matches_gather_autograd():
+    """Hand-derived backward of the depth merge (inverse gather of the permutation) against autograd through the reference's own
+    formulation cat + argsort + gather (multifields.py:339-398)."""
+    from lab4d_b200.render import compose_fields
+
+    g = torch.Generator(device="cpu").manual_seed(4)
+    M, N, Da, Db = 2, 19, 24, 40
+    mk = lambda *s: torch.rand(*s, generator=g).to(DEV)
+    base_a = {"depth": mk(M, N, Da, 1).sort(2).values, "rgb": mk(M, N, Da, 3), "density": mk(M, N, Da, 1), "feature": mk(M, N, Da, 16)}
+    base_b = {"depth": mk(M, N, Db, 1).sort(2).values, "rgb": mk(M, N, Db, 3), "density": mk(M, N, Db, 1), "flow": mk(M, N, Db, 3)}
+    da, db = mk(M, N, Da, 1), mk(M, N, Db, 1)
+    coef = {k: mk(M, N, Da + Db, c) for k, c in (("rgb", 3), ("density", 1), ("feature", 16), ("flow", 3), ("depth", 1))}
+
+    def run(fn):
+        fa = {k: v.clone().requires_grad_(True) for k, v in base_a.items()}
+        fb = {k: v.clone().requires_grad_(True) for k, v in base_b.items()}
+        out, dl = fn(fa, fb)
+        sum((coef[k] * out[k]).sum() for k in coef).backward()
+        return {"a/" + k: v.grad for k, v in fa.items()} | {"b/" + k: v.grad for k, v in fb.items()}, out
+
+    def ref(fa, fb):
+        keys = ["depth", "rgb", "density", "feature", "flow"]
+        cat = {k: torch.cat([f[k] if k in f else torch.zeros(M, N, f["depth"].shape[2], coef[k].shape[-1], device=DEV) for f in (fa, fb)], 2) for k in keys}
+        idx = cat["depth"].argsort(dim=2, stable=True)
+        return {k: torch.gather(v, 2, idx.expand_as(v)) for k, v in cat.items()}, None
+
+    g_ref, o_ref = run(ref)
+    g_got, o_got = run(lambda fa, fb: compose_fields([fa, fb], [da, db]))
+    for k in o_ref:
+        assert torch.equal(o_got[k], o_ref[k]), k
+    for k, v in g_ref.items():
+        assert (v is None) == (g_got[k] is None), k
+        if v is not None:
+            assert torch.equal(g_got[k], v), k
