@@ -73,6 +73,41 @@ __device__ __forceinline__ float lds32(uint32_t a) {
   return v;
 }
 
+// backward of the Fourier embedding (nnutils/embedding.py:69-125): accumulator columns [0, 3 + 6 nfreq) of this thread's
+// TMEM lane hold dL/d e; adds dL/dx = g_e[0:3] + sum_k 2^k (g_sin_k cos(2^k x) - g_cos_k sin(2^k x)) to gx, same
+// double-angle walk as the forward.  One out-of-line copy: it is called from six places of the kernel.
+__device__ __noinline__ void pe_backward_fn(uint32_t tD, const float3& x, int nfreq, float3& gx) {
+  float ge[96];  // dynamically indexed below: lives in local memory (L1), not in registers
+  const int ncol = 3 + 6 * nfreq;
+#pragma unroll 1
+  for (int c0 = 0; c0 < ncol; c0 += 32) {
+    float v[32];
+    tmem_ld32(tD + c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ge[c0 + j] = v[j];
+  }
+  float ax = ge[0], ay = ge[1], az = ge[2];
+  float fr = 1.0f, s0 = 0.f, s1 = 0.f, s2 = 0.f, c0 = 1.f, c1 = 1.f, c2 = 1.f;
+#pragma unroll 1
+  for (int kf = 0; kf < nfreq; ++kf) {
+    if ((kf & 3) == 0) {
+      sincosf(fr * x.x, &s0, &c0);
+      sincosf(fr * x.y, &s1, &c1);
+      sincosf(fr * x.z, &s2, &c2);
+    } else {
+      const float t0 = 2.f * s0 * c0, t1 = 2.f * s1 * c1, t2 = 2.f * s2 * c2;
+      c0 = 1.f - 2.f * s0 * s0; c1 = 1.f - 2.f * s1 * s1; c2 = 1.f - 2.f * s2 * s2;
+      s0 = t0; s1 = t1; s2 = t2;
+    }
+    const float* e = ge + 3 + 6 * kf;
+    ax += fr * (e[0] * c0 - e[3] * s0);
+    ay += fr * (e[1] * c1 - e[4] * s1);
+    az += fr * (e[2] * c2 - e[5] * s2);
+    fr *= 2.0f;
+  }
+  gx.x += ax; gx.y += ay; gx.z += az;
+}
+
 template <class Op, int B, int WIDTH, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -262,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
     };
     // finished GEMM of n (<= 128) columns: G = acc * relu'(slot) -> activations [0, n) and the gradient tape
     auto seq_dgrad = [&](int n, int mask_slot, int save_chunk) {
-      const uint4 mw = __ldg(reinterpret_cast<const uint4*>(mask_row + mask_slot * kMaskWords));
+      const uint4 mw = __ldg(reinterpret_cast<const uint4*>(mask_row + (size_t)mask_slot * (kTileRows * kMaskWords)));
       const uint32_t mws[4] = {mw.x, mw.y, mw.z, mw.w};
 #pragma unroll 1
       for (int blk = 0; blk < (n >> 5); ++blk) {
@@ -280,15 +315,22 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
     //   MODE 1 (rgb.0's input = base + colour features): the colour branch takes relu'(colorfield.linear_final) -> activations;
     //   the density branch adds the sdf head's gradient, takes relu'(basefield.linear_final) and goes to the tape only.
     float g_sdf = 0.f;
-    auto wide_dgrad = [&](auto mode_tag, int mask_slot, int save_chunk) {
+    uint4 pm_a = make_uint4(0u, 0u, 0u, 0u), pm_b = pm_a;  // sign words requested ahead for the next wide layer
+    auto prefetch_mask = [&](int slot) {
+      if (slot < 0) return;
+      const uint4* mp = reinterpret_cast<const uint4*>(mask_row + (size_t)slot * (kTileRows * kMaskWords));
+      pm_a = __ldg(mp);
+      if (NBLK > 2) pm_b = __ldg(mp + 1);
+    };
+    auto wide_dgrad = [&](auto mode_tag, int mask_slot, int save_chunk, int next_slot) {
       constexpr int MODE = decltype(mode_tag)::value;
       uint32_t hold[NBLK][16];
-      const uint4* mp = reinterpret_cast<const uint4*>(mask_row + mask_slot * kMaskWords);
-      const uint4 ma = __ldg(mp), mb = NBLK > 2 ? __ldg(mp + 1) : make_uint4(0u, 0u, 0u, 0u);
-      const uint32_t mws[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+      (void)mask_slot;  // its words were requested by the previous layer (prefetch_mask)
+      const uint32_t mws[8] = {pm_a.x, pm_a.y, pm_a.z, pm_a.w, pm_b.x, pm_b.y, pm_b.z, pm_b.w};
+      prefetch_mask(next_slot);
       uint32_t mw2[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
       if (MODE == 1) {
-        const uint4* mp2 = reinterpret_cast<const uint4*>(mask_row + TL.m_base[Dn] * kMaskWords);
+        const uint4* mp2 = reinterpret_cast<const uint4*>(mask_row + (size_t)TL.m_base[Dn] * (kTileRows * kMaskWords));
         const uint4 a2 = __ldg(mp2), b2 = NBLK > 2 ? __ldg(mp2 + 1) : make_uint4(0u, 0u, 0u, 0u);
         mw2[0] = a2.x; mw2[1] = a2.y; mw2[2] = a2.z; mw2[3] = a2.w; mw2[4] = b2.x; mw2[5] = b2.y; mw2[6] = b2.z; mw2[7] = b2.w;
       }
@@ -348,36 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
     };
     // backward of the Fourier embedding (nnutils/embedding.py:69-125): accumulator columns [0, 3 + 6 nfreq) hold dL/d e;
     // returns dL/dx = g_e[0:3] + sum_k 2^k (g_sin_k cos(2^k x) - g_cos_k sin(2^k x)), same double-angle walk as the forward
-    auto pe_backward = [&](const float3& x, int nfreq, float3& gx) {
-      float ge[96];  // dynamically indexed below: lives in local memory (L1), not in registers
-      const int ncol = 3 + 6 * nfreq;
-#pragma unroll 1
-      for (int c0 = 0; c0 < ncol; c0 += 32) {
-        float v[32];
-        tmem_ld32(tD + c0, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) ge[c0 + j] = v[j];
-      }
-      gx.x += ge[0]; gx.y += ge[1]; gx.z += ge[2];
-      float fr = 1.0f, s0 = 0.f, s1 = 0.f, s2 = 0.f, c0 = 1.f, c1 = 1.f, c2 = 1.f;
-#pragma unroll 1
-      for (int kf = 0; kf < nfreq; ++kf) {
-        if ((kf & 3) == 0) {
-          sincosf(fr * x.x, &s0, &c0);
-          sincosf(fr * x.y, &s1, &c1);
-          sincosf(fr * x.z, &s2, &c2);
-        } else {
-          const float t0 = 2.f * s0 * c0, t1 = 2.f * s1 * c1, t2 = 2.f * s2 * c2;
-          c0 = 1.f - 2.f * s0 * s0; c1 = 1.f - 2.f * s1 * s1; c2 = 1.f - 2.f * s2 * s2;
-          s0 = t0; s1 = t1; s2 = t2;
-        }
-        const float* e = ge + 3 + 6 * kf;
-        gx.x += fr * (e[0] * c0 - e[3] * s0);
-        gx.y += fr * (e[1] * c1 - e[4] * s1);
-        gx.z += fr * (e[2] * c2 - e[5] * s2);
-        fr *= 2.0f;
-      }
-    };
+    auto pe_backward = [&](const float3& x, int nfreq, float3& gx) { pe_backward_fn(tD, x, nfreq, gx); };
 
     for (int it = 0; it < iters; ++it) {
       const int tile_raw = (kGroups * it + g) * (int)gridDim.x + (int)blockIdx.x;
@@ -393,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
       // a dead tile (its partner group still has a real one) walks the same protocol on a scratch tile of the gradient tape
       gt_tile = p.tape_g + (size_t)(dead_tile ? p.n_tiles + (int)blockIdx.x : tile) * TL.n_g * kChunkBytes;
       at_tile = p.tape_a + (size_t)tile * TL.n_a * kChunkBytes;
-      mask_row = p.tape_mask + ((size_t)tile * kTileRows + row) * TL.n_mask * kMaskWords;
+      mask_row = p.tape_mask + ((size_t)tile * TL.n_mask * kTileRows + row) * kMaskWords;
 
       named_bar_sync(1 + g, kGroupThreads);
       {
@@ -442,6 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
 
       // ================================================================ rgb head, rgb.0, colour chain, density chain
       {
+        prefetch_mask(TL.m_col[2]);
         const float3 g_rgb = ld3(p.g.rgb);
         const float r0 = __ldg(p.saved.rgb + s * 3), r1 = __ldg(p.saved.rgb + s * 3 + 1), r2 = __ldg(p.saved.rgb + s * 3 + 2);
         const float go0 = g_rgb.x * r0 * (1.f - r0), go1 = g_rgb.y * r1 * (1.f - r1), go2 = g_rgb.z * r2 * (1.f - r2);
@@ -459,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
         }
         // G of rgb.0's pre-activation: (g_o W2) * relu'
         const uint32_t w2 = cblk_s + 4u * CL.rgb2_w;
-        const uint4 mw = __ldg(reinterpret_cast<const uint4*>(mask_row + TL.m_rgb0 * kMaskWords));
+        const uint4 mw = __ldg(reinterpret_cast<const uint4*>(mask_row + (size_t)TL.m_rgb0 * (kTileRows * kMaskWords)));
         const uint32_t mws[4] = {mw.x, mw.y, mw.z, mw.w};
         float3 g_dir = make_float3(0.f, 0.f, 0.f);
 #pragma unroll 1
@@ -499,9 +513,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
           red[6] += gd.z * h0; red[7] += gd.z * h1; red[8] += gd.z * h2;
         }
         arrive_all();
-        wide_dgrad(std::integral_constant<int, 1>{}, TL.m_col[2], TL.g_col[2]);   // through rgb.0: colour + density branches
-        wide_dgrad(std::integral_constant<int, 0>{}, TL.m_col[1], TL.g_col[1]);   // colorfield.linear_final
-        wide_dgrad(std::integral_constant<int, 0>{}, TL.m_col[0], TL.g_col[0]);   // colorfield.linear_2
+        wide_dgrad(std::integral_constant<int, 1>{}, TL.m_col[2], TL.g_col[2], TL.m_col[1]);   // through rgb.0: colour + density branches
+        wide_dgrad(std::integral_constant<int, 0>{}, TL.m_col[1], TL.g_col[1], TL.m_col[0]);   // colorfield.linear_final
+        wide_dgrad(std::integral_constant<int, 0>{}, TL.m_col[0], TL.g_col[0], TL.m_base[Dn - 1]);  // colorfield.linear_2
         wait_all();                                                                 // colorfield.linear_1 -> embedding columns
         pe_backward(xyz, p.desc.L_xyz + 2, g_xyz);
         // density chain
@@ -514,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
             pe_backward(xyz, p.desc.L_xyz, g_xyz);
             arrive_all();
           }
-          wide_dgrad(std::integral_constant<int, 0>{}, TL.m_base[i - 1], TL.g_base[i - 1]);
+          wide_dgrad(std::integral_constant<int, 0>{}, TL.m_base[i - 1], TL.g_base[i - 1], i >= 2 ? TL.m_base[i - 2] : -1);
         }
         wait_all();
         pe_backward(xyz, p.desc.L_xyz, g_xyz);
@@ -558,7 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
       {
         const float g_vis = ld1(p.g.vis);
         const uint32_t vw = cblk_s + 4u * CL.vis_w;
-        const uint2 mw = __ldg(reinterpret_cast<const uint2*>(mask_row + TL.m_vis[1] * kMaskWords));
+        const uint2 mw = __ldg(reinterpret_cast<const uint2*>(mask_row + (size_t)TL.m_vis[1] * (kTileRows * kMaskWords)));
         const uint32_t mws[2] = {mw.x, mw.y};
 #pragma unroll 1
         for (int blk = 0; blk < 2; ++blk) {
@@ -588,8 +602,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
         gtape_zero_row(TL.g_d3[w]);
         *reinterpret_cast<uint2*>(gt_tile + (size_t)TL.g_d3[w] * kChunkBytes + rowx) = make_uint2(Op::pack2_sat(gm0, gm1), Op::pack2_sat(gm2, 0.f));
         const float* w3 = p.dense_w3[m];  // (3, 256) head weight, read through L1 (every row reads the same addresses)
-        const uint4 ma = __ldg(reinterpret_cast<const uint4*>(mask_row + TL.m_dh2[w] * kMaskWords));
-        const uint4 mb = __ldg(reinterpret_cast<const uint4*>(mask_row + TL.m_dh2[w] * kMaskWords) + 1);
+        const uint4 ma = __ldg(reinterpret_cast<const uint4*>(mask_row + (size_t)TL.m_dh2[w] * (kTileRows * kMaskWords)));
+        const uint4 mb = __ldg(reinterpret_cast<const uint4*>(mask_row + (size_t)TL.m_dh2[w] * (kTileRows * kMaskWords)) + 1);
         const uint32_t mws[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
 #pragma unroll 1
         for (int blk = 0; blk < 8; ++blk) {
@@ -608,7 +622,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
         }
         tmem_st_wait();
         arrive_all();
-        wide_dgrad(std::integral_constant<int, 0>{}, TL.m_dh1[w], TL.g_d1[w]);  // linear_2
+        prefetch_mask(TL.m_dh1[w]);
+        wide_dgrad(std::integral_constant<int, 0>{}, TL.m_dh1[w], TL.g_d1[w], -1);  // linear_2
         wait_all();                                                                // linear_1 -> embedding columns
         float3 g_in = g_out;
         pe_backward(x_in, 6, g_in);

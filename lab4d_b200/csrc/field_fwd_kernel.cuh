@@ -338,7 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     // ---- training tape (SAVE): this row's slice of the current tile's chunk images / sign words
     const TapeLayout& TL = p.tape;
     uint8_t* tape_tile = nullptr;   // first chunk of the tile
-    uint32_t* mask_row = nullptr;   // sign words of this row: [slot][kMaskWords]
+    uint32_t* mask_row = nullptr;   // sign words of this row in slot 0; slot s is kTileRows * kMaskWords words further ([slot][row][word]:
+                                    // the lanes of a warp write / read consecutive 32-B groups)
     // 32 columns (16 packed registers) starting at column col0 of the operand whose first chunk is `chunk`
     auto tape_st32 = [&](int chunk, int col0, const uint32_t (&o)[16]) {
       if constexpr (SAVE) {
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     };
     auto mask_st = [&](int slot, int word, uint32_t bits) {
       if constexpr (SAVE) {
-        if (mask_row != nullptr && slot >= 0) mask_row[slot * kMaskWords + word] = bits;
+        if (mask_row != nullptr && slot >= 0) mask_row[(size_t)slot * (kTileRows * kMaskWords) + word] = bits;
       }
     };
 
@@ -447,6 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     auto chain_layer = [&](auto mode_tag, uint32_t bias, int save_chunk, int mask_slot) {
       constexpr int MODE = decltype(mode_tag)::value;
       uint32_t hold[SPLIT ? 1 : NBLK][16];
+      uint32_t mwords[SAVE ? 2 * NBLK : 1];
       auto math = [&](const uint32_t (&ra)[32], int col0, uint32_t (&o)[16], uint32_t (&ot)[16]) {  // col0: first feature of these 32 columns
         const uint32_t ba = bias + 4u * (uint32_t)col0;
         if (MODE == 0) {
@@ -514,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           math(ra, 32 * blk, hold[blk], hold[blk]);
           tape_st32(save_chunk, 32 * blk, hold[blk]);
         }
-        mask_st(mask_slot, blk, sign_word());
+        if constexpr (SAVE) mwords[blk] = sign_word();
       }
       if (SPLIT && MODE != 1) tmem_st_wait();
       tc_fence_before_sync();
@@ -548,7 +550,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         }
         if (MODE != 1) tmem_st16(tA + (HN >> 1) + 16 * blk, o);
         tape_st32(save_chunk, HN + 32 * blk, o);
-        mask_st(mask_slot, NBLK + blk, sign_word());
+        if constexpr (SAVE) mwords[NBLK + blk] = sign_word();
+      }
+      if constexpr (SAVE) {  // the layer's sign words in one (or two) 16-B stores
+        if (mask_row != nullptr && mask_slot >= 0) {
+          uint4* mp = reinterpret_cast<uint4*>(mask_row + (size_t)mask_slot * (kTileRows * kMaskWords));
+          mp[0] = make_uint4(mwords[0], mwords[1], mwords[2], mwords[3]);
+          if (NBLK > 2) mp[1] = make_uint4(mwords[4 % (2 * NBLK)], mwords[5 % (2 * NBLK)], mwords[6 % (2 * NBLK)], mwords[7 % (2 * NBLK)]);
+        }
       }
       if (MODE != 1) tmem_st_wait();
       tc_fence_before_sync();
@@ -633,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       const size_t s = (size_t)f * p.ND + r_in;
       if constexpr (SAVE) {
         tape_tile = dead_tile ? nullptr : p.tape_a + (size_t)tile * TL.n_a * kChunkBytes;
-        mask_row = dead_tile ? nullptr : p.tape_mask + ((size_t)tile * kTileRows + row) * TL.n_mask * kMaskWords;
+        mask_row = dead_tile ? nullptr : p.tape_mask + ((size_t)tile * TL.n_mask * kTileRows + row) * kMaskWords;
       }
 
       // ------------------------------------------------ stage this frame's block in shared memory

@@ -41,9 +41,10 @@ def test_header_is_plain_c_and_struct_sizes_match_ctypes(tmp_path):
         '#include <stdio.h>\n#include "b200r.h"\n'
         "int main(void) {\n"
         "  b200r_field_desc d = {0};\n"
-        '  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b200r_field_desc), sizeof(b200r_field_params), sizeof(b200r_frame_tables),\n'
+        '  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b200r_field_desc), sizeof(b200r_field_params), sizeof(b200r_frame_tables),\n'
         "         sizeof(b200r_ray_batch), sizeof(b200r_field_outputs), sizeof(b200r_composite_args), sizeof(b200r_composite_bwd_args),\n"
-        "         sizeof(b200r_compose_args), sizeof(b200r_point_batch), sizeof(b200r_importance_args), (size_t)b200r_layer_count(&d));\n"
+        "         sizeof(b200r_compose_args), sizeof(b200r_point_batch), sizeof(b200r_importance_args), sizeof(b200r_field_grads), sizeof(b200r_tape),\n"
+        "         sizeof(b200r_block_layout), sizeof(b200r_param_grads), sizeof(b200r_frame_grads), (size_t)b200r_layer_count(&d));\n"
         "  return 0;\n}\n")
     exe = tmp_path / "abi"
     libdir = os.path.join(ROOT, "lab4d_b200")
@@ -51,9 +52,10 @@ def test_header_is_plain_c_and_struct_sizes_match_ctypes(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                     "-L", libdir, "-l:libb200render.so", f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{cuda_lib}", f"-Wl,-rpath-link,{cuda_lib}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    sizes = [int(x) for x in out[:10]]
+    sizes = [int(x) for x in out[:15]]
     mirrors = [_lib.FieldDesc, _lib.FieldParams, _lib.FrameTables, _lib.RayBatch, _lib.FieldOutputs, _lib.CompositeArgs,
-               _lib.CompositeBwdArgs, _lib.ComposeArgs, _lib.PointBatch, _lib.ImportanceArgs]
+               _lib.CompositeBwdArgs, _lib.ComposeArgs, _lib.PointBatch, _lib.ImportanceArgs, _lib.FieldGrads, _lib.Tape,
+               _lib.BlockLayout, _lib.ParamGrads, _lib.FrameGrads]
     assert sizes == [C.sizeof(m) for m in mirrors]
 
 
@@ -85,3 +87,40 @@ def test_renderer_refuses_cpu():
 
     with pytest.raises(RuntimeError):
         FieldRenderer(spec.FG_BOB, device="cpu")
+
+
+def test_training_layouts_are_consistent():
+    """Host-side training metadata for every field type: tape sizes scale with the tile count, the block layout's offsets are
+    inside their blocks and disjoint, the flat gradient buffer of the renderer covers every hot-path parameter once."""
+    from lab4d_b200 import _lib, spec
+
+    lib = _lib.load()
+    for cfg in (spec.BG, spec.FG_RIGID, spec.FG_BOB, spec.FG_SKEL_HUMAN, spec.FG_COMP_QUAD):
+        d = _lib.FieldDesc(category=0 if cfg.category == "fg" else 1, D=cfg.D, W=cfg.W, L_xyz=cfg.L_xyz, L_dir=cfg.L_dir,
+                           appr_channels=cfg.appr_channels, skip=cfg.skip, n_bones=cfg.B if cfg.motion != "rigid" else 0,
+                           has_feature=int(cfg.has_feature), operand_dtype=0, dense=int(cfg.dense))
+        a, g, m = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        assert lib.b200r_tape_sizes(C.byref(d), 4, 16, 64, C.byref(a), C.byref(g), C.byref(m)) == 0
+        a2, g2, m2 = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        assert lib.b200r_tape_sizes(C.byref(d), 8, 16, 64, C.byref(a2), C.byref(g2), C.byref(m2)) == 0
+        assert a2.value == 2 * a.value and m2.value == 2 * m.value and a.value % 16384 == 0 and g2.value > g.value
+        assert lib.b200r_packed_t_bytes(C.byref(d)) > 0
+        lay = _lib.BlockLayout()
+        assert lib.b200r_get_block_layout(C.byref(d), C.byref(lay)) == 0
+        spans = []
+        for i in range(lay.n_cond):
+            c = lay.cond[i]
+            assert 0 <= c.frame_off and c.frame_off + c.n <= lay.frame_floats
+            spans.append((c.frame_off, c.frame_off + c.n))
+        spans += [(lay.f_cam, lay.f_cam + 24), (lay.f_cam_partner, lay.f_cam_partner + 24)]
+        if cfg.motion != "rigid":
+            B = cfg.B
+            for off, per in ((lay.f_binv_t, 12), (lay.f_se3_bwd, 8), (lay.f_binv_rest, 12), (lay.f_se3_fwd, 8),
+                             (lay.f_binv_rest_partner, 12), (lay.f_se3_fwd_partner, 8)):
+                assert off >= 0
+                spans.append((off, off + B * per))
+        spans.sort()
+        for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+            assert a1 <= b0, (cfg, spans)
+        assert spans[-1][1] <= lay.frame_floats
+        assert lay.c_scalars + 8 <= lay.const_floats and lay.c_sdf_w >= 0 and lay.c_rgb2_w >= 0

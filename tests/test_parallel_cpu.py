@@ -84,3 +84,48 @@ def test_shard_frames_properties():
             assert all(a % 2 == 0 and b % 2 == 0 for a, b in spans)
     with pytest.raises(ValueError):
         shard_frames(3, 0, 1)
+
+
+def _grad_worker(rank, world, port, q):
+    """One rank of the training step's collective: per-rank gradients of a parameter dict -> flat buffer -> mean all-reduce
+    -> written back into .grad (what bench.py / the adapter do with the renderer's flat gradient buffer over NCCL)."""
+    import torch.distributed as dist
+
+    from lab4d_b200 import parallel
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    P = {"a.weight": torch.randn(5, 7, requires_grad=True), "a.bias": torch.randn(5, requires_grad=True), "unused": torch.randn(3, requires_grad=True)}
+    x = torch.full((7,), float(rank + 1))
+    ((P["a.weight"] @ x + P["a.bias"]) ** 2).sum().backward()
+    local = {k: v.grad.clone() for k, v in P.items() if v.grad is not None}
+    flat = parallel.flat_grads([P])
+    assert flat.numel() == 5 * 7 + 5  # parameters without a gradient do not enter the buffer
+    parallel.allreduce_mean_(flat)
+    assert parallel.unflatten_grads_(flat, [P]) == flat.numel()
+    q.put((rank, {k: v.numpy() for k, v in local.items()}, {k: v.grad.numpy().copy() for k, v in P.items() if v.grad is not None}))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2():
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for k in ("a.weight", "a.bias"):
+        mean = 0.5 * (res[0][1][k] + res[1][1][k])
+        assert not np.allclose(res[0][1][k], res[1][1][k])
+        for r in res:
+            assert np.allclose(r[2][k], mean, rtol=1e-6), k
