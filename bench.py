@@ -71,6 +71,31 @@ def dram_traffic_from_profile(kernel):
     return None, None
 
 
+def kernel_shares_from_profile(precision):
+    """Mean device time (us) of every product kernel of one training step from the committed ncu launch list
+    (profiles/r02_launches_step_<precision>.csv; cold-cache, serialised: only the SHARES are used)."""
+    import collections
+    import csv
+
+    for name in (f"r02_launches_step_{precision}.csv", "r02_launches_step_fp16.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        hi = [i for i, r in enumerate(rows) if "Kernel Name" in r]
+        if not hi:
+            continue
+        h = rows[hi[0]]
+        ik, iv, iu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
+        agg = collections.defaultdict(list)
+        for r in rows[hi[0] + 1:]:
+            if len(r) > iv:
+                v = float(r[iv].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[iu], 1.0)
+                agg[r[ik].split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()].append(v)
+        return {k: float(np.mean(v)) for k, v in agg.items()}, name
+    return None, None
+
+
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons DURING the timed region, one nvidia-smi query loop (-lms) for the whole region."""
 
@@ -462,6 +487,25 @@ def main():
                                 "traffic_unit": f"DRAM bytes per field_fwd launch ({tsrc})" if tsrc else "no committed ncu capture found",
                                 "kernel_ms": kern_ms, "flop_per_sample": mult * flop_fwd,
                                 "peak_source": how + " bf16 dense burst (sustained also given)"}
+        if step.train and len(step.fields) == 1:
+            # per-kernel view: the backward call's measured time is split by the committed launch list's shares; the tape
+            # makes the two backward kernels HBM-bound by design (bytes = chunks each kernel must move)
+            shares, src = kernel_shares_from_profile(step.precision)
+            tiles = step.M * ((step.N * step.D + 127) // 128)
+            chunks = {"fg_bob": (79, 82, 161), "fg_skelhuman": (76, 82, 158)}.get(cfgd["field"])
+            if shares and chunks and "field_bwd_kernel" in shares and "wgrad_kernel" in shares:
+                tb = shares["field_bwd_kernel"] + shares["wgrad_kernel"]
+                bwd_k = {k: bwd_ms * shares[k] / tb for k in ("field_bwd_kernel", "wgrad_kernel")}
+                rk = []
+                a_b, g_b, u_b = (c * 16384.0 * tiles for c in chunks)
+                for kname, ms_k, nbytes in (("field_fwd_kernel (training forward)", fwd_ms, a_b), ("field_bwd_kernel", bwd_k["field_bwd_kernel"], g_b),
+                                            ("wgrad_kernel", bwd_k["wgrad_kernel"], u_b)):
+                    gbs = nbytes / (ms_k * 1e-3) / 1e9
+                    tr, _ = dram_traffic_from_profile(kname.split(" ")[0])
+                    rk.append({"kernel": kname, "bound": "hbm", "ms": ms_k, "achieved": gbs, "peak": peak_bw, "unit": "GB/s", "frac": gbs / peak_bw,
+                               "algorithmic_bytes": nbytes, "traffic": tr})
+                line["roofline_kernels"] = {"kernels": rk, "split_source": f"profiles/{src} (shares of the backward call)",
+                                            "note": "tape bytes each kernel must write / read once: forward 79, data-gradient 82, weight-gradient 161 chunks of 16 KB per 128-sample tile"}
         if step.flat is not None:
             line["grad_buffer_bytes"] = int(sum(fl.numel() for fl in step.flat) * 4)
         if not args.no_cpu_baseline and world == 1 and args.config == "c2":  # reported baseline: rank 0 at N = 1, ~10-20 s of CPU work

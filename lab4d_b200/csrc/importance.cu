@@ -49,6 +49,11 @@ __global__ void __launch_bounds__(kImpWarps * 32) importance_fwd_kernel(const b2
     fine[j] = mid[below] + (u - cdf[below]) / denom * (mid[above] - mid[below]);
   }
   __syncwarp();
+  // fp32 rounding at a bin boundary (or the denom < eps branch) can put a sample 1 ulp below its predecessor; the merge
+  // below ranks by binary search and needs a non-decreasing list (the reference sorts instead): running maximum
+  if (lane == 0)
+    for (int j = 1; j < Dc; ++j) fine[j] = fmaxf(fine[j], fine[j - 1]);
+  __syncwarp();
   // merge the two ascending lists (coarse first on ties, like a stable sort of cat([coarse, fine]))
   float* out = a.depth_out + (size_t)r * 2 * Dc;
   for (int t = lane; t < 2 * Dc; t += 32) {

@@ -192,6 +192,7 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int mode = MODE_FIE
   const bool split = d.operand_dtype == 2;  // every packed tile is followed by the fp16 tail of its rounding error
   if (d.dense != 0 && d.dense != 1) { bp.err = "dense must be 0 or 1"; return bp; }
   if (d.dense && d.n_bones == 0) { bp.err = "dense (ComposedWarp) needs a skinned field"; return bp; }
+  if (d.n_bones > 0 && d.W != 256) { bp.err = "skinned fields are built for W == 256 only"; return bp; }
   const LayerIds L = layer_ids(d);
   bp.layer_out.assign(L.count, 0);
   bp.layer_in.assign(L.count, 0);
