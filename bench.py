@@ -441,6 +441,27 @@ def main():
         torch.cuda.synchronize()
         phase["fwd_ms"].append(e[0].elapsed_time(e[1]))
         phase["bwd_ms"].append(e[1].elapsed_time(e[2]))
+    # the inference path of the same batch (no tape), parity mode and fast mode: short graph replays, reported beside the step
+    fwd_variants = {}
+    if step.train and len(step.fields) == 1 and not args.no_graph:
+        from lab4d_b200.render import FieldRenderer, render_pixel
+
+        for prec in ("fp16x3", "fp16"):
+            try:
+                rf = FieldRenderer(cfg0, device, operand_dtype=prec)
+
+                def fwd_only():
+                    rf.pack(P0d)
+                    ft, dl = rf.query_field(P0d, rays0, tab0, step.D)
+                    return render_pixel(ft, dl)
+
+                gfo = GraphedStep(fwd_only, warmup=2, device=device)
+                tms = timed(gfo.replay, 20)
+                fwd_variants[prec] = {"ms_per_step": float(np.mean(tms)), "value_per_gpu": step.S / (float(np.mean(tms)) * 1e-3), "unit": "ray-samples/s",
+                                      "what": "pack + query_field + render_pixel, no tape"}
+                gfo = None
+            except Exception as ex:
+                fwd_variants[prec] = {"error": str(ex)[:120]}
     clocks = sampler.stop()
     tot = torch.tensor([sum(ms), sum(ms_e2e)], device=device, dtype=torch.float64)
     Stot = torch.tensor([float(step.S)], device=device, dtype=torch.float64)
@@ -506,6 +527,8 @@ def main():
                                "algorithmic_bytes": nbytes, "traffic": tr})
                 line["roofline_kernels"] = {"kernels": rk, "split_source": f"profiles/{src} (shares of the backward call)",
                                             "note": "tape bytes each kernel must write / read once: forward 79, data-gradient 82, weight-gradient 161 chunks of 16 KB per 128-sample tile"}
+        if fwd_variants:
+            line["forward_only"] = fwd_variants
         if step.flat is not None:
             line["grad_buffer_bytes"] = int(sum(fl.numel() for fl in step.flat) * 4)
         if not args.no_cpu_baseline and world == 1 and args.config == "c2":  # reported baseline: rank 0 at N = 1, ~10-20 s of CPU work

@@ -15,9 +15,11 @@ pytestmark = pytest.mark.gpu
 SINGLE = [p for p in golden_files() if not p.split("/")[-1].startswith(("comp", "imp"))]
 DEV = "cuda"
 
-# Tolerances.  The MLPs run with fp16 operands and fp32 accumulation (reference: fp32 everywhere);
-# SURVEY.md §7 measured 4e-6 (rendered RGB) for that rounding on a trained-like field.  The synthetic
-# He-initialised weights used here are ~3x larger than trained ones, so per-sample bounds are looser.
+# FAST-MODE tolerances.  This file exercises the single-operand modes (`fp16`, `bf16`: 11- / 8-bit mantissas, fp32 accumulate)
+# - every kernel variant, entry point and shape class - with the bounds those modes can hold: rendered RGB 1e-4 ... 7.5e-4 of
+# the reference on the golden fixtures (asserted < 1e-3).  The north-star contract (rendered RGB <= 1e-4) is asserted in
+# tests/test_gpu_contract.py on the same fixtures and at the BASELINE config shapes in the split-operand mode `fp16x3`,
+# which is the mode bench.py reports.
 REL = {"rgb": 3e-3, "vis": 5e-3, "feature": 5e-3, "xyz": 2e-4, "xyz_cam": 1e-6, "depth": 1e-6, "skin_entropy": 2e-3,
        "delta_skin": 5e-3, "density": 2e-2, "density_fg": 2e-2, "density_bg": 2e-2, "gauss_density": 5e-3}
 ABS = {"flow": 0.15, "cyc_dist": 5e-4}  # cyc_dist chains two skinning (+ two dense) warps in 16-bit operands
