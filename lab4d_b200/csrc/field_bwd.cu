@@ -351,10 +351,19 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
       };
       wait_half(0);
 #pragma unroll
-      for (int blk = 0; blk < NBLK; ++blk) {
-        float v[32];
-        tmem_ld32(tD + 32 * blk, v);
-        math(v, blk, 32 * blk, hold[blk]);
+      for (int bp = 0; bp < NBLK; bp += 2) {  // two 32-column blocks per TMEM round trip
+        uint32_t rp[2][32];
+        tmem_ld32_issue(tD + 32 * bp, rp[0]);
+        tmem_ld32_issue(tD + 32 * (bp + 1), rp[1]);
+        tmem_ld_wait32(rp[0]);
+        tmem_ld_wait32(rp[1]);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rp[h2][j]);
+          math(v, bp + h2, 32 * (bp + h2), hold[bp + h2]);
+        }
       }
       tc_fence_before_sync();
       warp_arrive(&c2m_g[BAR_H0]);
@@ -362,12 +371,22 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
 #pragma unroll
       for (int blk = 0; blk < NBLK; ++blk) tmem_st16(tA + 16 * blk, hold[blk]);
 #pragma unroll
-      for (int blk = 0; blk < NBLK; ++blk) {
-        float v[32];
-        uint32_t o[16];
-        tmem_ld32(tD + 32 * blk, v);
-        math(v, NBLK + blk, HN + 32 * blk, o);
-        tmem_st16(tA + (HN >> 1) + 16 * blk, o);
+      for (int bp = 0; bp < NBLK; bp += 2) {
+        uint32_t rp[2][32];
+        tmem_ld32_issue(tD + 32 * bp, rp[0]);
+        tmem_ld32_issue(tD + 32 * (bp + 1), rp[1]);
+        tmem_ld_wait32(rp[0]);
+        tmem_ld_wait32(rp[1]);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int blk = bp + h2;
+          float v[32];
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rp[h2][j]);
+          math(v, NBLK + blk, HN + 32 * blk, o);
+          tmem_st16(tA + (HN >> 1) + 16 * blk, o);
+        }
       }
       tmem_st_wait();
       tc_fence_before_sync();

@@ -118,11 +118,20 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
   uint64_t* c2m = bars + 3 * kNumStages;      // [group][4] compute warps -> MMA thread, indexed by BAR_*
   uint64_t* m2c = bars + 3 * kNumStages + 8;  // [group][4] MMA thread (tcgen05.commit) -> compute warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kNumStages + 16);
+  // SPLIT + SAVE: tile group 1's warps are idle (their resources hold the operand tails) and act as TAPE WRITERS: group 0 posts
+  // (tile, chunk, first activation column, columns) after an epilogue has put its 16-bit heads into TMEM; the writers read
+  // them back (tcgen05.ld, same lane quadrants) and do the global stores, off the critical path of the one tile in flight.
+  uint64_t* act_ready = bars + 3 * kNumStages + 17;  // group 0 (4 warps) -> writers: command posted, activations complete
+  uint64_t* act_free = act_ready + 1;                // writers (4 warps) -> group 0: activations read, columns may be overwritten
+  volatile int32_t* proxy_cmd = reinterpret_cast<volatile int32_t*>(act_free + 1);  // [4]
+  constexpr bool kProxy = SPLIT && SAVE;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&full_bar[kNumStages + i], 1); mbar_init(&empty_bar[i], kCluster); }
     for (int i = 0; i < 8; ++i) { mbar_init(&c2m[i], 4); mbar_init(&m2c[i], 1); }  // one arrival per warp of the group
+    mbar_init(act_ready, 4);
+    mbar_init(act_free, 4);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, kTmemCols);
@@ -348,6 +357,32 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         }
       }
     };
+    // ---- tape-writer proxy (kProxy): group 0 side
+    uint32_t proxy_phase = 0;
+    bool proxy_pending = false;
+    int cur_tile = 0;
+    // activations [tcol, tcol + ncols) (TMEM columns of packed pairs, ncols a multiple of 16) are complete: hand them over
+    auto proxy_save = [&](int chunk, int tcol, int ncols) {
+      if constexpr (kProxy) {
+        if (tape_tile == nullptr || chunk < 0) return;
+        tc_fence_before_sync();
+        if (gtid == 0) { proxy_cmd[0] = cur_tile; proxy_cmd[1] = chunk; proxy_cmd[2] = tcol; proxy_cmd[3] = ncols; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(act_ready);
+        proxy_pending = true;
+      }
+    };
+    // before anything overwrites the activation columns: the writers must have read the last hand-over
+    auto proxy_wait = [&]() {
+      if constexpr (kProxy) {
+        if (proxy_pending) {
+          mbar_wait(act_free, proxy_phase);
+          proxy_phase ^= 1;
+          tc_fence_after_sync();
+          proxy_pending = false;
+        }
+      }
+    };
     auto mask_st = [&](int slot, int word, uint32_t bits) {
       if constexpr (SAVE) {
         if (mask_row != nullptr && slot >= 0) mask_row[(size_t)slot * (kTileRows * kMaskWords) + word] = bits;
@@ -423,6 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     };
     // finished GEMM of n (<= 128) columns: relu(acc + bias) -> activations [0, n)
     auto epi_relu_act = [&](uint32_t bias, int n, int save_chunk, int mask_slot) {
+      proxy_wait();
 #pragma unroll 1
       for (int blk = 0; blk < (n >> 5); ++blk) {
         uint32_t ra[32], o[16], ot[SPLIT ? 16 : 1];
@@ -435,10 +471,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           relu_pack32(ra, bias + 128u * blk, o, o);
         }
         tmem_st16(tA + 16 * blk, o);
-        tape_st32(save_chunk, 32 * blk, o);
+        if constexpr (!kProxy) tape_st32(save_chunk, 32 * blk, o);
         mask_st(mask_slot, blk, sign_word());
       }
       tmem_st_wait();
+      proxy_save(save_chunk, 0, n >> 1);
     };
     // One 2*hn-wide layer issued as two N-halves on this group's accumulator (program.h pipe5).
     //   MODE 0: relu(acc + bias) -> activations (in place: half 0 is held in registers until the layer's MMAs are done)
@@ -503,54 +540,71 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       // ---- N-half 0: drain the accumulator so the MMAs of half 1 can start
       wait_half(0);
 #pragma unroll
-      for (int blk = 0; blk < NBLK; ++blk) {
-        uint32_t ra[32];
-        tmem_ld32_issue(tD + 32 * blk, ra);
-        tmem_ld_wait32(ra);
-        if constexpr (SPLIT) {
-          uint32_t o[16], ot[16];
-          math(ra, 32 * blk, o, ot);
-          if (MODE != 1) { tmem_st16(tS + 16 * blk, o); tmem_st16(tS + 64 + 16 * blk, ot); }
-          tape_st32(save_chunk, 32 * blk, o);
-        } else {
-          math(ra, 32 * blk, hold[blk], hold[blk]);
-          tape_st32(save_chunk, 32 * blk, hold[blk]);
+      for (int bp = 0; bp < NBLK; bp += 2) {  // two 32-column blocks per TMEM round trip
+        uint32_t rp[2][32];
+        tmem_ld32_issue(tD + 32 * bp, rp[0]);
+        tmem_ld32_issue(tD + 32 * (bp + 1), rp[1]);
+        tmem_ld_wait32(rp[0]);
+        tmem_ld_wait32(rp[1]);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int blk = bp + h2;
+          if constexpr (SPLIT) {
+            uint32_t o[16], ot[16];
+            math(rp[h2], 32 * blk, o, ot);
+            if (MODE != 1) { tmem_st16(tS + 16 * blk, o); tmem_st16(tS + 64 + 16 * blk, ot); }
+            if (!kProxy || MODE == 1) tape_st32(save_chunk, 32 * blk, o);
+          } else {
+            math(rp[h2], 32 * blk, hold[blk], hold[blk]);
+            tape_st32(save_chunk, 32 * blk, hold[blk]);
+          }
+          if constexpr (SAVE) mwords[blk] = sign_word();
         }
-        if constexpr (SAVE) mwords[blk] = sign_word();
       }
       if (SPLIT && MODE != 1) tmem_st_wait();
       tc_fence_before_sync();
       warp_arrive(&c2m_g[BAR_H0]);
       // ---- N-half 1: the layer's input has been read, activations can be overwritten
       wait_half(1);
+      if (MODE != 1) proxy_wait();
       if (MODE != 1) {
+        if constexpr (SPLIT) {  // staged heads and tails -> activation buffers, NBLK blocks per TMEM round trip
 #pragma unroll
-        for (int blk = 0; blk < NBLK; ++blk) {
-          if constexpr (SPLIT) {  // staged heads and tails -> activation buffers
-            uint32_t t[16];
-            tmem_ld16u(tS + 16 * blk, t);
-            tmem_st16(tA + 16 * blk, t);
-            tmem_ld16u(tS + 64 + 16 * blk, t);
-            tmem_st16(tA + kTail + 16 * blk, t);
-          } else {
-            tmem_st16(tA + 16 * blk, hold[blk]);
+          for (int part = 0; part < 2; ++part) {
+            uint32_t t[NBLK][16];
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk) tmem_ld16u_issue(tS + 64 * part + 16 * blk, t[blk]);
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk) tmem_ld_wait16(t[blk]);
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk) tmem_st16(tA + (part ? kTail : 0u) + 16 * blk, t[blk]);
           }
+        } else {
+#pragma unroll
+          for (int blk = 0; blk < NBLK; ++blk) tmem_st16(tA + 16 * blk, hold[blk]);
         }
       }
 #pragma unroll
-      for (int blk = 0; blk < NBLK; ++blk) {
-        uint32_t ra[32], o[16], ot[SPLIT ? 16 : 1];
-        tmem_ld32_issue(tD + 32 * blk, ra);
-        tmem_ld_wait32(ra);
-        if constexpr (SPLIT) {
-          math(ra, HN + 32 * blk, o, ot);
-          if (MODE != 1) tmem_st16(tA + kTail + (HN >> 1) + 16 * blk, ot);
-        } else {
-          math(ra, HN + 32 * blk, o, o);
+      for (int bp = 0; bp < NBLK; bp += 2) {
+        uint32_t rp[2][32];
+        tmem_ld32_issue(tD + 32 * bp, rp[0]);
+        tmem_ld32_issue(tD + 32 * (bp + 1), rp[1]);
+        tmem_ld_wait32(rp[0]);
+        tmem_ld_wait32(rp[1]);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int blk = bp + h2;
+          uint32_t o[16], ot[SPLIT ? 16 : 1];
+          if constexpr (SPLIT) {
+            math(rp[h2], HN + 32 * blk, o, ot);
+            if (MODE != 1) tmem_st16(tA + kTail + (HN >> 1) + 16 * blk, ot);
+          } else {
+            math(rp[h2], HN + 32 * blk, o, o);
+          }
+          if (MODE != 1) tmem_st16(tA + (HN >> 1) + 16 * blk, o);
+          if (!kProxy || MODE == 1) tape_st32(save_chunk, HN + 32 * blk, o);
+          if constexpr (SAVE) mwords[NBLK + blk] = sign_word();
         }
-        if (MODE != 1) tmem_st16(tA + (HN >> 1) + 16 * blk, o);
-        tape_st32(save_chunk, HN + 32 * blk, o);
-        if constexpr (SAVE) mwords[NBLK + blk] = sign_word();
       }
       if constexpr (SAVE) {  // the layer's sign words in one (or two) 16-B stores
         if (mask_row != nullptr && mask_slot >= 0) {
@@ -562,6 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       if (MODE != 1) tmem_st_wait();
       tc_fence_before_sync();
       warp_arrive(&c2m_g[BAR_H1]);
+      if (MODE != 1) proxy_save(save_chunk, 0, HN);
     };
 
     // 16-bit element `c` (0..63) of this row in an operand chunk
@@ -629,6 +684,30 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       return make_float3(x.x + 0.1f * (m[0] + lds32(b3)), x.y + 0.1f * (m[1] + lds32(b3 + 4)), x.z + 0.1f * (m[2] + lds32(b3 + 8)));
     };
 
+    if constexpr (kProxy) {
+      if (g == 1) {  // ================================================= tape writers (see act_ready above)
+        uint32_t ph = 0;
+        for (;;) {
+          mbar_wait(act_ready, ph);
+          ph ^= 1;
+          tc_fence_after_sync();
+          const int c_tile = proxy_cmd[0], c_chunk = proxy_cmd[1], c_col = proxy_cmd[2], c_n = proxy_cmd[3];
+          if (c_chunk < 0) break;  // group 0 is done
+          uint32_t regs[8][16];
+          const int nblk = c_n >> 4;  // 16 columns = 32 values = one 64-B block of the row
+#pragma unroll
+          for (int b8 = 0; b8 < 8; ++b8)
+            if (b8 < nblk) tmem_ld16u(t_lane + kTmemAct + (uint32_t)c_col + 16u * b8, regs[b8]);
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(act_free);
+          uint8_t* tt = p.tape_a + (size_t)c_tile * TL.n_a * kChunkBytes;
+#pragma unroll
+          for (int b8 = 0; b8 < 8; ++b8)
+            if (b8 < nblk) chunk_st32(tt + (size_t)(c_chunk + (b8 >> 1)) * kChunkBytes, row, (uint32_t)(b8 & 1) * 4u, regs[b8]);
+        }
+      }
+    }
     for (int it = 0; it < (SPLIT && g == 1 ? 0 : iters); ++it) {  // SPLIT: group 1's resources hold the operand tails
       const int tile_raw = (kActive * it + g) * (int)gridDim.x + (int)blockIdx.x;
       const bool dead_tile = tile_raw >= p.n_tiles;
@@ -640,6 +719,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
       const int n = r_in / p.rays.D;
       const int k = r_in - n * p.rays.D;
       const size_t s = (size_t)f * p.ND + r_in;
+      cur_tile = tile;
       if constexpr (SAVE) {
         tape_tile = dead_tile ? nullptr : p.tape_a + (size_t)tile * TL.n_a * kChunkBytes;
         mask_row = dead_tile ? nullptr : p.tape_mask + ((size_t)tile * TL.n_mask * kTileRows + row) * kMaskWords;
@@ -734,6 +814,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
             pack_ht(v[2], v[3], u[3 * b2 + 1], ut[SPLIT ? 3 * b2 + 1 : 0]);
             pack_ht(v[4], v[5], u[3 * b2 + 2], ut[SPLIT ? 3 * b2 + 2 : 0]);
           }
+          proxy_wait();
           tmem_st32(tA, u);
           if (NP > 32) tmem_st8(tA + 32, u + (NP > 32 ? 32 : 0));
           if constexpr (SPLIT) {
@@ -1033,6 +1114,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         }
         a0 += lds32(sc_s + 4u * SC_RGB2_B0); a1 += lds32(sc_s + 4u * SC_RGB2_B1); a2 += lds32(sc_s + 4u * SC_RGB2_B2);
         st3(p.out.rgb, 1.f / (1.f + __expf(-a0)), 1.f / (1.f + __expf(-a1)), 1.f / (1.f + __expf(-a2)));
+      }
+    }
+    if constexpr (kProxy) {
+      if (g == 0) {  // tell the tape writers to leave
+        proxy_wait();
+        if (gtid == 0) proxy_cmd[1] = -1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(act_ready);
       }
     }
   }
