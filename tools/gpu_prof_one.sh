@@ -5,6 +5,17 @@ K=$1; TAG=$2; shift 2
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 -f -o gpurun_out/r02_$TAG \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph "$@" > gpurun_out/ncu_$TAG.log 2>&1
 ncu -i gpurun_out/r02_$TAG.ncu-rep --page raw --csv > gpurun_out/r02_${TAG}_raw.csv 2>/dev/null
+# top-sampled SASS instructions (the .ncu-rep itself is 25-35 MB: it stays on the box unless KEEP_REP=1)
+ncu -i gpurun_out/r02_$TAG.ncu-rep --page source --csv 2>/dev/null | python -c "
+import csv,sys
+rows=list(csv.reader(sys.stdin))
+h=rows[1]; isrc,isamp=h.index('Source'),h.index('# Samples')
+d=[(int(r[isamp]),i,r[isrc].strip()) for i,r in enumerate(rows[2:]) if len(r)>isamp and r[isamp].isdigit()]
+tot=sum(x[0] for x in d)
+print('total samples',tot,'instructions',len(d))
+for c,i,sx in sorted(d,reverse=True)[:25]: print('%7d %5.1f%%  #%5d  %s' % (c,100.0*c/tot,i,sx[:100]))
+" > gpurun_out/r02_${TAG}_top_sass.txt
+[ "$KEEP_REP" = "1" ] || rm -f gpurun_out/r02_$TAG.ncu-rep
 python - "$TAG" <<'PY'
 import csv,sys
 tag=sys.argv[1]
