@@ -141,14 +141,15 @@ static std::vector<WgradJob> build_jobs(const b200r_field_desc& d, const BuiltPr
 // split the (job, tile) line evenly over `grid` CTAs
 static void build_work(const std::vector<WgradJob>& jobs, int n_tiles, int grid, std::vector<WgradWork>& work, std::vector<int32_t>& first) {
   long long total = 0;
-  for (const auto& j : jobs) total += (long long)(j.n_g + j.n_a + 1) * n_tiles;
+  // cost of a job per tile: its chunks + a constant (a half-tile stage is latency-bound below ~3 chunks per operand pair)
+  for (const auto& j : jobs) total += (long long)(j.n_g + j.n_a + 3) * n_tiles;
   const long long per = (total + grid - 1) / grid;
   work.clear();
   first.assign(grid + 1, 0);
   int cta = 0;
   long long used = 0;  // cost already given to the current CTA
   for (int ji = 0; ji < (int)jobs.size(); ++ji) {
-    const long long c = jobs[ji].n_g + jobs[ji].n_a + 1;
+    const long long c = jobs[ji].n_g + jobs[ji].n_a + 3;
     int t = 0;
     while (t < n_tiles) {
       long long room = per - used;

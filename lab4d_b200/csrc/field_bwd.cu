@@ -280,10 +280,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
     const uint8_t* at_tile = nullptr;    // this tile's forward chunks
     const uint32_t* mask_row = nullptr;  // this row's ReLU sign words
     auto gtape_st32 = [&](int chunk, int col0, const uint32_t (&o)[16]) {
-      chunk_st32(gt_tile + (size_t)(chunk + (col0 >> 6)) * kChunkBytes, row, (uint32_t)(col0 & 63) >> 3, o);
+      chunk_st32(gt_tile + tape_row_off(TL.n_g, chunk + (col0 >> 6), row), row, (uint32_t)(col0 & 63) >> 3, o);
     };
     auto gtape_zero_row = [&](int chunk) {
-      uint8_t* base = gt_tile + (size_t)chunk * kChunkBytes + row * 128u;
+      uint8_t* base = gt_tile + tape_row_off(TL.n_g, chunk, row);
 #pragma unroll
       for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(base + 16 * j) = make_uint4(0u, 0u, 0u, 0u);
     };
@@ -396,11 +396,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
     auto load_g_to_act = [&](int chunk, int ncols) {
 #pragma unroll 1
       for (int blk = 0; blk < (ncols >> 5); ++blk) {
-        const uint8_t* base = gt_tile + (size_t)(chunk + (blk >> 1)) * kChunkBytes;
+        const uint8_t* base = gt_tile + tape_row_off(TL.n_g, chunk + (blk >> 1), row);
         uint32_t o[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint4 t = *reinterpret_cast<const uint4*>(base + (rowx ^ ((uint32_t)(4 * (blk & 1) + j) << 4)));
+          const uint4 t = *reinterpret_cast<const uint4*>(base + ((((uint32_t)(4 * (blk & 1) + j)) ^ (row & 7u)) << 4));
           o[4 * j] = t.x; o[4 * j + 1] = t.y; o[4 * j + 2] = t.z; o[4 * j + 3] = t.w;
         }
         tmem_st16(tA + 16 * blk, o);
@@ -487,8 +487,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
         const float g_vis = ld1(p.g.vis);
         {  // head chunk: columns 3 sdf, 4-6 rgb pre-sigmoid, 7 visibility logit (the order of the scalars block's biases)
           gtape_zero_row(TL.g_head);
-          uint8_t* base = gt_tile + (size_t)TL.g_head * kChunkBytes;
-          *reinterpret_cast<uint4*>(base + rowx) = make_uint4(0u, Op::pack2_sat(0.f, g_sdf), Op::pack2_sat(go0, go1), Op::pack2_sat(go2, g_vis));
+          uint8_t* base = gt_tile + tape_row_off(TL.n_g, TL.g_head, row);
+          *reinterpret_cast<uint4*>(base + ((row & 7u) << 4)) = make_uint4(0u, Op::pack2_sat(0.f, g_sdf), Op::pack2_sat(go0, go1), Op::pack2_sat(go2, g_vis));
         }
         // G of rgb.0's pre-activation: (g_o W2) * relu'
         const uint32_t w2 = cblk_s + 4u * CL.rgb2_w;
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
       auto dense_backward = [&](int m, int w, const float3& x_in, const float3& g_out) -> float3 {
         const float gm0 = 0.1f * g_out.x, gm1 = 0.1f * g_out.y, gm2 = 0.1f * g_out.z;
         gtape_zero_row(TL.g_d3[w]);
-        *reinterpret_cast<uint2*>(gt_tile + (size_t)TL.g_d3[w] * kChunkBytes + rowx) = make_uint2(Op::pack2_sat(gm0, gm1), Op::pack2_sat(gm2, 0.f));
+        *reinterpret_cast<uint2*>(gt_tile + tape_row_off(TL.n_g, TL.g_d3[w], row) + ((row & 7u) << 4)) = make_uint2(Op::pack2_sat(gm0, gm1), Op::pack2_sat(gm2, 0.f));
         const float* w3 = p.dense_w3[m];  // (3, 256) head weight, read through L1 (every row reads the same addresses)
         const uint4 ma = __ldg(reinterpret_cast<const uint4*>(mask_row + (size_t)TL.m_dh2[w] * (kTileRows * kMaskWords)));
         const uint4 mb = __ldg(reinterpret_cast<const uint4*>(mask_row + (size_t)TL.m_dh2[w] * (kTileRows * kMaskWords)) + 1);
@@ -711,10 +711,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
           float lw[B];   // logits -> softmax weights
           float zr[B];   // raw delta-MLP outputs
           {
-            const uint8_t* zb = at_tile + (size_t)TL.a_z[w] * kChunkBytes;
+            const uint8_t* zb = at_tile + tape_row_off(TL.n_a, TL.a_z[w], row);
 #pragma unroll
             for (int j = 0; j < (B + 7) / 8; ++j) {
-              const uint4 t = __ldg(reinterpret_cast<const uint4*>(zb + (rowx ^ ((uint32_t)j << 4))));
+              const uint4 t = __ldg(reinterpret_cast<const uint4*>(zb + (((uint32_t)j ^ (row & 7u)) << 4)));
               const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
@@ -802,10 +802,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
           }
           // operands of the bone-table gradients (wgrad kernel): [x y z 1 | g_qhr | g_qhd] and the signed weights
           {
-            uint8_t* xg = gt_tile + (size_t)TL.g_xg[w] * kChunkBytes;
+            uint8_t* xg = gt_tile + tape_row_off(TL.n_g, TL.g_xg[w], row);
             gtape_zero_row(TL.g_xg[w]);
-            *reinterpret_cast<uint4*>(xg + rowx) = make_uint4(Op::pack2(x.x, x.y), Op::pack2(x.z, 1.0f), Op::pack2_sat(g_qhr.w, g_qhr.x), Op::pack2_sat(g_qhr.y, g_qhr.z));
-            *reinterpret_cast<uint4*>(xg + (rowx ^ 16u)) = make_uint4(Op::pack2_sat(g_qhd.w, g_qhd.x), Op::pack2_sat(g_qhd.y, g_qhd.z), 0u, 0u);
+            *reinterpret_cast<uint4*>(xg + ((row & 7u) << 4)) = make_uint4(Op::pack2(x.x, x.y), Op::pack2(x.z, 1.0f), Op::pack2_sat(g_qhr.w, g_qhr.x), Op::pack2_sat(g_qhr.y, g_qhr.z));
+            *reinterpret_cast<uint4*>(xg + (((row & 7u) ^ 1u) << 4)) = make_uint4(Op::pack2_sat(g_qhd.w, g_qhd.x), Op::pack2_sat(g_qhd.y, g_qhd.z), 0u, 0u);
           }
           {
             uint32_t gz[16], wsp[16];

@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     auto tape_st32 = [&](int chunk, int col0, const uint32_t (&o)[16]) {
       if constexpr (SAVE) {
         if (tape_tile != nullptr && chunk >= 0) {
-          chunk_st32(tape_tile + (size_t)(chunk + (col0 >> 6)) * kChunkBytes, row, (uint32_t)(col0 & 63) >> 3, o);
+          chunk_st32(tape_tile + tape_row_off(TL.n_a, chunk + (col0 >> 6), row), row, (uint32_t)(col0 & 63) >> 3, o);
         }
       }
     };
@@ -659,10 +659,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
     auto tape_copy_row = [&](int chunk, uint32_t chunk_s, int ngroups) {
       if constexpr (SAVE) {
         if (tape_tile != nullptr && chunk >= 0) {
-          uint8_t* base = tape_tile + (size_t)chunk * kChunkBytes;
+          uint8_t* rp = tape_tile + tape_row_off(TL.n_a, chunk, row);
           for (int gq = 0; gq < ngroups; ++gq) {
-            const uint32_t off = rowx ^ ((uint32_t)gq << 4);
-            *reinterpret_cast<uint4*>(base + off) = lds128u(chunk_s + off);
+            const uint32_t slot = ((uint32_t)gq ^ (row & 7u)) << 4;
+            *reinterpret_cast<uint4*>(rp + slot) = lds128u(chunk_s + row * 128u + slot);
           }
         }
       }
@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
           uint8_t* tt = p.tape_a + (size_t)c_tile * TL.n_a * kChunkBytes;
 #pragma unroll
           for (int b8 = 0; b8 < 8; ++b8)
-            if (b8 < nblk) chunk_st32(tt + (size_t)(c_chunk + (b8 >> 1)) * kChunkBytes, row, (uint32_t)(b8 & 1) * 4u, regs[b8]);
+            if (b8 < nblk) chunk_st32(tt + tape_row_off(TL.n_a, c_chunk + (b8 >> 1), row), row, (uint32_t)(b8 & 1) * 4u, regs[b8]);
         }
       }
     }
@@ -825,8 +825,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
             if (tape_tile != nullptr) {
 #pragma unroll
               for (int j = 0; j < NP / 4; ++j) {
-                uint8_t* base = tape_tile + (size_t)(TL.a_xb[w] + (j >> 3)) * kChunkBytes;
-                *reinterpret_cast<uint4*>(base + (rowx ^ ((uint32_t)(j & 7) << 4))) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+                uint8_t* rp = tape_tile + tape_row_off(TL.n_a, TL.a_xb[w] + (j >> 3), row);
+                *reinterpret_cast<uint4*>(rp + ((((uint32_t)j & 7u) ^ (row & 7u)) << 4)) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
               }
             }
           }
@@ -1109,7 +1109,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_fwd_kernel(const __grid_con
         }
         if constexpr (SAVE) {  // raw view direction: the rgb.0 operand columns that stay in fp32 SIMT (bg fields)
           if (p.desc.L_dir == 0 && tape_tile != nullptr && TL.a_dir >= 0)
-            *reinterpret_cast<uint4*>(tape_tile + (size_t)TL.a_dir * kChunkBytes + rowx) =
+            *reinterpret_cast<uint4*>(tape_tile + tape_row_off(TL.n_a, TL.a_dir, row) + ((row & 7u) << 4)) =
                 make_uint4(Op::pack2(dir_f.x, dir_f.y), Op::pack2(dir_f.z, 0.f), 0u, 0u);
         }
         a0 += lds32(sc_s + 4u * SC_RGB2_B0); a1 += lds32(sc_s + 4u * SC_RGB2_B1); a2 += lds32(sc_s + 4u * SC_RGB2_B2);

@@ -494,7 +494,8 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int mode = MODE_FIE
 // ------------------------------------------------------------------------------------------------ training tape
 // A training-mode forward (b200r_field_fwd with a tape) records, per 128-sample tile, every MMA operand it produced
 // as [128 rows x 64] 16-bit chunks in the K-major SWIZZLE_128B image (16 KB each; row r at r * 128 B, 16-B group g at
-// ((g ^ (r & 7)) << 4)), plus one word of ReLU sign bits per (row, 32 columns).  The backward (b200r_field_bwd) adds
+// ((g ^ (r & 7)) << 4)), stored per tile as [64-row half][chunk][64 rows x 128 B] (ptx.cuh tape_row_off: the chunks of one
+// half are adjacent), plus one word of ReLU sign bits per (row, 32 columns).  The backward (b200r_field_bwd) adds
 // its masked gradients in the same format; the weight-gradient kernel then reads both straight into shared memory
 // with bulk copies and multiplies them as MN-major UMMA operands (reduction over the tile's rows).
 constexpr int kChunkBytes = kAChunkBytes;

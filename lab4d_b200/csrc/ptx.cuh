@@ -290,15 +290,21 @@ __device__ __forceinline__ void stg256(void* a, uint32_t r0, uint32_t r1, uint32
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(a), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4), "r"(r5), "r"(r6), "r"(r7)
                : "memory");
 }
-__device__ __forceinline__ void chunk_st32(uint8_t* chunk, uint32_t row, uint32_t g0, const uint32_t (&o)[16]) {
+// Tape layout of one tile with n_chunks chunks: [64-row half][chunk][64 rows x 128 B] - every chunk keeps the swizzled image
+// (a 64-row half of it is 8 KB, 1024-B aligned), and the chunks of one half are adjacent, so the weight-gradient kernel
+// fetches the G operand and the A operand of a half-tile stage with ONE contiguous bulk copy each.
+__host__ __device__ __forceinline__ size_t tape_row_off(int n_chunks, int chunk, uint32_t row) {
+  return ((size_t)(row >> 6) * (size_t)n_chunks + (size_t)chunk) * 8192u + (size_t)(row & 63u) * 128u;
+}
+// rowp = the 128 B of tile row `row` inside its chunk
+__device__ __forceinline__ void chunk_st32(uint8_t* rowp, uint32_t row, uint32_t g0, const uint32_t (&o)[16]) {
   const uint32_t r = row & 7u;
   const bool odd = (r & 1u) != 0;
-  uint8_t* rb = chunk + row * 128u;
 #pragma unroll
   for (int pr = 0; pr < 2; ++pr) {
     const uint32_t slot = ((g0 + 2u * pr) ^ r) & ~1u;
     const uint32_t* a = o + 8 * pr;
-    stg256(rb + (slot << 4), odd ? a[4] : a[0], odd ? a[5] : a[1], odd ? a[6] : a[2], odd ? a[7] : a[3], odd ? a[0] : a[4], odd ? a[1] : a[5],
+    stg256(rowp + (slot << 4), odd ? a[4] : a[0], odd ? a[5] : a[1], odd ? a[6] : a[2], odd ? a[7] : a[3], odd ? a[0] : a[4], odd ? a[1] : a[5],
            odd ? a[2] : a[6], odd ? a[3] : a[7]);
   }
 }

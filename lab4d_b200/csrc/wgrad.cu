@@ -72,22 +72,18 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         const uint8_t* gsrc = J.g_src ? p.tape_g : p.tape_a;
         const uint8_t* asrc = J.a_src ? p.tape_g : p.tape_a;
         const size_t gstride = (size_t)(J.g_src ? p.n_g : p.n_a) * kChunkBytes, astride = (size_t)(J.a_src ? p.n_g : p.n_a) * kChunkBytes;
-        // running source pointers: the loop below is the only work of this thread and must stay well under the ~1.4 us a
-        // 64 KB stage takes at this SM's share of the HBM bandwidth
-        const uint8_t* gp = gsrc + (size_t)W.tile0 * gstride + (size_t)J.g_chunk * kChunkBytes;
-        const uint8_t* ap = asrc + (size_t)W.tile0 * astride + (size_t)J.a_chunk * kChunkBytes;
         const int n_g = J.n_g, n_a = J.n_a;
-        const uint32_t bytes = (uint32_t)(n_g + n_a) * kHalfChunk;
-        for (int t = W.tile0; t < W.tile1; ++t, gp += gstride, ap += astride) {
+        const int gn = J.g_src ? p.n_g : p.n_a, an = J.a_src ? p.n_g : p.n_a;  // chunks per tile of each operand's tape
+        const uint32_t gbytes = (uint32_t)n_g * kHalfChunk, abytes = (uint32_t)n_a * kHalfChunk;
+        for (int t = W.tile0; t < W.tile1; ++t) {
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            mbar_arrive_expect_tx(&full_bar[stage], gbytes + abytes);
             uint8_t* dst = smem + stage * kStageBytes;
-#pragma unroll 4
-            for (int c = 0; c < n_g; ++c) tma_bulk_g2s(dst + c * kHalfChunk, gp + c * kChunkBytes + hh * kHalfChunk, kHalfChunk, &full_bar[stage]);
-#pragma unroll 4
-            for (int c = 0; c < n_a; ++c) tma_bulk_g2s(dst + kOperandBytes + c * kHalfChunk, ap + c * kChunkBytes + hh * kHalfChunk, kHalfChunk, &full_bar[stage]);
+            // tape layout [tile][64-row half][chunk]: the job's chunks of one half are one contiguous run
+            tma_bulk_g2s(dst, gsrc + (size_t)t * gstride + ((size_t)hh * gn + J.g_chunk) * kHalfChunk, gbytes, &full_bar[stage]);
+            tma_bulk_g2s(dst + kOperandBytes, asrc + (size_t)t * astride + ((size_t)hh * an + J.a_chunk) * kHalfChunk, abytes, &full_bar[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
