@@ -1,6 +1,7 @@
 // C ABI of the training path: tape sizes, block layouts, b200r_field_bwd (declarations: include/b200r.h).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -138,36 +139,72 @@ static std::vector<WgradJob> build_jobs(const b200r_field_desc& d, const BuiltPr
   return jobs;
 }
 
-// split the (job, tile) line evenly over `grid` CTAs
-static void build_work(const std::vector<WgradJob>& jobs, int n_tiles, int grid, std::vector<WgradWork>& work, std::vector<int32_t>& first) {
-  long long total = 0;
-  // cost of a job per tile: its chunks + a constant (a half-tile stage is latency-bound below ~3 chunks per operand pair)
-  for (const auto& j : jobs) total += (long long)(j.n_g + j.n_a + 3) * n_tiles;
-  const long long per = (total + grid - 1) / grid;
+// Split the (job, tile) line over `grid` CTAs so that every CTA gets the same estimated TIME.  Model (B200, measured shares):
+// a half-tile stage is latency-bound below ~3 chunks (1.2 us per tile), bandwidth-bound above (0.36 us per 16-KB chunk at
+// the SM's share of HBM); every work item ends with an accumulator flush of rows x cols fp32 atomics (~35 us per 64 K).
+static double model_const(const char* name, double dflt) {  // tuning hook: B200R_WG_LAT / _BW / _FLUSH (microseconds)
+  const char* e = getenv(name);
+  return e ? atof(e) : dflt;
+}
+static double job_tile_us(const WgradJob& j) {
+  static const double lat = model_const("B200R_WG_LAT", 2.5), per_chunk = model_const("B200R_WG_BW", 0.36);
+  const double bw = per_chunk * (j.n_g + j.n_a);
+  return bw > lat ? bw : lat;
+}
+static double job_flush_us(const WgradJob& j) {
+  static const double fl = model_const("B200R_WG_FLUSH", 50.0);
+  double area = 0;
+  for (int v = 0; v < j.n_views; ++v) area += (double)j.v[v].rows * ((j.v[v].cols + 31) / 32 * 32);
+  return 2.0 + fl * area / 65536.0;
+}
+// greedy assignment with a per-CTA time budget `per`; returns the largest load any CTA ends up with
+static double assign_work(const std::vector<WgradJob>& jobs, int n_tiles, int tiles_per_frame, int grid, double per, std::vector<WgradWork>& work,
+                          std::vector<int32_t>& first) {
   work.clear();
   first.assign(grid + 1, 0);
   int cta = 0;
-  long long used = 0;  // cost already given to the current CTA
+  double used = 0, worst = 0;
   for (int ji = 0; ji < (int)jobs.size(); ++ji) {
-    const long long c = jobs[ji].n_g + jobs[ji].n_a + 3;
+    const WgradJob& j = jobs[ji];
+    const double tt = job_tile_us(j) + (j.per_frame ? job_flush_us(j) / tiles_per_frame : 0.0);
+    const double fl = j.per_frame ? 0.0 : job_flush_us(j);
     int t = 0;
     while (t < n_tiles) {
-      long long room = per - used;
-      if (room < c && cta + 1 < grid) {  // next CTA
+      const double room = per - used - fl;
+      if (room < tt * 4 && cta + 1 < grid) {  // not worth a flush for a handful of tiles: next CTA
         ++cta;
         first[cta] = (int32_t)work.size();
         used = 0;
         continue;
       }
-      long long take = room / c;
+      long long take = (long long)(room / tt);
       if (take < 1) take = 1;
-      if (cta + 1 == grid || take > n_tiles - t) take = (cta + 1 == grid) ? n_tiles - t : (take > n_tiles - t ? n_tiles - t : take);
+      if (cta + 1 == grid || take > n_tiles - t) take = n_tiles - t;
       work.push_back({ji, t, t + (int)take});
-      used += take * c;
+      used += take * tt + fl;
+      worst = used > worst ? used : worst;
       t += (int)take;
     }
   }
   for (int c2 = cta + 1; c2 <= grid; ++c2) first[c2] = (int32_t)work.size();
+  return worst;
+}
+static void build_work(const std::vector<WgradJob>& jobs, int n_tiles, int tiles_per_frame, int grid, std::vector<WgradWork>& work,
+                       std::vector<int32_t>& first) {
+  double total = 0;
+  for (const auto& j : jobs) {
+    const double frames = j.per_frame ? (double)n_tiles / tiles_per_frame : 1.0;
+    total += job_tile_us(j) * n_tiles + job_flush_us(j) * (frames > 1 ? frames : 1.0);
+  }
+  // every cut adds a flush that `total` does not know about: smallest budget for which no CTA (the last one takes
+  // whatever is left) exceeds it
+  double lo = total / grid, hi = 2.0 * total / grid + 100.0;
+  for (int it = 0; it < 24; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (assign_work(jobs, n_tiles, tiles_per_frame, grid, mid, work, first) <= mid * 1.0001) hi = mid;
+    else lo = mid;
+  }
+  assign_work(jobs, n_tiles, tiles_per_frame, grid, hi, work, first);
 }
 
 }  // namespace b200r
@@ -301,7 +338,7 @@ int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
   std::vector<b200r::WgradWork> work;
   std::vector<int32_t> first;
   const int grid = h->n_sm;
-  b200r::build_work(jobs, n_tiles, grid, work, first);
+  b200r::build_work(jobs, n_tiles, tpf, grid, work, first);
   struct { b200r_field_desc d; int n_tiles, tpf, grid; } keyh = {dsc, n_tiles, tpf, grid};
   const std::string key = b200r::table_key("wg", &keyh, sizeof(keyh), out->weight_off, sizeof(out->weight_off));
   void* d_jobs = b200r::cached_table(h, key + "j", jobs.data(), jobs.size() * sizeof(b200r::WgradJob), stream, &e);
