@@ -279,6 +279,42 @@ int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
                     const b200r_field_grads* grads, const b200r_tape* tape, const b200r_param_grads* out,
                     const b200r_frame_grads* frame_grads, void* workspace, size_t workspace_bytes, b200r_stream stream);
 
+/* ------------------------------------------------------------------ eikonal term (NeRF.compute_eikonal)
+ * Replaces NeRF.compute_eikonal (lab4d/nnutils/nerf.py:416-453) and the second-order autograd it rests on
+ * (compute_gradient, lab4d/utils/torch_utils.py:4-28: autograd.grad(sdf, xyz, create_graph=True), differentiated again by
+ * total_loss.backward(), engine/trainer.py:344-345; through dqtorch for nothing - the points are detached).
+ * The reference evaluates g = d sdf / d xyz on all D samples of a random subset of the batch's rays and returns
+ * (|g| - 1)^2.  Here g is a REVERSE chain through the basefield with the ReLU signs the training forward left on the tape
+ * (b200r_eikonal_fwd, run after b200r_field_fwd_train of the same batch), and the gradient of a loss of g w.r.t. the
+ * basefield weights and sdf.weight is two FORWARD chains from dL/dg plus weight-gradient GEMMs of the chains' operands
+ * (b200r_eikonal_bwd) - both on tcgen05 with single 16-bit operands (fp32 accumulate).  Biases and instance codes get no
+ * gradient (they only move the ReLU signs), exactly as in the reference. */
+typedef struct {
+  int32_t n_rays;        /* selected rays (the reference: M*N / 16, torch.multinomial) */
+  int32_t pad_;
+  const int32_t* rays;   /* (n_rays) device: flat ray index f * N + n into the batch of the training forward */
+  void* a;               /* reverse-chain tape: written by b200r_eikonal_fwd, read by b200r_eikonal_bwd (1024-B aligned) */
+  void* v;               /* forward-chain tape: scratch of b200r_eikonal_bwd (1024-B aligned) */
+  size_t a_bytes, v_bytes;
+} b200r_eik_batch;
+
+/* Bytes of the two tapes for n_rays rays of D samples. */
+int b200r_eikonal_sizes(const b200r_field_desc* desc, int32_t n_rays, int32_t D, size_t* a_bytes, size_t* v_bytes);
+
+/* g_out (n_rays*D, 3) = d sdf / d xyz at the selected rays' samples.  `rays` is the training forward's ray batch (N, D),
+ * M its frame count, saved_xyz its per-sample canonical points (M*N*D, 3), `tape` its tape (sign words), packed_t the
+ * transposed operand tiles of b200r_pack_weights_t. */
+int b200r_eikonal_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* params,
+                      const b200r_ray_batch* rays, int32_t M, const float* saved_xyz, const b200r_tape* tape,
+                      const b200r_eik_batch* eik, float* g_out, b200r_stream stream);
+
+/* Given g_g (n_rays*D, 3) = dL/dg: ACCUMULATES dL/dW of basefield.linear_1..D, linear_final and sdf.weight into out->flat
+ * (weight_off of those layers and sdf_w; nothing else of `out` is used).  `packed` = the forward operand tiles
+ * (b200r_pack_weights; the heads of the split mode). */
+int b200r_eikonal_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* params,
+                      const b200r_ray_batch* rays, int32_t M, const float* saved_xyz, const b200r_tape* tape,
+                      const b200r_eik_batch* eik, const float* g_g, const b200r_param_grads* out, b200r_stream stream);
+
 /* NeRF.forward on given points (lab4d/nnutils/nerf.py:167-215), the boundary the reference's flat-point callers use
  * (geometry_init nerf.py:277, extract_canonical_mesh :328, eval-mode query_nerf :794-805): canonical points in, rgb /
  * density / sdf out.  Only the basefield, colorfield, sdf and rgb heads run (no ray placement, warps, visibility or

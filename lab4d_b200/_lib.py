@@ -116,7 +116,12 @@ class FrameGrads(C.Structure):
     _fields_ = [(n, f32p) for n in FRAME_GRADS]
 
 
-EXPORTS = ["b200r_tape_sizes", "b200r_field_fwd_train", "b200r_packed_t_bytes", "b200r_pack_weights_t", "b200r_get_block_layout",
+class EikBatch(C.Structure):
+    _fields_ = [("n_rays", C.c_int32), ("pad_", C.c_int32), ("rays", C.c_void_p), ("a", C.c_void_p), ("v", C.c_void_p),
+                ("a_bytes", C.c_size_t), ("v_bytes", C.c_size_t)]
+
+
+EXPORTS = ["b200r_eikonal_sizes", "b200r_eikonal_fwd", "b200r_eikonal_bwd", "b200r_tape_sizes", "b200r_field_fwd_train", "b200r_packed_t_bytes", "b200r_pack_weights_t", "b200r_get_block_layout",
            "b200r_field_bwd", "b200r_layer_count", "b200r_packed_bytes", "b200r_create", "b200r_destroy", "b200r_last_error",
            "b200r_pack_weights", "b200r_workspace_bytes", "b200r_field_fwd", "b200r_composite_fwd", "b200r_composite_bwd",
            "b200r_compose_fwd", "b200r_points_fwd", "b200r_warp_fwd", "b200r_importance_fwd"]
@@ -183,6 +188,14 @@ def load():
                                     C.POINTER(RayBatch), C.POINTER(FieldOutputs), C.POINTER(FieldGrads), C.POINTER(Tape),
                                     C.POINTER(ParamGrads), C.POINTER(FrameGrads), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.b200r_field_bwd.restype = C.c_int
+    lib.b200r_eikonal_sizes.argtypes = [C.POINTER(FieldDesc), C.c_int32, C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.b200r_eikonal_sizes.restype = C.c_int
+    lib.b200r_eikonal_fwd.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldParams), C.POINTER(RayBatch), C.c_int32,
+                                      C.c_void_p, C.POINTER(Tape), C.POINTER(EikBatch), C.c_void_p, C.c_void_p]
+    lib.b200r_eikonal_fwd.restype = C.c_int
+    lib.b200r_eikonal_bwd.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldParams), C.POINTER(RayBatch), C.c_int32,
+                                      C.c_void_p, C.POINTER(Tape), C.POINTER(EikBatch), C.c_void_p, C.POINTER(ParamGrads), C.c_void_p]
+    lib.b200r_eikonal_bwd.restype = C.c_int
     _lib = lib
     return lib
 

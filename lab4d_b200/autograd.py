@@ -8,6 +8,21 @@ from . import _lib
 _NO_GRAD_OUT = ("deltas", "eikonal", "xyz_t", "dir")
 
 
+def _bind_views(renderer, params):
+    """DDP's gradient_as_bucket_view arrangement: make the leaf parameters' .grad the views of the renderer's flat gradient
+    buffer (zeroed when no gradient has been written in this backward yet); the kernels then accumulate straight into it."""
+    flat, views = renderer.grad_buffer()
+    if all(p.grad is None for p in params.values()):
+        flat.zero_()
+    for n, p in params.items():
+        if p.grad is None:
+            p.grad = views[n]
+        elif p.grad.data_ptr() != views[n].data_ptr():  # another autograd path got there first: fold it in
+            views[n].copy_(p.grad)
+            p.grad = views[n]
+    return flat
+
+
 class FieldFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, renderer, meta, *tensors):
@@ -18,6 +33,7 @@ class FieldFunction(torch.autograd.Function):
         feat, deltas, c = renderer.query_field_train(P, rays, tab, meta["D"], flow_thresh=meta.get("flow_thresh"), depth=meta.get("depth"))
         keys = [k for k in feat if not k.startswith("density_")]
         meta["out_keys"] = keys
+        meta["ctx"] = c  # the eikonal term of the same batch reads the tape through it (`eikonal` below)
         ctx.renderer, ctx.c, ctx.keys, ctx.meta = renderer, c, keys, meta
         outs = [feat[k] for k in keys]
         ctx.mark_non_differentiable(deltas, *[o for k, o in zip(keys, outs) if k in _NO_GRAD_OUT])
@@ -29,16 +45,7 @@ class FieldFunction(torch.autograd.Function):
         meta = ctx.meta
         params = meta.get("bind")  # name -> leaf Parameter whose .grad should BE the flat buffer's view (no per-tensor copies)
         if params is not None:
-            # DDP's gradient_as_bucket_view arrangement: the kernels accumulate straight into the views
-            flat, views = ctx.renderer.grad_buffer()
-            if all(p.grad is None for p in params.values()):
-                flat.zero_()
-            for n, p in params.items():
-                if p.grad is None:
-                    p.grad = views[n]
-                elif p.grad.data_ptr() != views[n].data_ptr():  # another autograd path got there first: fold it in
-                    views[n].copy_(p.grad)
-                    p.grad = views[n]
+            _bind_views(ctx.renderer, params)
             _, tg = ctx.renderer.backward(ctx.c, grads, accumulate=True)
             pg = {}
         else:
@@ -54,7 +61,37 @@ class FieldFunction(torch.autograd.Function):
         return tuple(out)
 
 
-def query_field(renderer, P, rays, tab, D, flow_thresh=None, depth=None, bind_grads=False):
+class EikonalFunction(torch.autograd.Function):
+    """g = d sdf / d xyz on the samples of a subset of rays (NeRF.compute_eikonal, nnutils/nerf.py:416-453) with a
+    hand-derived backward to the basefield weights and sdf.weight - replaces the reference's autograd.grad(create_graph=True)
+    and the second-order pass through it (utils/torch_utils.py:4-28)."""
+
+    @staticmethod
+    def forward(ctx, renderer, c, ray_ids, bind, names, *weights):
+        g, ectx = renderer.eikonal_forward(c, ray_ids)
+        ctx.renderer, ctx.c, ctx.ectx, ctx.bind, ctx.names = renderer, c, ectx, bind, names
+        return g
+
+    @staticmethod
+    def backward(ctx, g_g):
+        if ctx.bind is not None:
+            flat = _bind_views(ctx.renderer, ctx.bind)
+            ctx.renderer.eikonal_backward(ctx.c, ctx.ectx, g_g, flat=flat)
+            return (None,) * (5 + len(ctx.names))
+        views = ctx.renderer.eikonal_backward(ctx.c, ctx.ectx, g_g)
+        return (None,) * 5 + tuple(views[n] for n in ctx.names)
+
+
+def eikonal(renderer, c, P, ray_ids, bind_grads=False):
+    """Differentiable sdf gradient on all samples of the rays `ray_ids` (flat indices into the (M, N) batch of the training
+    forward whose context is `c`, `query_field(..., return_ctx=True)`): (n_rays, D, 3), with autograd edges to the
+    basefield weights and sdf.weight of P.  bind_grads as in `query_field`."""
+    names = renderer.eikonal_weight_names()
+    bind = {k: v for k, v in P.items() if v.requires_grad and v.is_leaf} if bind_grads else None
+    return EikonalFunction.apply(renderer, c, ray_ids, bind, names, *[P[n] for n in names])
+
+
+def query_field(renderer, P, rays, tab, D, flow_thresh=None, depth=None, bind_grads=False, return_ctx=False):
     """Differentiable training-mode query_field: (feat_dict, deltas) like FieldRenderer.query_field, with autograd edges
     to P's tensors, tab's tensors and rays['Kinv'].  Call renderer.pack_train(P, alpha) first (every optimiser step).
     bind_grads: P's tensors are leaf parameters; their .grad become views of the renderer's flat gradient buffer and the
@@ -68,4 +105,6 @@ def query_field(renderer, P, rays, tab, D, flow_thresh=None, depth=None, bind_gr
     deltas, outs = res[0], res[1:]
     feat = dict(zip(meta["out_keys"], outs))
     feat["density_" + renderer.cfg.category] = feat["density"]  # the reference hands out the same tensor (nerf.py:809-812)
+    if return_ctx:
+        return feat, deltas, meta["ctx"]
     return feat, deltas

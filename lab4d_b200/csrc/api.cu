@@ -36,7 +36,7 @@ int b200r_create(int device, b200r_handle** out) {
   h->n_sm = prop.multiProcessorCount;
   h->d_scale = nullptr;
   cudaError_t e2 = cudaSetDevice(device);
-  if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&h->d_scale, 16);
+  if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&h->d_scale, 64);  // [0..2] field backward, [4..6] eikonal backward
   if (e2 != cudaSuccess) { delete h; return B200R_E_CUDA; }
   *out = h;
   return B200R_OK;

@@ -23,6 +23,7 @@ struct ScaleParams {
   float* scale;  // [0] scale, [1] 1 / scale
   unsigned int* amax_bits;
   int bf16;
+  float inv_extra;  // scale[1] = inv_extra / scale (0 = 1): the eikonal backward folds its reverse chain's fixed scale in
 };
 __global__ void absmax_kernel(const ScaleParams p) {
   float m = 0.f;
@@ -44,7 +45,7 @@ __global__ void scale_kernel(const ScaleParams p) {
   if (!p.bf16 && amax > 0.f) s = exp2f(floorf(log2f(1024.0f / amax)));  // fp16 tops out at 65504: 64x headroom, saturating packs beyond
   s = fminf(fmaxf(s, 1.0f / 16777216.0f), 1099511627776.0f);
   p.scale[0] = s;
-  p.scale[1] = 1.0f / s;
+  p.scale[1] = (p.inv_extra != 0.f ? p.inv_extra : 1.0f) / s;
 }
 
 // ---------------------------------------------------------------- weight-gradient job list
@@ -136,6 +137,40 @@ static std::vector<WgradJob> build_jobs(const b200r_field_desc& d, const BuiltPr
     layer_job(L.feat[4], T.g_feat[4], T.a_feat[3], 2, pe_f, 128);
     layer_job(L.feat[5], T.g_feat[5], T.a_feat[4], 2, 0, 128);
   }
+  return jobs;
+}
+
+// Weight-gradient jobs of the eikonal term (oracle/eikonal_backward.py weight_grads): G = reverse-chain tape (a_i), A = forward-chain
+// tape (v_0, chain A, chain B); dW_i = a_i^T (vA_{i-1} + vB_{i-1}), the embedding columns of linear_1 / the skip layer from v_0,
+// d sdf.weight = head^T (vA_D + vB_D).  No bias column sums: the chains carry no bias.
+static std::vector<WgradJob> build_eik_jobs(const b200r_field_desc& d, const BuiltProgram& bp, const EikLayout& E, const int64_t* woff, int64_t sdf_off) {
+  std::vector<WgradJob> jobs;
+  const LayerIds L = layer_ids(d);
+  const int W = d.W, KC = W / 64, pe_b = pe_dim(d.L_xyz), n_pe = pe_b < 63 ? pe_b : 63;
+  auto job = [&](int g_chunk, int n_g, int a_chunk, int n_a, int row0, int rows, int cols, int ld, int64_t off) {
+    WgradJob j;
+    memset(&j, 0, sizeof(j));
+    j.g_chunk = (int16_t)g_chunk; j.n_g = (int16_t)n_g; j.a_chunk = (int16_t)a_chunk; j.n_a = (int16_t)n_a;
+    j.g_src = 1; j.a_src = 0;
+    j.n_views = 1;
+    j.v[0].row0 = row0; j.v[0].col0 = 0; j.v[0].rows = rows; j.v[0].cols = cols; j.v[0].ld = ld; j.v[0].per_frame = DST_WEIGHTS; j.v[0].dst_off = off;
+    jobs.push_back(j);
+  };
+  for (int i = 0; i <= d.D; ++i) {
+    const int layer = L.base[i], ld = bp.layer_in[layer];
+    const int64_t off = woff[layer];
+    if (i == 0) {
+      job(E.a_base[i], KC, E.v0, 1, 0, W, n_pe, ld, off);
+    } else if (i == d.skip) {
+      job(E.a_base[i], KC, E.v0, 1, 0, W, n_pe, ld, off);
+      job(E.a_base[i], KC, E.vA[i - 1], KC, 0, W, W, ld, off + pe_b + 32);
+    } else {
+      job(E.a_base[i], KC, E.vA[i - 1], KC, 0, W, W, ld, off);
+      if (E.vB[i - 1] >= 0) job(E.a_base[i], KC, E.vB[i - 1], KC, 0, W, W, ld, off);
+    }
+  }
+  job(E.a_head, 1, E.vA[d.D], KC, 3, 1, W, W, sdf_off);
+  job(E.a_head, 1, E.vB[d.D], KC, 3, 1, W, W, sdf_off);
   return jobs;
 }
 
@@ -382,6 +417,171 @@ int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
       if (it.ptr && it.n && (e = cudaMemsetAsync(it.ptr, 0, it.n * 4, stream)) != cudaSuccess) return fail_cuda(h, e, "memset");
   }
   if ((e = b200r::launch_chain(cp, stream)) != cudaSuccess) return fail_cuda(h, e, "chain kernel");
+  return B200R_OK;
+}
+
+// ------------------------------------------------------------------ eikonal term
+static constexpr float kEikScaleA = 256.0f;  // scale of the reverse chain's unit cotangent in its 16-bit operands
+
+int b200r_eikonal_sizes(const b200r_field_desc* desc, int32_t n_rays, int32_t D, size_t* a_bytes, size_t* v_bytes) {
+  if (!desc || n_rays < 1 || D < 1) return B200R_E_INVALID;
+  const b200r::EikLayout E = b200r::eik_layout(*desc);
+  const size_t tiles = ((size_t)n_rays * D + b200r::kTileRows - 1) / b200r::kTileRows + b200r::kMaxCtas;  // + scratch tiles of dead pair halves
+  if (a_bytes) *a_bytes = tiles * E.n_a * b200r::kChunkBytes;
+  if (v_bytes) *v_bytes = tiles * E.n_v * b200r::kChunkBytes;
+  return B200R_OK;
+}
+
+static int eik_check(b200r_handle* h, const char* who, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
+                     const b200r_ray_batch* rays, int32_t M, const float* saved_xyz, const b200r_tape* tape, const b200r_eik_batch* eik, bool need_v) {
+  auto bad = [&](const char* msg) { return fail(h, B200R_E_INVALID, std::string(who) + ": " + msg); };
+  if (!desc || !packed || !par || !rays || !saved_xyz || !tape || !eik) return bad("null argument");
+  if (M < 1 || rays->N < 1 || rays->D < 1 || eik->n_rays < 1 || !eik->rays) return bad("need M, N, D, n_rays >= 1");
+  if (!tape->mask) return bad("the training tape (sign words) is missing");
+  size_t na, nv;
+  b200r_eikonal_sizes(desc, eik->n_rays, rays->D, &na, &nv);
+  if (!eik->a || eik->a_bytes < na || (reinterpret_cast<uintptr_t>(eik->a) & 1023)) return bad("reverse-chain tape missing, too small or not 1024-B aligned");
+  if (need_v && (!eik->v || eik->v_bytes < nv || (reinterpret_cast<uintptr_t>(eik->v) & 1023))) return bad("forward-chain tape missing, too small or not 1024-B aligned");
+  return B200R_OK;
+}
+
+static void eik_common(b200r::BwdKernelParams& kp, const b200r_field_desc& dsc, const b200r_field_desc& tape_desc, const b200r_ray_batch* rays,
+                       int32_t M, const float* saved_xyz, const b200r_tape* tape, const b200r_eik_batch* eik) {
+  kp.tape = b200r::tape_layout(tape_desc);
+  kp.desc = dsc;
+  kp.rays = *rays;
+  kp.saved.xyz = const_cast<float*>(saved_xyz);
+  kp.tape_mask = (const uint32_t*)tape->mask;
+  kp.M = M;
+  kp.ND = rays->N * rays->D;
+  kp.tiles_per_frame = (kp.ND + b200r::kTileRows - 1) / b200r::kTileRows;
+  kp.eik.n_points = eik->n_rays * rays->D;
+  kp.n_tiles = (kp.eik.n_points + b200r::kTileRows - 1) / b200r::kTileRows;
+  kp.eik.rays_sel = eik->rays;
+}
+
+int b200r_eikonal_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* par,
+                      const b200r_ray_batch* rays, int32_t M, const float* saved_xyz, const b200r_tape* tape,
+                      const b200r_eik_batch* eik, float* g_out, b200r_stream stream_) {
+  if (!h) return B200R_E_INVALID;
+  int rc = eik_check(h, "eikonal_fwd", desc, packed_t, par, rays, M, saved_xyz, tape, eik, false);
+  if (rc != B200R_OK) return rc;
+  if (!g_out || !par->sdf_w) return fail(h, B200R_E_INVALID, "eikonal_fwd: null argument");
+  b200r_field_desc dsc = *desc;
+  if (dsc.operand_dtype == 2) dsc.operand_dtype = 0;  // the W^T tiles are single fp16 (b200r_pack_weights_t)
+  b200r::BuiltProgram bp = b200r::build_bwd_program(dsc, /*density_only=*/true);
+  if (!bp.ok) return fail(h, B200R_E_INVALID, std::string("eikonal_fwd: ") + bp.err);
+  const b200r::EikLayout E = b200r::eik_layout(*desc);
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  b200r::BwdKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.prog = bp.prog;
+  eik_common(kp, dsc, *desc, rays, M, saved_xyz, tape, eik);
+  kp.packed_t = (const uint8_t*)packed_t;
+  kp.eik.mode = b200r::EIK_REVERSE;
+  kp.eik.g_out = g_out;
+  kp.eik.sdf_w = par->sdf_w;
+  kp.eik.tape = (uint8_t*)eik->a;
+  kp.eik.n_chunks = E.n_a;
+  kp.eik.scale_a = dsc.operand_dtype == 1 ? 1.0f : kEikScaleA;
+  kp.eik.head_chunk = (int16_t)E.a_head;
+  kp.eik.v0_chunk = -1;
+  for (int i = 0; i <= dsc.D; ++i) kp.eik.out_chunk[i] = (int16_t)E.a_base[i];
+  cudaError_t e = b200r::launch_field_bwd(kp, h->n_sm, (cudaStream_t)stream_);
+  if (e != cudaSuccess) return fail_cuda(h, e, "eikonal reverse chain");
+  return B200R_OK;
+}
+
+int b200r_eikonal_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
+                      const b200r_ray_batch* rays, int32_t M, const float* saved_xyz, const b200r_tape* tape,
+                      const b200r_eik_batch* eik, const float* g_g, const b200r_param_grads* out, b200r_stream stream_) {
+  if (!h) return B200R_E_INVALID;
+  int rc = eik_check(h, "eikonal_bwd", desc, packed, par, rays, M, saved_xyz, tape, eik, true);
+  if (rc != B200R_OK) return rc;
+  if (!g_g || !out || !out->flat || out->sdf_w < 0) return fail(h, B200R_E_INVALID, "eikonal_bwd: null argument");
+  b200r_field_desc dsc = *desc;            // the forward operand buffer's own layout (split mode: head + tail tiles) ...
+  b200r_field_desc kdsc = *desc;
+  if (kdsc.operand_dtype == 2) kdsc.operand_dtype = 0;  // ... read as single fp16 operands (the heads)
+  const b200r::EikLayout E = b200r::eik_layout(*desc);
+  const b200r::LayerIds ids = b200r::layer_ids(*desc);
+  for (int i = 0; i <= desc->D; ++i)
+    if (out->weight_off[ids.base[i]] < 0) return fail(h, B200R_E_INVALID, "eikonal_bwd: missing weight offset of a basefield layer");
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cudaError_t e;
+  const int P = eik->n_rays * rays->D;
+
+  // scale of dL/dg: the largest entry lands at ~4 (v_0 multiplies it by up to 2^(L-1)); 1 / (scale * reverse-chain scale) for the flush
+  float* d_sc = h->d_scale + 4;
+  const float scale_a = kdsc.operand_dtype == 1 ? 1.0f : kEikScaleA;
+  b200r::ScaleParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.ptr[0] = g_g; sp.n[0] = (long long)P * 3; sp.weight[0] = 256.0f;
+  sp.scale = d_sc;
+  sp.amax_bits = reinterpret_cast<unsigned int*>(d_sc + 2);
+  sp.bf16 = kdsc.operand_dtype == 1;
+  sp.inv_extra = 1.0f / scale_a;
+  if ((e = cudaMemsetAsync(d_sc + 2, 0, 4, stream)) != cudaSuccess) return fail_cuda(h, e, "memset");
+  b200r::absmax_kernel<<<h->n_sm, 256, 0, stream>>>(sp);
+  b200r::scale_kernel<<<1, 1, 0, stream>>>(sp);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail_cuda(h, e, "scale kernels");
+
+  // forward chains A and B
+  for (int which = b200r::EIK_CHAIN_A; which <= b200r::EIK_CHAIN_B; ++which) {
+    b200r::BuiltProgram bp = b200r::build_eik_chain_program(dsc, which);
+    if (!bp.ok) return fail(h, B200R_E_INVALID, std::string("eikonal_bwd: ") + bp.err);
+    b200r::BwdKernelParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.prog = bp.prog;
+    eik_common(kp, kdsc, *desc, rays, M, saved_xyz, tape, eik);
+    kp.packed_t = (const uint8_t*)packed;
+    kp.scale = d_sc;
+    kp.eik.mode = which;
+    kp.eik.gbar = g_g;
+    kp.eik.tape = (uint8_t*)eik->v;
+    kp.eik.n_chunks = E.n_v;
+    kp.eik.head_chunk = -1;
+    int nl = 0;
+    if (which == b200r::EIK_CHAIN_A) {
+      kp.eik.v0_chunk = (int16_t)E.v0;
+      for (int i = 0; i <= desc->D; ++i, ++nl) { kp.eik.mask_slot[nl] = kp.tape.m_base[i]; kp.eik.out_chunk[nl] = (int16_t)E.vA[i]; }
+    } else {
+      kp.eik.v0_chunk = -1;
+      for (int i = desc->skip; i <= desc->D; ++i, ++nl) { kp.eik.mask_slot[nl] = kp.tape.m_base[i]; kp.eik.out_chunk[nl] = (int16_t)E.vB[i]; }
+    }
+    kp.eik.n_layers = (int16_t)nl;
+    if ((e = b200r::launch_field_bwd(kp, h->n_sm, stream)) != cudaSuccess) return fail_cuda(h, e, "eikonal forward chain");
+  }
+
+  // weight gradients: reverse-chain tape x forward-chain tape
+  b200r::BuiltProgram bpl = b200r::build_program(kdsc);
+  if (!bpl.ok) return fail(h, B200R_E_INVALID, std::string("eikonal_bwd: ") + bpl.err);
+  std::vector<b200r::WgradJob> jobs = b200r::build_eik_jobs(kdsc, bpl, E, out->weight_off, out->sdf_w);
+  std::vector<b200r::WgradWork> work;
+  std::vector<int32_t> first;
+  const int n_tiles = (P + b200r::kTileRows - 1) / b200r::kTileRows;
+  const int grid = h->n_sm;
+  b200r::build_work(jobs, n_tiles, n_tiles, grid, work, first);
+  struct { b200r_field_desc d; int n_tiles, grid; int64_t sdf; } keyh = {kdsc, n_tiles, grid, out->sdf_w};
+  const std::string key = b200r::table_key("ek", &keyh, sizeof(keyh), out->weight_off, sizeof(out->weight_off));
+  void* d_jobs = b200r::cached_table(h, key + "j", jobs.data(), jobs.size() * sizeof(b200r::WgradJob), stream, &e);
+  void* d_work = b200r::cached_table(h, key + "w", work.data(), work.size() * sizeof(b200r::WgradWork), stream, &e);
+  void* d_first = b200r::cached_table(h, key + "f", first.data(), first.size() * sizeof(int32_t), stream, &e);
+  if (!d_jobs || !d_work || !d_first) return fail_cuda(h, e, "job table upload");
+  b200r::WgradParams wp;
+  memset(&wp, 0, sizeof(wp));
+  wp.tape_a = (const uint8_t*)eik->v;
+  wp.tape_g = (const uint8_t*)eik->a;
+  wp.n_a = E.n_v; wp.n_g = E.n_a;
+  wp.jobs = (const b200r::WgradJob*)d_jobs;
+  wp.work = (const b200r::WgradWork*)d_work;
+  wp.cta_first = (const int32_t*)d_first;
+  wp.grad = out->flat;
+  wp.tiles_per_frame = n_tiles;
+  wp.inv_scale = d_sc + 1;
+  if ((e = b200r::launch_wgrad(wp, grid, kdsc.operand_dtype, stream)) != cudaSuccess) return fail_cuda(h, e, "eikonal wgrad kernel");
   return B200R_OK;
 }
 

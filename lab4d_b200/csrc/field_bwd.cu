@@ -108,7 +108,34 @@ __device__ __noinline__ void pe_backward_fn(uint32_t tD, const float3& x, int nf
   gx.x += ax; gx.y += ay; gx.z += az;
 }
 
-template <class Op, int B, int WIDTH, bool DENSE>
+// directional derivative of the Fourier embedding along gb (eikonal forward chains): e[0:3] = gb, e[3 + 6k + d] = 2^k cos(2^k x_d) gb_d,
+// e[6 + 6k + d] = -2^k sin(2^k x_d) gb_d, zeros up to 64; same double-angle walk as the forward.  e lives in local memory.
+__device__ __noinline__ void pe_tangent_fn(const float3& x, int nfreq, const float3& gb, float* e) {
+#pragma unroll 1
+  for (int i = 0; i < 64; ++i) e[i] = 0.f;
+  e[0] = gb.x; e[1] = gb.y; e[2] = gb.z;
+  float fr = 1.0f, s0 = 0.f, s1 = 0.f, s2 = 0.f, c0 = 1.f, c1 = 1.f, c2 = 1.f;
+#pragma unroll 1
+  for (int kf = 0; kf < nfreq; ++kf) {
+    if ((kf & 3) == 0) {
+      sincosf(fr * x.x, &s0, &c0);
+      sincosf(fr * x.y, &s1, &c1);
+      sincosf(fr * x.z, &s2, &c2);
+    } else {
+      const float t0 = 2.f * s0 * c0, t1 = 2.f * s1 * c1, t2 = 2.f * s2 * c2;
+      c0 = 1.f - 2.f * s0 * s0; c1 = 1.f - 2.f * s1 * s1; c2 = 1.f - 2.f * s2 * s2;
+      s0 = t0; s1 = t1; s2 = t2;
+    }
+    float* o = e + 3 + 6 * kf;
+    o[0] = fr * c0 * gb.x; o[1] = fr * c1 * gb.y; o[2] = fr * c2 * gb.z;
+    o[3] = -fr * s0 * gb.x; o[4] = -fr * s1 * gb.y; o[5] = -fr * s2 * gb.z;
+    fr *= 2.0f;
+  }
+}
+
+// EIK: the eikonal instantiation (kernels.h EikParams) - the same producer / issuer / epilogue machinery running the masked
+// linear chains of the eikonal term on a list of rays; a separate instantiation, so the field backward's code is untouched.
+template <class Op, int B, int WIDTH, bool DENSE, bool EIK = false>
 __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -247,13 +274,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
     const uint32_t cblk_s = smem_u32(cblk), fblk_s = smem_u32(fblk_g);
     const uint32_t rowx = row * 128u + ((row & 7u) << 4);
     const uint32_t sc_s = cblk_s + 4u * CL.scalars;
-    {
+    if (p.workspace) {  // the eikonal modes read no block
       const float4* src = reinterpret_cast<const float4*>(p.workspace);
       float4* dst = reinterpret_cast<float4*>(cblk);
       for (int i = threadIdx.x; i < CL.n_floats / 4; i += kComputeThreads) dst[i] = __ldg(src + i);
     }
     named_bar_sync(3, kComputeThreads);
-    const float S = __ldg(p.scale);
+    const float S = p.scale ? __ldg(p.scale) : 1.0f;
 
     auto warp_arrive = [&](uint64_t* bar) {
       __syncwarp();
@@ -277,13 +304,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
 
     // per-tile pointers
     uint8_t* gt_tile = nullptr;          // this tile's gradient chunks
+    int n_gt = TL.n_g;                   // chunks per tile of the tape being written (the eikonal modes have their own)
     const uint8_t* at_tile = nullptr;    // this tile's forward chunks
     const uint32_t* mask_row = nullptr;  // this row's ReLU sign words
     auto gtape_st32 = [&](int chunk, int col0, const uint32_t (&o)[16]) {
-      chunk_st32(gt_tile + tape_row_off(TL.n_g, chunk + (col0 >> 6), row), row, (uint32_t)(col0 & 63) >> 3, o);
+      chunk_st32(gt_tile + tape_row_off(n_gt, chunk + (col0 >> 6), row), row, (uint32_t)(col0 & 63) >> 3, o);
     };
     auto gtape_zero_row = [&](int chunk) {
-      uint8_t* base = gt_tile + tape_row_off(TL.n_g, chunk, row);
+      uint8_t* base = gt_tile + tape_row_off(n_gt, chunk, row);
 #pragma unroll
       for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(base + 16 * j) = make_uint4(0u, 0u, 0u, 0u);
     };
@@ -322,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
       pm_a = __ldg(mp);
       if (NBLK > 2) pm_b = __ldg(mp + 1);
     };
-    auto wide_dgrad = [&](auto mode_tag, int mask_slot, int save_chunk, int next_slot) {
+    auto wide_dgrad = [&](auto mode_tag, int mask_slot, int save_chunk, int next_slot, bool last = false) {
       constexpr int MODE = decltype(mode_tag)::value;
       uint32_t hold[NBLK][16];
       (void)mask_slot;  // its words were requested by the previous layer (prefetch_mask)
@@ -390,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
       }
       tmem_st_wait();
       tc_fence_before_sync();
-      warp_arrive(&c2m_g[BAR_H1]);
+      if (!last) warp_arrive(&c2m_g[BAR_H1]);  // `last`: no block of this tile is left to consume the arrival
     };
     // gradient rows of a tape chunk range -> activations (the density chain starts from what the rgb.0 epilogue parked)
     auto load_g_to_act = [&](int chunk, int ncols) {
@@ -415,6 +443,88 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
       const int tile_raw = (kGroups * it + g) * (int)gridDim.x + (int)blockIdx.x;
       const bool dead_tile = tile_raw >= p.n_tiles;
       const int tile = dead_tile ? p.n_tiles - 1 : tile_raw;
+      if constexpr (EIK) {
+        // ================================================================ eikonal chains (nnutils/nerf.py:416-453)
+        const EikParams& E = p.eik;
+        const int pi_raw = tile * kTileRows + (int)row;
+        const bool live_p = !dead_tile && pi_raw < E.n_points;
+        const int pi = pi_raw < E.n_points ? pi_raw : E.n_points - 1;
+        const int DD = p.rays.D;
+        const int rsel = pi / DD, kk = pi - rsel * DD;
+        const int ray = __ldg(E.rays_sel + rsel);       // f * N + n in the training forward's batch
+        const int fm = ray / p.rays.N, r_in = (ray - fm * p.rays.N) * DD + kk;
+        const size_t s = (size_t)fm * p.ND + r_in;
+        // the sample's ReLU sign words sit in the training tape's tile (frame, r_in / 128), row r_in % 128
+        mask_row = p.tape_mask + ((size_t)(fm * p.tiles_per_frame + r_in / kTileRows) * TL.n_mask * kTileRows + (uint32_t)(r_in % kTileRows)) * kMaskWords;
+        n_gt = E.n_chunks;
+        gt_tile = E.tape + (size_t)(dead_tile ? p.n_tiles + (int)blockIdx.x : tile) * E.n_chunks * kChunkBytes;
+        const float3 x = make_float3(__ldg(p.saved.xyz + s * 3), __ldg(p.saved.xyz + s * 3 + 1), __ldg(p.saved.xyz + s * 3 + 2));
+        if (E.mode == 1) {
+          // ---- reverse chain: a_F = relu'(linear_final) * (scale * w_sdf) -> activations and tape, then the density chain's
+          // data-gradient GEMMs; the embedding columns come back as g = E(x)^T u
+          const float Sa = live_p ? E.scale_a : 0.f;
+          gtape_zero_row(E.head_chunk);
+          *reinterpret_cast<uint4*>(gt_tile + tape_row_off(n_gt, E.head_chunk, row) + ((row & 7u) << 4)) = make_uint4(0u, Op::pack2_sat(0.f, Sa), 0u, 0u);
+          {
+            const uint4* mp = reinterpret_cast<const uint4*>(mask_row + (size_t)TL.m_base[Dn] * (kTileRows * kMaskWords));
+            const uint4 ma = __ldg(mp), mb = NBLK > 2 ? __ldg(mp + 1) : make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t mws[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+#pragma unroll 1
+            for (int blk = 0; blk < WIDTH / 32; ++blk) {
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(E.sdf_w + 32 * blk + j));
+                v[j] = Sa * w4.x; v[j + 1] = Sa * w4.y; v[j + 2] = Sa * w4.z; v[j + 3] = Sa * w4.w;
+              }
+              uint32_t o[16];
+              mask_pack32(v, mws[blk], o);
+              tmem_st16(tA + 16 * blk, o);
+              gtape_st32(E.out_chunk[Dn], 32 * blk, o);
+            }
+            tmem_st_wait();
+          }
+          prefetch_mask(TL.m_base[Dn - 1]);
+          float3 gx = make_float3(0.f, 0.f, 0.f);
+          arrive_all();
+#pragma unroll 1
+          for (int i = Dn; i >= 1; --i) {
+            if (i == p.desc.skip) {
+              wait_all();
+              pe_backward(x, p.desc.L_xyz, gx);
+              arrive_all();
+            }
+            wide_dgrad(std::integral_constant<int, 0>{}, TL.m_base[i - 1], E.out_chunk[i - 1], i >= 2 ? TL.m_base[i - 2] : -1);
+          }
+          wait_all();
+          pe_backward(x, p.desc.L_xyz, gx);
+          if (live_p) {
+            const float inv = 1.0f / E.scale_a;
+            E.g_out[(size_t)pi * 3] = gx.x * inv; E.g_out[(size_t)pi * 3 + 1] = gx.y * inv; E.g_out[(size_t)pi * 3 + 2] = gx.z * inv;
+          }
+        } else {
+          // ---- forward chain A (mode 2) / B (mode 3): v_0 = E(x) (scale * gbar) -> 64 operand columns, then the layers
+          const float Sv = live_p ? S : 0.f;
+          const float3 gb = make_float3(Sv * __ldg(E.gbar + (size_t)pi * 3), Sv * __ldg(E.gbar + (size_t)pi * 3 + 1), Sv * __ldg(E.gbar + (size_t)pi * 3 + 2));
+          float e64[64];
+          pe_tangent_fn(x, p.desc.L_xyz, gb, e64);
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = Op::pack2_sat(e64[32 * hb + 2 * i], e64[32 * hb + 2 * i + 1]);
+            tmem_st16(tA + 16 * hb, o);
+            if (E.v0_chunk >= 0) gtape_st32(E.v0_chunk, 32 * hb, o);
+          }
+          tmem_st_wait();
+          prefetch_mask(E.mask_slot[0]);
+          arrive_all();
+#pragma unroll 1
+          for (int l = 0; l < E.n_layers; ++l)
+            wide_dgrad(std::integral_constant<int, 0>{}, E.mask_slot[l], E.out_chunk[l], l + 1 < E.n_layers ? E.mask_slot[l + 1] : -1, l + 1 == E.n_layers);
+        }
+        continue;
+      }
       const int f = tile / p.tiles_per_frame;
       const int r_raw = (tile - f * p.tiles_per_frame) * kTileRows + (int)row;
       const bool live = !dead_tile && r_raw < p.ND;
@@ -925,9 +1035,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
   }
 }
 
-template <class Op, int B, int WIDTH, bool DENSE>
+template <class Op, int B, int WIDTH, bool DENSE, bool EIK = false>
 static cudaError_t launch_one(const BwdKernelParams& p, int n_sm, cudaStream_t stream) {
-  auto kern = field_bwd_kernel<Op, B, WIDTH, DENSE>;
+  auto kern = field_bwd_kernel<Op, B, WIDTH, DENSE, EIK>;
   const int smem = 1024 + kSmemRing + (p.prog.cl.n_floats + kGroups * p.prog.fl.n_floats) * 4 + 256;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -957,6 +1067,11 @@ static cudaError_t launch_one(const BwdKernelParams& p, int n_sm, cudaStream_t s
 
 cudaError_t launch_field_bwd(const BwdKernelParams& p, int n_sm, cudaStream_t stream) {
   const bool bf = p.desc.operand_dtype == 1;
+  if (p.eik.mode != 0) {  // eikonal chains: the basefield only, whatever warps the field has
+    if (p.desc.W == 256) return bf ? bwd::launch_one<OpBF16, 0, 256, false, true>(p, n_sm, stream) : bwd::launch_one<OpF16, 0, 256, false, true>(p, n_sm, stream);
+    if (p.desc.W == 128) return bf ? bwd::launch_one<OpBF16, 0, 128, false, true>(p, n_sm, stream) : bwd::launch_one<OpF16, 0, 128, false, true>(p, n_sm, stream);
+    return cudaErrorInvalidValue;
+  }
 #define B200R_CASE(BN, WD, DN)                                                 \
   if (p.desc.n_bones == BN && p.desc.W == WD && (p.desc.dense != 0) == DN)     \
     return bf ? bwd::launch_one<OpBF16, BN, WD, DN>(p, n_sm, stream) : bwd::launch_one<OpF16, BN, WD, DN>(p, n_sm, stream);

@@ -15,7 +15,7 @@ struct b200r_handle {
   std::string err;
   struct Table { std::vector<uint8_t> host; void* dev; };
   std::map<std::string, Table> tables;
-  float* d_scale;  // [2] device scalars of the backward: gradient scale and its inverse
+  float* d_scale;  // device scalars of the backward: [0] gradient scale, [1] its inverse, [2] max bits; [4..6] the same for the eikonal backward
 };
 
 namespace b200r {

@@ -53,6 +53,29 @@ struct FieldKernelParams {
   TapeLayout tape;
 };
 
+// ---- eikonal modes of the field backward kernel (NeRF.compute_eikonal, lab4d/nnutils/nerf.py:416-453): masked LINEAR chains
+// over the basefield on the samples of a list of rays, with the ReLU signs the training forward put on the tape.
+//   mode 1 (reverse chain, b200r_eikonal_fwd): a_F = relu'(linear_final) * w_sdf, a_{l-1} = relu'_{l-1} * (W_l^T a_l), g = E(x)^T u
+//   mode 2 / 3 (forward chains A / B, b200r_eikonal_bwd): v_0 = E(x) gbar, v_l = relu'_l * (W_l v_{l-1}); chain A walks every
+//   layer (the skip layer takes its hidden columns only), chain B starts at the skip layer's embedding columns.
+struct EikParams {
+  int32_t mode;             // 0 = off (the kernel is the field backward)
+  int32_t n_points;         // n_rays * D
+  const int32_t* rays_sel;  // (n_rays) flat ray indices f * N + n of the training forward's batch
+  const float* gbar;        // (n_points, 3) dL/dg            (modes 2, 3)
+  float* g_out;             // (n_points, 3) g = d sdf / d x   (mode 1)
+  const float* sdf_w;       // sdf.weight (W)                  (mode 1)
+  uint8_t* tape;            // output chunks of this pass: n_tiles + kMaxCtas tiles of n_chunks chunks
+  int32_t n_chunks;
+  float scale_a;            // mode 1: power-of-two scale of the unit cotangent (16-bit operands)
+  int16_t n_layers;         // modes 2, 3: wide layers of the chain
+  int16_t v0_chunk;         // mode 2: chunk of v_0 (-1: not stored)
+  int16_t head_chunk;       // mode 1: chunk whose column 3 carries the scaled unit cotangent (operand of d sdf.weight)
+  int16_t pad_;
+  int16_t mask_slot[12];    // modes 2, 3: sign-word slot of every layer, in chain order
+  int16_t out_chunk[12];    // mode 1: chunk of a_i, i = 0..D (basefield layer order); modes 2, 3: chunk of every layer's v, in chain order
+};
+
 // ---- backward of the field kernel (csrc/field_bwd.cu)
 struct BwdKernelParams {
   Program prog;                // build_bwd_program: transposed-weight blocks, same constant / frame block layouts
@@ -70,7 +93,8 @@ struct BwdKernelParams {
   float* g_fblk;               // gradient of the frame blocks (zeroed by the caller)
   const float* scale;          // device scalar: power-of-two gradient scale
   const float* dense_w3[2];    // ComposedWarp: post_warp.{forward_map, backward_map}.linear_final.weight (3, 256)
-  int32_t M, ND, tiles_per_frame, n_tiles;
+  int32_t M, ND, tiles_per_frame, n_tiles;  // eikonal modes: ND / tiles_per_frame describe the training forward's batch, n_tiles the point tiles
+  EikParams eik;
 };
 cudaError_t launch_field_bwd(const BwdKernelParams& p, int n_sm, cudaStream_t stream);
 

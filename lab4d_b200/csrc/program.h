@@ -160,9 +160,13 @@ inline LayerIds layer_ids(const b200r_field_desc& d) {
   return L;
 }
 
+// one packed K chunk of a layer: offset of its (first) tile in the operand buffer, padded N, UMMA_K steps
+struct ChunkRef { uint32_t w_off; int n; int ksteps; };
+
 struct BuiltProgram {
   Program prog;
   std::vector<PackSlice> slices;
+  std::vector<std::vector<ChunkRef>> fwd_chunks, fwd_chunks_h1;  // per canonical layer (N-half 1 of the pipelined layers in _h1)
   std::vector<int> layer_out;  // N of each canonical layer
   std::vector<int> layer_in;   // fp32 source in_dim of each canonical layer
   size_t packed_bytes;
@@ -201,7 +205,7 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int mode = MODE_FIE
   const int W = d.W, HN = W / 2, KC = W / 64;  // half width of the pipelined layers, hidden K chunks
   uint32_t off = 0;
   // chunk lists per layer; pipelined layers keep one list per N-half
-  struct Chunk { uint32_t w_off; int n; int ksteps; };
+  using Chunk = ChunkRef;
   std::vector<std::vector<Chunk>> chunks(L.count), chunks_h1(L.count);
 
   auto sl = [](int col0, int ncols, int win = 0) {
@@ -288,6 +292,8 @@ inline BuiltProgram build_program(const b200r_field_desc& d, int mode = MODE_FIE
     }
   }
   bp.packed_bytes = off;
+  bp.fwd_chunks = chunks;
+  bp.fwd_chunks_h1 = chunks_h1;
 
   // ---- frame block: cameras, conditioned bias rows, bone tables
   FrameLayout& F = P.fl;
@@ -564,7 +570,9 @@ inline size_t tape_mask_bytes(const TapeLayout& T, int n_tiles) { return (size_t
 // code as the forward.  Block order = the order of csrc/field_bwd.cu's phases:
 //   rgb.0, colorfield (final, 2, 1), basefield (final, D..1; the skip layer first returns its embedding columns),
 //   feature field, visibility MLP, then per skinning warp w = 2, 1, 0: [dense map], delta MLP (final, 2, 1).
-inline BuiltProgram build_bwd_program(const b200r_field_desc& d) {
+// `density_only`: the step list holds the density chain alone (basefield final .. linear_1, the reverse chain of the eikonal
+// term, csrc/field_bwd.cu mode 1) - the tile offsets are those of the full program, so both read the same W^T buffer.
+inline BuiltProgram build_bwd_program(const b200r_field_desc& d, bool density_only = false) {
   BuiltProgram bp = build_program(d, MODE_FIELD);  // same constant / frame block layouts, same checks
   if (!bp.ok) return bp;
   bp.ok = false;
@@ -595,7 +603,9 @@ inline BuiltProgram build_bwd_program(const b200r_field_desc& d) {
     }
     return v;
   };
+  bool emit = !density_only;  // tiles are laid out for every block; steps only for the emitted ones
   auto block = [&](const std::vector<Chunk>& cs, int wait, int commit) {
+    if (!emit) return;
     if (P.n_blocks >= kMaxSteps) { ok = false; return; }
     MmaBlock& Bk = P.blocks[P.n_blocks++];
     Bk = MmaBlock{};
@@ -631,6 +641,7 @@ inline BuiltProgram build_bwd_program(const b200r_field_desc& d) {
   pipe(L.color[1], 0, W, BAR_H1);
   seq(L.color[0], 0, pe_c, 2, BAR_H1);
   // ---- density chain
+  if (density_only) emit = true;
   pipe(L.base[d.D], 0, W, BAR_ALL);
   for (int i = d.D - 1; i >= 1; --i) {
     if (i == d.skip) {
@@ -641,6 +652,7 @@ inline BuiltProgram build_bwd_program(const b200r_field_desc& d) {
     }
   }
   seq(L.base[0], 0, pe_b, 1, BAR_H1);
+  if (density_only) emit = false;
   // ---- feature field
   if (d.has_feature) {
     seq(L.feat[5], 0, 128);
@@ -669,6 +681,79 @@ inline BuiltProgram build_bwd_program(const b200r_field_desc& d) {
   if (!ok) { bp.err = "internal: backward program does not fit"; return bp; }
   bp.ok = true;
   return bp;
+}
+
+// ------------------------------------------------------------------------------------------------ eikonal chains
+// Forward chains of the eikonal term's backward (csrc/field_bwd.cu modes 2 / 3): v_l = relu'_l * (W_l v_{l-1}) over the
+// basefield with the FORWARD operand tiles (heads only in the split mode), every operand in TMEM, one tile per ring slot.
+//   chain A: linear_1 (embedding chunk), linear_2 .. final (the skip layer takes its hidden chunks only);
+//   chain B: the skip layer's embedding chunk, then the layers after it.
+enum : int { EIK_REVERSE = 1, EIK_CHAIN_A = 2, EIK_CHAIN_B = 3 };
+inline BuiltProgram build_eik_chain_program(const b200r_field_desc& d, int which) {
+  BuiltProgram bp = build_program(d, MODE_FIELD);
+  if (!bp.ok) return bp;
+  bp.ok = false;
+  Program& P = bp.prog;
+  P.n_steps = 0;
+  P.n_blocks = 0;
+  const LayerIds L = layer_ids(d);
+  int ns = 0;
+  bool ok = true;
+  auto block = [&](const std::vector<ChunkRef>& cs, size_t c0, size_t c1, int wait, int commit) {
+    if (c1 > cs.size() || c0 >= c1) { ok = false; return; }
+    for (size_t c = c0; c < c1; ++c) {
+      if (ns >= kMaxSteps) { ok = false; return; }
+      MmaStep& S = P.steps[ns++];
+      S = MmaStep{};
+      S.w_off = cs[c].w_off; S.n = (uint16_t)cs[c].n; S.n_sub = 1; S.a_kind = 1;
+      S.ksteps = (uint8_t)cs[c].ksteps;
+      S.accumulate = c > c0; S.wait = (uint8_t)(c == c0 ? wait : BAR_NONE); S.commit = (uint8_t)(c + 1 == c1 ? commit : BAR_NONE);
+      ok = ok && (cs[c].ksteps == 4 || c + 1 == c1);  // operand columns advance by 64 halves per slot
+    }
+  };
+  auto pipe = [&](int layer, size_t c0, size_t c1, int first_wait) {
+    block(bp.fwd_chunks[layer], c0, c1, first_wait, BAR_H0);
+    block(bp.fwd_chunks_h1[layer], c0, c1, BAR_H0, BAR_H1);
+  };
+  const size_t n_pe_chunks = bp.fwd_chunks[L.base[0]].size();  // embedding chunks of the basefield input
+  if (n_pe_chunks != 1) { bp.err = "eikonal chains need a one-chunk position embedding"; return bp; }
+  if (which == EIK_CHAIN_A) {
+    for (int i = 0; i <= d.D; ++i) {
+      const size_t n = bp.fwd_chunks[L.base[i]].size();
+      if (i == 0) pipe(L.base[i], 0, 1, BAR_ALL);
+      else if (i == d.skip) pipe(L.base[i], n_pe_chunks, n, BAR_H1);
+      else pipe(L.base[i], 0, n, BAR_H1);
+    }
+  } else if (which == EIK_CHAIN_B) {
+    pipe(L.base[d.skip], 0, 1, BAR_ALL);
+    for (int i = d.skip + 1; i <= d.D; ++i) pipe(L.base[i], 0, bp.fwd_chunks[L.base[i]].size(), BAR_H1);
+  } else {
+    bp.err = "internal: unknown eikonal chain";
+    return bp;
+  }
+  P.n_steps = ns;
+  if (!ok) { bp.err = "internal: eikonal chain program does not fit"; return bp; }
+  bp.ok = true;
+  return bp;
+}
+// chunk ids inside the two eikonal tapes (per 128-point tile, same [half][chunk] image as the training tape)
+struct EikLayout {
+  int n_a, n_v;  // chunks per tile of the reverse-chain tape / of the forward-chain tape
+  int a_base[10], a_head;            // reverse chain: a_i of basefield layer i (KC chunks each), head chunk
+  int v0, vA[10], vB[10];            // forward chains: v_0 (1 chunk), chain A / chain B outputs per layer (-1 = absent)
+};
+inline EikLayout eik_layout(const b200r_field_desc& d) {
+  EikLayout E;
+  const int KC = d.W / 64;
+  int a = 0, v = 0;
+  for (int i = 0; i < 10; ++i) { E.a_base[i] = -1; E.vA[i] = -1; E.vB[i] = -1; }
+  for (int i = 0; i <= d.D; ++i) { E.a_base[i] = a; a += KC; }
+  E.a_head = a++;
+  E.v0 = v++;
+  for (int i = 0; i <= d.D; ++i) { E.vA[i] = v; v += KC; }
+  for (int i = d.skip; i <= d.D; ++i) { E.vB[i] = v; v += KC; }
+  E.n_a = a; E.n_v = v;
+  return E;
 }
 
 inline size_t workspace_floats(const Program& P, int M) { return (size_t)P.cl.n_floats + (size_t)M * P.fl.n_floats; }

@@ -12,8 +12,8 @@ reference's small per-frame MLPs and handed over as tables.
 Training (autograd recording): query_field goes through lab4d_b200.autograd.FieldFunction - training forward with the
 tape, hand-derived backward kernels, gradients delivered to the reference modules' own Parameters and, through the
 per-frame tables, to the camera / articulation / embedding modules.  Eval mode: importance sampling + bounding-box
-masking + the reference's normals.  global_match / forward_project (feature.py:152-226) and the eikonal term stay the
-reference's own torch code, evaluated on the kernels' xyz / feature outputs.
+masking + the reference's normals.  The eikonal term of a training step runs on the eikonal kernels (compute_eikonal below);
+global_match / forward_project (feature.py:152-226) stay the reference's own torch code on the kernels' xyz / feature outputs.
 """
 import functools
 
@@ -92,10 +92,28 @@ def _hot_params(field, cfg):
     return {k: named[k] for k in field_param_shapes(cfg)}
 
 
+def compute_eikonal(field, renderer, ctx, P, xyz, sample_ratio=16, bind_grads=False):
+    """Replacement body of NeRF.compute_eikonal (nnutils/nerf.py:416-453) for the samples of a training forward: the same
+    random subset of rays (one torch.multinomial draw from the default CPU generator, like the reference), the sdf gradient
+    from the eikonal kernels, (|g| - 1)^2 scattered into zeros (M,N,D,1).  Gradients reach the basefield weights and
+    sdf.weight through lab4d_b200.autograd.EikonalFunction."""
+    from . import autograd as _ag
+
+    M, N, D, _ = xyz.shape
+    R = M * N
+    sample_size = max(R // sample_ratio, 1)
+    rand_inds = torch.multinomial(torch.ones(R), sample_size, replacement=False) if R > sample_size else torch.arange(R)
+    g = _ag.eikonal(renderer, ctx, P, rand_inds, bind_grads=bind_grads)
+    eik = torch.zeros(R, D, device=xyz.device, dtype=xyz.dtype)
+    eik[rand_inds.to(xyz.device)] = (g.norm(2, dim=-1) - 1) ** 2
+    return eik.view(M, N, D, 1)
+
+
 def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False):
     """Replacement body of NeRF.query_field (nnutils/nerf.py:580-684) for NeRF / FeatureNeRF / Deformable modules.
     Training mode: the fused kernels (with the tape and the hand-derived backward when autograd is recording); the
-    eikonal term stays the reference's own `compute_eikonal` (second-order autograd on 1/16 of the rays).
+    eikonal term runs on the eikonal kernels (`compute_eikonal` above: reverse chain with the tape's ReLU signs, hand-derived
+    second-order backward) - on the reference's own `compute_eikonal` only when no gradient is recorded.
     Eval mode (`lab4d/render.py` -> dvr_model.evaluate): importance sampling (nerf.py:686-738), samples outside the
     bounding boxes zeroed like the reference's masked query_nerf (nerf.py:495-528, 769-819), normals from the
     reference's `compute_normal`.  Returns (feat_dict, deltas, aux_dict) like the reference."""
@@ -114,12 +132,13 @@ def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype
             from . import autograd as _ag
 
             r.pack_train({k: v.detach() for k, v in P.items()}, alpha=alpha)
-            feat, deltas = _ag.query_field(r, P, rays, tab, n_depth, flow_thresh=flow_thresh, bind_grads=bind_grads)
+            feat, deltas, ctx = _ag.query_field(r, P, rays, tab, n_depth, flow_thresh=flow_thresh, bind_grads=bind_grads, return_ctx=True)
+            feat["eikonal"] = compute_eikonal(field, r, ctx, P, feat["xyz"], bind_grads=bind_grads)  # eikonal kernels on the tape's masks
         else:
             with torch.no_grad():
                 r.pack(P, alpha=alpha)
                 feat, deltas = r.query_field(P, rays, tab, n_depth, flow_thresh=flow_thresh)
-        feat["eikonal"] = field.compute_eikonal(feat["xyz"], inst_id=inst_id)  # reference: nerf.py:416-453
+            feat["eikonal"] = field.compute_eikonal(feat["xyz"], inst_id=inst_id)  # no tape: the reference's own (nerf.py:416-453)
     else:
         with torch.no_grad():
             tab = tables_from_module(field, samples_dict)

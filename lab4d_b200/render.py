@@ -432,14 +432,76 @@ class FieldRenderer:
         self._keep_bwd = keep
         return views, tg
 
+    # ------------------------------------------------------------------ eikonal term (NeRF.compute_eikonal)
+    def eikonal_weight_names(self):
+        """Parameters the eikonal term reaches: the basefield's weights and sdf.weight (biases and codes only move the masks)."""
+        c = self.cfg
+        return [f"basefield.linear_{i+1}.0.weight" for i in range(c.D)] + ["basefield.linear_final.0.weight", "sdf.weight"]
+
+    @torch.no_grad()
+    def eikonal_forward(self, ctx, ray_ids):
+        """g = d sdf / d xyz (n_rays, D, 3) at all D samples of the rays `ray_ids` (flat indices f * N + n) of the training
+        forward that produced `ctx` (nnutils/nerf.py:416-453, utils/torch_utils.py:4-28): the reverse chain of
+        b200r_eikonal_fwd with the tape's ReLU signs.  Returns (g, ectx); ectx goes to `eikonal_backward`."""
+        st = self._train_state()
+        ids = ray_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        n, D = int(ids.numel()), ctx["D"]
+        a, v = C.c_size_t(), C.c_size_t()
+        self.handle.check(self.handle.lib.b200r_eikonal_sizes(C.byref(self.desc), n, D, C.byref(a), C.byref(v)), "b200r_eikonal_sizes")
+        bufs = getattr(self, "_eik_bufs", None)
+        if bufs is None or bufs[0].numel() < a.value + 1024 or bufs[1].numel() < v.value + 1024:
+            bufs = (torch.empty(a.value + 1024, dtype=torch.uint8, device=self.device), torch.empty(v.value + 1024, dtype=torch.uint8, device=self.device))
+            self._eik_bufs = bufs
+        eb = _lib.EikBatch()
+        al = lambda b: (b.data_ptr() + 1023) // 1024 * 1024
+        eb.n_rays, eb.rays, eb.a, eb.v, eb.a_bytes, eb.v_bytes = n, ids.data_ptr(), al(bufs[0]), al(bufs[1]), a.value, v.value
+        g = torch.empty(n, D, 3, device=self.device)
+        rc = self.handle.lib.b200r_eikonal_fwd(self.handle.h, C.byref(self.desc), _ptr(st["packed_t"]), C.byref(ctx["par"]), C.byref(ctx["rb"]),
+                                               ctx["M"], ctx["out"]["xyz"].data_ptr(), C.byref(ctx["tape"]), C.byref(eb), g.data_ptr(),
+                                               _stream(self.device))
+        self.handle.check(rc, "b200r_eikonal_fwd")
+        return g, dict(eb=eb, ids=ids, n=n)
+
+    @torch.no_grad()
+    def eikonal_backward(self, ctx, ectx, g_g, flat=None):
+        """dL/dW of the basefield weights and sdf.weight for the cotangent g_g (n_rays, D, 3) of `eikonal_forward`'s g: two
+        forward chains + weight-gradient GEMMs (b200r_eikonal_bwd), ACCUMULATED into `flat` (default: a fresh zero buffer with
+        the layout of `grad_buffer()`).  Returns name -> view."""
+        st = self._train_state()
+        if flat is None:
+            flat = torch.zeros(st["total"], device=self.device)
+        slots = st["slots"]
+        views = {k: flat[slots[k][0]:slots[k][0] + slots[k][1]].view(slots[k][2]) for k in self.eikonal_weight_names()}
+        pgs = _lib.ParamGrads()
+        pgs.flat = flat.data_ptr()
+        for i in range(_lib.MAX_LAYERS):
+            pgs.weight_off[i], pgs.bias_off[i] = -1, -1
+        for i, (name, _) in enumerate(self._layers):
+            pgs.weight_off[i] = slots[name + ".weight"][0]
+        for fld in _lib.HEAD_GRADS:
+            setattr(pgs, fld, -1)
+        pgs.sdf_w = slots["sdf.weight"][0]
+        gg = _f32c(g_g.reshape(-1, 3))
+        alpha = getattr(self, "_alpha", None)
+        wn = [nl for nl in self._window_names() if nl[0].startswith("basefield.")] if alpha is not None else []
+        before = {nl: views[nl[0]].clone() for nl in wn}
+        rc = self.handle.lib.b200r_eikonal_bwd(self.handle.h, C.byref(self.desc), _ptr(self.packed), C.byref(ctx["par"]), C.byref(ctx["rb"]),
+                                               ctx["M"], ctx["out"]["xyz"].data_ptr(), C.byref(ctx["tape"]), C.byref(ectx["eb"]), gg.data_ptr(),
+                                               C.byref(pgs), _stream(self.device))
+        self.handle.check(rc, "b200r_eikonal_bwd")
+        if alpha is not None:  # the annealing window is folded into the packed weights: dW = dW_eff * window (as in `backward`)
+            self._apply_window(views, before, alpha, names=wn)
+        self._keep_eik = (gg, flat)
+        return views
+
     def _window_names(self):
         c = self.cfg
         return [("basefield.linear_1.0.weight", c.L_xyz), (f"basefield.linear_{c.skip + 1}.0.weight", c.L_xyz), ("colorfield.linear_1.0.weight", c.L_xyz + 2)]
 
-    def _apply_window(self, views, before, alpha):
+    def _apply_window(self, views, before, alpha, names=None):
         import math
 
-        for name, L in self._window_names():
+        for name, L in (self._window_names() if names is None else names):
             k = torch.arange(L, device=self.device, dtype=torch.float32)
             wdw = 0.5 * (1 + torch.cos(math.pi * torch.clamp(alpha * L - k, 0.0, 1.0) + math.pi))
             cols = slice(3, 3 + 6 * L)

@@ -1,0 +1,109 @@
+"""GPU parity of the eikonal kernels (b200r_eikonal_fwd / b200r_eikonal_bwd, NeRF.compute_eikonal nnutils/nerf.py:416-453)
+against the reference's way restated in the oracle (autograd.grad of the sdf with create_graph, then backward through it):
+the sdf gradient g at all samples of a subset of rays, and the gradient of a loss of g w.r.t. the basefield weights and
+sdf.weight.  The chains run on single 16-bit operands with the ReLU signs of the training forward's tape.
+
+Tolerances (stated): g rel-L2 <= 5e-3 with fp16 operands (8 dependent GEMMs on 11-bit operands, measured ~1e-3); the
+eikonal value (|g|-1)^2 is compared in absolute terms against its mean; weight gradients <= max(3e-2, 4 x the reference's own
+fp32-vs-fp64 distance) - products of two 16-bit chains, plus ReLU-sign flips like every gradient of this network."""
+import numpy as np
+import pytest
+import torch
+
+import eikonal_backward as EB
+import synth
+from test_gpu_parity import synth_tables
+from util import rel_l2, synth_params
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+G_TOL = {"fp16x3": 5e-3, "fp16": 5e-3, "bf16": 5e-2}
+W_TOL = 3e-2
+
+
+def _setup(name, M, N, D, prec):
+    from lab4d_b200 import spec
+    from lab4d_b200.render import FieldRenderer
+
+    cfg = {"bg": spec.BG, "fg_rigid": spec.FG_RIGID, "fg_bob": spec.FG_BOB}[name]
+    P = synth_params(cfg, 3, device=DEV)
+    rays = {k: torch.from_numpy(v).to(DEV) for k, v in synth.synth_rays(M, N, seed=21).items()}
+    tab = {k: v.clone() for k, v in synth_tables(cfg, M, DEV, seed=21, rays=rays, P=P).items()}
+    # distinct instance code rows per frame (C5: the masks depend on them)
+    g = torch.Generator().manual_seed(9)
+    tab["inst_base"] = (tab["inst_base"] + 0.3 * torch.randn(tab["inst_base"].shape, generator=g).to(DEV)).contiguous()
+    r = FieldRenderer(cfg, DEV, operand_dtype=prec)
+    r.pack_train(P)
+    feat, deltas, ctx = r.query_field_train(P, rays, tab, D)
+    return cfg, P, tab, r, feat, ctx
+
+
+def _oracle(cfg, P, tab, xyz_sel, ray_ids, N, coeff, dtype):
+    """Reference's way on the same points: g by autograd (create_graph), loss = sum coeff (|g|-1)^2, backward."""
+    Pg = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in P.items()}
+    inst = tab["inst_base"].to(dtype)[(ray_ids // N).to(tab["inst_base"].device)]
+    ocfg = dict(cfg.as_oracle_cfg(), skip=cfg.skip)
+    g = EB.sdf_gradient_autograd(Pg, ocfg, xyz_sel.to(dtype), inst)
+    loss = (coeff.to(dtype) * (g.norm(2, dim=-1) - 1) ** 2).sum()
+    loss.backward()
+    return g.detach(), {k: v.grad for k, v in Pg.items() if v.grad is not None and float(v.grad.abs().max()) > 0}
+
+
+@pytest.mark.parametrize("name,M,N,D,prec,n_sel", [("fg_bob", 4, 8, 32, "fp16x3", 5), ("fg_rigid", 2, 16, 40, "fp16", 7), ("bg", 4, 24, 33, "fp16x3", 9),
+                                                  ("fg_bob", 8, 16, 128, "fp16x3", 8), ("fg_rigid", 2, 16, 24, "bf16", 4)])
+def test_eikonal_kernels_match_second_order_autograd(name, M, N, D, prec, n_sel):
+    cfg, P, tab, r, feat, ctx = _setup(name, M, N, D, prec)
+    gen = torch.Generator().manual_seed(5)
+    ray_ids = torch.randperm(M * N, generator=gen)[:n_sel]
+    g, ectx = r.eikonal_forward(ctx, ray_ids)
+    torch.cuda.synchronize()
+    assert torch.isfinite(g).all()
+    xyz_sel = feat["xyz"].reshape(M * N, D, 3)[ray_ids.to(DEV)]
+    coeff = (torch.rand(n_sel, D, generator=gen) / (n_sel * D)).to(DEV)
+    g64, wg64 = _oracle(cfg, P, tab, xyz_sel, ray_ids, N, coeff, torch.float64)
+    g32, wg32 = _oracle(cfg, P, tab, xyz_sel, ray_ids, N, coeff, torch.float32)
+    e_g = rel_l2(g.cpu(), g64.cpu())
+    eik, eik64 = (g.norm(2, dim=-1) - 1) ** 2, (g64.norm(2, dim=-1) - 1) ** 2
+    e_eik = float((eik.double() - eik64).abs().max() / eik64.mean())
+    print(f"[eikonal] {name} {M}x{N}x{D} {prec} rays={n_sel}: g rel-L2 {e_g:.2e} (reference fp32 vs fp64 {rel_l2(g32.cpu(), g64.cpu()):.1e}), "
+          f"(|g|-1)^2 max abs err / mean {e_eik:.2e}, mean |g| {float(g64.norm(2, dim=-1).mean()):.3f}")
+    assert e_g <= G_TOL[prec], e_g
+    # backward: cotangent of g from the loss, evaluated at the kernel's own g (what autograd hands to EikonalFunction.backward)
+    gk = g.detach().clone().requires_grad_(True)
+    (coeff * (gk.norm(2, dim=-1) - 1) ** 2).sum().backward()
+    views = r.eikonal_backward(ctx, ectx, gk.grad)
+    torch.cuda.synchronize()
+    rows, bad = [], []
+    assert set(wg64) == set(r.eikonal_weight_names()), set(wg64) ^ set(r.eikonal_weight_names())
+    for k in r.eikonal_weight_names():
+        e, floor = rel_l2(views[k].cpu(), wg64[k].cpu()), rel_l2(wg32[k].cpu(), wg64[k].cpu())
+        rows.append(f"{k.replace('basefield.', '')}={e:.1e}/{floor:.1e}")
+        if not e <= max(W_TOL * (10.0 if prec == "bf16" else 1.0), 4 * floor):
+            bad.append((k, e, floor))
+    print(f"[eikonal] {name} weight gradients (ours vs fp64 / reference fp32 vs fp64): " + " ".join(rows))
+    assert not bad, bad
+
+
+def test_eikonal_autograd_function_accumulates_like_the_reference():
+    """lab4d_b200.autograd.eikonal: g carries autograd edges to the basefield weights and sdf.weight; a second backward
+    accumulates; parameters outside the chain (biases, codes) get nothing."""
+    from lab4d_b200 import autograd as ag
+
+    M, N, D = 4, 8, 32
+    cfg, P, tab, r, feat, ctx = _setup("fg_bob", M, N, D, "fp16x3")
+    Pl = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    ray_ids = torch.tensor([1, 7, 12, 30])
+    g = ag.eikonal(r, ctx, Pl, ray_ids)
+    loss = ((g.norm(2, dim=-1) - 1) ** 2).mean()
+    loss.backward()
+    names = set(r.eikonal_weight_names())
+    for k, v in Pl.items():
+        if k in names:
+            assert v.grad is not None and torch.isfinite(v.grad).all() and float(v.grad.abs().max()) > 0, k
+        else:
+            assert v.grad is None, k
+    first = {k: Pl[k].grad.clone() for k in names}
+    g2 = ag.eikonal(r, ctx, Pl, ray_ids)
+    ((g2.norm(2, dim=-1) - 1) ** 2).mean().backward()
+    for k in names:
+        assert rel_l2(Pl[k].grad.cpu(), (2 * first[k]).cpu()) < 1e-5, k
