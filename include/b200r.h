@@ -409,6 +409,39 @@ typedef struct {
 
 int b200r_compose_fwd(b200r_handle* h, const b200r_compose_args* args, b200r_stream stream);
 
+/* ------------------------------------------------------------------ per-ray feature matching (FeatureNeRF.global_match)
+ * lab4d/nnutils/feature.py:152-205: every ray's pixel feature is matched against K candidate samples of the batch,
+ *   score[r,k] = exp(logsigma) <feat_px[r], feat_can[idx[k]]>, prob = softmax_k, xyz_matched[r] = sum_k prob[r,k] xyz_can[idx[k]].
+ * The caller draws idx (the reference's torch.randperm(S)[:K], no duplicates), so the random stream stays the reference's.
+ * b200r_match_bwd is the hand-derived backward of autograd through it (engine/trainer.py:344-345): dense gradients of the
+ * per-sample features / points (rows idx[k] are ADDED to; zero the arrays first) and of logsigma (ADDED). */
+#define B200R_MATCH_CHANNELS 16
+#define B200R_MATCH_MAX_K 2048
+typedef struct {
+  int32_t R, K;             /* rays, candidates (K <= B200R_MATCH_MAX_K) */
+  const float* feat_px;     /* (R,16) pixel features */
+  const float* feat_can;    /* (S,16) canonical features of every sample of the batch (feat_dict["feature"]) */
+  const float* xyz_can;     /* (S,3)  canonical points of every sample (feat_dict["xyz"]) */
+  const int64_t* idx;       /* (K) device: candidate sample indices */
+  const float* logsigma;    /* (1) FeatureNeRF.logsigma */
+  float* xyz_matched;       /* (R,3) out */
+  float* lse;               /* (R) out: log-sum-exp of every ray's scores (kept for the backward), or NULL */
+} b200r_match_args;
+
+int b200r_match_fwd(b200r_handle* h, const b200r_match_args* args, b200r_stream stream);
+
+typedef struct {
+  b200r_match_args fwd;     /* the forward call's tensors (xyz_matched and lse as it wrote them) */
+  const float* g_out;       /* (R,3) gradient of xyz_matched */
+  float* g_feat_can;        /* (S,16) or NULL */
+  float* g_xyz_can;         /* (S,3) or NULL */
+  float* g_logsigma;        /* (1) or NULL */
+  float* scratch;           /* b200r_match_scratch_floats(R, K) floats */
+} b200r_match_bwd_args;
+
+size_t b200r_match_scratch_floats(int32_t R, int32_t K);
+int b200r_match_bwd(b200r_handle* h, const b200r_match_bwd_args* args, b200r_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,7 +121,16 @@ class EikBatch(C.Structure):
                 ("a_bytes", C.c_size_t), ("v_bytes", C.c_size_t)]
 
 
-EXPORTS = ["b200r_eikonal_sizes", "b200r_eikonal_fwd", "b200r_eikonal_bwd", "b200r_tape_sizes", "b200r_field_fwd_train", "b200r_packed_t_bytes", "b200r_pack_weights_t", "b200r_get_block_layout",
+class MatchArgs(C.Structure):
+    _fields_ = [("R", C.c_int32), ("K", C.c_int32), ("feat_px", f32p), ("feat_can", f32p), ("xyz_can", f32p), ("idx", C.c_void_p),
+                ("logsigma", f32p), ("xyz_matched", f32p), ("lse", f32p)]
+
+
+class MatchBwdArgs(C.Structure):
+    _fields_ = [("fwd", MatchArgs), ("g_out", f32p), ("g_feat_can", f32p), ("g_xyz_can", f32p), ("g_logsigma", f32p), ("scratch", f32p)]
+
+
+EXPORTS = ["b200r_match_fwd", "b200r_match_bwd", "b200r_match_scratch_floats", "b200r_eikonal_sizes", "b200r_eikonal_fwd", "b200r_eikonal_bwd", "b200r_tape_sizes", "b200r_field_fwd_train", "b200r_packed_t_bytes", "b200r_pack_weights_t", "b200r_get_block_layout",
            "b200r_field_bwd", "b200r_layer_count", "b200r_packed_bytes", "b200r_create", "b200r_destroy", "b200r_last_error",
            "b200r_pack_weights", "b200r_workspace_bytes", "b200r_field_fwd", "b200r_composite_fwd", "b200r_composite_bwd",
            "b200r_compose_fwd", "b200r_points_fwd", "b200r_warp_fwd", "b200r_importance_fwd"]
@@ -188,6 +197,12 @@ def load():
                                     C.POINTER(RayBatch), C.POINTER(FieldOutputs), C.POINTER(FieldGrads), C.POINTER(Tape),
                                     C.POINTER(ParamGrads), C.POINTER(FrameGrads), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.b200r_field_bwd.restype = C.c_int
+    lib.b200r_match_fwd.argtypes = [C.c_void_p, C.POINTER(MatchArgs), C.c_void_p]
+    lib.b200r_match_fwd.restype = C.c_int
+    lib.b200r_match_bwd.argtypes = [C.c_void_p, C.POINTER(MatchBwdArgs), C.c_void_p]
+    lib.b200r_match_bwd.restype = C.c_int
+    lib.b200r_match_scratch_floats.argtypes = [C.c_int32, C.c_int32]
+    lib.b200r_match_scratch_floats.restype = C.c_size_t
     lib.b200r_eikonal_sizes.argtypes = [C.POINTER(FieldDesc), C.c_int32, C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.b200r_eikonal_sizes.restype = C.c_int
     lib.b200r_eikonal_fwd.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldParams), C.POINTER(RayBatch), C.c_int32,

@@ -333,4 +333,38 @@ int b200r_compose_fwd(b200r_handle* h, const b200r_compose_args* a, b200r_stream
   return B200R_OK;
 }
 
+static int match_check(b200r_handle* h, const b200r_match_args* a, const char* who) {
+  auto bad = [&](const char* m) { return fail(h, B200R_E_INVALID, std::string(who) + ": " + m); };
+  if (!a) return bad("null argument");
+  if (a->R < 1 || a->K < 1 || a->K > B200R_MATCH_MAX_K) return bad("need R >= 1 and 1 <= K <= 2048");
+  if (!a->feat_px || !a->feat_can || !a->xyz_can || !a->idx || !a->logsigma || !a->xyz_matched) return bad("null tensor");
+  return B200R_OK;
+}
+
+int b200r_match_fwd(b200r_handle* h, const b200r_match_args* a, b200r_stream stream) {
+  if (!h) return B200R_E_INVALID;
+  int rc = match_check(h, a, "match_fwd");
+  if (rc != B200R_OK) return rc;
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaError_t e = b200r::launch_match_fwd(*a, h->n_sm, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(h, e, "match kernel");
+  return B200R_OK;
+}
+
+size_t b200r_match_scratch_floats(int32_t R, int32_t K) { return R < 1 || K < 1 ? 0 : b200r::match_partial_floats(R, K); }
+
+int b200r_match_bwd(b200r_handle* h, const b200r_match_bwd_args* b, b200r_stream stream) {
+  if (!h) return B200R_E_INVALID;
+  if (!b) return fail(h, B200R_E_INVALID, "match_bwd: null argument");
+  int rc = match_check(h, &b->fwd, "match_bwd");
+  if (rc != B200R_OK) return rc;
+  if (!b->g_out || !b->scratch || !b->fwd.lse) return fail(h, B200R_E_INVALID, "match_bwd: missing g_out, scratch or the forward's lse");
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaError_t e = b200r::launch_match_bwd(*b, b->scratch, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(h, e, "match backward kernels");
+  return B200R_OK;
+}
+
 }  // extern "C"

@@ -13,7 +13,8 @@ Training (autograd recording): query_field goes through lab4d_b200.autograd.Fiel
 tape, hand-derived backward kernels, gradients delivered to the reference modules' own Parameters and, through the
 per-frame tables, to the camera / articulation / embedding modules.  Eval mode: importance sampling + bounding-box
 masking + the reference's normals.  The eikonal term of a training step runs on the eikonal kernels (compute_eikonal below);
-global_match / forward_project (feature.py:152-226) stay the reference's own torch code on the kernels' xyz / feature outputs.
+global_match (feature.py:152-205) runs on the match kernels; forward_project (feature.py:207-226: one warp of N points per frame +
+the pinhole projection) stays the reference's own torch code on the matched points.
 """
 import functools
 
@@ -160,7 +161,7 @@ def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype
                                                                inst_id, samples_dict)
     aux = {}
     if hasattr(field, "global_match") and "feature" in samples_dict and "feature" in feat:  # FeatureNeRF.query_field, feature.py:119-131
-        xyz_matches = field.global_match(samples_dict["feature"], feat["feature"], feat["xyz"])
+        xyz_matches = _render.global_match(samples_dict["feature"], feat["feature"], feat["xyz"], field.logsigma)  # match kernels
         xy_reproj, xyz_reproj = field.forward_project(xyz_matches, samples_dict["field2cam"], samples_dict["Kinv"], samples_dict["frame_id"],
                                                        inst_id, samples_dict=samples_dict)
         aux.update(xyz_matches=xyz_matches, xyz_reproj=xyz_reproj, xy_reproj=xy_reproj)

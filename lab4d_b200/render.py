@@ -836,3 +836,53 @@ def compose_fields(feats, deltas_list):
             with torch.no_grad():
                 out, deltas = _merge_pair(h, device, out, f, deltas, d)
     return out, deltas
+
+
+# ---------------------------------------------------------------------------------------- per-ray feature matching
+class _Match(torch.autograd.Function):
+    """b200r_match_fwd / b200r_match_bwd: softmax matching of every ray's pixel feature against K candidate samples."""
+
+    @staticmethod
+    def forward(ctx, feat_px, feat_can, xyz_can, logsigma, idx):
+        dev = feat_can.device
+        h = _lib.handle_for(dev)
+        fp, fc, xc, ls = _f32c(feat_px.detach()), _f32c(feat_can.detach()), _f32c(xyz_can.detach()), _f32c(logsigma.detach())
+        R, K = fp.shape[0], int(idx.numel())
+        out, lse = torch.empty(R, 3, device=dev), torch.empty(R, device=dev)
+        a = _lib.MatchArgs()
+        a.R, a.K = R, K
+        a.feat_px, a.feat_can, a.xyz_can, a.idx, a.logsigma = fp.data_ptr(), fc.data_ptr(), xc.data_ptr(), idx.data_ptr(), ls.data_ptr()
+        a.xyz_matched, a.lse = out.data_ptr(), lse.data_ptr()
+        h.check(h.lib.b200r_match_fwd(h.h, C.byref(a), _stream(dev)), "b200r_match_fwd")
+        ctx.save_for_backward(fp, fc, xc, ls, idx, out, lse)
+        ctx.args = a
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        fp, fc, xc, ls, idx, out, lse = ctx.saved_tensors
+        dev = fc.device
+        h = _lib.handle_for(dev)
+        b = _lib.MatchBwdArgs()
+        b.fwd = ctx.args
+        gg = _f32c(g)
+        g_fc, g_xc, g_ls = torch.zeros_like(fc), torch.zeros_like(xc), torch.zeros_like(ls)
+        scratch = torch.empty(h.lib.b200r_match_scratch_floats(b.fwd.R, b.fwd.K), device=dev)
+        b.g_out, b.g_feat_can, b.g_xyz_can, b.g_logsigma, b.scratch = gg.data_ptr(), g_fc.data_ptr(), g_xc.data_ptr(), g_ls.data_ptr(), scratch.data_ptr()
+        h.check(h.lib.b200r_match_bwd(h.h, C.byref(b), _stream(dev)), "b200r_match_bwd")
+        return None, g_fc, g_xc, g_ls, None
+
+
+def global_match(feat_px, feat_canonical, xyz_canonical, logsigma, num_candidates=1024):
+    """FeatureNeRF.global_match (nnutils/feature.py:152-205): feat_px (M,N,16) pixel features, feat_canonical (M,N,D,16) and
+    xyz_canonical (M,N,D,3) of the batch's samples, logsigma (1) -> matched canonical points (M,N,3).  The candidates are
+    drawn like the reference (torch.randperm on the default CPU generator); differentiable w.r.t. feat_canonical,
+    xyz_canonical and logsigma."""
+    if feat_px.shape[-1] != 16 or feat_canonical.shape[-1] != 16:
+        raise NotImplementedError("global_match: built for 16 feature channels")
+    shape = feat_px.shape
+    fc, xc = feat_canonical.reshape(-1, 16), xyz_canonical.reshape(-1, 3)
+    K = min(int(num_candidates), fc.shape[0], 2048)
+    idx = torch.randperm(fc.shape[0])[:K].to(fc.device)
+    out = _Match.apply(feat_px.reshape(-1, 16), fc, xc, logsigma.reshape(1), idx)
+    return out.view(shape[:-1] + (3,))

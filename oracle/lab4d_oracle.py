@@ -500,3 +500,19 @@ def compose_fields(feats, deltas_list):
 CFG_FG_BOB = dict(category="fg", D=8, W=256, L_xyz=10, L_dir=-1, appr_channels=32, motion="bob", B=25, has_feature=True)
 CFG_FG_RIGID = dict(CFG_FG_BOB, motion="rigid", B=0)
 CFG_BG = dict(category="bg", D=5, W=128, L_xyz=6, L_dir=0, appr_channels=0, motion="rigid", B=0, has_feature=False)
+
+
+# --------------------------------------------------------------------------------------
+# stage 5: per-ray feature matching
+# --------------------------------------------------------------------------------------
+
+
+def global_match(feat_px, feat_canonical, xyz_canonical, logsigma, idx):
+    """FeatureNeRF.global_match (nnutils/feature.py:152-205) with the candidate draw `idx` given: softmax of the scaled
+    feature similarities over the candidates, expected canonical point.  feat_px (...,C) -> (...,3)."""
+    shape = feat_px.shape
+    fc = feat_canonical.reshape(-1, shape[-1])[idx]
+    xc = xyz_canonical.reshape(-1, 3)[idx]
+    score = (feat_px.reshape(-1, shape[-1]) @ fc.t()) * logsigma.exp()
+    prob = torch.softmax(score, dim=1)
+    return (prob[..., None] * xc).sum(1).view(shape[:-1] + (3,))
