@@ -442,6 +442,62 @@ typedef struct {
 size_t b200r_match_scratch_floats(int32_t R, int32_t K);
 int b200r_match_bwd(b200r_handle* h, const b200r_match_bwd_args* args, b200r_stream stream);
 
+/* ------------------------------------------------------------------ per-pixel reconstruction losses (dvr_model.compute_loss)
+ * lab4d/engine/model.py: get_mask_balance_wt (:386-412), compute_recon_loss (:415-498), mask_losses (:520-574) and
+ * apply_loss_weights (:576-611) for the terms compute_recon_loss creates, fused: every term k ends as
+ *   loss[k] = mean over the entries with value > 0 [/ train_res for flow, feat_reproj] * wt[k].
+ * Term order (the reference's loss_dict): 0 mask, 1 feature, 2 feat_reproj, 3 rgb, 4 depth, 5 flow, 6 vis, 7 reg_gauss_mask.
+ * All arrays are (M*N, c) row-major fp32 (booleans of the batch as 0 / 1).  Terms whose inputs are absent (bg fields have no
+ * feature / feat_reproj / reg_gauss_mask) come back as NaN and must be ignored. */
+#define B200R_LOSS_TERMS 8
+#define B200R_LOSS_STATS 24
+typedef struct {
+  int32_t M, N;               /* frames, rays per frame */
+  int32_t field_type;         /* 0 fg, 1 bg, 2 comp (config["field_type"]) */
+  float train_res;            /* config["train_res"] */
+  const float* r_mask;        /* (R)    rendered["mask"] */
+  const float* r_mask_fg;     /* (R)    rendered["mask_fg"] (comp) */
+  const float* r_rgb;         /* (R,3)  rendered["rgb"] */
+  const float* r_depth;       /* (R)    rendered["depth"] */
+  const float* r_flow;        /* (R,2)  rendered["flow"] */
+  const float* vis_fg;        /* (R)    aux_dict["fg"]["vis"] or NULL */
+  const float* vis_bg;        /* (R)    aux_dict["bg"]["vis"] or NULL (enters with 0.01) */
+  const float* a_feature;     /* (R,16) aux_dict["fg"]["feature"]   (fg / comp) */
+  const float* a_xy_reproj;   /* (R,2)  aux_dict["fg"]["xy_reproj"] (fg / comp) */
+  const float* a_gauss_mask;  /* (R)    aux_dict["fg"]["gauss_mask"] or NULL */
+  const float* b_mask;        /* (R)    batch["mask"] */
+  const float* b_vis2d;       /* (R)    batch["vis2d"] */
+  const float* b_is_detected; /* (M)    batch["is_detected"] */
+  const float* b_rgb;         /* (R,3) */
+  const float* b_depth;       /* (R) */
+  const float* b_flow;        /* (R,2) */
+  const float* b_flow_uct;    /* (R) */
+  const float* b_feature;     /* (R,16) */
+  const float* b_hxy;         /* (R,3) */
+  float wt[B200R_LOSS_TERMS]; /* config["<term>_wt"] (1 when absent) */
+  float* loss;                /* (8) out */
+  float* stats;               /* (B200R_LOSS_STATS) out: sums / counts of the positive entries, mask-balance weights (read by the backward) */
+} b200r_loss_args;
+
+int b200r_loss_fwd(b200r_handle* h, const b200r_loss_args* args, b200r_stream stream);
+
+typedef struct {
+  b200r_loss_args fwd;        /* the forward call's tensors (stats as it wrote them) */
+  const float* g_loss;        /* (8) gradient of every term (0 for absent terms) */
+  float* g_mask;              /* (R)   any of the outputs may be NULL; all are OVERWRITTEN */
+  float* g_mask_fg;           /* (R)   comp */
+  float* g_rgb;               /* (R,3) */
+  float* g_depth;             /* (R) */
+  float* g_flow;              /* (R,2) */
+  float* g_vis_fg;            /* (R) */
+  float* g_vis_bg;            /* (R) */
+  float* g_feature;           /* (R,16) */
+  float* g_xy_reproj;         /* (R,2) */
+  float* g_gauss_mask;        /* (R) */
+} b200r_loss_bwd_args;
+
+int b200r_loss_bwd(b200r_handle* h, const b200r_loss_bwd_args* args, b200r_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,6 +121,21 @@ class EikBatch(C.Structure):
                 ("a_bytes", C.c_size_t), ("v_bytes", C.c_size_t)]
 
 
+LOSS_TERMS = ["mask", "feature", "feat_reproj", "rgb", "depth", "flow", "vis", "reg_gauss_mask"]
+LOSS_INPUTS = ["r_mask", "r_mask_fg", "r_rgb", "r_depth", "r_flow", "vis_fg", "vis_bg", "a_feature", "a_xy_reproj", "a_gauss_mask", "b_mask",
+               "b_vis2d", "b_is_detected", "b_rgb", "b_depth", "b_flow", "b_flow_uct", "b_feature", "b_hxy"]
+LOSS_GRADS = ["g_mask", "g_mask_fg", "g_rgb", "g_depth", "g_flow", "g_vis_fg", "g_vis_bg", "g_feature", "g_xy_reproj", "g_gauss_mask"]
+
+
+class LossArgs(C.Structure):
+    _fields_ = ([("M", C.c_int32), ("N", C.c_int32), ("field_type", C.c_int32), ("train_res", C.c_float)] + [(n, f32p) for n in LOSS_INPUTS]
+                + [("wt", C.c_float * 8), ("loss", f32p), ("stats", f32p)])
+
+
+class LossBwdArgs(C.Structure):
+    _fields_ = [("fwd", LossArgs), ("g_loss", f32p)] + [(n, f32p) for n in LOSS_GRADS]
+
+
 class MatchArgs(C.Structure):
     _fields_ = [("R", C.c_int32), ("K", C.c_int32), ("feat_px", f32p), ("feat_can", f32p), ("xyz_can", f32p), ("idx", C.c_void_p),
                 ("logsigma", f32p), ("xyz_matched", f32p), ("lse", f32p)]
@@ -130,7 +145,7 @@ class MatchBwdArgs(C.Structure):
     _fields_ = [("fwd", MatchArgs), ("g_out", f32p), ("g_feat_can", f32p), ("g_xyz_can", f32p), ("g_logsigma", f32p), ("scratch", f32p)]
 
 
-EXPORTS = ["b200r_match_fwd", "b200r_match_bwd", "b200r_match_scratch_floats", "b200r_eikonal_sizes", "b200r_eikonal_fwd", "b200r_eikonal_bwd", "b200r_tape_sizes", "b200r_field_fwd_train", "b200r_packed_t_bytes", "b200r_pack_weights_t", "b200r_get_block_layout",
+EXPORTS = ["b200r_loss_fwd", "b200r_loss_bwd", "b200r_match_fwd", "b200r_match_bwd", "b200r_match_scratch_floats", "b200r_eikonal_sizes", "b200r_eikonal_fwd", "b200r_eikonal_bwd", "b200r_tape_sizes", "b200r_field_fwd_train", "b200r_packed_t_bytes", "b200r_pack_weights_t", "b200r_get_block_layout",
            "b200r_field_bwd", "b200r_layer_count", "b200r_packed_bytes", "b200r_create", "b200r_destroy", "b200r_last_error",
            "b200r_pack_weights", "b200r_workspace_bytes", "b200r_field_fwd", "b200r_composite_fwd", "b200r_composite_bwd",
            "b200r_compose_fwd", "b200r_points_fwd", "b200r_warp_fwd", "b200r_importance_fwd"]
@@ -197,6 +212,10 @@ def load():
                                     C.POINTER(RayBatch), C.POINTER(FieldOutputs), C.POINTER(FieldGrads), C.POINTER(Tape),
                                     C.POINTER(ParamGrads), C.POINTER(FrameGrads), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.b200r_field_bwd.restype = C.c_int
+    lib.b200r_loss_fwd.argtypes = [C.c_void_p, C.POINTER(LossArgs), C.c_void_p]
+    lib.b200r_loss_fwd.restype = C.c_int
+    lib.b200r_loss_bwd.argtypes = [C.c_void_p, C.POINTER(LossBwdArgs), C.c_void_p]
+    lib.b200r_loss_bwd.restype = C.c_int
     lib.b200r_match_fwd.argtypes = [C.c_void_p, C.POINTER(MatchArgs), C.c_void_p]
     lib.b200r_match_fwd.restype = C.c_int
     lib.b200r_match_bwd.argtypes = [C.c_void_p, C.POINTER(MatchBwdArgs), C.c_void_p]

@@ -367,4 +367,39 @@ int b200r_match_bwd(b200r_handle* h, const b200r_match_bwd_args* b, b200r_stream
   return B200R_OK;
 }
 
+static int loss_check(b200r_handle* h, const b200r_loss_args* a, const char* who) {
+  auto bad = [&](const char* m) { return fail(h, B200R_E_INVALID, std::string(who) + ": " + m); };
+  if (!a) return bad("null argument");
+  if (a->M < 1 || a->N < 1 || a->field_type < 0 || a->field_type > 2 || !(a->train_res > 0.f)) return bad("bad M, N, field_type or train_res");
+  if (!a->r_mask || !a->r_rgb || !a->r_depth || !a->r_flow || !a->b_mask || !a->b_vis2d || !a->b_is_detected || !a->b_rgb || !a->b_depth ||
+      !a->b_flow || !a->b_flow_uct || !a->loss || !a->stats)
+    return bad("null tensor");
+  if (a->field_type == 2 && !a->r_mask_fg) return bad("comp needs rendered mask_fg");
+  if (a->field_type != 1 && (!a->a_feature || !a->a_xy_reproj || !a->b_feature || !a->b_hxy)) return bad("fg / comp need the feature and reprojection tensors");
+  return B200R_OK;
+}
+
+int b200r_loss_fwd(b200r_handle* h, const b200r_loss_args* a, b200r_stream stream) {
+  if (!h) return B200R_E_INVALID;
+  int rc = loss_check(h, a, "loss_fwd");
+  if (rc != B200R_OK) return rc;
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaError_t e = b200r::launch_loss_fwd(*a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(h, e, "loss kernel");
+  return B200R_OK;
+}
+
+int b200r_loss_bwd(b200r_handle* h, const b200r_loss_bwd_args* b, b200r_stream stream) {
+  if (!h) return B200R_E_INVALID;
+  if (!b || !b->g_loss) return fail(h, B200R_E_INVALID, "loss_bwd: null argument");
+  int rc = loss_check(h, &b->fwd, "loss_bwd");
+  if (rc != B200R_OK) return rc;
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaError_t e = b200r::launch_loss_bwd(*b, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(h, e, "loss backward kernel");
+  return B200R_OK;
+}
+
 }  // extern "C"

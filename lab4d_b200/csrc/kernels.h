@@ -147,6 +147,8 @@ cudaError_t launch_composite_fwd(const b200r_composite_args& a, cudaStream_t str
 cudaError_t launch_composite_bwd(const b200r_composite_bwd_args& b, cudaStream_t stream);
 cudaError_t launch_importance_fwd(const b200r_importance_args& a, cudaStream_t stream);
 cudaError_t launch_compose_fwd(const b200r_compose_args& a, cudaStream_t stream);
+cudaError_t launch_loss_fwd(const b200r_loss_args& a, cudaStream_t stream);
+cudaError_t launch_loss_bwd(const b200r_loss_bwd_args& b, cudaStream_t stream);
 size_t match_partial_floats(int R, int K);
 cudaError_t launch_match_fwd(const b200r_match_args& a, int n_sm, cudaStream_t stream);
 cudaError_t launch_match_bwd(const b200r_match_bwd_args& b, float* partial, cudaStream_t stream);

@@ -4,6 +4,7 @@
     lab4d.nnutils.nerf.NeRF.query_field            (also reached by FeatureNeRF / Deformable via super())
     lab4d.nnutils.deformable.Deformable.query_field
     lab4d.utils.render_utils.render_pixel and the by-name import lab4d.engine.model.render_pixel
+    lab4d.nnutils.multifields.MultiFields.compose_fields, lab4d.engine.model.dvr_model.compute_loss (reconstruction terms)
 so that lab4d.engine.model.dvr_model.render_samples (engine/model.py:328-361) and lab4d/render.py call the
 B200 renderer unchanged.  Parameters stay nn.Parameters of the reference modules (checkpoints, optimiser
 param groups and DDP are untouched); per-frame codes / cameras / articulations are still produced by the
@@ -208,6 +209,19 @@ def compose_fields(multifields_dict, deltas_dict):
     return _render.compose_fields([multifields_dict[c] for c in cats], [deltas_dict[c] for c in cats])
 
 
+def compute_loss(model, batch, results):
+    """Replacement body of dvr_model.compute_loss (lab4d/engine/model.py:374-398): the per-pixel reconstruction terms
+    (compute_recon_loss + mask_losses + apply_loss_weights, ~40 small launches and their backward) on the loss kernels; the
+    regularisers (compute_reg_loss: a few scalars and four per-pixel maps) keep the reference's code."""
+    config = model.config
+    loss_dict = _render.recon_losses(results["rendered"], results["aux_dict"], batch, config)
+    reg = {}
+    model.compute_reg_loss(reg, results)
+    type(model).apply_loss_weights(reg, config)
+    loss_dict.update(reg)
+    return loss_dict
+
+
 def install(lab4d=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False):
     """Patch an imported reference package in place; returns a function that undoes the patch.
     operand_dtype: "fp16x3" (parity mode, default), "fp16" or "bf16" (fast modes).
@@ -225,7 +239,8 @@ def install(lab4d=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False):
 
     saved = [(rnerf.NeRF, "query_field", rnerf.NeRF.query_field), (rfeat.FeatureNeRF, "query_field", rfeat.FeatureNeRF.query_field),
              (rdef.Deformable, "query_field", rdef.Deformable.query_field), (rru, "render_pixel", rru.render_pixel),
-             (rmodel, "render_pixel", rmodel.render_pixel), (rmf.MultiFields, "compose_fields", rmf.MultiFields.__dict__["compose_fields"])]
+             (rmodel, "render_pixel", rmodel.render_pixel), (rmf.MultiFields, "compose_fields", rmf.MultiFields.__dict__["compose_fields"]),
+             (rmodel.dvr_model, "compute_loss", rmodel.dvr_model.compute_loss)]
 
     def _qf(self, samples_dict, flow_thresh=None):
         return query_field(self, samples_dict, flow_thresh=flow_thresh, n_depth=n_depth, operand_dtype=operand_dtype, bind_grads=bind_grads)
@@ -237,6 +252,7 @@ def install(lab4d=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False):
     rru.render_pixel = _render.render_pixel
     rmodel.render_pixel = _render.render_pixel
     rmf.MultiFields.compose_fields = staticmethod(compose_fields)
+    rmodel.dvr_model.compute_loss = compute_loss
 
     def undo():
         for obj, name, val in saved:

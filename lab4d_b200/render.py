@@ -886,3 +886,86 @@ def global_match(feat_px, feat_canonical, xyz_canonical, logsigma, num_candidate
     idx = torch.randperm(fc.shape[0])[:K].to(fc.device)
     out = _Match.apply(feat_px.reshape(-1, 16), fc, xc, logsigma.reshape(1), idx)
     return out.view(shape[:-1] + (3,))
+
+
+# ---------------------------------------------------------------------------------------- per-pixel reconstruction losses
+_FIELD_TYPES = {"fg": 0, "bg": 1, "comp": 2}
+# (struct field of the rendered input, its gradient field, channels)
+_LOSS_DIFF = [("r_mask", "g_mask", 1), ("r_mask_fg", "g_mask_fg", 1), ("r_rgb", "g_rgb", 3), ("r_depth", "g_depth", 1), ("r_flow", "g_flow", 2),
+              ("vis_fg", "g_vis_fg", 1), ("vis_bg", "g_vis_bg", 1), ("a_feature", "g_feature", 16), ("a_xy_reproj", "g_xy_reproj", 2),
+              ("a_gauss_mask", "g_gauss_mask", 1)]
+
+
+class _Losses(torch.autograd.Function):
+    """b200r_loss_fwd / b200r_loss_bwd over the rendered tensors `diff` (name -> tensor, differentiable) and the batch
+    tensors `data` (name -> tensor): returns the 8 weighted loss terms as one vector."""
+
+    @staticmethod
+    def forward(ctx, meta, *diff_vals):
+        names, data = meta["names"], meta["data"]
+        dev = diff_vals[0].device
+        h = _lib.handle_for(dev)
+        a = _lib.LossArgs()
+        a.M, a.N, a.field_type, a.train_res = meta["M"], meta["N"], meta["field_type"], float(meta["train_res"])
+        keep = []
+        for n, t in list(zip(names, diff_vals)) + list(data.items()):
+            t = _f32c(t.detach())
+            keep.append(t)
+            setattr(a, n, t.data_ptr())
+        for k in range(8):
+            a.wt[k] = float(meta["wt"][k])
+        loss, stats = torch.empty(8, device=dev), torch.empty(24, device=dev)
+        a.loss, a.stats = loss.data_ptr(), stats.data_ptr()
+        h.check(h.lib.b200r_loss_fwd(h.h, C.byref(a), _stream(dev)), "b200r_loss_fwd")
+        ctx.a, ctx.keep, ctx.names, ctx.dev = a, keep + [loss, stats], names, dev
+        ctx.shapes = [t.shape for t in diff_vals]
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        h = _lib.handle_for(ctx.dev)
+        b = _lib.LossBwdArgs()
+        b.fwd = ctx.a
+        gl = _f32c(torch.nan_to_num(g_loss, nan=0.0))
+        b.g_loss = gl.data_ptr()
+        R = ctx.a.M * ctx.a.N
+        gfield = {f: (g, c) for f, g, c in _LOSS_DIFF}
+        outs = []
+        for n, shp in zip(ctx.names, ctx.shapes):
+            gname, c = gfield[n]
+            t = torch.empty(R, c, device=ctx.dev)
+            setattr(b, gname, t.data_ptr())
+            outs.append(t.view(shp))
+        h.check(h.lib.b200r_loss_bwd(h.h, C.byref(b), _stream(ctx.dev)), "b200r_loss_bwd")
+        return (None, *outs)
+
+
+def recon_losses(rendered, aux_dict, batch, config):
+    """The reconstruction part of dvr_model.compute_loss (lab4d/engine/model.py:374-611: get_mask_balance_wt,
+    compute_recon_loss, mask_losses and apply_loss_weights for the keys compute_recon_loss creates) as two kernels.
+    rendered / aux_dict[cate]: (M,N,c) tensors as render_samples returns them; batch: the reshaped dataloader batch
+    (mask, vis2d, is_detected, rgb, depth, flow, flow_uct, feature, hxy); config: field_type, train_res, `<key>_wt`.
+    Returns the loss_dict entries (0-d tensors, the reference's key order)."""
+    ft = config["field_type"]
+    M, N = rendered["rgb"].shape[:2]
+    diff = {"r_mask": rendered["mask"], "r_rgb": rendered["rgb"], "r_depth": rendered["depth"], "r_flow": rendered["flow"]}
+    if ft == "comp":
+        diff["r_mask_fg"] = rendered["mask_fg"]
+    for cate in aux_dict:
+        diff["vis_" + cate] = aux_dict[cate]["vis"]
+    keys = ["mask", "rgb", "depth", "flow", "vis"]
+    if ft in ("fg", "comp"):
+        diff["a_feature"], diff["a_xy_reproj"] = aux_dict["fg"]["feature"], aux_dict["fg"]["xy_reproj"]
+        keys = ["mask", "feature", "feat_reproj", "rgb", "depth", "flow", "vis"]
+        if "gauss_mask" in rendered:
+            diff["a_gauss_mask"] = aux_dict["fg"]["gauss_mask"]
+            keys.append("reg_gauss_mask")
+    data = {"b_mask": batch["mask"].float(), "b_vis2d": batch["vis2d"].float(), "b_is_detected": batch["is_detected"].float(),
+            "b_rgb": batch["rgb"], "b_depth": batch["depth"], "b_flow": batch["flow"], "b_flow_uct": batch["flow_uct"]}
+    if ft in ("fg", "comp"):
+        data["b_feature"], data["b_hxy"] = batch["feature"], batch["hxy"]
+    names = list(diff)
+    meta = dict(names=names, data=data, M=M, N=N, field_type=_FIELD_TYPES[ft], train_res=config["train_res"],
+                wt=[config.get(k + "_wt", 1.0) for k in _lib.LOSS_TERMS])
+    vec = _Losses.apply(meta, *[diff[n] for n in names])
+    return {k: vec[_lib.LOSS_TERMS.index(k)] for k in keys}
