@@ -274,6 +274,9 @@ class Step:
                            ("mask_fg", 1), ("cyc_dist", 1))}
         self.launches = 0
         self.flat = None
+        self.ctxs = {}
+        g = torch.Generator().manual_seed(6)
+        self.eik_rays = torch.randperm(self.M * self.N, generator=g)[:max(self.M * self.N // 16, 1)].to(device=device, dtype=torch.int32)
 
     def run(self, fields=None):
         from lab4d_b200 import autograd as b2grad
@@ -285,7 +288,7 @@ class Step:
         for r, (cfg, P, rays, tab) in zip(self.renderers, fields):
             if self.train:
                 r.pack_train(P)
-                feat, deltas = b2grad.query_field(r, P, rays, tab, self.D, bind_grads=True)
+                feat, deltas, self.ctxs[id(r)] = b2grad.query_field(r, P, rays, tab, self.D, bind_grads=True, return_ctx=True)
                 self.launches += 2 + 2  # pack, pack^T; prologue + field_fwd(train)
             else:
                 r.pack(P)
@@ -293,11 +296,20 @@ class Step:
                 self.launches += 1 + 2
             feats.append(feat)
             dls.append(deltas)
+        if self.train and self.args.with_eikonal:  # NeRF.compute_eikonal on R/16 rays of every field (nnutils/nerf.py:416-453)
+            for r, (cfg, P, rays, tab), feat in zip(self.renderers, fields, feats):
+                g = b2grad.eikonal(r, self.ctxs[id(r)], P, self.eik_rays, bind_grads=True)
+                eik = torch.zeros(self.M * self.N, self.D, device=self.device)
+                eik[self.eik_rays] = (g.norm(2, dim=-1) - 1) ** 2
+                feat["eikonal"] = eik.view(self.M, self.N, self.D, 1)
+                self.launches += 1 + 1 + 4  # reverse chain; absmax, scale, chain A, chain B, weight gradients
         fd, dl = (feats[0], dls[0]) if len(feats) == 1 else compose_fields(feats, dls)
         rend = render_pixel(fd, dl)
         self.launches += 1 + (len(feats) > 1) * 2
         if self.train:
             loss = sum((self.coeff[k] * rend[k]).sum() for k in self.coeff if k in rend)
+            if self.args.with_eikonal:
+                loss = loss + 1e-3 * rend["eikonal"].mean()
             for _, P, _, _ in fields:
                 for v in P.values():
                     v.grad = None
@@ -321,6 +333,9 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--precision", default=None, choices=["fp16x3", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-eikonal", action="store_true",
+                    help="the step also evaluates the eikonal term on 1/16 of the rays (reverse chain, loss, forward chains + weight gradients: "
+                         "NeRF.compute_eikonal and its second-order backward)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of replaying the step as a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -429,6 +444,31 @@ def main():
         f_fn, b_fn = gf.replay, (gb.replay if gb else None)
     except Exception:
         f_fn, b_fn = ph_fwd, (ph_bwd if step.train else None)
+    # the eikonal term alone (R/16 rays): reverse chain, then forward chains + weight gradients, as their own graph
+    eik_ms = []
+    if step.train and not args.no_graph:
+        try:
+            ph_fwd()
+            n_e = int(step.eik_rays.numel())
+            gbar = (1e-6 * torch.randn(n_e, step.D, 3, generator=torch.Generator().manual_seed(8))).to(device)
+            eflat = torch.zeros(r0._train_state()["total"], device=device)
+
+            def ph_eik():
+                _, ectx = r0.eikonal_forward(hold["ctx"], step.eik_rays)
+                r0.eikonal_backward(hold["ctx"], ectx, gbar, flat=eflat)
+
+            ge = GraphedStep(ph_eik, warmup=2, device=device)
+            for i in range(20):
+                flush.fill_(i & 0xFF)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ge.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                eik_ms.append(e0.elapsed_time(e1))
+            ge = None
+        except Exception as ex:
+            print(f"bench: eikonal phase not timed ({type(ex).__name__}: {str(ex)[:160]})", file=sys.stderr)
     for i in range(min(args.steps, 50)):
         flush.fill_(i & 0xFF)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -490,7 +530,8 @@ def main():
                       "fp16": "f16 operands / f32 accumulate", "bf16": "bf16 operands / f32 accumulate"}[step.precision]
                      + ("; backward GEMMs f16 (scaled) / f32 accumulate" if step.train else ""),
             "data": "synthetic",
-            "config": {"workload": cfgd["desc"] + (", training step (fwd + bwd + grad all-reduce)" if step.train else ", forward query_field + render_pixel"),
+            "config": {"workload": cfgd["desc"] + (", training step (fwd + bwd + grad all-reduce)" if step.train else ", forward query_field + render_pixel")
+                                   + (" + eikonal term on 1/16 of the rays" if step.train and args.with_eikonal else ""),
                        "pass": args.passes, "precision": step.precision, "rays_per_gpu": step.M * step.N, "samples_per_ray": step.D * len(step.fields),
                        "l2": "flushed between iterations (256 MB write)", "per_gpu": "BASELINE metric ray-samples/s/GPU = value / n_gpus",
                        "parallelism": f"dp{world}: rays sharded" + (", one NCCL all-reduce (mean) of the flat gradient buffer per step" if step.train else ", no data-path collective in forward")},
@@ -498,6 +539,9 @@ def main():
                     "d2h_bytes_per_step": rgb_host.numel() * 4},
             "gpu_launches": n_launch, "cuda_graph": graphed,
             "phases_ms": {"forward_call": fwd_ms, "backward_call": bwd_ms, "step": ms_step,
+                          "eikonal_call": (float(np.mean(eik_ms)) if eik_ms else None),
+                          "eikonal_note": "b200r_eikonal_fwd + b200r_eikonal_bwd on R/16 rays (reverse chain, 2 forward chains, weight gradients); "
+                                          + ("inside the step" if args.with_eikonal else "NOT inside the step (--with-eikonal adds it)"),
                           "note": "CUDA events around FieldRenderer.query_field[_train] (prologue + field kernel) and FieldRenderer.backward (prologue, scale, data-gradient kernel, weight-gradient kernel, per-frame chain)"},
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }

@@ -1,9 +1,8 @@
 // Alpha compositing along rays (render_pixel / compute_weights / integrate,
 // lab4d/utils/render_utils.py:59-184) and its hand-derived backward.
 //
-// HBM/L2-bound.  Forward: one 128-thread block per ray (block scan of the optical depth, flat coalesced walks
-// over the value arrays); backward: one warp per ray, lanes across samples, warp-shuffle inclusive scan with a
-// running carry.  Per-ray weights stay in shared memory while the value channels are reduced.  Algorithmic traffic = 4 B x (2 + sum of channel widths) per sample read + O(c) per ray.
+// HBM/L2-bound.  Forward and backward: one 128-thread block per ray (block scan of the optical depth, flat coalesced walks
+// over the value / gradient arrays; the backward's reverse scan runs on one warp with a running carry).  Per-ray weights stay in shared memory while the value channels are reduced.  Algorithmic traffic = 4 B x (2 + sum of channel widths) per sample read + O(c) per ray.
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -11,7 +10,6 @@
 
 namespace b200r {
 
-constexpr int kWarpsPerBlock = 8;
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -246,61 +244,100 @@ __device__ __forceinline__ void tau_backward(const float* gw_s, const float* w_s
   }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_bwd_kernel(const b200r_composite_bwd_args b) {
+// One 128-thread block per ray, like the forward: every per-sample array of the ray (values in, gradients out) is walked as
+// one flat, fully coalesced run of D * nch floats; the per-sample weight gradient gw_s[k] collects the channels' contributions
+// (lanes that share a sample reduce by shuffle, one writer per sample: no atomics); warp 0 then runs the reverse scan.
+__global__ void __launch_bounds__(kFwdThreads) composite_bwd_kernel(const b200r_composite_bwd_args b) {
   extern __shared__ float sm[];
   const b200r_composite_args& a = b.fwd;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int D = a.D;
-  float* w_s = sm + (size_t)warp * 3 * D;
-  float* T_s = w_s + D;
-  float* gw_s = T_s + D;
-  const int r = blockIdx.x * kWarpsPerBlock + warp;
-  if (r >= a.R) return;
+  float* w_s = sm;
+  float* T_s = sm + D;
+  float* gw_s = sm + 2 * D;
+  float* red = sm + 3 * D;  // kFwdWarps * 32 floats
+  const int r = blockIdx.x;
   const size_t base = (size_t)r * D;
-  const float mask = ray_weights(a.density + base, a.deltas + base, D, lane, w_s, T_s);
-  __syncwarp();
+  const float mask = block_ray_weights(a.density + base, a.deltas + base, D, warp, lane, w_s, T_s, red);
   const float inv = 1.0f / (mask + 1e-6f);
   const float gm = b.g_mask ? b.g_mask[r] : 0.f;
-  for (int k = lane; k < D; k += 32) gw_s[k] = gm;
-  __syncwarp();
+  for (int k = tid; k < D; k += kFwdThreads) gw_s[k] = gm;
+  __syncthreads();
 
   for (int c = 0; c < a.n_channels; ++c) {
     const int nch = a.nch[c], mode = a.mode[c];
     const float* __restrict__ src = a.src[c] + base * nch;
     const float* g = b.g_dst[c];
     float* gs = b.g_src[c] ? b.g_src[c] + base * nch : nullptr;
+    const int n_el = D * nch;
     if (mode == B200R_CH_NORM || mode == B200R_CH_NORM_FROZEN) {
-      if (!g) { if (gs) for (int e = lane; e < D * nch; e += 32) gs[e] = 0.f; continue; }
-      // out_j recomputed: sum_k wn_k v_kj
-      for (int j = 0; j < nch; ++j) {
+      if (!g) { if (gs) for (int e = tid; e < n_el; e += kFwdThreads) gs[e] = 0.f; continue; }
+      const bool live_w = mode == B200R_CH_NORM;  // frozen channels: weights detached
+      if (nch <= 32 && (32 % nch) == 0) {
+        const int sh = __ffs(nch) - 1, j = tid & (nch - 1);  // the channel of a thread is fixed
         const float gj = g[(size_t)r * nch + j];
-        float o = 0.f;
-        if (mode == B200R_CH_NORM) {
-          for (int k = lane; k < D; k += 32) o += w_s[k] * inv * src[(size_t)k * nch + j];
-          o = warp_sum(o);
+        float oj = 0.f;
+        if (live_w) {  // out_j = sum_k w_k inv v_kj
+          float acc = 0.f;
+          for (int e = tid; e < n_el; e += kFwdThreads) acc += w_s[e >> sh] * src[e];
+          for (int o = nch; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          __syncthreads();
+          if (lane < nch) red[warp * 32 + lane] = acc;
+          __syncthreads();
+#pragma unroll
+          for (int i = 0; i < kFwdWarps; ++i) oj += red[i * 32 + j];
+          oj *= inv;
         }
-        for (int k = lane; k < D; k += 32) {
-          if (gs) gs[(size_t)k * nch + j] = gj * w_s[k] * inv;
-          if (mode == B200R_CH_NORM) gw_s[k] += gj * (src[(size_t)k * nch + j] - o) * inv;
+        for (int e0 = 0; e0 < n_el; e0 += kFwdThreads) {  // uniform trip count: the shuffles below need whole warps
+          const int e = e0 + tid;
+          const bool in = e < n_el;
+          const int k = in ? e >> sh : 0;
+          if (in && gs) gs[e] = gj * w_s[k] * inv;
+          if (live_w) {
+            float cg = in ? gj * (src[e] - oj) * inv : 0.f;
+            for (int o = 1; o < nch; o <<= 1) cg += __shfl_xor_sync(0xffffffffu, cg, o);
+            if (in && j == 0) gw_s[k] += cg;
+          }
+        }
+      } else {  // any other width (3: rgb, xyz): one thread per sample
+        float* o_s = red;  // out_j, j < nch <= 16
+        if (live_w) {
+          for (int j = 0; j < nch; ++j) {
+            float acc = 0.f;
+            for (int k = tid; k < D; k += kFwdThreads) acc += w_s[k] * src[(size_t)k * nch + j];
+            const float t = block_sum(acc, red + 32, warp, lane) * inv;
+            if (tid == 0) o_s[j] = t;
+          }
+          __syncthreads();
+        }
+        for (int k = tid; k < D; k += kFwdThreads) {
+          float cg = 0.f;
+          for (int j = 0; j < nch; ++j) {
+            const float gj = g[(size_t)r * nch + j];
+            if (gs) gs[(size_t)k * nch + j] = gj * w_s[k] * inv;
+            if (live_w) cg += gj * (src[(size_t)k * nch + j] - o_s[j]) * inv;
+          }
+          if (live_w) gw_s[k] += cg;
         }
       }
+      __syncthreads();
     } else if (mode == B200R_CH_MEAN) {
       if (gs) {
-        const float gv = g ? g[r] / (float)(D * nch) : 0.f;
-        for (int e = lane; e < D * nch; e += 32) gs[e] = gv;
+        const float gv = g ? g[r] / (float)n_el : 0.f;
+        for (int e = tid; e < n_el; e += kFwdThreads) gs[e] = gv;
       }
     } else if (mode == B200R_CH_FLOW) {
-      if (!g) { if (gs) for (int e = lane; e < D * 3; e += 32) gs[e] = 0.f; continue; }
+      if (!g) { if (gs) for (int e = tid; e < D * 3; e += kFwdThreads) gs[e] = 0.f; continue; }
       float sw = 0.f, sx = 0.f, sy = 0.f;
-      for (int k = lane; k < D; k += 32) {
+      for (int k = tid; k < D; k += kFwdThreads) {
         const float wf = w_s[k] * src[(size_t)k * 3 + 2];
         sw += wf; sx += wf * src[(size_t)k * 3]; sy += wf * src[(size_t)k * 3 + 1];
       }
-      sw = warp_sum(sw); sx = warp_sum(sx); sy = warp_sum(sy);
+      sw = block_sum(sw, red, warp, lane); sx = block_sum(sx, red, warp, lane); sy = block_sum(sy, red, warp, lane);
       const float invf = 1.0f / (sw + 1e-6f);
       const float ox = sx * invf, oy = sy * invf;
       const float gx = g[(size_t)r * 2], gy = g[(size_t)r * 2 + 1];
-      for (int k = lane; k < D; k += 32) {
+      for (int k = tid; k < D; k += kFwdThreads) {
         const float val = src[(size_t)k * 3 + 2];
         const float vx = src[(size_t)k * 3], vy = src[(size_t)k * 3 + 1];
         gw_s[k] += (gx * (vx - ox) + gy * (vy - oy)) * invf * val;
@@ -310,18 +347,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_bwd_kernel(cons
           gs[(size_t)k * 3 + 2] = 0.f;  // validity flag is piecewise constant
         }
       }
+      __syncthreads();
     } else if (mode == B200R_CH_VIS) {
       // transmittance is detached (render_utils.py:83): only the logit receives gradient
       if (gs) {
         const float g0 = g ? g[(size_t)r * 2] : 0.f;
-        for (int k = lane; k < D; k += 32) {
+        for (int k = tid; k < D; k += kFwdThreads) {
           const float x = src[k];
           gs[k] = g0 * T_s[k] * (1.f / (1.f + expf(x)));  // d logsigmoid = sigmoid(-x)
         }
       }
     }
   }
-  __syncwarp();
+  __syncthreads();
+  if (warp != 0) return;  // the reverse scans are O(D): one warp
   tau_backward(gw_s, w_s, a.density + base, a.deltas + base, D, lane, b.g_density + base, false);
   __syncwarp();
   // density-type channels: their own weights
@@ -347,12 +386,11 @@ cudaError_t launch_composite_fwd(const b200r_composite_args& a, cudaStream_t str
 }
 
 cudaError_t launch_composite_bwd(const b200r_composite_bwd_args& b, cudaStream_t stream) {
-  const size_t smem = (size_t)kWarpsPerBlock * 3 * b.fwd.D * sizeof(float);
+  const size_t smem = ((size_t)3 * b.fwd.D + kFwdWarps * 32 + 32) * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int blocks = (b.fwd.R + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  composite_bwd_kernel<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(b);
+  composite_bwd_kernel<<<b.fwd.R, kFwdThreads, smem, stream>>>(b);
   return cudaGetLastError();
 }
 

@@ -32,19 +32,48 @@ def main():
         r = fwd()
         (r["rgb"].sum() + r["mask"].sum() + r["flow"].sum() * 1e-3).backward()
 
-    for name, fn, ctx in (("forward", fwd, torch.no_grad()), ("forward+backward", step, torch.enable_grad())):
-        with ctx:
-            for _ in range(2):
-                fn()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            n = 5
-            for _ in range(n):
-                fn()
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / n
-        print(f"reference on CUDA fg-bob {M}x{N}x{D} {name}: {dt*1e3:.1f} ms -> {M*N*D/dt:.3e} ray-samples/s, "
-              f"peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB")
+    def step_full():  # what a training step of the reference evaluates on one field: + eikonal term and feature matching in the loss
+        field.zero_grad()
+        s = field.get_samples(Kinv, batch)
+        feat, deltas, aux = field.query_field(s, flow_thresh=None)
+        r = render_pixel(feat, deltas)
+        loss = r["rgb"].sum() + r["mask"].sum() + r["flow"].sum() * 1e-3 + r["eikonal"].mean()
+        if "xy_reproj" in aux:
+            loss = loss + 1e-3 * aux["xy_reproj"].mean()
+        loss.backward()
+
+    g = torch.Generator().manual_seed(3)
+    batch["feature"] = torch.nn.functional.normalize(torch.randn(M, N, 16, generator=g), dim=-1).to(dev)
+
+    def timed(tag):
+        for name, fn, ctx in (("forward", fwd, torch.no_grad()), ("forward+backward", step, torch.enable_grad()),
+                              ("forward+backward incl. eikonal + matching in the loss", step_full, torch.enable_grad())):
+            torch.cuda.reset_peak_memory_stats()
+            with ctx:
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                n = 5
+                for _ in range(n):
+                    fn()
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / n
+            print(f"{tag} fg-bob {M}x{N}x{D} {name}: {dt*1e3:.1f} ms -> {M*N*D/dt:.3e} ray-samples/s, "
+                  f"peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB", flush=True)
+
+    timed("reference on CUDA")
+    # the same calls with the B200 renderer patched in (lab4d_b200.nnutils.install): eager launches through the reference's own
+    # entry points, the reference's per-frame modules (cameras, articulations, embeddings) still torch
+    sys.path.insert(0, ROOT)
+    from lab4d_b200 import nnutils
+
+    for prec in ("fp16x3", "fp16"):
+        undo = nnutils.install(n_depth=D, operand_dtype=prec)
+        try:
+            timed(f"patched reference ({prec})")
+        finally:
+            undo()
 
 
 if __name__ == "__main__":
