@@ -502,6 +502,24 @@ def main():
                 gfo = None
             except Exception as ex:
                 fwd_variants[prec] = {"error": str(ex)[:120]}
+    # the same step with the eikonal term inside (R/16 rays: reverse chain, loss, forward chains, weight gradients), beside the default
+    step_variants = {}
+    if step.train and not args.with_eikonal and not args.no_graph and len(step.fields) == 1 and world == 1:
+        try:
+            import copy
+
+            a2 = copy.copy(args)
+            a2.with_eikonal = True
+            st2 = Step(a2, device, rank, world)
+            for _ in range(3):
+                st2.run()
+            g2 = GraphedStep(st2.run, warmup=2, device=device)
+            tms = timed(g2.replay, 30)
+            step_variants["with_eikonal"] = {"ms_per_step": float(np.mean(tms)), "value_per_gpu": st2.S / (float(np.mean(tms)) * 1e-3), "unit": "ray-samples/s",
+                                             "what": "the default step + NeRF.compute_eikonal on 1/16 of the rays and its second-order backward (eikonal kernels)"}
+            g2 = st2 = None
+        except Exception as ex:
+            step_variants["with_eikonal"] = {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
     clocks = sampler.stop()
     tot = torch.tensor([sum(ms), sum(ms_e2e)], device=device, dtype=torch.float64)
     Stot = torch.tensor([float(step.S)], device=device, dtype=torch.float64)
@@ -573,6 +591,8 @@ def main():
                                             "note": "tape bytes each kernel must write / read once: forward 79, data-gradient 82, weight-gradient 161 chunks of 16 KB per 128-sample tile"}
         if fwd_variants:
             line["forward_only"] = fwd_variants
+        if step_variants:
+            line["step_variants"] = step_variants
         if step.flat is not None:
             line["grad_buffer_bytes"] = int(sum(fl.numel() for fl in step.flat) * 4)
         if not args.no_cpu_baseline and world == 1 and args.config == "c2":  # reported baseline: rank 0 at N = 1, ~10-20 s of CPU work

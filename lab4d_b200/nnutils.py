@@ -111,7 +111,7 @@ def compute_eikonal(field, renderer, ctx, P, xyz, sample_ratio=16, bind_grads=Fa
     return eik.view(M, N, D, 1)
 
 
-def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False):
+def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False, match_rng="reference"):
     """Replacement body of NeRF.query_field (nnutils/nerf.py:580-684) for NeRF / FeatureNeRF / Deformable modules.
     Training mode: the fused kernels (with the tape and the hand-derived backward when autograd is recording); the
     eikonal term runs on the eikonal kernels (`compute_eikonal` above: reverse chain with the tape's ReLU signs, hand-derived
@@ -162,7 +162,7 @@ def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype
                                                                inst_id, samples_dict)
     aux = {}
     if hasattr(field, "global_match") and "feature" in samples_dict and "feature" in feat:  # FeatureNeRF.query_field, feature.py:119-131
-        xyz_matches = _render.global_match(samples_dict["feature"], feat["feature"], feat["xyz"], field.logsigma)  # match kernels
+        xyz_matches = _render.global_match(samples_dict["feature"], feat["feature"], feat["xyz"], field.logsigma, rng=match_rng)  # match kernels
         xy_reproj, xyz_reproj = field.forward_project(xyz_matches, samples_dict["field2cam"], samples_dict["Kinv"], samples_dict["frame_id"],
                                                        inst_id, samples_dict=samples_dict)
         aux.update(xyz_matches=xyz_matches, xyz_reproj=xyz_reproj, xy_reproj=xy_reproj)
@@ -222,12 +222,14 @@ def compute_loss(model, batch, results):
     return loss_dict
 
 
-def install(lab4d=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False):
+def install(lab4d=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False, match_rng="reference"):
     """Patch an imported reference package in place; returns a function that undoes the patch.
     operand_dtype: "fp16x3" (parity mode, default), "fp16" or "bf16" (fast modes).
     bind_grads: make the hot-path parameters' .grad views of the renderer's flat gradient buffer (no per-tensor gradient
     copies; all-reduce the buffer yourself) - leave False under DistributedDataParallel, whose reducer waits for autograd's
-    per-parameter hooks (engine/trainer.py:110-115)."""
+    per-parameter hooks (engine/trainer.py:110-115).
+    match_rng: "reference" draws global_match's candidates with the reference's own torch.randperm call on the CPU generator
+    (same random stream, ~2 ms of host time per step); "device" draws them on the GPU."""
     if lab4d is None:
         import lab4d  # noqa: F401
     import lab4d.engine.model as rmodel
@@ -243,7 +245,8 @@ def install(lab4d=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False):
              (rmodel.dvr_model, "compute_loss", rmodel.dvr_model.compute_loss)]
 
     def _qf(self, samples_dict, flow_thresh=None):
-        return query_field(self, samples_dict, flow_thresh=flow_thresh, n_depth=n_depth, operand_dtype=operand_dtype, bind_grads=bind_grads)
+        return query_field(self, samples_dict, flow_thresh=flow_thresh, n_depth=n_depth, operand_dtype=operand_dtype, bind_grads=bind_grads,
+                           match_rng=match_rng)
 
     # one body for the three classes: the kernels already produce what FeatureNeRF / Deformable add on top of NeRF
     # (feature field, Gaussian bone density); the per-ray matching of FeatureNeRF runs inside query_field above

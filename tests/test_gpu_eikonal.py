@@ -68,7 +68,9 @@ def test_eikonal_kernels_match_second_order_autograd(name, M, N, D, prec, n_sel)
     e_g = rel_l2(g.cpu(), g64.cpu())
     eik, eik64 = (g.norm(2, dim=-1) - 1) ** 2, (g64.norm(2, dim=-1) - 1) ** 2
     e_eik = float((eik.double() - eik64).abs().max() / eik64.mean())
+    pp = ((g.double() - g64).norm(dim=-1) / g64.norm(dim=-1)).flatten().sort().values  # per-point error: a flipped ReLU sign shows as an outlier
     print(f"[eikonal] {name} {M}x{N}x{D} {prec} rays={n_sel}: g rel-L2 {e_g:.2e} (reference fp32 vs fp64 {rel_l2(g32.cpu(), g64.cpu()):.1e}), "
+          f"per point median {float(pp[len(pp) // 2]):.1e} p90 {float(pp[int(0.9 * len(pp))]):.1e} max {float(pp[-1]):.1e}, "
           f"(|g|-1)^2 max abs err / mean {e_eik:.2e}, mean |g| {float(g64.norm(2, dim=-1).mean()):.3f}")
     assert e_g <= G_TOL[prec], e_g
     # backward: cotangent of g from the loss, evaluated at the kernel's own g (what autograd hands to EikonalFunction.backward)
