@@ -498,6 +498,21 @@ typedef struct {
 
 int b200r_loss_bwd(b200r_handle* h, const b200r_loss_bwd_args* args, b200r_stream stream);
 
+/* ------------------------------------------------------------------ quaternion operators (the dqtorch extension)
+ * Stand-alone replacements of the reference's only native code, lab4d/third_party/quaternion/src/quaternion.cu:29-217
+ * (bindings.cpp:7-16: quaternion_mul_forward / _backward / _backward_backward, quaternion_conjugate), which
+ * lab4d/utils/quat_transform.py:36-113 calls on flattened (B, 3|4) operands.  a (B,D1), b (B,D2), D in {3, 4}: a 3-vector is a pure
+ * quaternion (w = 0).  fp32, contiguous, 16-B aligned for 4-wide operands.  Outputs are OVERWRITTEN.
+ *   fwd:      out (B,4) = a b
+ *   bwd:      g_a (B,D1) = [G b*],  g_b (B,D2) = [a* G]                     (G = gradient of out; [.] drops w for 3-vectors)
+ *   bwd_bwd:  for cotangents u1 (B,D1), u2 (B,D2) of (g_a, g_b):  g_G (B,4) = u1 b + a u2,  g_a' = [G u2*],  g_b' = [u1* G] */
+int b200r_quat_mul_fwd(b200r_handle* h, const float* a, const float* b, float* out, int64_t B, int32_t D1, int32_t D2, b200r_stream stream);
+int b200r_quat_mul_bwd(b200r_handle* h, const float* grad, const float* a, const float* b, float* g_a, float* g_b, int64_t B, int32_t D1,
+                       int32_t D2, b200r_stream stream);
+int b200r_quat_mul_bwd_bwd(b200r_handle* h, const float* u1, const float* u2, const float* grad, const float* a, const float* b, float* g_grad,
+                           float* g_a, float* g_b, int64_t B, int32_t D1, int32_t D2, b200r_stream stream);
+int b200r_quat_conj(b200r_handle* h, const float* q, float* out, int64_t B, b200r_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200render.so")
-SOURCES = ["api.cu", "api_train.cu", "field_fwd.cu", "field_fwd_train.cu", "field_bwd.cu", "wgrad.cu", "chain.cu", "prologue.cu", "pack.cu", "composite.cu", "compose.cu", "importance.cu", "match.cu", "losses.cu"]
+SOURCES = ["api.cu", "api_train.cu", "field_fwd.cu", "field_fwd_train.cu", "field_bwd.cu", "wgrad.cu", "chain.cu", "prologue.cu", "pack.cu", "composite.cu", "compose.cu", "importance.cu", "match.cu", "losses.cu", "quat.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-DB200R_CLUSTER=" + os.environ.get("B200R_CLUSTER", "2"), "-DB200R_WATCHDOG=" + os.environ.get("B200R_WATCHDOG", "1")]
 

@@ -402,4 +402,42 @@ int b200r_loss_bwd(b200r_handle* h, const b200r_loss_bwd_args* b, b200r_stream s
   return B200R_OK;
 }
 
+static int quat_check(b200r_handle* h, const char* who, int64_t B, int32_t D1, int32_t D2) {
+  if (B < 0 || !(D1 == 3 || D1 == 4) || !(D2 == 3 || D2 == 4)) return fail(h, B200R_E_INVALID, std::string(who) + ": need B >= 0 and operand widths 3 or 4");
+  return B200R_OK;
+}
+#define B200R_QUAT_ENTRY(CALL, WHO)                                                      \
+  b200r::DeviceGuard guard(h->device);                                                   \
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");                   \
+  if (B == 0) return B200R_OK;                                                           \
+  cudaError_t e = CALL;                                                                  \
+  if (e != cudaSuccess) return fail_cuda(h, e, WHO);                                     \
+  return B200R_OK;
+
+int b200r_quat_mul_fwd(b200r_handle* h, const float* a, const float* b, float* out, int64_t B, int32_t D1, int32_t D2, b200r_stream stream) {
+  if (!h) return B200R_E_INVALID;
+  if (quat_check(h, "quat_mul_fwd", B, D1, D2)) return B200R_E_INVALID;
+  if (B > 0 && (!a || !b || !out)) return fail(h, B200R_E_INVALID, "quat_mul_fwd: null tensor");
+  B200R_QUAT_ENTRY(b200r::launch_quat_mul_fwd(a, b, out, B, D1, D2, (cudaStream_t)stream), "quat_mul kernel")
+}
+int b200r_quat_mul_bwd(b200r_handle* h, const float* grad, const float* a, const float* b, float* g_a, float* g_b, int64_t B, int32_t D1, int32_t D2,
+                       b200r_stream stream) {
+  if (!h) return B200R_E_INVALID;
+  if (quat_check(h, "quat_mul_bwd", B, D1, D2)) return B200R_E_INVALID;
+  if (B > 0 && (!grad || !a || !b || !g_a || !g_b)) return fail(h, B200R_E_INVALID, "quat_mul_bwd: null tensor");
+  B200R_QUAT_ENTRY(b200r::launch_quat_mul_bwd(grad, a, b, g_a, g_b, B, D1, D2, (cudaStream_t)stream), "quat_mul backward kernel")
+}
+int b200r_quat_mul_bwd_bwd(b200r_handle* h, const float* u1, const float* u2, const float* grad, const float* a, const float* b, float* g_grad, float* g_a,
+                           float* g_b, int64_t B, int32_t D1, int32_t D2, b200r_stream stream) {
+  if (!h) return B200R_E_INVALID;
+  if (quat_check(h, "quat_mul_bwd_bwd", B, D1, D2)) return B200R_E_INVALID;
+  if (B > 0 && (!u1 || !u2 || !grad || !a || !b || !g_grad || !g_a || !g_b)) return fail(h, B200R_E_INVALID, "quat_mul_bwd_bwd: null tensor");
+  B200R_QUAT_ENTRY(b200r::launch_quat_mul_bwd_bwd(u1, u2, grad, a, b, g_grad, g_a, g_b, B, D1, D2, (cudaStream_t)stream), "quat_mul second backward kernel")
+}
+int b200r_quat_conj(b200r_handle* h, const float* q, float* out, int64_t B, b200r_stream stream) {
+  if (!h) return B200R_E_INVALID;
+  if (B < 0 || (B > 0 && (!q || !out))) return fail(h, B200R_E_INVALID, "quat_conj: bad argument");
+  B200R_QUAT_ENTRY(b200r::launch_quat_conj(q, out, B, (cudaStream_t)stream), "quat_conj kernel")
+}
+
 }  // extern "C"

@@ -147,6 +147,11 @@ cudaError_t launch_composite_fwd(const b200r_composite_args& a, cudaStream_t str
 cudaError_t launch_composite_bwd(const b200r_composite_bwd_args& b, cudaStream_t stream);
 cudaError_t launch_importance_fwd(const b200r_importance_args& a, cudaStream_t stream);
 cudaError_t launch_compose_fwd(const b200r_compose_args& a, cudaStream_t stream);
+cudaError_t launch_quat_mul_fwd(const float* a, const float* b, float* out, long long B, int D1, int D2, cudaStream_t s);
+cudaError_t launch_quat_mul_bwd(const float* g, const float* a, const float* b, float* ga, float* gb, long long B, int D1, int D2, cudaStream_t s);
+cudaError_t launch_quat_mul_bwd_bwd(const float* u1, const float* u2, const float* g, const float* a, const float* b, float* gg, float* gga, float* ggb,
+                                    long long B, int D1, int D2, cudaStream_t s);
+cudaError_t launch_quat_conj(const float* q, float* out, long long B, cudaStream_t s);
 cudaError_t launch_loss_fwd(const b200r_loss_args& a, cudaStream_t stream);
 cudaError_t launch_loss_bwd(const b200r_loss_bwd_args& b, cudaStream_t stream);
 size_t match_partial_floats(int R, int K);

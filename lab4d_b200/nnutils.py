@@ -222,12 +222,33 @@ def compute_loss(model, batch, results):
     return loss_dict
 
 
-def install(lab4d=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False, match_rng="reference"):
+def _dq_mul(a, b):
+    """lab4d.utils.quat_transform.quaternion_mul (quat_transform.py:106-113) on the quaternion kernels; operands that the
+    reference would have to broadcast by hand are broadcast here (3-vectors stay 3-wide: pure quaternions)."""
+    from . import quaternion as _q
+
+    if not a.is_cuda:
+        raise RuntimeError("lab4d_b200: quaternion operators run on CUDA only")
+    lead = torch.broadcast_shapes(a.shape[:-1], b.shape[:-1])
+    a2 = a.expand(lead + a.shape[-1:]).reshape(-1, a.shape[-1])
+    b2 = b.expand(lead + b.shape[-1:]).reshape(-1, b.shape[-1])
+    return _q.quaternion_mul(a2, b2).view(lead + (4,))
+
+
+def _dq_conj(q):
+    from . import quaternion as _q
+
+    return _q.quaternion_conjugate(q.reshape(-1, 4)).view(q.shape)
+
+
+def install(lab4d=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False, match_rng="reference", dqtorch=False):
     """Patch an imported reference package in place; returns a function that undoes the patch.
     operand_dtype: "fp16x3" (parity mode, default), "fp16" or "bf16" (fast modes).
     bind_grads: make the hot-path parameters' .grad views of the renderer's flat gradient buffer (no per-tensor gradient
     copies; all-reduce the buffer yourself) - leave False under DistributedDataParallel, whose reducer waits for autograd's
     per-parameter hooks (engine/trainer.py:110-115).
+    dqtorch: also rebind lab4d.utils.quat_transform.quaternion_mul / quaternion_conjugate (the dqtorch extension,
+    third_party/quaternion) to the quaternion kernels (lab4d_b200/quaternion.py) in every loaded lab4d module.
     match_rng: "reference" draws global_match's candidates with the reference's own torch.randperm call on the CPU generator
     (same random stream, ~2 ms of host time per step); "device" draws them on the GPU."""
     if lab4d is None:
@@ -256,6 +277,22 @@ def install(lab4d=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False, ma
     rmodel.render_pixel = _render.render_pixel
     rmf.MultiFields.compose_fields = staticmethod(compose_fields)
     rmodel.dvr_model.compute_loss = compute_loss
+    if dqtorch:
+        # the dqtorch operators behind lab4d.utils.quat_transform (third_party/quaternion): every loaded lab4d module that holds
+        # the reference's quaternion_mul / quaternion_conjugate by name gets the kernels' versions
+        import sys
+
+        import lab4d.utils.quat_transform as qt
+
+        old = {"quaternion_mul": qt.quaternion_mul, "quaternion_conjugate": qt.quaternion_conjugate}
+        new = {"quaternion_mul": _dq_mul, "quaternion_conjugate": _dq_conj}
+        for mname, mod in list(sys.modules.items()):
+            if mod is None or not mname.startswith("lab4d"):
+                continue
+            for fname, fold in old.items():
+                if getattr(mod, fname, None) is fold:
+                    saved.append((mod, fname, fold))
+                    setattr(mod, fname, new[fname])
 
     def undo():
         for obj, name, val in saved:

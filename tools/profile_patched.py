@@ -26,7 +26,9 @@ def main():
     from lab4d_b200 import autograd as ag
     from lab4d_b200 import nnutils, render
 
-    undo = nnutils.install(n_depth=D)
+    dq = "--dq" in sys.argv  # quaternion kernels for the reference's remaining torch code + candidate draw on the device
+    undo = nnutils.install(n_depth=D, dqtorch=dq, match_rng="device" if dq else "reference")
+    print(f"install(dqtorch={dq})")
     import lab4d.utils.render_utils as rru
 
     T = collections.OrderedDict()

@@ -68,10 +68,10 @@ def main():
     sys.path.insert(0, ROOT)
     from lab4d_b200 import nnutils
 
-    for prec in ("fp16x3", "fp16"):
-        undo = nnutils.install(n_depth=D, operand_dtype=prec)
+    for prec, kw in (("fp16x3", {}), ("fp16", {}), ("fp16x3", dict(dqtorch=True, match_rng="device"))):
+        undo = nnutils.install(n_depth=D, operand_dtype=prec, **kw)
         try:
-            timed(f"patched reference ({prec})")
+            timed(f"patched reference ({prec}{', quaternion kernels + device candidate draw' if kw else ''})")
         finally:
             undo()
 
