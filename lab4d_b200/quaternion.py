@@ -17,9 +17,11 @@ def _call(fn_name, dev, *args):
 
 
 def _c(t):
+    """fp32 contiguous operand.  An operand that already is one is handed on AS IS (not detached): the Functions save their
+    inputs, and autograd reconnects saved inputs to the graph when the backward is differentiated again (the reference saves
+    `inputs.contiguous()` the same way, quaternion.py:62-75)."""
     if not t.is_cuda:
         raise RuntimeError("lab4d_b200.quaternion: CUDA tensors only (no CPU path)")
-    t = t.detach()
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
 
