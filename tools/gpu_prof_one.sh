@@ -2,7 +2,7 @@
 # one ncu --set full capture: tools/gpu_prof_one.sh <kernel regex> <tag> <bench args...>
 mkdir -p gpurun_out
 K=$1; TAG=$2; shift 2
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 -f -o gpurun_out/r02_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s ${SKIP:-4} -c 1 -f -o gpurun_out/r02_$TAG \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph "$@" > gpurun_out/ncu_$TAG.log 2>&1
 ncu -i gpurun_out/r02_$TAG.ncu-rep --page raw --csv > gpurun_out/r02_${TAG}_raw.csv 2>/dev/null
 # top-sampled SASS instructions (the .ncu-rep itself is 25-35 MB: it stays on the box unless KEEP_REP=1)
