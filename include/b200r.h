@@ -341,6 +341,22 @@ int b200r_warp_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* pa
                    const b200r_frame_tables* frames, const b200r_point_batch* points, int32_t backward,
                    const b200r_field_outputs* out, void* workspace, size_t workspace_bytes, b200r_stream stream);
 
+/* The FORWARD warp (canonical -> time-t space, the frame's own articulation) on given points as a differentiable pair: what
+ * FeatureNeRF.forward_project (lab4d/nnutils/feature.py:207-226) and NeRF.forward_warp (nerf.py:846-870) run on the matched
+ * points in a training step, and autograd through them (engine/trainer.py:344-345).  b200r_warp_fwd_train = b200r_warp_fwd
+ * (backward = 0) that also records the warp's slice of the tape (sizes: b200r_tape_sizes(desc, M, P, 1)); `out` keeps xyz (the
+ * warped points; warp_pts too for ComposedWarp fields).  b200r_warp_bwd takes g_xyz (M*P,3), the cotangent of the warped points,
+ * and returns g_points (M*P,3) w.r.t. the given points, ACCUMULATES the gradients of the delta MLP (and soft-deformation map)
+ * weights / biases, log_gauss into out->flat and OVERWRITES the per-frame gradients (articulations, skinning / dense codes) of
+ * frame_grads - same conventions and scratch blocks as b200r_field_bwd.  `saved`: the forward's warp_pts (ComposedWarp), else unused. */
+int b200r_warp_fwd_train(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* params,
+                         const b200r_frame_tables* frames, const b200r_point_batch* points, const b200r_field_outputs* out,
+                         const b200r_tape* tape, void* workspace, size_t workspace_bytes, b200r_stream stream);
+int b200r_warp_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* params,
+                   const b200r_frame_tables* frames, const b200r_point_batch* points, const b200r_field_outputs* saved, const float* g_xyz,
+                   const b200r_tape* tape, const b200r_param_grads* out, const b200r_frame_grads* frame_grads, float* g_points,
+                   void* workspace, size_t workspace_bytes, b200r_stream stream);
+
 /* ------------------------------------------------------------------ compositing (render_pixel) */
 #define B200R_MAX_CHANNELS 16
 /* how a per-sample array (R*D, nch) is reduced along the ray */

@@ -61,6 +61,51 @@ class FieldFunction(torch.autograd.Function):
         return tuple(out)
 
 
+class WarpFunction(torch.autograd.Function):
+    """The forward skinning warp (+ soft deformation) of given points, b200r_warp_fwd_train / b200r_warp_bwd: differentiable
+    w.r.t. the points, the warp's parameters and the per-frame tables it reads (articulations, skinning / dense codes)."""
+
+    @staticmethod
+    def forward(ctx, renderer, meta, xyz, *tensors):
+        p_names, t_names = meta["p_names"], meta["t_names"]
+        tab = dict(zip(t_names, tensors[len(p_names):]))
+        out, c = renderer.warp_points_train(meta["P_all"], xyz, tab)  # the kernels read the field's whole parameter table by pointer
+        ctx.renderer, ctx.c, ctx.meta = renderer, c, meta
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        meta, r = ctx.meta, ctx.renderer
+        bind = meta.get("bind")
+        if bind is not None:
+            flat = _bind_views(r, bind)
+            g_pts, _, tg = r.warp_backward(ctx.c, g_out, flat=flat)
+            pg = {}
+        else:
+            g_pts, pg, tg = r.warp_backward(ctx.c, g_out)
+        out = [None, None, g_pts]
+        for n in meta["p_names"]:
+            out.append(pg.get(n))
+        for n in meta["t_names"]:
+            g = tg.get(n)
+            out.append(g if g is None else g.reshape(ctx.c["tab"][n].shape))
+        return tuple(out)
+
+
+def warp_points(renderer, P, xyz, tab, bind_grads=False):
+    """Differentiable forward warp (canonical -> time-t space) of points xyz (M,P,3) with the frames' own articulations:
+    autograd edges to xyz, to the warp's parameters in P and to tab's tensors.  Call renderer.pack_train first."""
+    p_names = [k for k in renderer.warp_weight_names() if k in P]
+    warp_tabs = ("inst_skin", "skin_t_embed", "skin_t_embed_mean", "dense_t_embed", "inst_dense_fwd", "inst_dense_bwd", "t_articulation_qr",
+                 "t_articulation_qd", "rest_articulation_qr", "rest_articulation_qd")
+    t_names = [k for k in warp_tabs if torch.is_tensor(tab.get(k))]
+    meta = dict(p_names=p_names, t_names=t_names)
+    if bind_grads:
+        meta["bind"] = {k: v for k, v in P.items() if v.requires_grad and v.is_leaf}
+    meta["P_all"] = {k: v.detach() for k, v in P.items()}
+    return WarpFunction.apply(renderer, meta, xyz, *[P[k] for k in p_names], *[tab[k] for k in t_names])
+
+
 class EikonalFunction(torch.autograd.Function):
     """g = d sdf / d xyz on the samples of a subset of rays (NeRF.compute_eikonal, nnutils/nerf.py:416-453) with a
     hand-derived backward to the basefield weights and sdf.weight - replaces the reference's autograd.grad(create_graph=True)

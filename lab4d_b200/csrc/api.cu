@@ -136,7 +136,7 @@ static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* 
     if (!pts->xyz) return bad("missing points");
     if (out->rgb || out->density || out->sdf || out->vis || out->xyz_cam || out->xyz_t || out->dir || out->depth || out->deltas ||
         out->feature || out->flow || out->cyc_dist || out->gauss_density)
-      return bad("only xyz, skin_entropy and delta_skin are produced");
+      return bad("only xyz, skin_entropy and delta_skin (and warp_pts with a tape) are produced");
   } else {
     if (!pts->xyz) return bad("missing points");
     if (desc->L_dir == 0 && !pts->dir && out->rgb) return bad("rgb needs view directions for this field");
@@ -214,7 +214,9 @@ static int run_field(b200r_handle* h, const b200r_field_desc* desc, const void* 
     size_t need_a = b200r::tape_a_bytes(kp.tape, kp.n_tiles), need_m = b200r::tape_mask_bytes(kp.tape, kp.n_tiles);
     if (!tape->a || !tape->mask || tape->a_bytes < need_a || tape->mask_bytes < need_m) return bad("tape buffers missing or too small (b200r_tape_sizes)");
     if ((reinterpret_cast<uintptr_t>(tape->a) & 1023) || (reinterpret_cast<uintptr_t>(tape->mask) & 15)) return bad("tape buffers must be 1024-B / 16-B aligned");
-    if (!out->xyz || !out->rgb || !out->sdf || (desc->has_feature && (!out->feature || !out->feat_norm)) || (desc->dense && !out->warp_pts))
+    if (warp) {
+      if (!out->xyz || (desc->dense && !out->warp_pts)) return bad("the training warp must keep xyz (and warp_pts for ComposedWarp fields)");
+    } else if (!out->xyz || !out->rgb || !out->sdf || (desc->has_feature && (!out->feature || !out->feat_norm)) || (desc->dense && !out->warp_pts))
       return bad("the training forward must keep xyz, rgb, sdf (and feature, feat_norm; warp_pts for ComposedWarp fields)");
     kp.tape_a = (uint8_t*)tape->a;
     kp.tape_mask = (uint32_t*)tape->mask;
@@ -257,6 +259,14 @@ int b200r_warp_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* pa
   if (!pts) return fail(h, B200R_E_INVALID, "warp_fwd: null argument");
   return run_field(h, desc, packed, par, fr, nullptr, pts, backward ? b200r::MODE_WARP_BWD : b200r::MODE_WARP_FWD, out, workspace,
                    workspace_bytes, stream_);
+}
+
+int b200r_warp_fwd_train(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
+                         const b200r_frame_tables* fr, const b200r_point_batch* pts, const b200r_field_outputs* out, const b200r_tape* tape,
+                         void* workspace, size_t workspace_bytes, b200r_stream stream_) {
+  if (!h) return B200R_E_INVALID;
+  if (!pts || !tape) return fail(h, B200R_E_INVALID, "warp_fwd_train: null argument");
+  return run_field(h, desc, packed, par, fr, nullptr, pts, b200r::MODE_WARP_FWD, out, workspace, workspace_bytes, stream_, tape);
 }
 
 static int check_composite(b200r_handle* h, const b200r_composite_args* a) {

@@ -51,7 +51,8 @@ __global__ void scale_kernel(const ScaleParams p) {
 // ---------------------------------------------------------------- weight-gradient job list
 enum : int { DST_WEIGHTS = 0, DST_FRAME = 1, DST_CONST = 2 };
 
-static std::vector<WgradJob> build_jobs(const b200r_field_desc& d, const BuiltProgram& bp, const TapeLayout& T, const int64_t* woff) {
+// only_w >= 0: the jobs of that skinning warp alone (b200r_warp_bwd)
+static std::vector<WgradJob> build_jobs(const b200r_field_desc& d, const BuiltProgram& bp, const TapeLayout& T, const int64_t* woff, int only_w = -1) {
   std::vector<WgradJob> jobs;
   const Program& P = bp.prog;
   const LayerIds L = layer_ids(d);
@@ -88,6 +89,7 @@ static std::vector<WgradJob> build_jobs(const b200r_field_desc& d, const BuiltPr
   };
   const int n_pe = pe_b < 63 ? pe_b : 63;
   for (int w = 0; w < 3 && B > 0; ++w) {
+    if (only_w >= 0 && w != only_w) continue;
     layer_job(L.delta[0], T.g_z1[w], T.a_xb[w], (3 * B + 63) / 64, 0, 3 * B, w == 0 ? -1 : P.fl.delta1_fwd);
     layer_job(L.delta[1], T.g_z2[w], T.a_h1[w], 1, 0, 64);
     layer_job(L.delta[2], T.g_z[w], T.a_h2[w], 1, 0, 64);
@@ -105,6 +107,7 @@ static std::vector<WgradJob> build_jobs(const b200r_field_desc& d, const BuiltPr
       layer_job(L.dense[3 * m + 2], T.g_d3[w], T.a_dh2[w], 4, 0, 256);
     }
   }
+  if (only_w >= 0) return jobs;
   layer_job(L.vis[0], T.g_vis[0], T.a_pe, 1, 0, pe_v);
   layer_job(L.vis[1], T.g_vis[1], T.a_vis[0], 1, 0, 64);
   // heads: rows of the head chunk x their input operand
@@ -284,22 +287,35 @@ int b200r_get_block_layout(const b200r_field_desc* desc, b200r_block_layout* out
   return B200R_OK;
 }
 
-int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* par,
-                    const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_field_outputs* saved,
-                    const b200r_field_grads* grads, const b200r_tape* tape, const b200r_param_grads* out,
-                    const b200r_frame_grads* fgr, void* workspace, size_t workspace_bytes, b200r_stream stream_) {
+// shared body of b200r_field_bwd (rays) and b200r_warp_bwd (pts: one forward skinning warp of given points, cotangent g_points)
+static int run_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* par,
+                         const b200r_frame_tables* fr, const b200r_ray_batch* rays_in, const b200r_point_batch* pts, const float* g_points,
+                         float* g_points_out, const b200r_field_outputs* saved, const b200r_field_grads* grads, const b200r_tape* tape,
+                         const b200r_param_grads* out, const b200r_frame_grads* fgr, void* workspace, size_t workspace_bytes, b200r_stream stream_) {
   if (!h) return B200R_E_INVALID;
-  auto bad = [&](const char* msg) { return fail(h, B200R_E_INVALID, std::string("field_bwd: ") + msg); };
-  if (!desc || !packed_t || !par || !fr || !rays || !saved || !grads || !tape || !out || !workspace) return bad("null argument");
+  const char* who = pts ? "warp_bwd: " : "field_bwd: ";
+  auto bad = [&](const char* msg) { return fail(h, B200R_E_INVALID, std::string(who) + msg); };
+  if (!desc || !packed_t || !par || !fr || (!rays_in && !pts) || !saved || !grads || !tape || !out || !workspace) return bad("null argument");
   b200r_field_desc dsc = *desc;
   if (dsc.operand_dtype == 2) dsc.operand_dtype = 0;  // gradients run on single fp16 operands (scaled), whatever the forward used
-  b200r::BuiltProgram bp = b200r::build_bwd_program(dsc);
+  b200r::BuiltProgram bp = b200r::build_bwd_program(dsc, false, pts ? 2 : -1);
   if (!bp.ok) return bad(bp.err);
+  b200r_ray_batch rays_pts;
+  memset(&rays_pts, 0, sizeof(rays_pts));
+  if (pts) { rays_pts.N = pts->P; rays_pts.D = 1; rays_pts.flow_thresh = -1.f; }
+  const b200r_ray_batch* rays = pts ? &rays_pts : rays_in;
   const int M = fr->M, N = rays->N, D = rays->D;
-  if (M < 1 || N < 1 || D < 2) return bad("need M,N >= 1 and D >= 2");
-  if (M >= 2 && (M & 1)) return bad("frames must come in adjacent pairs (M even)");
-  if (!rays->hxy || !fr->Kinv || !fr->near_far || !fr->field2cam_q || !fr->field2cam_t) return bad("missing ray/camera input");
-  if (!saved->xyz || !saved->rgb || !saved->sdf || (desc->has_feature && (!saved->feature || !saved->feat_norm))) return bad("missing saved forward outputs");
+  if (pts) {
+    if (desc->n_bones <= 0) return bad("needs a skinned field");
+    if (M < 1 || N < 1 || !pts->xyz || !g_points || !g_points_out) return bad("missing points or their cotangent");
+    if (!fr->inst_skin || !fr->skin_t_embed || !fr->skin_t_embed_mean || !fr->t_art_qr || !fr->t_art_qd || !fr->rest_art_qr || !fr->rest_art_qd)
+      return bad("missing skinning input");
+  } else {
+    if (M < 1 || N < 1 || D < 2) return bad("need M,N >= 1 and D >= 2");
+    if (M >= 2 && (M & 1)) return bad("frames must come in adjacent pairs (M even)");
+    if (!rays->hxy || !fr->Kinv || !fr->near_far || !fr->field2cam_q || !fr->field2cam_t) return bad("missing ray/camera input");
+    if (!saved->xyz || !saved->rgb || !saved->sdf || (desc->has_feature && (!saved->feature || !saved->feat_norm))) return bad("missing saved forward outputs");
+  }
   if (!out->flat || !out->const_block || !out->frame_block) return bad("missing gradient outputs");
   const b200r::TapeLayout T = b200r::tape_layout(*desc);
   const int ND = N * D, tpf = (ND + b200r::kTileRows - 1) / b200r::kTileRows, n_tiles = M * tpf;
@@ -322,6 +338,11 @@ int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
   pp.workspace = (float*)workspace;
   pp.n_layers = nl; pp.rgb0_layer = ids.rgb0;
   for (int i = 0; i < nl; ++i) { pp.layer_out[i] = (int16_t)bp.layer_out[i]; pp.layer_in[i] = (int16_t)bp.layer_in[i]; }
+  if (pts) {  // as in b200r_warp_fwd: no cameras; bias rows whose codes are absent are skipped
+    pp.skip_cams = 1;
+    for (int i = 0; i < nl; ++i)
+      if (!par->bias[i]) pp.cl.plain_off[i] = -1;
+  }
   if ((e = b200r::launch_prologue(pp, stream)) != cudaSuccess) return fail_cuda(h, e, "prologue kernel");
 
   // gradient scale
@@ -332,6 +353,10 @@ int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
                          grads->cyc_dist, grads->delta_skin, grads->skin_entropy, grads->gauss_density};
   const int gw[12] = {3, 1, 1, 16, 3, 3, 1, 3, 1, 1, 1, 1};
   for (int i = 0; i < 12; ++i) { sp.ptr[i] = gp[i]; sp.n[i] = (long long)S * gw[i]; sp.weight[i] = i == 1 ? -1.f : 1.f; }
+  if (pts) {
+    memset(sp.ptr, 0, sizeof(sp.ptr));
+    sp.ptr[0] = g_points; sp.n[0] = (long long)S * 3; sp.weight[0] = 1.f;
+  }
   sp.logibeta = par->logibeta;
   sp.scale = h->d_scale;
   sp.amax_bits = reinterpret_cast<unsigned int*>(h->d_scale + 2);
@@ -366,15 +391,21 @@ int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
     kp.dense_w3[1] = par->weight[ids.dense[5]];
   }
   kp.M = M; kp.ND = ND; kp.tiles_per_frame = tpf; kp.n_tiles = n_tiles;
+  if (pts) {
+    kp.rays = rays_pts;
+    kp.saved.xyz = const_cast<float*>(pts->xyz);  // the warp's input points take the canonical point's place
+    kp.g_points = g_points;
+    kp.g_points_out = g_points_out;
+  }
   if ((e = b200r::launch_field_bwd(kp, h->n_sm, stream)) != cudaSuccess) return fail_cuda(h, e, "field_bwd kernel");
 
   // weight gradients
-  std::vector<b200r::WgradJob> jobs = b200r::build_jobs(dsc, bp, T, out->weight_off);
+  std::vector<b200r::WgradJob> jobs = b200r::build_jobs(dsc, bp, T, out->weight_off, pts ? 2 : -1);
   std::vector<b200r::WgradWork> work;
   std::vector<int32_t> first;
   const int grid = h->n_sm;
   b200r::build_work(jobs, n_tiles, tpf, grid, work, first);
-  struct { b200r_field_desc d; int n_tiles, tpf, grid; } keyh = {dsc, n_tiles, tpf, grid};
+  struct { b200r_field_desc d; int n_tiles, tpf, grid, warp; } keyh = {dsc, n_tiles, tpf, grid, pts ? 1 : 0};
   const std::string key = b200r::table_key("wg", &keyh, sizeof(keyh), out->weight_off, sizeof(out->weight_off));
   void* d_jobs = b200r::cached_table(h, key + "j", jobs.data(), jobs.size() * sizeof(b200r::WgradJob), stream, &e);
   void* d_work = b200r::cached_table(h, key + "w", work.data(), work.size() * sizeof(b200r::WgradWork), stream, &e);
@@ -418,6 +449,24 @@ int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* p
   }
   if ((e = b200r::launch_chain(cp, stream)) != cudaSuccess) return fail_cuda(h, e, "chain kernel");
   return B200R_OK;
+}
+
+int b200r_field_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* par,
+                    const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_field_outputs* saved,
+                    const b200r_field_grads* grads, const b200r_tape* tape, const b200r_param_grads* out,
+                    const b200r_frame_grads* fgr, void* workspace, size_t workspace_bytes, b200r_stream stream_) {
+  if (h && !rays) return fail(h, B200R_E_INVALID, "field_bwd: null argument");
+  return run_field_bwd(h, desc, packed_t, par, fr, rays, nullptr, nullptr, nullptr, saved, grads, tape, out, fgr, workspace, workspace_bytes, stream_);
+}
+
+int b200r_warp_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* par,
+                   const b200r_frame_tables* fr, const b200r_point_batch* pts, const b200r_field_outputs* saved, const float* g_xyz,
+                   const b200r_tape* tape, const b200r_param_grads* out, const b200r_frame_grads* fgr, float* g_points, void* workspace,
+                   size_t workspace_bytes, b200r_stream stream_) {
+  if (h && !pts) return fail(h, B200R_E_INVALID, "warp_bwd: null argument");
+  b200r_field_grads none;
+  memset(&none, 0, sizeof(none));
+  return run_field_bwd(h, desc, packed_t, par, fr, nullptr, pts, g_xyz, g_points, saved, &none, tape, out, fgr, workspace, workspace_bytes, stream_);
 }
 
 // ------------------------------------------------------------------ eikonal term

@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(256) chain_kernel(const __grid_constant__ Chai
     const float* gp = p.g_fblk + fn * FF + F.cam_partner;  // the partner's block holds this frame's camera
     if (p.gf.Kinv)
       for (int i = 0; i < 9; ++i) p.gf.Kinv[(size_t)f * 9 + i] = gc[i] + gp[i];
+    if (!p.fr.field2cam_q || !p.fr.field2cam_t) return;  // point entries (b200r_warp_bwd) have no cameras
     // qi = conj(q), ti = R(qi) (-t): cotangents (g_qi, g_ti) -> (g_q, g_t)
     const Q4 q = ld4(p.fr.field2cam_q + (size_t)f * 4), qi = qconj(q);
     const float mt[3] = {-p.fr.field2cam_t[f * 3], -p.fr.field2cam_t[f * 3 + 1], -p.fr.field2cam_t[f * 3 + 2]};

@@ -135,7 +135,10 @@ __device__ __noinline__ void pe_tangent_fn(const float3& x, int nfreq, const flo
 
 // EIK: the eikonal instantiation (kernels.h EikParams) - the same producer / issuer / epilogue machinery running the masked
 // linear chains of the eikonal term on a list of rays; a separate instantiation, so the field backward's code is untouched.
-template <class Op, int B, int WIDTH, bool DENSE, bool EIK = false>
+// WARPONLY: backward of one forward skinning warp (+ soft deformation) of GIVEN points (b200r_warp_bwd: the backward of
+// FeatureNeRF.forward_project's warp, nnutils/feature.py:207-226) - the w = 2 iteration of the warp loop below with the points'
+// own cotangent; everything else of the field backward is compiled out.
+template <class Op, int B, int WIDTH, bool DENSE, bool EIK = false, bool WARPONLY = false>
 __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -546,8 +549,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
       named_bar_sync(1 + g, kGroupThreads);
 
       // ------------------------------------------------ geometry of the sample (as the forward)
-      const float* hx = p.rays.hxy + ((size_t)f * p.rays.N + n) * 3;
-      const float h0 = __ldg(hx), h1 = __ldg(hx + 1), h2 = __ldg(hx + 2);
+      const float* hx = WARPONLY ? nullptr : p.rays.hxy + ((size_t)f * p.rays.N + n) * 3;  // point entries have no rays
+      const float h0 = WARPONLY ? 0.f : __ldg(hx), h1 = WARPONLY ? 0.f : __ldg(hx + 1), h2 = WARPONLY ? 1.f : __ldg(hx + 2);
       const float* cam = fblk_g + FL.cam;
       const float3 dvec = make_float3(h0 * cam[0] + h1 * cam[1] + h2 * cam[2], h0 * cam[3] + h1 * cam[4] + h2 * cam[5],
                                       h0 * cam[6] + h1 * cam[7] + h2 * cam[8]);
@@ -582,6 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
 #pragma unroll
       for (int i = 0; i < 32; ++i) red[i] = 0.f;
 
+      if constexpr (!WARPONLY) {
       // ================================================================ rgb head, rgb.0, colour chain, density chain
       {
         prefetch_mask(TL.m_col[2]);
@@ -723,6 +727,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
         pe_backward(xyz, 10, g_xyz);
       }
 
+      }  // !WARPONLY
       float3 g_xyz_t = make_float3(0.f, 0.f, 0.f);
       // DenseWarp.forward backward (nnutils/warping.py:143-170): x' = x + 0.1 CondMLP([PE6(x), t, inst]); map m = 0 forward_map,
       // 1 backward_map; w = tape slot of the stage.  Returns dL/dx for the cotangent g_out of x'.
@@ -784,7 +789,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
 
       if constexpr (B > 0) {
         // ================================================================ Gaussian bone density
-        {
+        if constexpr (!WARPONLY) {
           float best = INFINITY;
           int sel = 0;
           const uint32_t ctr = cblk_s + 4u * CL.center;
@@ -813,7 +818,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
           for (int i = 0; i < 3; ++i) x_soft[i] = make_float3(__ldg(p.saved.warp_pts + s * 9 + 3 * i), __ldg(p.saved.warp_pts + s * 9 + 3 * i + 1), __ldg(p.saved.warp_pts + s * 9 + 3 * i + 2));
         }
 #pragma unroll 1
-        for (int w = 2; w >= 0; --w) {
+        for (int w = 2; w >= (WARPONLY ? 2 : 0); --w) {
           const float3 x = w == 0 ? xyz_t : (DENSE ? x_soft[w] : xyz);
           const uint32_t binv = fblk_s + 4u * (w == 0 ? FL.binv_t : (w == 1 ? FL.binv_rest_partner : FL.binv_rest));
           const uint32_t se3 = fblk_s + 4u * (w == 0 ? FL.se3_bwd : (w == 1 ? FL.se3_fwd_partner : FL.se3_fwd));
@@ -871,7 +876,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
           // ---- cotangent of the warped point
           float3 g_xo;
           float ge = g_ent, gk = g_dsk;
-          if (w == 2) {  // cycle: |x_cyc - xyz_t|
+          if (WARPONLY) {  // the warped point's own cotangent
+            g_xo = make_float3(Sl * __ldg(p.g_points + s * 3), Sl * __ldg(p.g_points + s * 3 + 1), Sl * __ldg(p.g_points + s * 3 + 2));
+          } else if (w == 2) {  // cycle: |x_cyc - xyz_t|
             const float dx = xo.x - xyz_t.x, dy = xo.y - xyz_t.y, dz = xo.z - xyz_t.z;
             const float cyc = sqrtf(dx * dx + dy * dy + dz * dz);
             const float gs = cyc > 0.f ? g_cyc / cyc : 0.f;
@@ -985,6 +992,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
         g_xyz_t = make_float3(g_xyz.x + gx.x, g_xyz.y + gx.y, g_xyz.z + gx.z);
       }
 
+      if constexpr (WARPONLY) {  // gradient w.r.t. the given point; no camera, no ray
+        if (live) {
+          const float inv = 1.0f / S;
+          p.g_points_out[s * 3] = g_xyz.x * inv; p.g_points_out[s * 3 + 1] = g_xyz.y * inv; p.g_points_out[s * 3 + 2] = g_xyz.z * inv;
+        }
+        continue;
+      }
       // ================================================================ camera -> field, sample placement
       {
         red[13] += g_xyz_t.x; red[14] += g_xyz_t.y; red[15] += g_xyz_t.z;
@@ -1035,9 +1049,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
   }
 }
 
-template <class Op, int B, int WIDTH, bool DENSE, bool EIK = false>
+template <class Op, int B, int WIDTH, bool DENSE, bool EIK = false, bool WARPONLY = false>
 static cudaError_t launch_one(const BwdKernelParams& p, int n_sm, cudaStream_t stream) {
-  auto kern = field_bwd_kernel<Op, B, WIDTH, DENSE, EIK>;
+  auto kern = field_bwd_kernel<Op, B, WIDTH, DENSE, EIK, WARPONLY>;
   const int smem = 1024 + kSmemRing + (p.prog.cl.n_floats + kGroups * p.prog.fl.n_floats) * 4 + 256;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1070,6 +1084,17 @@ cudaError_t launch_field_bwd(const BwdKernelParams& p, int n_sm, cudaStream_t st
   if (p.eik.mode != 0) {  // eikonal chains: the basefield only, whatever warps the field has
     if (p.desc.W == 256) return bf ? bwd::launch_one<OpBF16, 0, 256, false, true>(p, n_sm, stream) : bwd::launch_one<OpF16, 0, 256, false, true>(p, n_sm, stream);
     if (p.desc.W == 128) return bf ? bwd::launch_one<OpBF16, 0, 128, false, true>(p, n_sm, stream) : bwd::launch_one<OpF16, 0, 128, false, true>(p, n_sm, stream);
+    return cudaErrorInvalidValue;
+  }
+  if (p.g_points_out) {  // one forward warp of given points (b200r_warp_bwd)
+#define B200R_WCASE(BN, DN)                                                                                              \
+  if (p.desc.n_bones == BN && p.desc.W == 256 && (p.desc.dense != 0) == DN)                                               \
+    return bf ? bwd::launch_one<OpBF16, BN, 256, DN, false, true>(p, n_sm, stream) : bwd::launch_one<OpF16, BN, 256, DN, false, true>(p, n_sm, stream);
+    B200R_WCASE(18, false)
+    B200R_WCASE(25, false)
+    B200R_WCASE(18, true)
+    B200R_WCASE(25, true)
+#undef B200R_WCASE
     return cudaErrorInvalidValue;
   }
 #define B200R_CASE(BN, WD, DN)                                                 \

@@ -93,6 +93,8 @@ struct BwdKernelParams {
   float* g_fblk;               // gradient of the frame blocks (zeroed by the caller)
   const float* scale;          // device scalar: power-of-two gradient scale
   const float* dense_w3[2];    // ComposedWarp: post_warp.{forward_map, backward_map}.linear_final.weight (3, 256)
+  const float* g_points;       // warp entry (b200r_warp_bwd): cotangent of the warped points (M*P, 3); the points themselves ride in saved.xyz
+  float* g_points_out;         // warp entry: gradient w.r.t. the given points (M*P, 3); non-NULL selects the warp-only instantiation
   int32_t M, ND, tiles_per_frame, n_tiles;  // eikonal modes: ND / tiles_per_frame describe the training forward's batch, n_tiles the point tiles
   EikParams eik;
 };

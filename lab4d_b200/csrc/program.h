@@ -572,7 +572,9 @@ inline size_t tape_mask_bytes(const TapeLayout& T, int n_tiles) { return (size_t
 //   feature field, visibility MLP, then per skinning warp w = 2, 1, 0: [dense map], delta MLP (final, 2, 1).
 // `density_only`: the step list holds the density chain alone (basefield final .. linear_1, the reverse chain of the eikonal
 // term, csrc/field_bwd.cu mode 1) - the tile offsets are those of the full program, so both read the same W^T buffer.
-inline BuiltProgram build_bwd_program(const b200r_field_desc& d, bool density_only = false) {
+// `warp_w` in {0, 1, 2}: the step list holds that skinning warp's blocks alone (delta MLP in reverse and its dense map) - the
+// backward of one warp of given points (csrc/field_bwd.cu WARPONLY).
+inline BuiltProgram build_bwd_program(const b200r_field_desc& d, bool density_only = false, int warp_w = -1) {
   BuiltProgram bp = build_program(d, MODE_FIELD);  // same constant / frame block layouts, same checks
   if (!bp.ok) return bp;
   bp.ok = false;
@@ -603,7 +605,7 @@ inline BuiltProgram build_bwd_program(const b200r_field_desc& d, bool density_on
     }
     return v;
   };
-  bool emit = !density_only;  // tiles are laid out for every block; steps only for the emitted ones
+  bool emit = !density_only && warp_w < 0;  // tiles are laid out for every block; steps only for the emitted ones
   auto block = [&](const std::vector<Chunk>& cs, int wait, int commit) {
     if (!emit) return;
     if (P.n_blocks >= kMaxSteps) { ok = false; return; }
@@ -670,6 +672,7 @@ inline BuiltProgram build_bwd_program(const b200r_field_desc& d, bool density_on
       pipe(L.dense[3 * m + 1], 0, 256, BAR_ALL);
       seq(L.dense[3 * m + 0], 0, pe_d, 0, BAR_H1);
     };
+    if (warp_w >= 0) emit = w == warp_w;
     if (d.dense && w == 0) dense(1);
     seq(L.delta[2], 0, 64);
     seq(L.delta[1], 0, 64);

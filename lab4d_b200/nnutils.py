@@ -111,6 +111,21 @@ def compute_eikonal(field, renderer, ctx, P, xyz, sample_ratio=16, bind_grads=Fa
     return eik.view(M, N, D, 1)
 
 
+def forward_project(field, renderer, P, tab, xyz, samples_dict, bind_grads=False):
+    """Replacement body of FeatureNeRF.forward_project (nnutils/feature.py:207-226) for skinned fields in a training step:
+    Deformable.forward_warp (deformable.py:154-171) = the forward skinning warp of the matched points - on the kernels, with its
+    hand-derived backward (lab4d_b200.autograd.warp_points) - then the reference's own field_to_cam and pinhole projection
+    (a handful of (M,N,3) ops).  xyz (M,N,3) -> (xy (M,N,2), xyz_cam (M,N,3))."""
+    from lab4d.utils.geom_utils import Kmatinv, pinhole_projection
+
+    from . import autograd as _ag
+
+    xyz_next = _ag.warp_points(renderer, P, xyz, tab, bind_grads=bind_grads)
+    xyz_cam = field.field_to_cam(xyz_next[:, :, None], samples_dict["field2cam"])[:, :, 0]
+    xy = pinhole_projection(Kmatinv(samples_dict["Kinv"]), xyz_cam)[..., :2]
+    return xy, xyz_cam
+
+
 def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False, match_rng="reference"):
     """Replacement body of NeRF.query_field (nnutils/nerf.py:580-684) for NeRF / FeatureNeRF / Deformable modules.
     Training mode: the fused kernels (with the tape and the hand-derived backward when autograd is recording); the
@@ -163,8 +178,12 @@ def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype
     aux = {}
     if hasattr(field, "global_match") and "feature" in samples_dict and "feature" in feat:  # FeatureNeRF.query_field, feature.py:119-131
         xyz_matches = _render.global_match(samples_dict["feature"], feat["feature"], feat["xyz"], field.logsigma, rng=match_rng)  # match kernels
-        xy_reproj, xyz_reproj = field.forward_project(xyz_matches, samples_dict["field2cam"], samples_dict["Kinv"], samples_dict["frame_id"],
-                                                       inst_id, samples_dict=samples_dict)
+        if field.training and cfg.motion != "rigid" and torch.is_grad_enabled() and xyz_matches.requires_grad:
+            # forward_project (feature.py:207-226) with the warp of the matched points on the kernels (autograd.WarpFunction)
+            xy_reproj, xyz_reproj = forward_project(field, r, P, tab, xyz_matches, samples_dict, bind_grads)
+        else:
+            xy_reproj, xyz_reproj = field.forward_project(xyz_matches, samples_dict["field2cam"], samples_dict["Kinv"], samples_dict["frame_id"],
+                                                           inst_id, samples_dict=samples_dict)
         aux.update(xyz_matches=xyz_matches, xyz_reproj=xyz_reproj, xy_reproj=xy_reproj)
     return feat, deltas, aux
 

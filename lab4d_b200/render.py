@@ -297,14 +297,16 @@ class FieldRenderer:
         self._keep_t = keep
         self._alpha = alpha
 
-    def _tape(self, M, N, D):
+    def _tape(self, M, N, D, slot="field"):
+        """Tape buffers of one training forward; `slot` keeps the field's tape and the point-warp's tape apart."""
         a, g, m = C.c_size_t(), C.c_size_t(), C.c_size_t()
         self.handle.check(self.handle.lib.b200r_tape_sizes(C.byref(self.desc), M, N, D, C.byref(a), C.byref(g), C.byref(m)), "b200r_tape_sizes")
         need = (a.value, g.value, m.value)
-        bufs = getattr(self, "_tape_bufs", None)
-        if bufs is None or any(b.numel() < n for b, n in zip(bufs, need)):
+        store = self.__dict__.setdefault("_tape_slots", {})
+        bufs = store.get(slot)
+        if bufs is None or any(b.numel() < n + 1024 for b, n in zip(bufs, need)):
             bufs = tuple(torch.empty(n + 1024, dtype=torch.uint8, device=self.device) for n in need)
-            self._tape_bufs = bufs
+            store[slot] = bufs
         t = _lib.Tape()
         al = lambda b: (b.data_ptr() + 1023) // 1024 * 1024
         t.a, t.g, t.mask = al(bufs[0]), al(bufs[1]), al(bufs[2])
@@ -431,6 +433,90 @@ class FieldRenderer:
         self.last_blocks = (g_const, g_frame)
         self._keep_bwd = keep
         return views, tg
+
+    # ------------------------------------------------------------------ forward warp of points, differentiable (forward_project)
+    def warp_weight_names(self):
+        """Parameters the forward warp of points reaches: the skinning delta MLP, the Gaussian bone scales and, for a
+        ComposedWarp, the forward soft-deformation map."""
+        names = ["warp.skinning_model.log_gauss"]
+        for lyr in ("linear_1.0", "linear_2.0", "linear_final"):
+            names += [f"warp.skinning_model.delta_field.{lyr}.weight", f"warp.skinning_model.delta_field.{lyr}.bias"]
+        if self.cfg.dense:
+            for lyr in ("linear_1.0", "linear_2.0", "linear_final"):
+                names += [f"warp.post_warp.forward_map.{lyr}.weight", f"warp.post_warp.forward_map.{lyr}.bias"]
+        return names
+
+    @torch.no_grad()
+    def warp_points_train(self, P, xyz, tab):
+        """SkinningWarp / ComposedWarp forward (canonical -> time-t space, the frame's own articulation; nnutils/warping.py:277-336,
+        445-483 with backward=False) on points xyz (M,P,3) with a tape: returns (xyz' (M,P,3), ctx) for `warp_backward`.
+        Call `pack_train` first.  What FeatureNeRF.forward_project (feature.py:207-226) runs on the matched points."""
+        if self.cfg.motion == "rigid":
+            raise RuntimeError("warp_points_train: the field has no skinning warp")
+        xyz = _f32c(xyz)
+        M, Pn = xyz.shape[:2]
+        par, keep = self._params(P)
+        keep.append(xyz)
+        fr = _lib.FrameTables()
+        fr.M = M
+        for field, key in self._TAB_KEYS.items():
+            if key in tab and tab[key] is not None and not field.startswith("field2cam"):
+                t = _f32c(tab[key])
+                keep.append(t)
+                setattr(fr, field, t.data_ptr())
+        pb = _lib.PointBatch()
+        pb.P, pb.xyz = Pn, xyz.data_ptr()
+        out, oa = {}, _lib.FieldOutputs()
+        for name, nch in (("xyz", 3),) + ((("warp_pts", 9),) if self.cfg.dense else ()):
+            out[name] = torch.empty(M * Pn, nch, dtype=torch.float32, device=self.device)
+            setattr(oa, name, out[name].data_ptr())
+        wbytes = self.handle.lib.b200r_workspace_bytes(C.byref(self.desc), M)
+        if getattr(self, "_ws", None) is None or self._ws.numel() < wbytes:
+            self._ws = torch.empty(wbytes, dtype=torch.uint8, device=self.device)
+        tape = self._tape(M, Pn, 1, slot="warp")
+        rc = self.handle.lib.b200r_warp_fwd_train(self.handle.h, C.byref(self.desc), _ptr(self.packed), C.byref(par), C.byref(fr), C.byref(pb),
+                                                  C.byref(oa), C.byref(tape), _ptr(self._ws), self._ws.numel(), _stream(self.device))
+        self.handle.check(rc, "b200r_warp_fwd_train")
+        ctx = dict(out=out, par=par, fr=fr, pb=pb, tape=tape, keep=keep, M=M, Pn=Pn, tab=tab)
+        return out["xyz"].view(M, Pn, 3), ctx
+
+    @torch.no_grad()
+    def warp_backward(self, ctx, g_xyz, flat=None):
+        """Backward of `warp_points_train` for the cotangent g_xyz (M,P,3) of the warped points (b200r_warp_bwd): returns
+        (g_points (M,P,3), name -> view of the flat gradient buffer `flat` (ACCUMULATED; default: a fresh zero buffer),
+        table gradients name -> tensor)."""
+        st = self._train_state()
+        if flat is None:
+            flat = torch.zeros(st["total"], device=self.device)
+        M, Pn = ctx["M"], ctx["Pn"]
+        layout, slots = st["layout"], st["slots"]
+        gx = _f32c(g_xyz.reshape(M * Pn, 3))
+        g_pts = torch.empty(M * Pn, 3, device=self.device)
+        g_const = torch.empty(layout.const_floats, device=self.device)
+        g_frame = torch.empty(M, layout.frame_floats, device=self.device)
+        pgs = _lib.ParamGrads()
+        pgs.flat, pgs.const_block, pgs.frame_block = flat.data_ptr(), g_const.data_ptr(), g_frame.data_ptr()
+        for i in range(_lib.MAX_LAYERS):
+            pgs.weight_off[i], pgs.bias_off[i] = -1, -1
+        for i, (name, _) in enumerate(self._layers):
+            pgs.weight_off[i], pgs.bias_off[i] = slots[name + ".weight"][0], slots[name + ".bias"][0]
+        for fld, name in self._HEAD_NAMES.items():
+            setattr(pgs, fld, slots[name][0] if name in slots else -1)
+        tg, fgr, tab = {}, _lib.FrameGrads(), ctx["tab"]
+        for field, key in self._TAB_KEYS.items():
+            if tab.get(key) is not None and field in _lib.FRAME_GRADS and not field.startswith("field2cam"):
+                tg[key] = torch.empty(tab[key].shape, device=self.device)
+                setattr(fgr, field, tg[key].data_ptr())
+        saved = _lib.FieldOutputs()
+        if "warp_pts" in ctx["out"]:
+            saved.warp_pts = ctx["out"]["warp_pts"].data_ptr()
+        rc = self.handle.lib.b200r_warp_bwd(self.handle.h, C.byref(self.desc), _ptr(st["packed_t"]), C.byref(ctx["par"]), C.byref(ctx["fr"]),
+                                            C.byref(ctx["pb"]), C.byref(saved), gx.data_ptr(), C.byref(ctx["tape"]), C.byref(pgs), C.byref(fgr),
+                                            g_pts.data_ptr(), _ptr(self._ws), self._ws.numel(), _stream(self.device))
+        self.handle.check(rc, "b200r_warp_bwd")
+        views = {k: flat[slots[k][0]:slots[k][0] + slots[k][1]].view(slots[k][2]) for k in self.warp_weight_names()}
+        self._keep_warp = (gx, g_const, g_frame, flat)
+        return g_pts.view(M, Pn, 3), views, tg
 
     # ------------------------------------------------------------------ eikonal term (NeRF.compute_eikonal)
     def eikonal_weight_names(self):
