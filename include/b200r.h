@@ -315,6 +315,16 @@ int b200r_eikonal_bwd(b200r_handle* h, const b200r_field_desc* desc, const void*
                       const b200r_ray_batch* rays, int32_t M, const float* saved_xyz, const b200r_tape* tape,
                       const b200r_eik_batch* eik, const float* g_g, const b200r_param_grads* out, b200r_stream stream);
 
+/* Eval-mode normals (NeRF.compute_normal, lab4d/nnutils/nerf.py:455-493; lab4d/render.py -> dvr_model.evaluate): g_cam (M*N*D, 3)
+ * = d sdf / d xyz_cam at every sample - the gradient of the sdf through the basefield AND the backward warp w.r.t. the
+ * camera-space point, which the reference takes with autograd.grad over the whole batch.  Runs after a b200r_field_fwd_train
+ * of the same batch (its tape holds the ReLU signs and the warp's operands; tape->g is scratch): reverse chain of the density
+ * branch from a unit sdf cotangent, the backward warp's backward, the camera rotation.  No parameter gradients.
+ * The caller forms eikonal = (|g| - 1)^2 and normal = g / |g| * (1, -1, -1). */
+int b200r_field_normals(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* params,
+                        const b200r_frame_tables* frames, const b200r_ray_batch* rays, const b200r_field_outputs* saved,
+                        const b200r_tape* tape, float* g_cam, void* workspace, size_t workspace_bytes, b200r_stream stream);
+
 /* NeRF.forward on given points (lab4d/nnutils/nerf.py:167-215), the boundary the reference's flat-point callers use
  * (geometry_init nerf.py:277, extract_canonical_mesh :328, eval-mode query_nerf :794-805): canonical points in, rgb /
  * density / sdf out.  Only the basefield, colorfield, sdf and rgb heads run (no ray placement, warps, visibility or

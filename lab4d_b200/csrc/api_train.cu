@@ -469,6 +469,64 @@ int b200r_warp_bwd(b200r_handle* h, const b200r_field_desc* desc, const void* pa
   return run_field_bwd(h, desc, packed_t, par, fr, nullptr, pts, g_xyz, g_points, saved, &none, tape, out, fgr, workspace, workspace_bytes, stream_);
 }
 
+int b200r_field_normals(b200r_handle* h, const b200r_field_desc* desc, const void* packed_t, const b200r_field_params* par,
+                        const b200r_frame_tables* fr, const b200r_ray_batch* rays, const b200r_field_outputs* saved, const b200r_tape* tape,
+                        float* g_cam, void* workspace, size_t workspace_bytes, b200r_stream stream_) {
+  if (!h) return B200R_E_INVALID;
+  auto bad = [&](const char* msg) { return fail(h, B200R_E_INVALID, std::string("field_normals: ") + msg); };
+  if (!desc || !packed_t || !par || !fr || !rays || !saved || !tape || !g_cam || !workspace) return bad("null argument");
+  b200r_field_desc dsc = *desc;
+  if (dsc.operand_dtype == 2) dsc.operand_dtype = 0;
+  b200r::BuiltProgram bp = b200r::build_bwd_program(dsc, /*density_only=*/true, /*warp_w=*/0);
+  if (!bp.ok) return bad(bp.err);
+  const int M = fr->M, N = rays->N, D = rays->D;
+  if (M < 1 || N < 1 || D < 2) return bad("need M,N >= 1 and D >= 2");
+  if (!rays->hxy || !fr->Kinv || !fr->near_far || !fr->field2cam_q || !fr->field2cam_t) return bad("missing ray/camera input");
+  if (!saved->xyz || (desc->dense && !saved->warp_pts)) return bad("missing saved forward outputs (xyz; warp_pts for ComposedWarp fields)");
+  const b200r::TapeLayout T = b200r::tape_layout(*desc);
+  const int ND = N * D, tpf = (ND + b200r::kTileRows - 1) / b200r::kTileRows, n_tiles = M * tpf;
+  size_t na, ng, nm;
+  b200r_tape_sizes(desc, M, N, D, &na, &ng, &nm);
+  if (!tape->a || !tape->g || !tape->mask || tape->a_bytes < na || tape->g_bytes < ng || tape->mask_bytes < nm) return bad("tape buffers missing or too small");
+  if ((reinterpret_cast<uintptr_t>(tape->g) & 1023)) return bad("tape buffers must be 1024-B aligned");
+  if (workspace_bytes < b200r_workspace_bytes(desc, M)) return bad("workspace too small");
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cudaError_t e;
+  const int nl = (int)bp.layer_out.size();
+  const b200r::LayerIds ids = b200r::layer_ids(*desc);
+  b200r::PrologueParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.cl = bp.prog.cl; pp.fl = bp.prog.fl; pp.desc = *desc; pp.par = *par; pp.fr = *fr;
+  pp.workspace = (float*)workspace;
+  pp.n_layers = nl; pp.rgb0_layer = ids.rgb0;
+  for (int i = 0; i < nl; ++i) { pp.layer_out[i] = (int16_t)bp.layer_out[i]; pp.layer_in[i] = (int16_t)bp.layer_in[i]; }
+  if ((e = b200r::launch_prologue(pp, stream)) != cudaSuccess) return fail_cuda(h, e, "prologue kernel");
+  b200r::BwdKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.prog = bp.prog;
+  kp.tape = T;
+  kp.desc = dsc;
+  kp.rays = *rays;
+  kp.saved = *saved;
+  kp.packed_t = (const uint8_t*)packed_t;
+  kp.workspace = (const float*)workspace;
+  kp.tape_a = (const uint8_t*)tape->a;
+  kp.tape_g = (uint8_t*)tape->g;
+  kp.tape_mask = (const uint32_t*)tape->mask;
+  kp.g_points_out = g_cam;
+  kp.normals = 1;
+  kp.eik.scale_a = dsc.operand_dtype == 1 ? 1.0f : 256.0f;
+  if (desc->dense) {
+    kp.dense_w3[0] = par->weight[ids.dense[2]];
+    kp.dense_w3[1] = par->weight[ids.dense[5]];
+  }
+  kp.M = M; kp.ND = ND; kp.tiles_per_frame = tpf; kp.n_tiles = n_tiles;
+  if ((e = b200r::launch_field_bwd(kp, h->n_sm, stream)) != cudaSuccess) return fail_cuda(h, e, "normals kernel");
+  return B200R_OK;
+}
+
 // ------------------------------------------------------------------ eikonal term
 static constexpr float kEikScaleA = 256.0f;  // scale of the reverse chain's unit cotangent in its 16-bit operands
 

@@ -138,7 +138,10 @@ __device__ __noinline__ void pe_tangent_fn(const float3& x, int nfreq, const flo
 // WARPONLY: backward of one forward skinning warp (+ soft deformation) of GIVEN points (b200r_warp_bwd: the backward of
 // FeatureNeRF.forward_project's warp, nnutils/feature.py:207-226) - the w = 2 iteration of the warp loop below with the points'
 // own cotangent; everything else of the field backward is compiled out.
-template <class Op, int B, int WIDTH, bool DENSE, bool EIK = false, bool WARPONLY = false>
+// NORMALS: d sdf / d xyz_cam of every sample (NeRF.compute_normal, nnutils/nerf.py:455-493: the gradient of the sdf through the
+// basefield AND the backward warp w.r.t. the camera-space point) - the density chain started from a unit sdf cotangent, the
+// w = 0 iteration of the warp loop, the camera rotation; no parameter gradients (b200r_field_normals).
+template <class Op, int B, int WIDTH, bool DENSE, bool EIK = false, bool WARPONLY = false, bool NORMALS = false>
 __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -585,7 +588,43 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
 #pragma unroll
       for (int i = 0; i < 32; ++i) red[i] = 0.f;
 
-      if constexpr (!WARPONLY) {
+      if constexpr (NORMALS) {
+        // ================================================================ unit cotangent on the sdf -> density chain -> dL/d xyz
+        const float Sa = live ? p.eik.scale_a : 0.f;
+        {
+          const uint4* mp = reinterpret_cast<const uint4*>(mask_row + (size_t)TL.m_base[Dn] * (kTileRows * kMaskWords));
+          const uint4 ma = __ldg(mp), mb = NBLK > 2 ? __ldg(mp + 1) : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t mws[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+#pragma unroll 1
+          for (int blk = 0; blk < WIDTH / 32; ++blk) {
+            float v[32];
+            const uint32_t wa = cblk_s + 4u * (CL.sdf_w + 32 * blk);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 w4 = lds128(wa + 4u * j);
+              v[j] = Sa * w4.x; v[j + 1] = Sa * w4.y; v[j + 2] = Sa * w4.z; v[j + 3] = Sa * w4.w;
+            }
+            uint32_t o[16];
+            mask_pack32(v, mws[blk], o);
+            tmem_st16(tA + 16 * blk, o);
+            gtape_st32(TL.g_base[Dn], 32 * blk, o);
+          }
+          tmem_st_wait();
+        }
+        prefetch_mask(TL.m_base[Dn - 1]);
+        arrive_all();
+#pragma unroll 1
+        for (int i = Dn; i >= 1; --i) {
+          if (i == p.desc.skip) {
+            wait_all();
+            pe_backward(xyz, p.desc.L_xyz, g_xyz);
+            arrive_all();
+          }
+          wide_dgrad(std::integral_constant<int, 0>{}, TL.m_base[i - 1], TL.g_base[i - 1], i >= 2 ? TL.m_base[i - 2] : -1);
+        }
+        wait_all();
+        pe_backward(xyz, p.desc.L_xyz, g_xyz);
+      } else if constexpr (!WARPONLY) {
       // ================================================================ rgb head, rgb.0, colour chain, density chain
       {
         prefetch_mask(TL.m_col[2]);
@@ -789,7 +828,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
 
       if constexpr (B > 0) {
         // ================================================================ Gaussian bone density
-        if constexpr (!WARPONLY) {
+        if constexpr (!WARPONLY && !NORMALS) {
           float best = INFINITY;
           int sel = 0;
           const uint32_t ctr = cblk_s + 4u * CL.center;
@@ -818,7 +857,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
           for (int i = 0; i < 3; ++i) x_soft[i] = make_float3(__ldg(p.saved.warp_pts + s * 9 + 3 * i), __ldg(p.saved.warp_pts + s * 9 + 3 * i + 1), __ldg(p.saved.warp_pts + s * 9 + 3 * i + 2));
         }
 #pragma unroll 1
-        for (int w = 2; w >= (WARPONLY ? 2 : 0); --w) {
+        for (int w = NORMALS ? 0 : 2; w >= (WARPONLY ? 2 : 0); --w) {
           const float3 x = w == 0 ? xyz_t : (DENSE ? x_soft[w] : xyz);
           const uint32_t binv = fblk_s + 4u * (w == 0 ? FL.binv_t : (w == 1 ? FL.binv_rest_partner : FL.binv_rest));
           const uint32_t se3 = fblk_s + 4u * (w == 0 ? FL.se3_bwd : (w == 1 ? FL.se3_fwd_partner : FL.se3_fwd));
@@ -988,14 +1027,27 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
         }
       } else {
         // rigid field: canonical point = time-t point; the flow sees it through the partner camera only
-        const float3 gx = flow_backward(xyz);
-        g_xyz_t = make_float3(g_xyz.x + gx.x, g_xyz.y + gx.y, g_xyz.z + gx.z);
+        if constexpr (NORMALS) {
+          g_xyz_t = g_xyz;
+        } else {
+          const float3 gx = flow_backward(xyz);
+          g_xyz_t = make_float3(g_xyz.x + gx.x, g_xyz.y + gx.y, g_xyz.z + gx.z);
+        }
       }
 
       if constexpr (WARPONLY) {  // gradient w.r.t. the given point; no camera, no ray
         if (live) {
           const float inv = 1.0f / S;
           p.g_points_out[s * 3] = g_xyz.x * inv; p.g_points_out[s * 3 + 1] = g_xyz.y * inv; p.g_points_out[s * 3 + 2] = g_xyz.z * inv;
+        }
+        continue;
+      }
+      if constexpr (NORMALS) {  // xyz_t = R(qi) xyz_cam + ti: the gradient w.r.t. the camera-space point
+        Q4 gq; float3 gxc;
+        qrot_bwd(qi, xyz_cam, g_xyz_t, gq, gxc);
+        if (live) {
+          const float inv = 1.0f / p.eik.scale_a;
+          p.g_points_out[s * 3] = gxc.x * inv; p.g_points_out[s * 3 + 1] = gxc.y * inv; p.g_points_out[s * 3 + 2] = gxc.z * inv;
         }
         continue;
       }
@@ -1049,9 +1101,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_bwd_kernel(const __grid_con
   }
 }
 
-template <class Op, int B, int WIDTH, bool DENSE, bool EIK = false, bool WARPONLY = false>
+template <class Op, int B, int WIDTH, bool DENSE, bool EIK = false, bool WARPONLY = false, bool NORMALS = false>
 static cudaError_t launch_one(const BwdKernelParams& p, int n_sm, cudaStream_t stream) {
-  auto kern = field_bwd_kernel<Op, B, WIDTH, DENSE, EIK, WARPONLY>;
+  auto kern = field_bwd_kernel<Op, B, WIDTH, DENSE, EIK, WARPONLY, NORMALS>;
   const int smem = 1024 + kSmemRing + (p.prog.cl.n_floats + kGroups * p.prog.fl.n_floats) * 4 + 256;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1084,6 +1136,19 @@ cudaError_t launch_field_bwd(const BwdKernelParams& p, int n_sm, cudaStream_t st
   if (p.eik.mode != 0) {  // eikonal chains: the basefield only, whatever warps the field has
     if (p.desc.W == 256) return bf ? bwd::launch_one<OpBF16, 0, 256, false, true>(p, n_sm, stream) : bwd::launch_one<OpF16, 0, 256, false, true>(p, n_sm, stream);
     if (p.desc.W == 128) return bf ? bwd::launch_one<OpBF16, 0, 128, false, true>(p, n_sm, stream) : bwd::launch_one<OpF16, 0, 128, false, true>(p, n_sm, stream);
+    return cudaErrorInvalidValue;
+  }
+  if (p.normals) {  // d sdf / d xyz_cam of every sample (b200r_field_normals)
+#define B200R_NCASE(BN, WD, DN)                                                                                          \
+  if (p.desc.n_bones == BN && p.desc.W == WD && (p.desc.dense != 0) == DN)                                                \
+    return bf ? bwd::launch_one<OpBF16, BN, WD, DN, false, false, true>(p, n_sm, stream) : bwd::launch_one<OpF16, BN, WD, DN, false, false, true>(p, n_sm, stream);
+    B200R_NCASE(0, 128, false)
+    B200R_NCASE(0, 256, false)
+    B200R_NCASE(18, 256, false)
+    B200R_NCASE(25, 256, false)
+    B200R_NCASE(18, 256, true)
+    B200R_NCASE(25, 256, true)
+#undef B200R_NCASE
     return cudaErrorInvalidValue;
   }
   if (p.g_points_out) {  // one forward warp of given points (b200r_warp_bwd)

@@ -95,6 +95,8 @@ struct BwdKernelParams {
   const float* dense_w3[2];    // ComposedWarp: post_warp.{forward_map, backward_map}.linear_final.weight (3, 256)
   const float* g_points;       // warp entry (b200r_warp_bwd): cotangent of the warped points (M*P, 3); the points themselves ride in saved.xyz
   float* g_points_out;         // warp entry: gradient w.r.t. the given points (M*P, 3); non-NULL selects the warp-only instantiation
+                               // normals entry: d sdf / d xyz_cam of every sample (S, 3)
+  int32_t normals;             // 1: the normals instantiation (b200r_field_normals); eik.scale_a = scale of the unit cotangent
   int32_t M, ND, tiles_per_frame, n_tiles;  // eikonal modes: ND / tiles_per_frame describe the training forward's batch, n_tiles the point tiles
   EikParams eik;
 };

@@ -574,6 +574,7 @@ inline size_t tape_mask_bytes(const TapeLayout& T, int n_tiles) { return (size_t
 // term, csrc/field_bwd.cu mode 1) - the tile offsets are those of the full program, so both read the same W^T buffer.
 // `warp_w` in {0, 1, 2}: the step list holds that skinning warp's blocks alone (delta MLP in reverse and its dense map) - the
 // backward of one warp of given points (csrc/field_bwd.cu WARPONLY).
+// density_only together with warp_w: both block groups (density chain, then that warp) - the normals entry (csrc/field_bwd.cu NORMALS).
 inline BuiltProgram build_bwd_program(const b200r_field_desc& d, bool density_only = false, int warp_w = -1) {
   BuiltProgram bp = build_program(d, MODE_FIELD);  // same constant / frame block layouts, same checks
   if (!bp.ok) return bp;

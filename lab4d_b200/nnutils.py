@@ -132,8 +132,9 @@ def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype
     eikonal term runs on the eikonal kernels (`compute_eikonal` above: reverse chain with the tape's ReLU signs, hand-derived
     second-order backward) - on the reference's own `compute_eikonal` only when no gradient is recorded.
     Eval mode (`lab4d/render.py` -> dvr_model.evaluate): importance sampling (nerf.py:686-738), samples outside the
-    bounding boxes zeroed like the reference's masked query_nerf (nerf.py:495-528, 769-819), normals from the
-    reference's `compute_normal`.  Returns (feat_dict, deltas, aux_dict) like the reference."""
+    bounding boxes zeroed like the reference's masked query_nerf (nerf.py:495-528, 769-819), normals and the eval eikonal
+    from the normals kernel (`FieldRenderer.sdf_gradient_cam`, nerf.py:455-493).  Returns (feat_dict, deltas, aux_dict) like
+    the reference."""
     if field.pos_embedding.alpha is not None and field.pos_embedding_color.alpha != field.pos_embedding.alpha:
         raise NotImplementedError("different annealing windows for density and colour embeddings")
     dev = samples_dict["hxy"].device
@@ -159,22 +160,24 @@ def query_field(field, samples_dict, flow_thresh=None, n_depth=64, operand_dtype
     else:
         with torch.no_grad():
             tab = tables_from_module(field, samples_dict)
-            r.pack(P, alpha=alpha)
+            Pd = {k: v.detach() for k, v in P.items()}
+            r.pack_train(Pd, alpha=alpha)
             depth = r.importance_depths(P, rays, tab, n_depth)
-            want = ("rgb", "density", "vis", "xyz", "xyz_cam", "xyz_t", "depth", "deltas") + (("gauss_density",) if cfg.motion != "rigid" else ())
-            feat, deltas = r.query_field(P, rays, tab, n_depth, depth=depth, want=want)
-            xyz_t = r.last_aux["xyz_t"]
+            # the training-form forward (with a tape) on the importance-sampled depths: the normals kernel reads its ReLU signs
+            feat, deltas, nctx = r.query_field_train(Pd, rays, tab, n_depth, depth=depth)
+            for k in ("cyc_dist", "delta_skin", "skin_entropy", "flow", "feature", "eikonal"):  # train-only outputs (nerf.py:590-684)
+                feat.pop(k, None)
+            xyz_t = nctx["out"]["xyz_t"].view(feat["xyz"].shape)
             valid = field.get_valid_idx(feat["xyz"], xyz_t, feat["vis"], samples_dict)
             if valid is not None:  # the reference evaluates only these samples and leaves zeros elsewhere
                 m = valid[..., None].to(feat["rgb"].dtype)
                 feat["rgb"], feat["density"] = feat["rgb"] * m, feat["density"] * m
                 feat["density_" + cfg.category] = feat["density"]
-        # normals: autograd of the SDF through the backward warp w.r.t. camera-space points (nerf.py:455-493)
-        hxy, Kinv = samples_dict["hxy"], samples_dict["Kinv"]
-        d = hxy @ Kinv.permute(0, 2, 1)
-        dir_cam = torch.nn.functional.normalize(d, 2, -1)[:, :, None].expand_as(feat["xyz_cam"])
-        feat["eikonal"], feat["normal"] = field.compute_normal(feat["xyz_cam"], dir_cam, samples_dict["field2cam"], samples_dict["frame_id"],
-                                                               inst_id, samples_dict)
+            # normals (nerf.py:455-493): the gradient of the sdf through the basefield and the backward warp w.r.t. the camera-space
+            # points - the normals kernel instead of the reference's autograd.grad over the whole batch
+            g = r.sdf_gradient_cam(nctx)
+            feat["eikonal"] = (g.norm(2, dim=-1, keepdim=True) - 1) ** 2
+            feat["normal"] = torch.nn.functional.normalize(g, dim=-1) * torch.tensor([1.0, -1.0, -1.0], device=g.device)
     aux = {}
     if hasattr(field, "global_match") and "feature" in samples_dict and "feature" in feat:  # FeatureNeRF.query_field, feature.py:119-131
         xyz_matches = _render.global_match(samples_dict["feature"], feat["feature"], feat["xyz"], field.logsigma, rng=match_rng)  # match kernels

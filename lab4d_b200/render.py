@@ -434,6 +434,25 @@ class FieldRenderer:
         self._keep_bwd = keep
         return views, tg
 
+    # ------------------------------------------------------------------ eval-mode normals (NeRF.compute_normal)
+    @torch.no_grad()
+    def sdf_gradient_cam(self, ctx):
+        """d sdf / d xyz_cam (M,N,D,3) at every sample of the training-form forward that produced `ctx` (query_field_train, e.g.
+        with importance-sampled depths): the gradient NeRF.compute_normal (nnutils/nerf.py:455-493) takes with autograd through
+        the backward warp and the basefield - b200r_field_normals.  eikonal = (|g| - 1)^2, normal = g / |g| * (1, -1, -1)."""
+        st = self._train_state()
+        M, N, D = ctx["M"], ctx["N"], ctx["D"]
+        g = torch.empty(M * N * D, 3, device=self.device)
+        saved, out = _lib.FieldOutputs(), ctx["out"]
+        for k in ("xyz", "warp_pts"):
+            if k in out:
+                setattr(saved, k, out[k].data_ptr())
+        rc = self.handle.lib.b200r_field_normals(self.handle.h, C.byref(self.desc), _ptr(st["packed_t"]), C.byref(ctx["par"]), C.byref(ctx["fr"]),
+                                                 C.byref(ctx["rb"]), C.byref(saved), C.byref(ctx["tape"]), g.data_ptr(), _ptr(self._ws),
+                                                 self._ws.numel(), _stream(self.device))
+        self.handle.check(rc, "b200r_field_normals")
+        return g.view(M, N, D, 3)
+
     # ------------------------------------------------------------------ forward warp of points, differentiable (forward_project)
     def warp_weight_names(self):
         """Parameters the forward warp of points reaches: the skinning delta MLP, the Gaussian bone scales and, for a

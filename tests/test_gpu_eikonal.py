@@ -24,7 +24,7 @@ G_TOL = {"fp16x3": 1e-2, "fp16": 1e-1, "bf16": 3e-1}
 W_TOL = {"fp16x3": 3e-2, "fp16": 3e-1, "bf16": 6e-1}
 
 
-def _setup(name, M, N, D, prec):
+def _setup(name, M, N, D, prec, alpha=None):
     from lab4d_b200 import spec
     from lab4d_b200.render import FieldRenderer
 
@@ -36,17 +36,17 @@ def _setup(name, M, N, D, prec):
     g = torch.Generator().manual_seed(9)
     tab["inst_base"] = (tab["inst_base"] + 0.3 * torch.randn(tab["inst_base"].shape, generator=g).to(DEV)).contiguous()
     r = FieldRenderer(cfg, DEV, operand_dtype=prec)
-    r.pack_train(P)
+    r.pack_train(P, alpha=alpha)
     feat, deltas, ctx = r.query_field_train(P, rays, tab, D)
     return cfg, P, tab, r, feat, ctx
 
 
-def _oracle(cfg, P, tab, xyz_sel, ray_ids, N, coeff, dtype):
+def _oracle(cfg, P, tab, xyz_sel, ray_ids, N, coeff, dtype, alpha=None):
     """Reference's way on the same points: g by autograd (create_graph), loss = sum coeff (|g|-1)^2, backward."""
     Pg = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in P.items()}
     inst = tab["inst_base"].to(dtype)[(ray_ids // N).to(tab["inst_base"].device)]
     ocfg = dict(cfg.as_oracle_cfg(), skip=cfg.skip)
-    g = EB.sdf_gradient_autograd(Pg, ocfg, xyz_sel.to(dtype), inst)
+    g = EB.sdf_gradient_autograd(Pg, ocfg, xyz_sel.to(dtype), inst, alpha)
     loss = (coeff.to(dtype) * (g.norm(2, dim=-1) - 1) ** 2).sum()
     loss.backward()
     return g.detach(), {k: v.grad for k, v in Pg.items() if v.grad is not None and float(v.grad.abs().max()) > 0}
@@ -87,6 +87,27 @@ def test_eikonal_kernels_match_second_order_autograd(name, M, N, D, prec, n_sel)
             bad.append((k, e, floor))
     print(f"[eikonal] {name} weight gradients (ours vs fp64 / reference fp32 vs fp64): " + " ".join(rows))
     assert not bad, bad
+
+
+def test_eikonal_with_the_annealing_window():
+    """PosEmbedding's coarse-to-fine window (nnutils/embedding.py:112-125, set_alpha): folded into the packed operands, so the
+    chains see W * window; the weight gradients of the embedding columns are scaled back by the window on the host."""
+    M, N, D, alpha = 4, 8, 32, 0.55
+    cfg, P, tab, r, feat, ctx = _setup("fg_rigid", M, N, D, "fp16x3", alpha=alpha)
+    gen = torch.Generator().manual_seed(11)
+    ray_ids = torch.randperm(M * N, generator=gen)[:6]
+    g, ectx = r.eikonal_forward(ctx, ray_ids)
+    xyz_sel = feat["xyz"].reshape(M * N, D, 3)[ray_ids.to(DEV)]
+    coeff = (torch.rand(6, D, generator=gen) / (6 * D)).to(DEV)
+    g64, wg64 = _oracle(cfg, P, tab, xyz_sel, ray_ids, N, coeff, torch.float64, alpha)
+    e_g = rel_l2(g.cpu(), g64.cpu())
+    gk = g.detach().clone().requires_grad_(True)
+    (coeff * (gk.norm(2, dim=-1) - 1) ** 2).sum().backward()
+    views = r.eikonal_backward(ctx, ectx, gk.grad)
+    errs = {k: rel_l2(views[k].cpu(), wg64[k].cpu()) for k in r.eikonal_weight_names()}
+    print(f"[eikonal] window alpha={alpha}: g rel-L2 {e_g:.2e}; weight gradients " + " ".join(f"{k.replace('basefield.', '')}={v:.1e}" for k, v in errs.items()))
+    assert e_g <= G_TOL["fp16x3"]
+    assert all(v <= W_TOL["fp16x3"] for v in errs.values()), errs
 
 
 def test_eikonal_autograd_function_accumulates_like_the_reference():
