@@ -21,6 +21,11 @@ def main():
     rays = synth.synth_rays(M, N, seed=10)
     Kinv, batch = H.make_batch(field, rays, dev)
     from lab4d.utils.render_utils import render_pixel
+    import lab4d.nnutils.nerf as rnerf
+
+    # the reference's importance_sampling takes n_depth as a keyword default (nerf.py:697): align it with D for the eval timing
+    _imp = rnerf.NeRF.importance_sampling
+    rnerf.NeRF.importance_sampling = lambda self, *a, **k: _imp(self, *a, **dict(k, n_depth=D))
 
     def fwd():
         s = field.get_samples(Kinv, batch)
@@ -45,9 +50,19 @@ def main():
     g = torch.Generator().manual_seed(3)
     batch["feature"] = torch.nn.functional.normalize(torch.randn(M, N, 16, generator=g), dim=-1).to(dev)
 
+    def eval_render():  # lab4d/render.py -> dvr_model.evaluate: eval-mode query_field (importance sampling, masking, normals) + render_pixel
+        field.eval()
+        try:
+            s = field.get_samples(Kinv, batch)
+            feat, deltas, aux = field.query_field(s, flow_thresh=None)
+            return render_pixel(feat, deltas)
+        finally:
+            field.train()
+
     def timed(tag):
         for name, fn, ctx in (("forward", fwd, torch.no_grad()), ("forward+backward", step, torch.enable_grad()),
-                              ("forward+backward incl. eikonal + matching in the loss", step_full, torch.enable_grad())):
+                              ("forward+backward incl. eikonal + matching in the loss", step_full, torch.enable_grad()),
+                              ("eval-mode render (importance sampling + normals)", eval_render, torch.no_grad())):
             torch.cuda.reset_peak_memory_stats()
             with ctx:
                 for _ in range(2):
