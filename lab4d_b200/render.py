@@ -469,7 +469,8 @@ class FieldRenderer:
     def warp_points_train(self, P, xyz, tab):
         """SkinningWarp / ComposedWarp forward (canonical -> time-t space, the frame's own articulation; nnutils/warping.py:277-336,
         445-483 with backward=False) on points xyz (M,P,3) with a tape: returns (xyz' (M,P,3), ctx) for `warp_backward`.
-        Call `pack_train` first.  What FeatureNeRF.forward_project (feature.py:207-226) runs on the matched points."""
+        Call `pack_train` first.  What FeatureNeRF.forward_project (feature.py:207-226) runs on the matched points.  The warp's
+        tape belongs to the renderer (slot "warp", apart from the field's): one point warp may be in flight per renderer."""
         if self.cfg.motion == "rigid":
             raise RuntimeError("warp_points_train: the field has no skinning warp")
         xyz = _f32c(xyz)
@@ -547,7 +548,8 @@ class FieldRenderer:
     def eikonal_forward(self, ctx, ray_ids):
         """g = d sdf / d xyz (n_rays, D, 3) at all D samples of the rays `ray_ids` (flat indices f * N + n) of the training
         forward that produced `ctx` (nnutils/nerf.py:416-453, utils/torch_utils.py:4-28): the reverse chain of
-        b200r_eikonal_fwd with the tape's ReLU signs.  Returns (g, ectx); ectx goes to `eikonal_backward`."""
+        b200r_eikonal_fwd with the tape's ReLU signs.  Returns (g, ectx); ectx goes to `eikonal_backward`.  The chain tapes
+        belong to the renderer: one eikonal term may be in flight per renderer (run its backward before the next forward)."""
         st = self._train_state()
         ids = ray_ids.to(device=self.device, dtype=torch.int32).contiguous()
         n, D = int(ids.numel()), ctx["D"]
