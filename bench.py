@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: ray-samples/s on BASELINE.json's configs.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pass step|forward] [--config c2|c3|c4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pass step|forward] [--config c2|c3|c4|c5] [--with-eikonal]
                   [--precision fp16x3|fp16|bf16]
 
 Default = configs[1] (C2): fg-bob deformable field, 2048 rays x 128 samples per GPU, synthetic rays and synthetic
@@ -34,11 +34,15 @@ import torch
 
 # algorithmic FLOPs per ray-sample (hook-measured on the reference): F_query,fwd incl. the 1/16-ray
 # eikonal forward (71 616 for fg fields), which this renderer does not compute.  Training step = 3 x forward (dgrad + wgrad).
-FLOP_FWD = {"fg_bob": 1_914_380 - 71_616, "fg_skelhuman": 1_903_572 - 71_616, "comp": 1_479_732 - 35_808}
+FLOP_FWD = {"fg_bob": 1_914_380 - 71_616, "fg_skelhuman": 1_903_572 - 71_616, "comp": 1_479_732 - 35_808,
+            # skel-human + DenseWarp (C5): the skel-human figure plus three soft-deformation stages of 2 x (199 x 256 + 256 x 256 + 3 x 256) FLOP
+            "fg_comphuman": 1_903_572 - 71_616 + 3 * 2 * (199 * 256 + 256 * 256 + 3 * 256)}
 CONFIGS = {
     "c2": dict(field="fg_bob", M=128, N=16, D=128, precision="fp16x3", desc="fg-bob 2048 rays x 128 samples per GPU (configs[1])"),
     "c3": dict(field="fg_skelhuman", M=256, N=16, D=192, precision="bf16", desc="skel-human 4096 rays x 192 samples per GPU, bf16 operands (configs[2])"),
     "c4": dict(field="comp", M=256, N=16, D=128, precision="fp16x3", desc="comp skel-quad+dense fg + bg, 4096 rays x 256 samples TOTAL, ray-sharded (configs[3])"),
+    "c5": dict(field="fg_comphuman", M=256, N=16, D=128, precision="fp16x3", n_inst=50,
+               desc="comp_skel-human_dense fg, 50 instance codes (frame f uses video f % 50), 4096 rays x 128 samples per GPU (configs[4])"),
 }
 
 
@@ -137,11 +141,13 @@ class ClockSampler(threading.Thread):
 def field_cfgs(name):
     from lab4d_b200 import spec
 
-    return {"fg_bob": [spec.FG_BOB], "fg_skelhuman": [spec.FG_SKEL_HUMAN], "comp": [spec.BG, spec.FG_COMP_QUAD]}[name]
+    return {"fg_bob": [spec.FG_BOB], "fg_skelhuman": [spec.FG_SKEL_HUMAN], "comp": [spec.BG, spec.FG_COMP_QUAD],
+            "fg_comphuman": [spec.FieldConfig(motion="skel", B=18, symm_idx=spec.HUMAN_SYMM, dense=True)]}[name]
 
 
-def make_problem(device, rank, field, M, N, D):
-    """Per field: (cfg, params, rays, tables); synthetic 'trained-like' weights, seeded rays."""
+def make_problem(device, rank, field, M, N, D, n_inst=1):
+    """Per field: (cfg, params, rays, tables); synthetic 'trained-like' weights, seeded rays.  n_inst > 1: every frame takes
+    the instance code rows of video f % n_inst (RAC-style multi-video batches, lab4d/nnutils/embedding.py:259-281)."""
     import synth
     from lab4d_b200 import spec
     from test_gpu_parity import synth_tables
@@ -155,6 +161,11 @@ def make_problem(device, rank, field, M, N, D):
         if cfg.category == "bg" and field == "comp":
             rays["near_far"] = rays["near_far"] * torch.tensor([[0.93, 1.11]], device=device)
         tab = {k: v.clone() for k, v in synth_tables(cfg, M, device, seed=10 + rank, rays=rays, P=P).items()}
+        if n_inst > 1:
+            g = torch.Generator().manual_seed(77)
+            vid = torch.arange(M) % n_inst
+            for k in [k for k in tab if k.startswith("inst_")]:
+                tab[k] = (0.5 * torch.randn(n_inst, tab[k].shape[-1], generator=g))[vid].to(device).contiguous()
         out.append((cfg, P, rays, tab))
     return out
 
@@ -261,7 +272,7 @@ class Step:
             M = hi - lo
         self.M, self.N, self.D = M, cfgd["N"], cfgd["D"]
         self.S = self.M * self.N * self.D * len(field_cfgs(cfgd["field"]))
-        self.fields = make_problem(device, rank, cfgd["field"], self.M, self.N, self.D)
+        self.fields = make_problem(device, rank, cfgd["field"], self.M, self.N, self.D, n_inst=cfgd.get("n_inst", 1))
         self.precision = args.precision or cfgd["precision"]
         self.renderers = [FieldRenderer(cfg, device, operand_dtype=self.precision) for cfg, *_ in self.fields]
         self.train = args.passes == "step"

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200render.so")
+LIB_PATH = os.environ.get("B200R_LIB") or os.path.join(HERE, "libb200render.so")  # B200R_LIB: A/B of a build variant (tools/gpu_ab2.sh)
 
 MAX_LAYERS = 32
 MAX_CHANNELS = 16
