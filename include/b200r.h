@@ -217,6 +217,12 @@ size_t b200r_packed_t_bytes(const b200r_field_desc* desc);
 int b200r_pack_weights_t(b200r_handle* h, const b200r_field_desc* desc, const b200r_field_params* params, float alpha,
                          void* packed_t, size_t packed_bytes, b200r_stream stream);
 
+/* Host-side introspection (no device work): number of tensor-core steps (weight-ring slots) of one per-tile program of a field, or
+ * B200R_E_INVALID when the configuration does not build.  kind: 0 forward (query_field), 1 backward (data gradient), 2 its density
+ * chain alone (eikonal reverse chain), 3 the forward warp w = 2 alone (b200r_warp_bwd), 4 density chain + backward warp (normals),
+ * 5 / 6 eikonal forward chains A / B, 7 the backward warp w = 0 alone. */
+int b200r_program_steps(const b200r_field_desc* desc, int32_t kind);
+
 /* Float offsets inside the constant block and inside one frame block (-1 = absent). */
 #define B200R_MAX_COND 12
 typedef struct {

@@ -145,7 +145,7 @@ class MatchBwdArgs(C.Structure):
     _fields_ = [("fwd", MatchArgs), ("g_out", f32p), ("g_feat_can", f32p), ("g_xyz_can", f32p), ("g_logsigma", f32p), ("scratch", f32p)]
 
 
-EXPORTS = ["b200r_field_normals", "b200r_warp_fwd_train", "b200r_warp_bwd", "b200r_quat_mul_fwd", "b200r_quat_mul_bwd", "b200r_quat_mul_bwd_bwd", "b200r_quat_conj", "b200r_loss_fwd", "b200r_loss_bwd", "b200r_match_fwd", "b200r_match_bwd", "b200r_match_scratch_floats", "b200r_eikonal_sizes", "b200r_eikonal_fwd", "b200r_eikonal_bwd", "b200r_tape_sizes", "b200r_field_fwd_train", "b200r_packed_t_bytes", "b200r_pack_weights_t", "b200r_get_block_layout",
+EXPORTS = ["b200r_program_steps", "b200r_field_normals", "b200r_warp_fwd_train", "b200r_warp_bwd", "b200r_quat_mul_fwd", "b200r_quat_mul_bwd", "b200r_quat_mul_bwd_bwd", "b200r_quat_conj", "b200r_loss_fwd", "b200r_loss_bwd", "b200r_match_fwd", "b200r_match_bwd", "b200r_match_scratch_floats", "b200r_eikonal_sizes", "b200r_eikonal_fwd", "b200r_eikonal_bwd", "b200r_tape_sizes", "b200r_field_fwd_train", "b200r_packed_t_bytes", "b200r_pack_weights_t", "b200r_get_block_layout",
            "b200r_field_bwd", "b200r_layer_count", "b200r_packed_bytes", "b200r_create", "b200r_destroy", "b200r_last_error",
            "b200r_pack_weights", "b200r_workspace_bytes", "b200r_field_fwd", "b200r_composite_fwd", "b200r_composite_bwd",
            "b200r_compose_fwd", "b200r_points_fwd", "b200r_warp_fwd", "b200r_importance_fwd"]
@@ -212,6 +212,8 @@ def load():
                                     C.POINTER(RayBatch), C.POINTER(FieldOutputs), C.POINTER(FieldGrads), C.POINTER(Tape),
                                     C.POINTER(ParamGrads), C.POINTER(FrameGrads), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.b200r_field_bwd.restype = C.c_int
+    lib.b200r_program_steps.argtypes = [C.POINTER(FieldDesc), C.c_int32]
+    lib.b200r_program_steps.restype = C.c_int
     lib.b200r_field_normals.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldParams), C.POINTER(FrameTables),
                                         C.POINTER(RayBatch), C.POINTER(FieldOutputs), C.POINTER(Tape), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.b200r_field_normals.restype = C.c_int

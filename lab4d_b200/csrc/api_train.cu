@@ -259,6 +259,26 @@ int b200r_tape_sizes(const b200r_field_desc* desc, int32_t M, int32_t N, int32_t
   return B200R_OK;
 }
 
+int b200r_program_steps(const b200r_field_desc* desc, int32_t kind) {
+  if (!desc) return B200R_E_INVALID;
+  b200r_field_desc d = *desc;
+  b200r_field_desc d16 = d;
+  if (d16.operand_dtype == 2) d16.operand_dtype = 0;  // the backward-side programs run single 16-bit operands
+  b200r::BuiltProgram bp;
+  switch (kind) {
+    case 0: bp = b200r::build_program(d, b200r::MODE_FIELD); break;
+    case 1: bp = b200r::build_bwd_program(d16); break;
+    case 2: bp = b200r::build_bwd_program(d16, true); break;
+    case 3: bp = b200r::build_bwd_program(d16, false, 2); break;
+    case 4: bp = b200r::build_bwd_program(d16, true, 0); break;
+    case 5: bp = b200r::build_eik_chain_program(d, b200r::EIK_CHAIN_A); break;
+    case 6: bp = b200r::build_eik_chain_program(d, b200r::EIK_CHAIN_B); break;
+    case 7: bp = b200r::build_bwd_program(d16, false, 0); break;
+    default: return B200R_E_INVALID;
+  }
+  return bp.ok ? bp.prog.n_steps : B200R_E_INVALID;
+}
+
 int b200r_get_block_layout(const b200r_field_desc* desc, b200r_block_layout* out) {
   if (!desc || !out) return B200R_E_INVALID;
   b200r::BuiltProgram bp = b200r::build_program(*desc);

@@ -246,11 +246,10 @@ def compute_loss(model, batch, results):
 
 def _dq_mul(a, b):
     """lab4d.utils.quat_transform.quaternion_mul (quat_transform.py:106-113) on the quaternion kernels; operands that the
-    reference would have to broadcast by hand are broadcast here (3-vectors stay 3-wide: pure quaternions)."""
+    reference would have to broadcast by hand are broadcast here (3-vectors stay 3-wide: pure quaternions).  CUDA tensors only:
+    `install(dqtorch=True)` leaves the reference's own function in charge of CPU tensors (model set-up, data loading)."""
     from . import quaternion as _q
 
-    if not a.is_cuda:
-        raise RuntimeError("lab4d_b200: quaternion operators run on CUDA only")
     lead = torch.broadcast_shapes(a.shape[:-1], b.shape[:-1])
     a2 = a.expand(lead + a.shape[-1:]).reshape(-1, a.shape[-1])
     b2 = b.expand(lead + b.shape[-1:]).reshape(-1, b.shape[-1])
@@ -307,7 +306,10 @@ def install(lab4d=None, n_depth=64, operand_dtype="fp16x3", bind_grads=False, ma
         import lab4d.utils.quat_transform as qt
 
         old = {"quaternion_mul": qt.quaternion_mul, "quaternion_conjugate": qt.quaternion_conjugate}
-        new = {"quaternion_mul": _dq_mul, "quaternion_conjugate": _dq_conj}
+        old_mul, old_conj = old["quaternion_mul"], old["quaternion_conjugate"]
+        # the kernels take CUDA tensors; CPU tensors (the reference's set-up and data-loading code) keep the reference's own functions
+        new = {"quaternion_mul": lambda a, b: _dq_mul(a, b) if a.is_cuda else old_mul(a, b),
+               "quaternion_conjugate": lambda q: _dq_conj(q) if q.is_cuda else old_conj(q)}
         for mname, mod in list(sys.modules.items()):
             if mod is None or not mname.startswith("lab4d"):
                 continue

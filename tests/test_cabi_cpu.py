@@ -134,3 +134,30 @@ def test_training_layouts_are_consistent():
             assert a1 <= b0, (cfg, spans)
         assert spans[-1][1] <= lay.frame_floats
         assert lay.c_scalars + 8 <= lay.const_floats and lay.c_sdf_w >= 0 and lay.c_rgb2_w >= 0
+
+
+def test_per_tile_programs_of_every_entry_build():
+    """Host logic of the program builders (csrc/program.h) for every field type and every entry: the step lists exist, the
+    sub-programs are consistent with the full backward program, the eikonal chains have the expected slot counts."""
+    from lab4d_b200 import _lib, spec
+
+    lib = _lib.load()
+    comphuman = spec.FieldConfig(motion="skel", B=18, symm_idx=spec.HUMAN_SYMM, dense=True)
+    for cfg in (spec.BG, spec.FG_RIGID, spec.FG_BOB, spec.FG_SKEL_HUMAN, spec.FG_COMP_QUAD, comphuman):
+        for dtype in (0, 1, 2):
+            d = _lib.FieldDesc(category=0 if cfg.category == "fg" else 1, D=cfg.D, W=cfg.W, L_xyz=cfg.L_xyz, L_dir=cfg.L_dir,
+                               appr_channels=cfg.appr_channels, skip=cfg.skip, n_bones=cfg.B if cfg.motion != "rigid" else 0,
+                               has_feature=int(cfg.has_feature), operand_dtype=dtype, dense=int(cfg.dense))
+            n = {k: lib.b200r_program_steps(C.byref(d), k) for k in range(8)}
+            skinned = cfg.motion != "rigid"
+            assert n[0] > 0 and n[1] > 0 and n[2] > 0, (cfg, dtype, n)
+            assert 0 < n[2] < n[1]
+            if skinned:
+                assert n[3] > 0 and n[7] > 0 and n[4] == n[2] + n[7]
+                assert n[1] >= n[2] + n[3] + n[7]
+            else:
+                assert n[3] == 0 and n[7] == 0 and n[4] == n[2]
+            KC = cfg.W // 64
+            assert n[5] == 2 * (1 + KC * cfg.D), (cfg, n[5])            # linear_1 (one embedding chunk), D layers of KC hidden chunks, two N-halves
+            assert n[6] == 2 * (1 + KC * (cfg.D - cfg.skip)), (cfg, n[6])  # the skip layer's embedding chunk, the layers after it
+    assert lib.b200r_program_steps(C.byref(d), 99) < 0
