@@ -59,14 +59,15 @@ def _run(field, Kinv, batch, train, coeff=None):
     return {k: v.detach() for k, v in rend.items()}, {k: v.detach() for k, v in aux.items()}, grads, coeff
 
 
-@pytest.mark.parametrize("field_type,motion", [("fg", "bob"), ("bg", "rigid")])
-def test_patched_reference_trains_like_the_reference(field_type, motion):
+@pytest.mark.parametrize("field_type,motion,dq", [("fg", "bob", False), ("bg", "rigid", False), ("fg", "bob", True)])
+def test_patched_reference_trains_like_the_reference(field_type, motion, dq):
+    """dq: also the reference's quaternion operators (lab4d.utils.quat_transform) on the quaternion kernels."""
     from lab4d_b200 import nnutils
 
     M, N, D = 4, 16, 32
     mf, field, Kinv, batch = _setup(field_type, motion, M, N, D)
     rend_ref, aux_ref, g_ref, coeff = _run(field, Kinv, batch, train=True)
-    undo = nnutils.install(n_depth=D)
+    undo = nnutils.install(n_depth=D, dqtorch=dq)
     try:
         rend, aux, g, _ = _run(field, Kinv, batch, train=True, coeff=coeff)
     finally:
