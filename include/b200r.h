@@ -441,6 +441,21 @@ typedef struct {
 
 int b200r_compose_fwd(b200r_handle* h, const b200r_compose_args* args, b200r_stream stream);
 
+/* Backward of b200r_compose_fwd (autograd through multifields.py:393-397): the gradient of every merged per-sample array goes
+ * back to the two fields through the permutation the forward wrote (`perm`).  g_a / g_b are OVERWRITTEN (every sample of a
+ * field appears exactly once in the merge); NULL = that field lacks the key. */
+typedef struct {
+  int32_t R, Da, Db;
+  int32_t n_channels;
+  const int32_t* perm;                       /* (R*(Da+Db)) from the forward */
+  const float* g_dst[B200R_MAX_CHANNELS];    /* (R*(Da+Db), nch) gradient of the merged array */
+  float* g_a[B200R_MAX_CHANNELS];            /* (R*Da, nch) or NULL */
+  float* g_b[B200R_MAX_CHANNELS];            /* (R*Db, nch) or NULL */
+  int32_t nch[B200R_MAX_CHANNELS];
+} b200r_compose_bwd_args;
+
+int b200r_compose_bwd(b200r_handle* h, const b200r_compose_bwd_args* args, b200r_stream stream);
+
 /* ------------------------------------------------------------------ per-ray feature matching (FeatureNeRF.global_match)
  * lab4d/nnutils/feature.py:152-205: every ray's pixel feature is matched against K candidate samples of the batch,
  *   score[r,k] = exp(logsigma) <feat_px[r], feat_can[idx[k]]>, prob = softmax_k, xyz_matched[r] = sum_k prob[r,k] xyz_can[idx[k]].

@@ -71,6 +71,11 @@ class ComposeArgs(C.Structure):
                 ("dst", f32p * MAX_CHANNELS), ("nch", C.c_int32 * MAX_CHANNELS)]
 
 
+class ComposeBwdArgs(C.Structure):
+    _fields_ = [("R", C.c_int32), ("Da", C.c_int32), ("Db", C.c_int32), ("n_channels", C.c_int32), ("perm", C.c_void_p),
+                ("g_dst", f32p * MAX_CHANNELS), ("g_a", f32p * MAX_CHANNELS), ("g_b", f32p * MAX_CHANNELS), ("nch", C.c_int32 * MAX_CHANNELS)]
+
+
 GRAD_KEYS = ["rgb", "density", "vis", "feature", "xyz", "xyz_cam", "depth", "flow", "cyc_dist", "delta_skin", "skin_entropy",
              "gauss_density"]
 
@@ -145,7 +150,7 @@ class MatchBwdArgs(C.Structure):
     _fields_ = [("fwd", MatchArgs), ("g_out", f32p), ("g_feat_can", f32p), ("g_xyz_can", f32p), ("g_logsigma", f32p), ("scratch", f32p)]
 
 
-EXPORTS = ["b200r_program_steps", "b200r_field_normals", "b200r_warp_fwd_train", "b200r_warp_bwd", "b200r_quat_mul_fwd", "b200r_quat_mul_bwd", "b200r_quat_mul_bwd_bwd", "b200r_quat_conj", "b200r_loss_fwd", "b200r_loss_bwd", "b200r_match_fwd", "b200r_match_bwd", "b200r_match_scratch_floats", "b200r_eikonal_sizes", "b200r_eikonal_fwd", "b200r_eikonal_bwd", "b200r_tape_sizes", "b200r_field_fwd_train", "b200r_packed_t_bytes", "b200r_pack_weights_t", "b200r_get_block_layout",
+EXPORTS = ["b200r_compose_bwd", "b200r_program_steps", "b200r_field_normals", "b200r_warp_fwd_train", "b200r_warp_bwd", "b200r_quat_mul_fwd", "b200r_quat_mul_bwd", "b200r_quat_mul_bwd_bwd", "b200r_quat_conj", "b200r_loss_fwd", "b200r_loss_bwd", "b200r_match_fwd", "b200r_match_bwd", "b200r_match_scratch_floats", "b200r_eikonal_sizes", "b200r_eikonal_fwd", "b200r_eikonal_bwd", "b200r_tape_sizes", "b200r_field_fwd_train", "b200r_packed_t_bytes", "b200r_pack_weights_t", "b200r_get_block_layout",
            "b200r_field_bwd", "b200r_layer_count", "b200r_packed_bytes", "b200r_create", "b200r_destroy", "b200r_last_error",
            "b200r_pack_weights", "b200r_workspace_bytes", "b200r_field_fwd", "b200r_composite_fwd", "b200r_composite_bwd",
            "b200r_compose_fwd", "b200r_points_fwd", "b200r_warp_fwd", "b200r_importance_fwd"]
@@ -212,6 +217,8 @@ def load():
                                     C.POINTER(RayBatch), C.POINTER(FieldOutputs), C.POINTER(FieldGrads), C.POINTER(Tape),
                                     C.POINTER(ParamGrads), C.POINTER(FrameGrads), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.b200r_field_bwd.restype = C.c_int
+    lib.b200r_compose_bwd.argtypes = [C.c_void_p, C.POINTER(ComposeBwdArgs), C.c_void_p]
+    lib.b200r_compose_bwd.restype = C.c_int
     lib.b200r_program_steps.argtypes = [C.POINTER(FieldDesc), C.c_int32]
     lib.b200r_program_steps.restype = C.c_int
     lib.b200r_field_normals.argtypes = [C.c_void_p, C.POINTER(FieldDesc), C.c_void_p, C.POINTER(FieldParams), C.POINTER(FrameTables),

@@ -261,6 +261,21 @@ int b200r_warp_fwd(b200r_handle* h, const b200r_field_desc* desc, const void* pa
                    workspace_bytes, stream_);
 }
 
+int b200r_compose_bwd(b200r_handle* h, const b200r_compose_bwd_args* b, b200r_stream stream) {
+  if (!h) return B200R_E_INVALID;
+  if (!b) return fail(h, B200R_E_INVALID, "compose_bwd: null argument");
+  if (b->R < 1 || b->Da < 1 || b->Db < 1 || !b->perm) return fail(h, B200R_E_INVALID, "compose_bwd: need R, Da, Db >= 1 and the forward's permutation");
+  if (b->Da + b->Db > 8192) return fail(h, B200R_E_INVALID, "compose_bwd: more than 8192 samples per ray unsupported");
+  if (b->n_channels < 0 || b->n_channels > B200R_MAX_CHANNELS) return fail(h, B200R_E_INVALID, "compose_bwd: bad channel count");
+  for (int c = 0; c < b->n_channels; ++c)
+    if (!b->g_dst[c] || b->nch[c] < 1) return fail(h, B200R_E_INVALID, "compose_bwd: null channel gradient or bad width");
+  b200r::DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, B200R_E_CUDA, "cudaSetDevice failed");
+  cudaError_t e = b200r::launch_compose_bwd(*b, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(h, e, "compose backward kernel");
+  return B200R_OK;
+}
+
 int b200r_warp_fwd_train(b200r_handle* h, const b200r_field_desc* desc, const void* packed, const b200r_field_params* par,
                          const b200r_frame_tables* fr, const b200r_point_batch* pts, const b200r_field_outputs* out, const b200r_tape* tape,
                          void* workspace, size_t workspace_bytes, b200r_stream stream_) {

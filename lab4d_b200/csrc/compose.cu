@@ -59,6 +59,41 @@ __global__ void __launch_bounds__(kComposeThreads) compose_fwd_kernel(const b200
   }
 }
 
+// Backward: the merge is a permutation of the concatenated samples, so every key's gradient goes back through it - merged
+// sample `pos` of ray r came from concatenated sample perm[pos].  Reads run flat over the merged gradient (coalesced), writes land
+// in the two fields' arrays (rows of nch floats); a field that lacks the key (NULL) drops its share.  One launch for up to 16 keys
+// instead of one index build + one torch.gather per key and field.
+__global__ void __launch_bounds__(kComposeThreads) compose_bwd_kernel(const b200r_compose_bwd_args b) {
+  extern __shared__ int sperm[];
+  const int Da = b.Da, Dt = b.Da + b.Db;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  for (int t = tid; t < Dt; t += kComposeThreads) sperm[t] = b.perm[(size_t)r * Dt + t];
+  __syncthreads();
+  for (int c = 0; c < b.n_channels; ++c) {
+    const int nch = b.nch[c];
+    const float* g = b.g_dst[c] + (size_t)r * Dt * nch;
+    float* ga = b.g_a[c];
+    float* gb = b.g_b[c];
+    const int n_el = Dt * nch;
+    for (int e = tid; e < n_el; e += kComposeThreads) {
+      const int pos = e / nch, ch = e - pos * nch;
+      const int t = sperm[pos];
+      const float v = g[e];
+      if (t < Da) { if (ga) ga[((size_t)r * Da + t) * nch + ch] = v; }
+      else if (gb) gb[((size_t)r * b.Db + (t - Da)) * nch + ch] = v;
+    }
+  }
+}
+
+cudaError_t launch_compose_bwd(const b200r_compose_bwd_args& b, cudaStream_t stream) {
+  const size_t smem = (size_t)(b.Da + b.Db) * sizeof(int);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(compose_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  compose_bwd_kernel<<<b.R, kComposeThreads, smem, stream>>>(b);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_compose_fwd(const b200r_compose_args& a, cudaStream_t stream) {
   const size_t smem = (size_t)(a.Da + a.Db) * 2 * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;

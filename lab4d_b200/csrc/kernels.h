@@ -151,6 +151,7 @@ cudaError_t launch_composite_fwd(const b200r_composite_args& a, cudaStream_t str
 cudaError_t launch_composite_bwd(const b200r_composite_bwd_args& b, cudaStream_t stream);
 cudaError_t launch_importance_fwd(const b200r_importance_args& a, cudaStream_t stream);
 cudaError_t launch_compose_fwd(const b200r_compose_args& a, cudaStream_t stream);
+cudaError_t launch_compose_bwd(const b200r_compose_bwd_args& b, cudaStream_t stream);
 cudaError_t launch_quat_mul_fwd(const float* a, const float* b, float* out, long long B, int D1, int D2, cudaStream_t s);
 cudaError_t launch_quat_mul_bwd(const float* g, const float* a, const float* b, float* ga, float* gb, long long B, int D1, int D2, cudaStream_t s);
 cudaError_t launch_quat_mul_bwd_bwd(const float* u1, const float* u2, const float* g, const float* a, const float* b, float* gg, float* gga, float* ggb,

@@ -884,7 +884,7 @@ def _merge_pair(h, device, fa, fb, da, db, want_perm=False):
 
 class _Compose(torch.autograd.Function):
     """compose_fields of two fields with the hand-derived backward: the merge is a permutation of the concatenated samples
-    (multifields.py:393-397), so every key's gradient is the inverse gather of the merged gradient."""
+    (multifields.py:393-397), so every key's gradient goes back through it (b200r_compose_bwd: one launch per 16 keys)."""
 
     @staticmethod
     def forward(ctx, keys_a, keys_b, da, db, *vals):
@@ -903,21 +903,28 @@ class _Compose(torch.autograd.Function):
     def backward(ctx, g_deltas, *g_outs):
         (perm,) = ctx.saved_tensors
         R, Dt = perm.shape
-        # inverse permutation: position of concatenated sample j in the merged list
-        inv = torch.empty(R, Dt, dtype=torch.int64, device=perm.device)
-        inv.scatter_(1, perm.long(), torch.arange(Dt, device=perm.device).expand(R, Dt))
+        device = perm.device
+        h = _lib.handle_for(device)
         g = dict(zip(ctx.out_keys, g_outs))
-        res = [None, None, None, None]
-        for keys, lo, hi in ((ctx.keys_a, 0, ctx.Da), (ctx.keys_b, ctx.Da, Dt)):
-            for k in keys:
-                go = g.get(k)
-                if go is None:
-                    res.append(None)
-                    continue
+        keys = [k for k in ctx.out_keys if g.get(k) is not None]
+        ga, gb, keep = {}, {}, []
+        for c0 in range(0, len(keys), _lib.MAX_CHANNELS):  # b200r_compose_bwd: one launch per 16 keys, both fields
+            part = keys[c0:c0 + _lib.MAX_CHANNELS]
+            b = _lib.ComposeBwdArgs()
+            b.R, b.Da, b.Db, b.n_channels, b.perm = R, ctx.Da, ctx.Db, len(part), perm.data_ptr()
+            for i, k in enumerate(part):
+                go = _f32c(g[k])
+                keep.append(go)
                 M, N, _, c = go.shape
-                idx = inv[:, lo:hi].reshape(M, N, hi - lo, 1).expand(M, N, hi - lo, c)
-                res.append(torch.gather(go, 2, idx))
-        return tuple(res)
+                b.g_dst[i], b.nch[i] = go.data_ptr(), c
+                if k in ctx.keys_a:
+                    ga[k] = torch.empty(M, N, ctx.Da, c, device=device)
+                    b.g_a[i] = ga[k].data_ptr()
+                if k in ctx.keys_b:
+                    gb[k] = torch.empty(M, N, ctx.Db, c, device=device)
+                    b.g_b[i] = gb[k].data_ptr()
+            h.check(h.lib.b200r_compose_bwd(h.h, C.byref(b), _stream(device)), "b200r_compose_bwd")
+        return (None, None, None, None, *[ga.get(k) for k in ctx.keys_a], *[gb.get(k) for k in ctx.keys_b])
 
 
 def compose_fields(feats, deltas_list):
